@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py -- sequences/sec of the MegaCRN training step (12-step encoder + 12-step decoder,
+forward + trainer loss + backward [+ one gradient all-reduce when N > 1]) on N B200s.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference        # the reference's CPU path (oracle port) on host cores
+
+Workload = BASELINE.json configs[1]: METR-LA shape N=207, T_in=T_out=12, H=64, batch 64 per GPU
+(weak scaling), synthetic inputs, random-init weights.  Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CONFIGS = {   # name -> (Dims kwargs, per-GPU batch, T_in)
+    "c2": (dict(num_nodes=207, horizon=12, rnn_units=64), 64, 12),
+    "c3": (dict(num_nodes=325, horizon=12, rnn_units=64), 64, 12),
+    "c4": (dict(num_nodes=1843, horizon=6, rnn_units=64), 32, 6),
+    "c5": (dict(num_nodes=2841, horizon=12, rnn_units=128), 32, 12),
+}
+
+
+def fwd_flops(d, B, t_in):
+    """Algorithmic forward FLOPs: identity blocks and hoisted T2 counted once."""
+    N, H, D, M, dm = d.num_nodes, d.rnn_units, d.rnn_units + d.mem_dim, d.mem_num, d.mem_dim
+    def agcn(C, O):
+        return 2 * 4 * N * N * B * C + 2 * B * N * 6 * C * O
+    enc = t_in * (agcn(d.input_dim + H, 2 * H) + agcn(d.input_dim + H, H))
+    cd = d.output_dim + d.ycov_dim
+    dec = d.horizon * (agcn(cd + D, 2 * D) + agcn(cd + D, D))
+    misc = 4 * N ** 3 + 4 * N * N * dm + 4 * N * M * dm + 2 * B * N * H * dm + 4 * B * N * dm * M + 2 * d.horizon * B * N * D
+    return enc + dec + misc
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        j = json.load(open(path))
+        return dict(bf16_burst=j["bf16_tflops"], bf16_sustained=j["bf16_tflops_sustained"], hbm=j["hbm_gbs"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_step(d, B, t_in, threads):
+    """One training step of the reference's CPU path: the oracle port (torch CPU ops + autograd),
+    same workload, all host threads.  Returns a callable."""
+    from oracle import megacrn_oracle as O
+    torch.set_num_threads(threads)
+    p = O.init_params(d, seed=0)
+    x, y_cov, labels = O.synthetic_batch(d, B, t_in, seed=1234)
+    flags = [True] * d.horizon
+
+    def step():
+        loss, _, _ = O.loss_and_grads(d, p, x, y_cov, labels, flags)
+        return float(loss)
+    return step
+
+
+def run_reference_arm(args, d, B, t_in):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    step = cpu_reference_step(d, B, t_in, threads)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = B * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "sequences/sec (12-step enc+dec fwd+bwd)", "value": val, "unit": "sequences/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.config}: N={d.num_nodes} T={t_in}/{d.horizon} H={d.rnn_units} batch={B}, "
+                               "train step fwd+loss+bwd on host CPU"},
+        "cpu_baseline": {"value": val, "unit": "sequences/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} steps of batch {B} (oracle port of the reference, torch CPU fp32)"},
+        "e2e": {"value": val, "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=list(CONFIGS))
+    ap.add_argument("--engine", default="default", choices=["default", "simt"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+
+    from oracle import megacrn_oracle as O   # Dims + synthetic inputs + (cpu_baseline leg only) the CPU port
+    kw, B, t_in = CONFIGS[args.config]
+    d = O.Dims(**kw)
+    if args.impl == "reference":
+        run_reference_arm(args, d, B, t_in)
+        return
+
+    import torch.distributed as dist
+    from megacrn_b200 import MegaCRN, _abi
+    from megacrn_b200.ddp import allreduce_gradients
+    from megacrn_b200.train_step import train_step
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert world == args.gpus or world == 1, f"WORLD_SIZE={world} but --gpus {args.gpus}"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _abi.load()
+    lib.mcrn_set_engine(1 if args.engine == "simt" else 0)
+
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = MegaCRN(d.num_nodes, d.input_dim, d.output_dim, d.horizon, d.rnn_units, mem_num=d.mem_num,
+                    mem_dim=d.mem_dim).to(dev).train()
+    hx, hy, hl = O.synthetic_batch(d, B, t_in, seed=1234 + rank)
+    hx, hy, hl = hx.pin_memory(), hy.pin_memory(), hl.pin_memory()
+    dx, dy, dl = hx.to(dev), hy.to(dev), hl.to(dev)
+    params = list(model.parameters())
+    loss_host = torch.zeros(1).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    stream = torch.cuda.current_stream(dev)
+
+    def step_device():
+        for p in params:
+            p.grad = None
+        loss = train_step(model, dx, dy, dl, batches_seen=0)
+        allreduce_gradients(params)
+        return loss
+
+    def step_e2e():
+        dx.copy_(hx, non_blocking=True); dy.copy_(hy, non_blocking=True); dl.copy_(hl, non_blocking=True)
+        loss = step_device()
+        loss_host.copy_(loss, non_blocking=True)
+        stream.synchronize()
+        return loss_host
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        """K steps, each bracketed by CUDA events on the launching stream, L2 flushed between steps."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        l0 = lib.mcrn_launch_count()
+        for s, e in evs:
+            flush.zero_()
+            s.record(stream)
+            fn()
+            e.record(stream)
+        barrier()
+        launches = lib.mcrn_launch_count() - l0
+        total_ms = sum(s.elapsed_time(e) for s, e in evs)
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches
+
+    for _ in range(args.warmup):
+        step_device()
+    step_e2e()
+    barrier()
+    with ClockSampler(local) as clocks:
+        dev_ms, launches = timed(step_device, args.steps)
+        e2e_ms, _ = timed(step_e2e, args.steps)
+    final_loss = float(step_e2e().item())
+
+    if rank == 0:
+        peaks = measured_peaks()
+        gB = B * world
+        value = gB * args.steps / (dev_ms / 1e3)
+        e2e_value = gB * args.steps / (e2e_ms / 1e3)
+        # ---- roofline of the dominant kernel: decoder propagation GEMM [KS*N x N] x [N x B*D] ----
+        KS, N, D = 4, d.num_nodes, d.rnn_units + d.mem_dim
+        M_, N_, K_ = KS * N, B * D, N
+        ld = lib.mcrn_support_ld(N)
+        a = torch.randn(M_, ld, device=dev); b = torch.randn(K_, N_, device=dev); c = torch.empty(M_, N_, device=dev)
+        eng = 1 if args.engine == "simt" else 0
+        call = lambda: lib.mcrn_gemm(M_, N_, K_, a.data_ptr(), ld, 0, b.data_ptr(), N_, 0, c.data_ptr(), N_, eng,
+                                     stream.cuda_stream)
+        for _ in range(3):
+            call()
+        reps = 20
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        s.record(stream)
+        for _ in range(reps):
+            call()
+        e.record(stream)
+        torch.cuda.synchronize(dev)
+        k_ms = s.elapsed_time(e) / reps
+        k_tflops = 2.0 * M_ * N_ * K_ / (k_ms * 1e-3) / 1e12
+        step_flops = 3 * fwd_flops(d, B, t_in)
+        line = {
+            "metric": "sequences/sec (12-step enc+dec fwd+bwd)", "value": value, "unit": "sequences/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.engine == "simt" else "tf32", "data": "synthetic",
+            "config": {"workload": f"{args.config}: METR-LA-shaped N={d.num_nodes} T_in={t_in} T_out={d.horizon} "
+                                   f"H={d.rnn_units} batch={B}/GPU, train step = forward + trainer loss + backward"
+                                   + (" + 1 NCCL grad all-reduce" if world > 1 else ""),
+                       "global_batch": gB, "parallelism": f"dp{world}", "engine": args.engine,
+                       "l2": "256 MiB memset between timed steps (flush) + 1.2 GB/step activation working set",
+                       "final_loss": final_loss},
+            "e2e": {"value": e2e_value, "unit": "sequences/s", "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": int(4 * (hx.numel() + hy.numel() + hl.numel())), "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "tensor", "kernel": f"propagation GEMM [{M_}x{K_}]x[{K_}x{N_}] (decoder S*[h])",
+                         "achieved": k_tflops, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
+                         "frac": k_tflops / peaks["bf16_burst"], "traffic": None, "kernel_ms": k_ms,
+                         "peak_source": peaks["source"] + "; bf16 burst; the kernel computes in TF32 (half the bf16 rate)",
+                         "step_tflops": step_flops / (dev_ms / args.steps * 1e-3) / 1e12,
+                         "step_frac_of_sustained": step_flops / (dev_ms / args.steps * 1e-3) / 1e12 / peaks["bf16_sustained"]},
+        }
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            cstep = cpu_reference_step(d, B, t_in, threads)
+            cstep()
+            n_cpu = 3
+            t0 = time.perf_counter()
+            for _ in range(n_cpu):
+                cstep()
+            cdt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": B * n_cpu / cdt, "unit": "sequences/s", "cores": threads, "kind": "port",
+                                    "sample": f"{n_cpu} steps of batch {B} (oracle port of the reference, torch CPU fp32)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

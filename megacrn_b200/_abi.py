@@ -1,0 +1,118 @@
+"""ctypes binding of libmegacrn_b200.so (C ABI declared in include/megacrn_b200.h).
+
+There is no fallback: if the shared library is missing or the device is not an
+sm_100 part, every compute call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmegacrn_b200.so")
+
+MCRN_FWD_SAVE_FOR_BACKWARD = 1
+ABI_VERSION = 1
+
+PARAM_FIELDS = (
+    "memory", "wq", "we1", "we2",
+    "enc_gate_w", "enc_gate_b", "enc_update_w", "enc_update_b",
+    "dec_gate_w", "dec_gate_b", "dec_update_w", "dec_update_b",
+    "proj_w", "proj_b",
+)
+# state_dict key of each field, in the reference's registration order
+STATE_DICT_KEYS = (
+    "memory.Memory", "memory.Wq", "memory.We1", "memory.We2",
+    "encoder.dcrnn_cells.0.gate.weights", "encoder.dcrnn_cells.0.gate.bias",
+    "encoder.dcrnn_cells.0.update.weights", "encoder.dcrnn_cells.0.update.bias",
+    "decoder.dcrnn_cells.0.gate.weights", "decoder.dcrnn_cells.0.gate.bias",
+    "decoder.dcrnn_cells.0.update.weights", "decoder.dcrnn_cells.0.update.bias",
+    "proj.0.weight", "proj.0.bias",
+)
+
+
+class Dims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "batch", "num_nodes", "seq_len", "horizon", "input_dim", "output_dim", "ycov_dim",
+        "rnn_units", "num_layers", "cheb_k", "mem_num", "mem_dim")]
+
+
+class Params(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in PARAM_FIELDS]
+
+
+class MegaCRNLibraryError(RuntimeError):
+    pass
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MegaCRNLibraryError(
+            f"{LIB_PATH} is missing: build it with `make -C megacrn_b200/csrc` "
+            "(or `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "megacrn_b200 has no CPU / PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, u8p, fp = C.c_void_p, C.c_char_p, C.c_void_p
+    lib.mcrn_abi_version.restype = C.c_int
+    lib.mcrn_last_error.restype = C.c_char_p
+    lib.mcrn_device_ok.restype = C.c_int
+    lib.mcrn_launch_count.restype = C.c_uint64
+    lib.mcrn_set_engine.argtypes = [C.c_int]
+    lib.mcrn_get_engine.restype = C.c_int
+    lib.mcrn_support_ld.argtypes = [C.c_int]
+    lib.mcrn_workspace_bytes.restype = C.c_size_t
+    lib.mcrn_workspace_bytes.argtypes = [C.POINTER(Dims), C.c_uint32]
+    lib.mcrn_forward.restype = C.c_int
+    lib.mcrn_forward.argtypes = [C.POINTER(Dims), C.POINTER(Params), fp, fp, fp, u8p,
+                                 fp, fp, fp, fp, fp, vp, C.c_size_t, C.c_uint32, vp]
+    lib.mcrn_backward.restype = C.c_int
+    lib.mcrn_backward.argtypes = [C.POINTER(Dims), C.POINTER(Params), fp, fp, fp, u8p,
+                                  fp, fp, fp, fp, fp, C.POINTER(Params), vp, C.c_size_t, vp]
+    lib.mcrn_trainer_loss.restype = C.c_int
+    lib.mcrn_trainer_loss.argtypes = [C.POINTER(Dims), fp, fp, fp, fp, fp, C.c_float, C.c_float, C.c_float,
+                                      C.c_float, fp, fp, fp, vp, C.c_size_t, vp]
+    lib.mcrn_supports_fwd.restype = C.c_int
+    lib.mcrn_supports_fwd.argtypes = [C.POINTER(Dims), fp, fp, fp, fp, vp, C.c_size_t, vp]
+    lib.mcrn_gemm.restype = C.c_int
+    lib.mcrn_gemm.argtypes = [C.c_int, C.c_int, C.c_int, fp, C.c_int, C.c_int, fp, C.c_int, C.c_int,
+                              fp, C.c_int, C.c_int, vp]
+    lib.mcrn_host_workspace_bytes.restype = C.c_size_t
+    lib.mcrn_host_workspace_bytes.argtypes = [C.POINTER(Dims), C.c_uint32]
+    lib.mcrn_forward_host.restype = C.c_int
+    lib.mcrn_forward_host.argtypes = [C.POINTER(Dims), C.POINTER(Params), fp, fp, fp, u8p,
+                                      fp, fp, fp, fp, fp, vp, C.c_size_t, C.c_uint32, vp]
+    if lib.mcrn_abi_version() != ABI_VERSION:
+        raise MegaCRNLibraryError(f"ABI mismatch: library {lib.mcrn_abi_version()} vs binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = load().mcrn_last_error().decode("utf-8", "replace")
+        raise MegaCRNLibraryError(f"{what} failed with status {status}: {msg}")
+
+
+def ptr(t) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def make_params(tensors: Sequence) -> Params:
+    p = Params()
+    for name, t in zip(PARAM_FIELDS, tensors):
+        setattr(p, name, t.data_ptr())
+    return p
+
+
+def tf_bytes(flags: Optional[Sequence[bool]], horizon: int) -> bytes:
+    if flags is None:
+        return bytes(horizon)
+    assert len(flags) == horizon
+    return bytes(1 if f else 0 for f in flags)

@@ -1,0 +1,92 @@
+// The training step's loss, fused: masked MAE on inverse-scaled values
+// (model/utils.py:126-133, :45-54) + lamb*TripletMarginLoss(margin=1) + lamb1*MSELoss on
+// query vs. (detached) pos/neg (model/traintest_MegaCRN.py:118-125).
+#pragma once
+
+#include "small_kernels.cuh"
+
+namespace mcrn {
+
+// scratch[0] = #(y_true != 0), [1] = sum |y_pred-y_true|*mask, [2] = sum triplet hinge, [3] = sum (q-p)^2
+__global__ void __launch_bounds__(256) k_loss_reduce_out(const float* __restrict__ out, const float* __restrict__ lab,
+                                                         int64_t n, float mean, float std, float* __restrict__ scratch) {
+  __shared__ float sh[8];
+  float cnt = 0.f, sabs = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float yt = __fadd_rn(__fmul_rn(lab[i], std), mean);
+    float yp = __fadd_rn(__fmul_rn(out[i], std), mean);
+    if (yt != 0.f) { cnt += 1.f; sabs += fabsf(yp - yt); }
+  }
+  cnt = block_sum_256(cnt, sh);
+  sabs = block_sum_256(sabs, sh);
+  if (threadIdx.x == 0) { atomicAdd(scratch + 0, cnt); atomicAdd(scratch + 1, sabs); }
+}
+
+// one warp per (b, n) row of query/pos/neg [rows][d]
+__global__ void __launch_bounds__(256) k_loss_reduce_rows(const float* __restrict__ q, const float* __restrict__ p,
+                                                          const float* __restrict__ ng, int64_t rows, int d,
+                                                          float* __restrict__ scratch) {
+  __shared__ float sh[8];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float trip = 0.f, mse = 0.f;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < rows; row += (int64_t)gridDim.x * 8) {
+    float sp = 0.f, sn = 0.f, sm = 0.f;
+    for (int j = lane; j < d; j += 32) {
+      float qq = q[row * d + j], pp = p[row * d + j], nn = ng[row * d + j];
+      float a = qq - pp + 1e-6f, b = qq - nn + 1e-6f, c = qq - pp;
+      sp = fmaf(a, a, sp); sn = fmaf(b, b, sn); sm = fmaf(c, c, sm);
+    }
+    sp = warp_sum(sp); sn = warp_sum(sn); sm = warp_sum(sm);
+    if (lane == 0) { trip += fmaxf(sqrtf(sp) - sqrtf(sn) + 1.0f, 0.f); mse += sm; }
+  }
+  trip = block_sum_256(trip, sh);
+  mse = block_sum_256(mse, sh);
+  if (threadIdx.x == 0) { atomicAdd(scratch + 2, trip); atomicAdd(scratch + 3, mse); }
+}
+
+__global__ void k_loss_finish(const float* __restrict__ scratch, int64_t rows, int d, float lamb, float lamb1,
+                              float* __restrict__ loss_out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float cnt = scratch[0];
+    float l1 = cnt > 0.f ? scratch[1] / cnt : 0.f;
+    loss_out[0] = l1 + lamb * scratch[2] / (float)rows + lamb1 * scratch[3] / ((float)rows * (float)d);
+  }
+}
+
+__global__ void k_loss_grad_out(const float* __restrict__ out, const float* __restrict__ lab, int64_t n, float mean,
+                                float std, const float* __restrict__ scratch, float* __restrict__ d_out) {
+  float cnt = scratch[0];
+  float sc = cnt > 0.f ? std / cnt : 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float yt = __fadd_rn(__fmul_rn(lab[i], std), mean);
+    float yp = __fadd_rn(__fmul_rn(out[i], std), mean);
+    float df = yp - yt;
+    float g = (yt != 0.f) ? (df > 0.f ? sc : (df < 0.f ? -sc : 0.f)) : 0.f;
+    d_out[i] = g;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_loss_grad_rows(const float* __restrict__ q, const float* __restrict__ p,
+                                                        const float* __restrict__ ng, int64_t rows, int d, float lamb,
+                                                        float lamb1, float* __restrict__ d_q) {
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < rows; row += (int64_t)gridDim.x * 8) {
+    float sp = 0.f, sn = 0.f;
+    for (int j = lane; j < d; j += 32) {
+      float qq = q[row * d + j];
+      float a = qq - p[row * d + j] + 1e-6f, b = qq - ng[row * d + j] + 1e-6f;
+      sp = fmaf(a, a, sp); sn = fmaf(b, b, sn);
+    }
+    sp = sqrtf(warp_sum(sp)); sn = sqrtf(warp_sum(sn));
+    bool active = (sp - sn + 1.0f) > 0.f;
+    float ct = lamb / (float)rows, cm = 2.0f * lamb1 / ((float)rows * (float)d);
+    for (int j = lane; j < d; j += 32) {
+      float qq = q[row * d + j], pp = p[row * d + j], nn = ng[row * d + j];
+      float g = cm * (qq - pp);
+      if (active) g += ct * ((qq - pp + 1e-6f) / sp - (qq - nn + 1e-6f) / sn);
+      d_q[row * d + j] = g;
+    }
+  }
+}
+
+}  // namespace mcrn

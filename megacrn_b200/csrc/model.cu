@@ -1,0 +1,495 @@
+// Orchestration of the MegaCRN hot path on one B200: supports prologue, encoder, memory
+// query, decoder (forward) and the BPTT backward, as sequences of GEMM-engine calls with
+// fused epilogues plus the small HBM-bound kernels.  The decomposition is the one proven in
+// tests/kernel_spec.py; reference lines are cited per stage.
+#include <stdarg.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "engine.cuh"
+#include "plan.cuh"
+#include "loss.cuh"
+#include "small_kernels.cuh"
+
+namespace mcrn {
+
+// ---- error / counters ---------------------------------------------------------------
+static thread_local char t_err[1024] = "";
+std::atomic<uint64_t> g_launches{0};
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_err, sizeof(t_err), fmt, ap);
+  va_end(ap);
+}
+
+int make_geo(const mcrn_dims* dm, Geo* g) {
+  if (!dm) { set_error("dims is null"); return MCRN_ERR_BAD_POINTER; }
+  if (dm->batch < 1 || dm->num_nodes < 2 || dm->seq_len < 1 || dm->horizon < 1 || dm->input_dim < 1 ||
+      dm->output_dim < 1 || dm->ycov_dim < 0 || dm->rnn_units < 1 || dm->mem_num < 2 || dm->mem_dim < 1) {
+    set_error("bad dims: B=%d N=%d T_in=%d T_out=%d Cin=%d Cout=%d ycov=%d H=%d M=%d d=%d", dm->batch, dm->num_nodes,
+              dm->seq_len, dm->horizon, dm->input_dim, dm->output_dim, dm->ycov_dim, dm->rnn_units, dm->mem_num,
+              dm->mem_dim);
+    return MCRN_ERR_BAD_DIMS;
+  }
+  if (dm->num_layers != 1) {
+    set_error("num_layers=%d: only the reference default num_layers=1 is implemented", dm->num_layers);
+    return MCRN_ERR_BAD_DIMS;
+  }
+  if (dm->cheb_k < 2) { set_error("cheb_k=%d: need >= 2", dm->cheb_k); return MCRN_ERR_BAD_DIMS; }
+  g->B = dm->batch; g->N = dm->num_nodes; g->T_in = dm->seq_len; g->T_out = dm->horizon;
+  g->Cin = dm->input_dim; g->Cout = dm->output_dim; g->Ycov = dm->ycov_dim;
+  g->H = dm->rnn_units; g->M = dm->mem_num; g->d = dm->mem_dim; g->D = g->H + g->d;
+  g->cheb_k = dm->cheb_k; g->KS = 2 * (dm->cheb_k - 1); g->NB = 1 + g->KS;
+  g->Cdec = g->Cout + g->Ycov;
+  g->ldS = support_ld(g->N);
+  g->R = (int64_t)g->N * g->B;
+  int cm = g->Cin > g->Cdec ? g->Cin : g->Cdec;
+  if (g->NB * cm > 16) {
+    set_error("(1+2(cheb_k-1))*max(input_dim, output_dim+ycov_dim) = %d exceeds 16", g->NB * cm);
+    return MCRN_ERR_BAD_DIMS;
+  }
+  if (g->R * (int64_t)(2 * g->D) >= (int64_t)1 << 31) { set_error("N*B*2D overflows int32 row indexing"); return MCRN_ERR_BAD_DIMS; }
+  return MCRN_OK;
+}
+
+static inline int ew_grid(int64_t n) { int64_t b = (n + 255) / 256; return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b)); }
+
+// ---- one AGCRN cell -------------------------------------------------------------------
+struct CellW {           // folded weights of one cell (plan buffers)
+  const float *wg_st, *wg_in, *bg, *wu_st, *wu_in, *bu;
+  int Hs, Cin;
+};
+struct CellBufs {        // per-step activations
+  const float* xpin; int64_t xp_k, xp_n;
+  float *xpg, *xpu, *z, *r, *hc;
+};
+
+// propagation  XP[1..KS] = S * XP[0]      (model/MegaCRN.py:24-25 for the KS real supports)
+static int propagate(const Geo& g, const float* S, float* xp, int C, cudaStream_t st) {
+  GemmDesc q;
+  q.A = S; q.a_row = g.ldS; q.a_k = 1; q.M = g.KS * g.N; q.Kseg = g.N;
+  q.B = xp; q.b_k = (int64_t)g.B * C; q.b_n = 1; q.N = g.B * C;
+  EpiStore e{xp + (int64_t)g.R * C, (int64_t)g.B * C, 0, 1.0f, nullptr, nullptr};
+  return gemm(q, e, st);
+}
+
+static int cell_forward(const Geo& g, const float* S, const CellW& w, const CellBufs& b, float* h_out, cudaStream_t st) {
+  const int Hs = w.Hs;
+  MCRN_TRY(propagate(g, S, b.xpg, Hs, st));
+  {  // gate AGCN + sigmoid + z*h                                   model/MegaCRN.py:42-45
+    GemmDesc q;
+    q.A = b.xpg; q.a_row = Hs; q.a_k = 1; q.a_seg = g.R * Hs; q.nseg = g.NB; q.Kseg = Hs; q.M = (int)g.R;
+    q.B = w.wg_st; q.b_seg = (int64_t)Hs * 2 * Hs; q.b_k = 2 * Hs; q.b_n = 1; q.N = 2 * Hs;
+    EpiGate e{InTerm{b.xpin, b.xp_k, b.xp_n, w.wg_in, w.bg, g.NB, w.Cin, 2 * Hs, g.B}, Hs, b.xpg, b.z, b.r, b.xpu};
+    MCRN_TRY(gemm(q, e, st));
+  }
+  MCRN_TRY(propagate(g, S, b.xpu, Hs, st));
+  {  // update AGCN + tanh + blend                                  model/MegaCRN.py:46-47
+    GemmDesc q;
+    q.A = b.xpu; q.a_row = Hs; q.a_k = 1; q.a_seg = g.R * Hs; q.nseg = g.NB; q.Kseg = Hs; q.M = (int)g.R;
+    q.B = w.wu_st; q.b_seg = (int64_t)Hs * Hs; q.b_k = Hs; q.b_n = 1; q.N = Hs;
+    EpiUpdate e{InTerm{b.xpin, b.xp_k, b.xp_n, w.wu_in, w.bu, g.NB, w.Cin, Hs, g.B}, Hs, b.xpg, b.r, b.hc, h_out};
+    MCRN_TRY(gemm(q, e, st));
+  }
+  return MCRN_OK;
+}
+
+// input-channel propagation  XPin[1..KS] = S * XPin[0]  with XPin(k, node, col) strides
+static int propagate_in(const Geo& g, const float* S, float* xpin, int64_t xp_k, int64_t xp_n, int cols, cudaStream_t st) {
+  GemmDesc q;
+  q.A = S; q.a_row = g.ldS; q.a_k = 1; q.M = g.N; q.Kseg = g.N; q.a_batch = (int64_t)g.N * g.ldS;
+  q.B = xpin; q.b_k = xp_n; q.b_n = 1; q.N = cols; q.b_batch = 0; q.nbatch = g.KS;
+  EpiStore e{xpin + xp_k, xp_n, xp_k, 1.0f, nullptr, nullptr};
+  return gemm(q, e, st);
+}
+
+struct Ptrs {            // resolved workspace pointers
+  float* w;
+  const Plan* p;
+  float* at(size_t off) const { return w + off; }
+};
+
+static int supports_forward(const Geo& g, const Plan& p, float* ws, const float* mem, const float* we1, const float* we2,
+                            float* S, cudaStream_t st) {
+  float *E1 = ws + p.E1, *E2 = ws + p.E2, *L1 = ws + p.L1, *L2 = ws + p.L2;
+  for (int i = 0; i < 2; ++i) {  // E_i = We_i * Memory                         model/MegaCRN.py:169-170
+    GemmDesc q;
+    q.A = i ? we2 : we1; q.a_row = g.M; q.a_k = 1; q.M = g.N; q.Kseg = g.M;
+    q.B = mem; q.b_k = g.d; q.b_n = 1; q.N = g.d;
+    EpiStore e{i ? E2 : E1, g.d, 0, 1.0f, nullptr, nullptr};
+    MCRN_TRY(gemm(q, e, st));
+  }
+  const int per = g.cheb_k - 1;
+  for (int i = 0; i < 2; ++i) {  // logits E1 E2^T / E2 E1^T, relu, row softmax   :171-172
+    GemmDesc q;
+    q.A = i ? E2 : E1; q.a_row = g.d; q.a_k = 1; q.M = g.N; q.Kseg = g.d;
+    q.B = i ? E1 : E2; q.b_k = 1; q.b_n = g.d; q.N = g.N;
+    EpiStore e{i ? L2 : L1, g.ldS, 0, 1.0f, nullptr, nullptr};
+    MCRN_TRY(gemm(q, e, st));
+    float* gi = S + (int64_t)i * per * g.N * g.ldS;
+    MCRN_LAUNCH(k_relu_softmax_rows, g.N, 256, 0, st, i ? L2 : L1, gi, g.N, g.ldS);
+    for (int k = 2; k < g.cheb_k; ++k) {  // T_k = 2 g T_{k-1} - T_{k-2}          :21-22 (hoisted)
+      float* tk = gi + (int64_t)(k - 1) * g.N * g.ldS;
+      const float* tkm1 = gi + (int64_t)(k - 2) * g.N * g.ldS;
+      const float* tkm2 = (k >= 3) ? gi + (int64_t)(k - 3) * g.N * g.ldS : nullptr;
+      GemmDesc c;
+      c.A = gi; c.a_row = g.ldS; c.a_k = 1; c.M = g.N; c.Kseg = g.N;
+      c.B = tkm1; c.b_k = g.ldS; c.b_n = 1; c.N = g.N;
+      EpiCheb e{tk, g.ldS, tkm2};
+      MCRN_TRY(gemm(c, e, st));
+    }
+  }
+  return MCRN_OK;
+}
+
+static int fold_all_weights(const Geo& g, const Plan& p, float* ws, const mcrn_params* prm, cudaStream_t st) {
+  MCRN_LAUNCH(k_fold_weights, 128, 256, 0, st, prm->enc_gate_w, ws + p.e_wg_st, ws + p.e_wg_in, g.Cin, g.H, 2 * g.H, g.cheb_k);
+  MCRN_LAUNCH(k_fold_weights, 128, 256, 0, st, prm->enc_update_w, ws + p.e_wu_st, ws + p.e_wu_in, g.Cin, g.H, g.H, g.cheb_k);
+  MCRN_LAUNCH(k_fold_weights, 128, 256, 0, st, prm->dec_gate_w, ws + p.d_wg_st, ws + p.d_wg_in, g.Cdec, g.D, 2 * g.D, g.cheb_k);
+  MCRN_LAUNCH(k_fold_weights, 128, 256, 0, st, prm->dec_update_w, ws + p.d_wu_st, ws + p.d_wu_in, g.Cdec, g.D, g.D, g.cheb_k);
+  return MCRN_OK;
+}
+
+static CellBufs enc_bufs(const Geo& g, const Plan& p, float* ws, int t) {
+  int s = t % p.enc_slots;
+  CellBufs b;
+  b.xpin = ws + p.enc_xpin + (int64_t)t * g.B * g.Cin;          // layout [NB][N][T][B][Cin]
+  b.xp_k = (int64_t)g.N * g.T_in * g.B * g.Cin;
+  b.xp_n = (int64_t)g.T_in * g.B * g.Cin;
+  b.xpg = ws + p.enc_xpg + p.enc_xp_sz * s;
+  b.xpu = ws + p.enc_xpu + p.enc_xp_sz * s;
+  b.z = p.save ? ws + p.enc_z + p.enc_v_sz * s : nullptr;
+  b.r = ws + p.enc_r + p.enc_v_sz * s;
+  b.hc = p.save ? ws + p.enc_hc + p.enc_v_sz * s : nullptr;
+  return b;
+}
+static CellBufs dec_bufs(const Geo& g, const Plan& p, float* ws, int t) {
+  int s = t % p.dec_slots;
+  CellBufs b;
+  b.xpin = ws + p.dec_xpin + p.dec_xpin_sz * s;                 // layout [NB][N][B][Cdec]
+  b.xp_k = (int64_t)g.R * g.Cdec;
+  b.xp_n = (int64_t)g.B * g.Cdec;
+  b.xpg = ws + p.dec_xpg + p.dec_xp_sz * s;
+  b.xpu = ws + p.dec_xpu + p.dec_xp_sz * s;
+  b.z = p.save ? ws + p.dec_z + p.dec_v_sz * s : nullptr;
+  b.r = ws + p.dec_r + p.dec_v_sz * s;
+  b.hc = p.save ? ws + p.dec_hc + p.dec_v_sz * s : nullptr;
+  return b;
+}
+static CellW enc_w(const Geo& g, const Plan& p, float* ws, const mcrn_params* prm) {
+  return CellW{ws + p.e_wg_st, ws + p.e_wg_in, prm->enc_gate_b, ws + p.e_wu_st, ws + p.e_wu_in, prm->enc_update_b, g.H, g.Cin};
+}
+static CellW dec_w(const Geo& g, const Plan& p, float* ws, const mcrn_params* prm) {
+  return CellW{ws + p.d_wg_st, ws + p.d_wg_in, prm->dec_gate_b, ws + p.d_wu_st, ws + p.d_wu_in, prm->dec_update_b, g.D, g.Cdec};
+}
+
+// ======================================================================================
+// forward                                                        model/MegaCRN.py:168-194
+// ======================================================================================
+int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const float* x, const float* y_cov,
+                 const float* labels, const uint8_t* tf, float* output, float* h_att, float* query, float* pos,
+                 float* neg, float* ws, cudaStream_t st) {
+  float* S = ws + p.S;
+  MCRN_TRY(supports_forward(g, p, ws, prm->memory, prm->we1, prm->we2, S, st));
+  MCRN_TRY(fold_all_weights(g, p, ws, prm, st));
+  // ---- encoder (ADCRNN_Encoder.forward :65-83; zero initial state :50-51, :174) ----
+  {
+    int64_t n_in = (int64_t)g.N * g.T_in * g.B * g.Cin;
+    MCRN_LAUNCH(k_stage_encoder_input, ew_grid(n_in), 256, 0, st, x, ws + p.enc_xpin, g.B, g.T_in, g.N, g.Cin);
+    MCRN_TRY(propagate_in(g, S, ws + p.enc_xpin, (int64_t)g.N * g.T_in * g.B * g.Cin, (int64_t)g.T_in * g.B * g.Cin,
+                          g.T_in * g.B * g.Cin, st));
+    MCRN_CUDA_OK(cudaMemsetAsync(ws + p.enc_xpg, 0, (size_t)g.R * g.H * sizeof(float), st));
+    CellW w = enc_w(g, p, ws, prm);
+    for (int t = 0; t < g.T_in; ++t) {
+      CellBufs b = enc_bufs(g, p, ws, t);
+      float* h_out = (t + 1 < g.T_in) ? enc_bufs(g, p, ws, t + 1).xpg : ws + p.h_enc;
+      MCRN_TRY(cell_forward(g, S, w, b, h_out, st));
+    }
+  }
+  // ---- memory query (:159-166) + decoder initial state (:179) ----
+  {
+    CellBufs b0 = dec_bufs(g, p, ws, 0);
+    size_t shm = 8 * (g.d + g.M) * sizeof(float);
+    MCRN_LAUNCH(k_memory_query, (int)ceil_div64(g.R, 8), 256, shm, st, ws + p.h_enc, prm->wq, prm->memory,
+                ws + p.mq_q, ws + p.mq_att, reinterpret_cast<int*>(ws + p.mq_ind), h_att, query, pos, neg, b0.xpg,
+                g.B, g.N, g.H, g.M, g.d);
+  }
+  // ---- decoder loop (:181-192) ----
+  {
+    CellW w = dec_w(g, p, ws, prm);
+    for (int t = 0; t < g.T_out; ++t) {
+      CellBufs b = dec_bufs(g, p, ws, t);
+      const float* go_src = nullptr;
+      if (t > 0) go_src = (tf && tf[t - 1]) ? labels : output;
+      int64_t n_in = (int64_t)g.R * g.Cdec;
+      MCRN_LAUNCH(k_stage_decoder_input, ew_grid(n_in), 256, 0, st, go_src, y_cov, const_cast<float*>(b.xpin), g.B,
+                  g.T_out, g.N, g.Cout, g.Ycov, t);
+      MCRN_TRY(propagate_in(g, S, const_cast<float*>(b.xpin), b.xp_k, b.xp_n, g.B * g.Cdec, st));
+      float* h_out = (t + 1 < g.T_out) ? dec_bufs(g, p, ws, t + 1).xpg : ws + p.h_dec_last;
+      MCRN_TRY(cell_forward(g, S, w, b, h_out, st));
+      MCRN_LAUNCH(k_proj_fwd, (int)ceil_div64(g.R, 8), 256, 0, st, h_out, prm->proj_w, prm->proj_b, output, g.B,
+                  g.T_out, g.N, g.D, g.Cout, t);
+    }
+  }
+  return MCRN_OK;
+}
+
+// ======================================================================================
+// backward (BPTT)                                     tests/kernel_spec.py: cell_bwd, model_bwd
+// ======================================================================================
+struct CellAcc { float *wg_st, *wg_in, *bg, *wu_st, *wu_in, *bu; };
+
+static int split_for(int64_t tiles, int64_t k_iters) {
+  // aim for ~4 waves of 148 CTAs, at least 4 k-iterations per split
+  int64_t s = (148 * 4 + tiles - 1) / tiles;
+  int64_t cap = k_iters / 4 > 0 ? k_iters / 4 : 1;
+  if (s > cap) s = cap;
+  if (s < 1) s = 1;
+  if (s > 256) s = 256;
+  return (int)s;
+}
+
+// dW_st[k] += XP[k]^T * dV     (M = Hs, N = O, K = R, batched over the NB blocks, split-K atomics)
+static int acc_dw(const Geo& g, const float* xp, int Hs, const float* dv, int O, float* dw, cudaStream_t st) {
+  GemmDesc q;
+  q.A = xp; q.a_row = 1; q.a_k = Hs; q.a_batch = g.R * Hs; q.M = Hs; q.Kseg = (int)g.R;
+  q.B = dv; q.b_k = O; q.b_n = 1; q.b_batch = 0; q.N = O; q.nbatch = g.NB;
+  q.splits = split_for((int64_t)ceil_div(Hs, 64) * ceil_div(O, 64) * g.NB, g.R / 16);
+  EpiAtomicAdd e{dw, O, (int64_t)Hs * O};
+  return gemm(q, e, st);
+}
+// dXP[k] = dV * W_st[k]^T      (M = R, N = NB*Hs, K = O), stored block-wise
+static int make_dxp(const Geo& g, const float* dv, int O, const float* wst, int Hs, float* dxp, cudaStream_t st) {
+  GemmDesc q;
+  q.A = dv; q.a_row = O; q.a_k = 1; q.M = (int)g.R; q.Kseg = O;
+  q.B = wst; q.b_k = 1; q.b_n = O; q.N = g.NB * Hs;
+  EpiBlocks e{dxp, Hs, g.R * Hs};
+  return gemm(q, e, st);
+}
+// out = add1 + add2 + dXP[0] + sum_k S_k^T dXP[1+k]    (M = N nodes, N = B*C, K = KS*N)
+static int propagate_T(const Geo& g, const float* S, const float* dxp, int C, const float* add2, float* out, cudaStream_t st) {
+  GemmDesc q;
+  q.A = S; q.a_row = 1; q.a_k = g.ldS; q.M = g.N; q.Kseg = g.KS * g.N;
+  q.B = dxp + g.R * C; q.b_k = (int64_t)g.B * C; q.b_n = 1; q.N = g.B * C;
+  EpiStore e{out, (int64_t)g.B * C, 0, 1.0f, dxp, add2};
+  return gemm(q, e, st);
+}
+// dS_k += dXP[1+k] * X^T       (M = KS*N, N = N nodes, K = B*C; X(node, col) = x + node*x_n + col)
+static int acc_ds(const Geo& g, const float* dp, int64_t dp_row, const float* x, int64_t x_n, int cols, float* dS, cudaStream_t st) {
+  GemmDesc q;
+  q.A = dp; q.a_row = dp_row; q.a_k = 1; q.M = g.KS * g.N; q.Kseg = cols;
+  q.B = x; q.b_k = 1; q.b_n = x_n; q.N = g.N;
+  q.splits = split_for((int64_t)ceil_div(q.M, 64) * ceil_div(q.N, 64), cols / 16);
+  EpiAtomicAdd e{dS, g.ldS, 0};
+  return gemm(q, e, st);
+}
+
+// One cell backward.  dH (in) = grad of h'; dH_out (out) = grad of h; if dxin != null also writes
+// d(xin)[N][B][Cin].
+static int cell_backward(const Geo& g, const Plan& p, float* ws, const float* S, const CellW& w, const CellBufs& b,
+                         const CellAcc& a, const float* dH, float* dH_out, float* dxin, cudaStream_t st) {
+  const int Hs = w.Hs;
+  const int64_t nH = g.R * Hs;
+  float *dU = ws + p.dU, *dG = ws + p.dG, *dXP = ws + p.dXP, *dZH = ws + p.dZH, *dHp = ws + p.dHp;
+  float *dXPin = ws + p.dXPin, *dS = ws + p.dS;
+  MCRN_LAUNCH(k_bwd_du, ew_grid(nH), 256, 0, st, dH, b.r, b.hc, dU, nH);
+  // ---- update AGCN ----
+  MCRN_TRY(make_dxp(g, dU, Hs, w.wu_st, Hs, dXP, st));
+  MCRN_TRY(acc_dw(g, b.xpu, Hs, dU, Hs, a.wu_st, st));
+  MCRN_TRY(propagate_T(g, S, dXP, Hs, nullptr, dZH, st));
+  MCRN_TRY(acc_ds(g, dXP + nH, (int64_t)g.B * Hs, b.xpu, (int64_t)g.B * Hs, g.B * Hs, dS, st));
+  MCRN_LAUNCH(k_bwd_dg, ew_grid(nH), 256, 0, st, dZH, dH, b.xpg, b.z, b.r, b.hc, dG, dHp, g.R, Hs);
+  // ---- gate AGCN ----
+  MCRN_TRY(make_dxp(g, dG, 2 * Hs, w.wg_st, Hs, dXP, st));
+  MCRN_TRY(acc_dw(g, b.xpg, Hs, dG, 2 * Hs, a.wg_st, st));
+  MCRN_TRY(propagate_T(g, S, dXP, Hs, dHp, dH_out, st));
+  MCRN_TRY(acc_ds(g, dXP + nH, (int64_t)g.B * Hs, b.xpg, (int64_t)g.B * Hs, g.B * Hs, dS, st));
+  // ---- biases + input channels ----
+  size_t shm = (size_t)64 * g.NB * w.Cin * sizeof(float);
+  int rb = (int)ceil_div64(g.R, 64);
+  MCRN_LAUNCH(k_bwd_bias_win, rb, 256, shm, st, dU, Hs, b.xpin, b.xp_k, b.xp_n, g.NB, w.Cin, g.B, g.R, a.bu, a.wu_in);
+  MCRN_LAUNCH(k_bwd_bias_win, rb, 256, shm, st, dG, 2 * Hs, b.xpin, b.xp_k, b.xp_n, g.NB, w.Cin, g.B, g.R, a.bg, a.wg_in);
+  MCRN_LAUNCH(k_bwd_dxpin, (int)ceil_div64(g.R, 8), 256, 0, st, dU, w.wu_in, Hs, dG, w.wg_in, 2 * Hs, g.NB, w.Cin,
+              g.R, dXPin);
+  MCRN_TRY(acc_ds(g, dXPin + g.R * w.Cin, (int64_t)g.B * w.Cin, b.xpin, b.xp_n, g.B * w.Cin, dS, st));
+  if (dxin) MCRN_TRY(propagate_T(g, S, dXPin, w.Cin, nullptr, dxin, st));
+  return MCRN_OK;
+}
+
+static int supports_backward(const Geo& g, const Plan& p, float* ws, const mcrn_params* prm, const mcrn_params* grads,
+                             cudaStream_t st) {
+  const int per = g.cheb_k - 1;
+  const int64_t mat = (int64_t)g.N * g.ldS;
+  float* S = ws + p.S;
+  float* dS = ws + p.dS;
+  float* dg[2] = {ws + p.dg1, ws + p.dg2};
+  for (int i = 0; i < 2; ++i) {
+    float* gi = S + (int64_t)i * per * mat;
+    float* dt = dS + (int64_t)i * per * mat;                 // dt[k-1] = d T_k, k = 1..cheb_k-1
+    for (int k = g.cheb_k - 1; k >= 2; --k) {
+      float* dtk = dt + (int64_t)(k - 1) * mat;
+      {  // dg += 2 * dT_k * T_{k-1}^T
+        GemmDesc q;
+        q.A = dtk; q.a_row = g.ldS; q.a_k = 1; q.M = g.N; q.Kseg = g.N;
+        q.B = gi + (int64_t)(k - 2) * mat; q.b_k = 1; q.b_n = g.ldS; q.N = g.N;
+        EpiStore e{dg[i], g.ldS, 0, 2.0f, dg[i], nullptr};
+        MCRN_TRY(gemm(q, e, st));
+      }
+      {  // dT_{k-1} += 2 * g^T * dT_k
+        float* dtm1 = dt + (int64_t)(k - 2) * mat;
+        GemmDesc q;
+        q.A = gi; q.a_row = 1; q.a_k = g.ldS; q.M = g.N; q.Kseg = g.N;
+        q.B = dtk; q.b_k = g.ldS; q.b_n = 1; q.N = g.N;
+        EpiStore e{dtm1, g.ldS, 0, 2.0f, dtm1, nullptr};
+        MCRN_TRY(gemm(q, e, st));
+      }
+      if (k - 2 >= 1) {  // dT_{k-2} -= dT_k
+        float* dtm2 = dt + (int64_t)(k - 3) * mat;
+        MCRN_LAUNCH(k_axpy, ew_grid(mat), 256, 0, st, dtm2, dtk, -1.0f, mat);
+      }
+    }
+    MCRN_LAUNCH(k_add_inplace, ew_grid(mat), 256, 0, st, dg[i], dt, mat);      // dg += dT_1
+  }
+  float *dLa = ws + p.dLa, *dLb = ws + p.dLb, *dL1 = ws + p.dL1, *dE1 = ws + p.dE1, *dE2 = ws + p.dE2;
+  MCRN_LAUNCH(k_relu_softmax_rows_bwd, g.N, 256, 0, st, ws + p.L1, S, dg[0], dLa, g.N, g.ldS);
+  MCRN_LAUNCH(k_relu_softmax_rows_bwd, g.N, 256, 0, st, ws + p.L2, S + (int64_t)per * mat, dg[1], dLb, g.N, g.ldS);
+  MCRN_LAUNCH(k_add_transpose, dim3(ceil_div(g.N, 32), ceil_div(g.N, 32)), dim3(32, 8), 0, st, dLa, dLb, dL1, g.N, g.ldS);
+  {  // dE1 = dL1 * E2 ; dE2 = dL1^T * E1
+    GemmDesc q;
+    q.A = dL1; q.a_row = g.ldS; q.a_k = 1; q.M = g.N; q.Kseg = g.N;
+    q.B = ws + p.E2; q.b_k = g.d; q.b_n = 1; q.N = g.d;
+    EpiStore e{dE1, g.d, 0, 1.0f, nullptr, nullptr};
+    MCRN_TRY(gemm(q, e, st));
+    q.A = dL1; q.a_row = 1; q.a_k = g.ldS; q.B = ws + p.E1;
+    EpiStore e2{dE2, g.d, 0, 1.0f, nullptr, nullptr};
+    MCRN_TRY(gemm(q, e2, st));
+  }
+  for (int i = 0; i < 2; ++i) {
+    const float* dE = i ? dE2 : dE1;
+    {  // dWe_i = dE_i * Memory^T                     [N x M]
+      GemmDesc q;
+      q.A = dE; q.a_row = g.d; q.a_k = 1; q.M = g.N; q.Kseg = g.d;
+      q.B = prm->memory; q.b_k = 1; q.b_n = g.d; q.N = g.M;
+      EpiStore e{i ? grads->we2 : grads->we1, g.M, 0, 1.0f, nullptr, nullptr};
+      MCRN_TRY(gemm(q, e, st));
+    }
+    {  // dMemory += We_i^T * dE_i                    [M x d]
+      GemmDesc q;
+      q.A = i ? prm->we2 : prm->we1; q.a_row = 1; q.a_k = g.M; q.M = g.M; q.Kseg = g.N;
+      q.B = dE; q.b_k = g.d; q.b_n = 1; q.N = g.d;
+      EpiStore e{grads->memory, g.d, 0, 1.0f, grads->memory, nullptr};
+      MCRN_TRY(gemm(q, e, st));
+    }
+  }
+  return MCRN_OK;
+}
+
+int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uint8_t* tf, const float* d_output,
+                  const float* d_hatt, const float* d_query, const float* d_pos, const float* d_neg,
+                  const mcrn_params* grads, float* ws, cudaStream_t st) {
+  const float* S = ws + p.S;
+  // zero accumulators and the directly-accumulated outputs
+  MCRN_CUDA_OK(cudaMemsetAsync(ws + p.acc_begin, 0, (p.acc_end - p.acc_begin) * sizeof(float), st));
+  MCRN_CUDA_OK(cudaMemsetAsync(grads->memory, 0, (size_t)g.M * g.d * sizeof(float), st));
+  MCRN_CUDA_OK(cudaMemsetAsync(grads->enc_gate_b, 0, (size_t)2 * g.H * sizeof(float), st));
+  MCRN_CUDA_OK(cudaMemsetAsync(grads->enc_update_b, 0, (size_t)g.H * sizeof(float), st));
+  MCRN_CUDA_OK(cudaMemsetAsync(grads->dec_gate_b, 0, (size_t)2 * g.D * sizeof(float), st));
+  MCRN_CUDA_OK(cudaMemsetAsync(grads->dec_update_b, 0, (size_t)g.D * sizeof(float), st));
+  MCRN_CUDA_OK(cudaMemsetAsync(grads->proj_w, 0, (size_t)g.Cout * g.D * sizeof(float), st));
+  MCRN_CUDA_OK(cudaMemsetAsync(grads->proj_b, 0, (size_t)g.Cout * sizeof(float), st));
+  float *dH = ws + p.dH, *dXin = ws + p.dXin;
+  // ---- decoder, reverse time ----
+  {
+    CellW w = dec_w(g, p, ws, prm);
+    CellAcc a{ws + p.a_d_wg_st, ws + p.a_d_wg_in, grads->dec_gate_b, ws + p.a_d_wu_st, ws + p.a_d_wu_in, grads->dec_update_b};
+    bool have_dgo = false;
+    for (int t = g.T_out - 1; t >= 0; --t) {
+      CellBufs b = dec_bufs(g, p, ws, t);
+      const float* h_t = (t + 1 < g.T_out) ? dec_bufs(g, p, ws, t + 1).xpg : ws + p.h_dec_last;
+      bool use_dgo = have_dgo && !(tf && tf[t]);
+      size_t shm = (size_t)32 * g.Cout * sizeof(float);
+      MCRN_LAUNCH(k_proj_bwd, (int)ceil_div64(g.R, 32), 256, shm, st, d_output, use_dgo ? dXin : nullptr, g.Cdec, h_t,
+                  prm->proj_w, dH, (t == g.T_out - 1) ? 1 : 0, grads->proj_w, grads->proj_b, g.B, g.T_out, g.N, g.D,
+                  g.Cout, t);
+      // d(go_t) is needed only when go_t was the model's own prediction of step t-1
+      bool need_dxin = (t > 0) && !(tf && tf[t - 1]);
+      MCRN_TRY(cell_backward(g, p, ws, S, w, b, a, dH, dH, need_dxin ? dXin : nullptr, st));
+      have_dgo = need_dxin;
+    }
+  }
+  // ---- memory query ----
+  {
+    size_t shm = 8 * (g.d + g.M) * sizeof(float);
+    float *dv = ws + p.mq_dv, *dsc = ws + p.mq_dsc, *dq = ws + p.mq_dq;
+    MCRN_LAUNCH(k_memory_query_bwd_rows, (int)ceil_div64(g.R, 8), 256, shm, st, dH, d_hatt, d_query, d_pos, d_neg,
+                prm->memory, ws + p.mq_att, reinterpret_cast<const int*>(ws + p.mq_ind), dv, dsc, dq, grads->memory,
+                g.B, g.N, g.H, g.M, g.d);
+    int sp = split_for(1, g.R / 16);
+    {  // dMemory += att^T dv + dsc^T query            [M x d], K = R
+      GemmDesc q;
+      q.A = ws + p.mq_att; q.a_row = 1; q.a_k = g.M; q.M = g.M; q.Kseg = (int)g.R;
+      q.B = dv; q.b_k = g.d; q.b_n = 1; q.N = g.d; q.splits = sp;
+      EpiAtomicAdd e{grads->memory, g.d, 0};
+      MCRN_TRY(gemm(q, e, st));
+      q.A = dsc; q.B = ws + p.mq_q;
+      MCRN_TRY(gemm(q, e, st));
+    }
+    {  // dWq = h_enc^T dq                             [H x d], K = R
+      MCRN_CUDA_OK(cudaMemsetAsync(grads->wq, 0, (size_t)g.H * g.d * sizeof(float), st));
+      GemmDesc q;
+      q.A = ws + p.h_enc; q.a_row = 1; q.a_k = g.H; q.M = g.H; q.Kseg = (int)g.R;
+      q.B = dq; q.b_k = g.d; q.b_n = 1; q.N = g.d; q.splits = sp;
+      EpiAtomicAdd e{grads->wq, g.d, 0};
+      MCRN_TRY(gemm(q, e, st));
+    }
+    {  // dH_enc = dH0[:, :H] + dq Wq^T                [R x H], K = d
+      GemmDesc q;
+      q.A = dq; q.a_row = g.d; q.a_k = 1; q.M = (int)g.R; q.Kseg = g.d;
+      q.B = prm->wq; q.b_k = 1; q.b_n = g.d; q.N = g.H;
+      EpiStoreStrideAdd e{ws + p.dHenc, g.H, dH, g.D};
+      MCRN_TRY(gemm(q, e, st));
+    }
+  }
+  // ---- encoder, reverse time ----
+  {
+    CellW w = enc_w(g, p, ws, prm);
+    CellAcc a{ws + p.a_e_wg_st, ws + p.a_e_wg_in, grads->enc_gate_b, ws + p.a_e_wu_st, ws + p.a_e_wu_in, grads->enc_update_b};
+    float* dHe = ws + p.dHenc;
+    for (int t = g.T_in - 1; t >= 0; --t) {
+      CellBufs b = enc_bufs(g, p, ws, t);
+      MCRN_TRY(cell_backward(g, p, ws, S, w, b, a, dHe, dHe, nullptr, st));
+    }
+  }
+  MCRN_TRY(supports_backward(g, p, ws, prm, grads, st));
+  // ---- un-fold weight gradients into the reference layout ----
+  MCRN_LAUNCH(k_unfold_grads, 128, 256, 0, st, ws + p.a_e_wg_st, ws + p.a_e_wg_in, grads->enc_gate_w, g.Cin, g.H, 2 * g.H, g.cheb_k);
+  MCRN_LAUNCH(k_unfold_grads, 128, 256, 0, st, ws + p.a_e_wu_st, ws + p.a_e_wu_in, grads->enc_update_w, g.Cin, g.H, g.H, g.cheb_k);
+  MCRN_LAUNCH(k_unfold_grads, 128, 256, 0, st, ws + p.a_d_wg_st, ws + p.a_d_wg_in, grads->dec_gate_w, g.Cdec, g.D, 2 * g.D, g.cheb_k);
+  MCRN_LAUNCH(k_unfold_grads, 128, 256, 0, st, ws + p.a_d_wu_st, ws + p.a_d_wu_in, grads->dec_update_w, g.Cdec, g.D, g.D, g.cheb_k);
+  return MCRN_OK;
+}
+
+int supports_forward_entry(const Geo& g, const Plan& p, float* ws, const float* mem, const float* we1,
+                           const float* we2, float* S, cudaStream_t st) {
+  return supports_forward(g, p, ws, mem, we1, we2, S, st);
+}
+
+int trainer_loss_impl(const Geo& g, const float* output, const float* labels, const float* query, const float* pos,
+                      const float* neg, float mean, float std, float lamb, float lamb1, float* loss_out,
+                      float* d_output, float* d_query, float* scratch, cudaStream_t st) {
+  const int64_t n_out = (int64_t)g.B * g.T_out * g.N * g.Cout, rows = (int64_t)g.B * g.N;
+  MCRN_CUDA_OK(cudaMemsetAsync(scratch, 0, 4 * sizeof(float), st));
+  MCRN_LAUNCH(k_loss_reduce_out, ew_grid(n_out) > 296 ? 296 : ew_grid(n_out), 256, 0, st, output, labels, n_out, mean, std, scratch);
+  int rgrid = (int)(ceil_div64(rows, 8) > 296 ? 296 : ceil_div64(rows, 8));
+  MCRN_LAUNCH(k_loss_reduce_rows, rgrid, 256, 0, st, query, pos, neg, rows, g.d, scratch);
+  MCRN_LAUNCH(k_loss_finish, 1, 32, 0, st, scratch, rows, g.d, lamb, lamb1, loss_out);
+  if (d_output) MCRN_LAUNCH(k_loss_grad_out, ew_grid(n_out), 256, 0, st, output, labels, n_out, mean, std, scratch, d_output);
+  if (d_query) MCRN_LAUNCH(k_loss_grad_rows, (int)ceil_div64(rows, 8), 256, 0, st, query, pos, neg, rows, g.d, lamb, lamb1, d_query);
+  return MCRN_OK;
+}
+
+const char* last_error() { return t_err; }
+
+}  // namespace mcrn

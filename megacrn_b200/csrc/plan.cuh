@@ -1,0 +1,122 @@
+// Workspace layout ("plan") of one forward(+backward) of the MegaCRN hot path.
+// All buffers live in ONE caller-provided device allocation; offsets are a pure function of
+// the dims and the save-for-backward flag, so forward and backward agree without any state.
+#pragma once
+
+#include "common.cuh"
+
+namespace mcrn {
+
+struct Plan {
+  Geo g;
+  bool save;
+  int enc_slots, dec_slots;
+  size_t bytes;
+  // ---- offsets in floats --------------------------------------------------
+  size_t S, E1, E2, L1, L2;
+  size_t e_wg_st, e_wg_in, e_wu_st, e_wu_in, d_wg_st, d_wg_in, d_wu_st, d_wu_in;   // folded weights
+  size_t enc_xpin;                       // [NB][N][T_in][B][Cin]
+  size_t enc_xpg, enc_xpu, enc_z, enc_r, enc_hc;   // per slot strides below
+  size_t h_enc;                          // [R][H]
+  size_t mq_q, mq_att, mq_ind;           // [R][d], [R][M], int[R][2]
+  size_t dec_xpin, dec_xpg, dec_xpu, dec_z, dec_r, dec_hc;
+  size_t h_dec_last;                     // [R][D]
+  // per-slot sizes (floats)
+  size_t enc_xp_sz, enc_v_sz, dec_xpin_sz, dec_xp_sz, dec_v_sz;
+  // ---- backward temporaries -------------------------------------------------
+  size_t dH, dU, dG, dXP, dZH, dHp, dXPin, dXin, mq_dv, mq_dsc, mq_dq, dHenc;
+  size_t acc_begin, acc_end;             // zeroed at the start of backward
+  size_t dS, a_e_wg_st, a_e_wg_in, a_e_wu_st, a_e_wu_in, a_d_wg_st, a_d_wg_in, a_d_wu_st, a_d_wu_in;
+  size_t dg1, dg2;
+  size_t dLa, dLb, dL1, dE1, dE2;
+  // loss scratch
+  size_t loss_scratch;                   // 8 floats
+};
+
+static inline int make_plan(const Geo& g, bool save, Plan* p) {
+  memset(p, 0, sizeof(*p));
+  p->g = g;
+  p->save = save;
+  size_t off = 0;
+  auto take = [&](size_t nfloats) {
+    size_t o = off;
+    off += (nfloats + 63) / 64 * 64;      // 256-byte granularity keeps every buffer TMA/vector aligned
+    return o;
+  };
+  const size_t R = (size_t)g.R, N = g.N, ldS = g.ldS, NB = g.NB, KS = g.KS;
+  p->S = take(KS * N * ldS);
+  p->E1 = take(N * g.d);
+  p->E2 = take(N * g.d);
+  p->L1 = take(N * ldS);
+  p->L2 = take(N * ldS);
+  p->e_wg_st = take(NB * g.H * 2 * g.H);
+  p->e_wg_in = take(NB * g.Cin * 2 * g.H);
+  p->e_wu_st = take(NB * g.H * g.H);
+  p->e_wu_in = take(NB * g.Cin * g.H);
+  p->d_wg_st = take(NB * g.D * 2 * g.D);
+  p->d_wg_in = take(NB * g.Cdec * 2 * g.D);
+  p->d_wu_st = take(NB * g.D * g.D);
+  p->d_wu_in = take(NB * g.Cdec * g.D);
+  p->enc_slots = save ? g.T_in : 2;
+  p->dec_slots = save ? g.T_out : 2;
+  p->enc_xpin = take(NB * N * g.T_in * g.B * g.Cin);
+  p->enc_xp_sz = (NB * R * g.H + 63) / 64 * 64;
+  p->enc_v_sz = (R * g.H + 63) / 64 * 64;
+  p->enc_xpg = take(p->enc_xp_sz * p->enc_slots);
+  p->enc_xpu = take(p->enc_xp_sz * p->enc_slots);
+  p->enc_z = take(p->enc_v_sz * p->enc_slots);
+  p->enc_r = take(p->enc_v_sz * p->enc_slots);
+  p->enc_hc = take(p->enc_v_sz * p->enc_slots);
+  p->h_enc = take(R * g.H);
+  p->mq_q = take(R * g.d);
+  p->mq_att = take(R * g.M);
+  p->mq_ind = take(R * 2);
+  p->dec_xpin_sz = (NB * R * g.Cdec + 63) / 64 * 64;
+  p->dec_xp_sz = (NB * R * g.D + 63) / 64 * 64;
+  p->dec_v_sz = (R * g.D + 63) / 64 * 64;
+  p->dec_xpin = take(p->dec_xpin_sz * p->dec_slots);
+  p->dec_xpg = take(p->dec_xp_sz * p->dec_slots);
+  p->dec_xpu = take(p->dec_xp_sz * p->dec_slots);
+  p->dec_z = take(p->dec_v_sz * p->dec_slots);
+  p->dec_r = take(p->dec_v_sz * p->dec_slots);
+  p->dec_hc = take(p->dec_v_sz * p->dec_slots);
+  p->h_dec_last = take(R * g.D);
+  p->loss_scratch = take(64);
+  if (save) {
+    const size_t Cm = (size_t)(g.Cin > g.Cdec ? g.Cin : g.Cdec);
+    p->dH = take(R * g.D);
+    p->dU = take(R * g.D);
+    p->dG = take(R * 2 * g.D);
+    p->dXP = take(NB * R * g.D);
+    p->dZH = take(R * g.D);
+    p->dHp = take(R * g.D);
+    p->dXPin = take(NB * R * Cm);
+    p->dXin = take(R * Cm);
+    p->mq_dv = take(R * g.d);
+    p->mq_dsc = take(R * g.M);
+    p->mq_dq = take(R * g.d);
+    p->dHenc = take(R * g.H);
+    p->acc_begin = off;
+    p->dS = take(KS * N * ldS);
+    p->a_e_wg_st = take(NB * g.H * 2 * g.H);
+    p->a_e_wg_in = take(NB * g.Cin * 2 * g.H);
+    p->a_e_wu_st = take(NB * g.H * g.H);
+    p->a_e_wu_in = take(NB * g.Cin * g.H);
+    p->a_d_wg_st = take(NB * g.D * 2 * g.D);
+    p->a_d_wg_in = take(NB * g.Cdec * 2 * g.D);
+    p->a_d_wu_st = take(NB * g.D * g.D);
+    p->a_d_wu_in = take(NB * g.Cdec * g.D);
+    p->dg1 = take(N * ldS);
+    p->dg2 = take(N * ldS);
+    p->acc_end = off;
+    p->dLa = take(N * ldS);
+    p->dLb = take(N * ldS);
+    p->dL1 = take(N * ldS);
+    p->dE1 = take(N * g.d);
+    p->dE2 = take(N * g.d);
+  }
+  p->bytes = off * sizeof(float);
+  return MCRN_OK;
+}
+
+}  // namespace mcrn
