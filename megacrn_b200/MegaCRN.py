@@ -95,10 +95,9 @@ class _MegaCRNFunction(torch.autograd.Function):
     """forward = mcrn_forward, backward = mcrn_backward (include/megacrn_b200.h)."""
 
     @staticmethod
-    def forward(ctx, module, x, y_cov, labels, tf, *params):
+    def forward(ctx, module, need_grad, x, y_cov, labels, tf, *params):
         lib = _abi.load()
         dims = module._dims(x)
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         flags = _abi.MCRN_FWD_SAVE_FOR_BACKWARD if need_grad else 0
         ws = module._workspace(dims, flags, x.device)
         B, N, d = x.shape[0], module.num_nodes, module.mem_dim
@@ -143,7 +142,7 @@ class _MegaCRNFunction(torch.autograd.Function):
                                    ctx.ws.nbytes, stream)
         _abi.check(st, "mcrn_backward")
         ctx.ws.busy = False
-        return (None, None, None, None, None) + tuple(grads)
+        return (None, None, None, None, None, None) + tuple(grads)
 
 
 class MegaCRN(nn.Module):
@@ -240,7 +239,9 @@ class MegaCRN(nn.Module):
         f32 = lambda t: None if t is None else t.to(device=x.device, dtype=torch.float32).contiguous()
         x, y_cov, labels = f32(x), f32(y_cov[:, :self.horizon]), f32(labels)
         tf = _abi.tf_bytes(flags, self.horizon)
-        return _MegaCRNFunction.apply(self, x, y_cov, labels, tf, *self._ordered_params())
+        params = self._ordered_params()
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        return _MegaCRNFunction.apply(self, need_grad, x, y_cov, labels, tf, *params)
 
 
 def print_params(model):

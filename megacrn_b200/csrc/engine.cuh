@@ -3,6 +3,7 @@
 #pragma once
 
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 
 namespace mcrn {
 
@@ -10,6 +11,11 @@ extern int g_engine;   // 0 = default, 1 = force SIMT, 2 = force tcgen05 (error 
 
 template <class Epi>
 int gemm(const GemmDesc& q, const Epi& e, cudaStream_t st) {
+  if (g_engine != 1 && tc::eligible(q)) return tc::gemm_tc(q, e, st);
+  if (g_engine == 2) {
+    set_error("engine 2 (tcgen05) forced but the problem is not eligible (alignment / strides)");
+    return MCRN_ERR_BAD_DIMS;
+  }
   return gemm_simt(q, e, st);
 }
 

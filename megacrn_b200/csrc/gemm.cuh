@@ -19,7 +19,19 @@ struct GemmDesc {
   const float* B = nullptr;
   int64_t b_k = 0, b_n = 0, b_seg = 0, b_batch = 0;
   int M = 0, N = 0, Kseg = 0, nseg = 1, nbatch = 1, splits = 1;
+  int a_nseg = 0, b_nseg = 0;   // distinct segments of A / B (0 = nseg); segment index wraps (hi/lo weight split)
+  int prec_exact = 0;           // 1 = this contraction must run in exact fp32 (SIMT engine)
+  __host__ __device__ int nseg_a() const { return a_nseg ? a_nseg : nseg; }
+  __host__ __device__ int nseg_b() const { return b_nseg ? b_nseg : nseg; }
 };
+
+// Round-to-nearest TF32 (cvt.rna): producers of tensor-core operands store rounded values so that the
+// tensor core's mantissa truncation is exact and the contraction behaves as round-to-nearest TF32.
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
 
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
@@ -31,6 +43,7 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf
 struct EpiStore {
   float* C; int64_t ldc, c_batch; float alpha;
   const float* add1; const float* add2;     // optional, same layout as C
+  int rnd = 0;                              // 1: store TF32-rounded (the output is a tensor-core operand)
   template <int V>
   __device__ __forceinline__ void apply(int bz, int m, int n0, int nv, const float (&acc)[V]) const {
     int64_t off = (int64_t)bz * c_batch + (int64_t)m * ldc + n0;
@@ -40,7 +53,7 @@ struct EpiStore {
         float v = alpha * acc[j];
         if (add1) v += add1[off + j];
         if (add2) v += add2[off + j];
-        C[off + j] = v;
+        C[off + j] = rnd ? tf32_rn(v) : v;
       }
     }
   }
@@ -73,25 +86,32 @@ struct EpiAtomicAdd {
 // prev == nullptr means T_{k-2} = I.
 struct EpiCheb {
   float* C; int64_t ldc; const float* prev;
+  float* Cr;                                 // TF32-rounded copy (tensor-core operand), may alias nothing
   template <int V>
   __device__ __forceinline__ void apply(int, int m, int n0, int nv, const float (&acc)[V]) const {
     int64_t off = (int64_t)m * ldc + n0;
 #pragma unroll
-    for (int j = 0; j < V; ++j)
-      if (j < nv) C[off + j] = 2.0f * acc[j] - (prev ? prev[off + j] : ((n0 + j) == m ? 1.0f : 0.0f));
+    for (int j = 0; j < V; ++j) {
+      if (j < nv) {
+        float v = 2.0f * acc[j] - (prev ? prev[off + j] : ((n0 + j) == m ? 1.0f : 0.0f));
+        C[off + j] = v;
+        if (Cr) Cr[off + j] = tf32_rn(v);
+      }
+    }
   }
 };
 
 // Column n = blk*W + c is stored at C[blk][m][c]  (the dXP block buffers).
 struct EpiBlocks {
   float* C; int W; int64_t blk_stride;
+  int rnd = 0;                               // 1: blocks >= 1 (tensor-core operands downstream) are TF32-rounded
   template <int V>
   __device__ __forceinline__ void apply(int, int m, int n0, int nv, const float (&acc)[V]) const {
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       if (j < nv) {
         int n = n0 + j, blk = n / W, c = n - blk * W;
-        C[(int64_t)blk * blk_stride + (int64_t)m * W + c] = acc[j];
+        C[(int64_t)blk * blk_stride + (int64_t)m * W + c] = (rnd && blk > 0) ? tf32_rn(acc[j]) : acc[j];
       }
     }
   }
@@ -119,8 +139,9 @@ struct InTerm {
 // columns [0,H) are z, [H,2H) are r;  writes z, r and z*h (the update AGCN's state input).
 struct EpiGate {
   InTerm in; int H;
-  const float* h;   // [R][H] current state (XPg block 0)
+  const float* h;   // [R][H] current state, exact fp32
   float* z; float* r; float* zh;
+  int rnd;          // 1: zh (a tensor-core operand only) is stored TF32-rounded
   template <int V>
   __device__ __forceinline__ void apply(int, int m, int n0, int nv, const float (&acc)[V]) const {
 #pragma unroll
@@ -131,7 +152,8 @@ struct EpiGate {
         if (col < H) {
           int64_t o = (int64_t)m * H + col;
           if (z) z[o] = s;
-          zh[o] = s * h[o];
+          float t = s * h[o];
+          zh[o] = rnd ? tf32_rn(t) : t;
         } else {
           r[(int64_t)m * H + (col - H)] = s;
         }
@@ -144,8 +166,9 @@ struct EpiGate {
 // h' = r*h + (1-r)*hc.
 struct EpiUpdate {
   InTerm in; int H;
-  const float* h; const float* r;
-  float* hc; float* h_out;
+  const float* h; const float* r;   // exact state, r gate
+  float* hc; float* h_out;          // h_out: exact new state
+  float* h_mma; int rnd;            // h_mma: the copy the next propagation / gate GEMM reads (TF32-rounded if rnd)
   template <int V>
   __device__ __forceinline__ void apply(int, int m, int n0, int nv, const float (&acc)[V]) const {
 #pragma unroll
@@ -156,7 +179,9 @@ struct EpiUpdate {
         float c = tanhf(acc[j] + in.eval(m, col));
         float rr = r[o];
         if (hc) hc[o] = c;
-        h_out[o] = rr * h[o] + (1.0f - rr) * c;
+        float hn = rr * h[o] + (1.0f - rr) * c;
+        h_out[o] = hn;
+        if (h_mma) h_mma[o] = rnd ? tf32_rn(hn) : hn;
       }
     }
   }

@@ -1,2 +1,65 @@
-// tcgen05 TF32 GEMM instantiations (placeholder translation unit until the kernel lands).
-#include "common.cuh"
+// Host side of the tcgen05 engine: TMA tensor-map encoding (driver entry point resolved at run
+// time, so the library has no link-time dependency on libcuda) and the eligibility rules.
+#include "gemm_tc.cuh"
+
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+namespace mcrn {
+namespace tc {
+
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+static std::once_flag g_once;
+
+static void resolve_encode() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  else cudaGetLastError();
+}
+
+int encode_tensor_map(CUtensorMap* out, const float* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                      const uint32_t box[4]) {
+  std::call_once(g_once, resolve_encode);
+  if (!g_encode) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return MCRN_ERR_CUDA; }
+  cuuint64_t gdim[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t gstr[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstr, bx, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): dims=[%llu,%llu,%llu,%llu] strides=[%llu,%llu,%llu] box=[%u,%u,%u,%u] base=%p",
+              (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+              (unsigned long long)dims[3], (unsigned long long)strides_bytes[0], (unsigned long long)strides_bytes[1],
+              (unsigned long long)strides_bytes[2], box[0], box[1], box[2], box[3], (const void*)base);
+    return MCRN_ERR_CUDA;
+  }
+  return MCRN_OK;
+}
+
+static bool ok_stride(int64_t elems) { return elems > 0 && (elems % 4) == 0 && elems * 4 < ((int64_t)1 << 40); }
+
+bool eligible(const GemmDesc& g) {
+  if (g.prec_exact) return false;
+  if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.B) & 15)) return false;
+  if (g.M < 1 || g.N < 1 || g.Kseg < 1) return false;
+  // A: exactly one of (K contiguous, M contiguous); the other stride 16-byte aligned
+  if (g.a_k == 1) { if (!ok_stride(g.a_row)) return false; }
+  else if (g.a_row == 1) { if (!ok_stride(g.a_k)) return false; }
+  else return false;
+  if (g.b_k == 1) { if (!ok_stride(g.b_n)) return false; }
+  else if (g.b_n == 1) { if (!ok_stride(g.b_k)) return false; }
+  else return false;
+  if (g.a_seg && g.nseg_a() > 1 && !ok_stride(g.a_seg)) return false;
+  if (g.b_seg && g.nseg_b() > 1 && !ok_stride(g.b_seg)) return false;
+  if (g.a_batch && g.nbatch > 1 && !ok_stride(g.a_batch)) return false;
+  if (g.b_batch && g.nbatch > 1 && !ok_stride(g.b_batch)) return false;
+  return true;
+}
+
+}  // namespace tc
+}  // namespace mcrn

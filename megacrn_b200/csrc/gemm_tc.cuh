@@ -1,0 +1,272 @@
+// tcgen05 TF32 GEMM for sm_100a: TMA (cp.async.bulk.tensor) stages fp32 operand tiles into
+// 128B-swizzled shared memory, one elected thread issues tcgen05.mma.kind::tf32 with the fp32
+// accumulator in TMEM, four epilogue warps read it back with tcgen05.ld and run the fused
+// epilogue functor (gemm.cuh).  One 128 x BN output tile per CTA, warp-specialised:
+//   warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+//
+// Operand storage (all four combinations are instantiated):
+//   K-major  : K contiguous  -> tile rows of 32 fp32 = one 128-byte swizzle row
+//   MN-major : M/N contiguous -> slabs of [32 k][32 m] (128-byte rows along M/N)
+// Inputs must already hold TF32-representable values if round-to-nearest behaviour is wanted
+// (the tensor core truncates the low 13 mantissa bits); producers round with cvt.rna (gemm.cuh).
+#pragma once
+
+#include <cuda.h>
+
+#include "gemm.cuh"
+
+namespace mcrn {
+namespace tc {
+
+constexpr int BM = 128, BK = 32, THREADS = 192;
+constexpr uint32_t SLAB_BYTES = 32 * 128;       // [32 k-rows][128 B] slab of an MN-major operand
+
+struct TcParams {
+  int M, N, Kseg, nseg, a_seg_mod, b_seg_mod, nbatch, splits, a_batched, b_batched;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2,
+// a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major), N>>3 [17,23), M>>4 [24,29).
+template <bool A_K, bool B_K, int BN>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((A_K ? 0u : 1u) << 15) | ((B_K ? 0u : 1u) << 16) |
+         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <int BN, int STAGES>
+constexpr size_t smem_bytes() { return (size_t)STAGES * (BM * BK * 4 + BN * BK * 4) + 1024; }
+
+template <bool A_K, bool B_K, int BN, int STAGES, class Epi>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p, Epi epi) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_slot;
+  constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bz = blockIdx.z / p.splits, split = blockIdx.z - bz * p.splits;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kt = (p.Kseg + BK - 1) / BK;
+  const int total = p.nseg * kt;
+  const int per = (total + p.splits - 1) / p.splits;
+  const int it0 = split * per;
+  const int nit = max(0, min(total, it0 + per) - it0);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&tmem_full_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (nit > 0) {
+    if (warp == 0) {
+      if (lane == 0) {                                   // ===== TMA producer =====
+        const int bza = bz * p.a_batched, bzb = bz * p.b_batched;
+        for (int i = 0; i < nit; ++i) {
+          const int s = i % STAGES;
+          const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+          const uint32_t fb = smem_u32(&full_bar[s]);
+          mbar_expect_tx(fb, STAGE_BYTES);
+          const int it = it0 + i, seg = it / kt, k0 = (it - seg * kt) * BK;
+          const int sa = seg % p.a_seg_mod, sb = seg % p.b_seg_mod;
+          const uint32_t a_dst = smem_base + (uint32_t)s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
+          if (A_K) {
+            tma_load_4d(a_dst, &tmA, fb, k0, m0, sa, bza);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 32; ++j) tma_load_4d(a_dst + j * SLAB_BYTES, &tmA, fb, m0 + 32 * j, k0, sa, bza);
+          }
+          if (B_K) {
+            tma_load_4d(b_dst, &tmB, fb, k0, n0, sb, bzb);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 32; ++j) tma_load_4d(b_dst + j * SLAB_BYTES, &tmB, fb, n0 + 32 * j, k0, sb, bzb);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {                                   // ===== MMA issuer =====
+        constexpr uint32_t idesc = make_idesc<A_K, B_K, BN>();
+        for (int i = 0; i < nit; ++i) {
+          const int s = i % STAGES;
+          const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+          mbar_wait(smem_u32(&full_bar[s]), ph);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_base + (uint32_t)s * STAGE_BYTES, b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BK / 8; ++kk) {          // UMMA_K = 8 for tf32
+            const uint64_t ad = A_K ? make_smem_desc(a_addr + kk * 32, 16, 1024) : make_smem_desc(a_addr + kk * 1024, SLAB_BYTES, 1024);
+            const uint64_t bd = B_K ? make_smem_desc(b_addr + kk * 32, 16, 1024) : make_smem_desc(b_addr + kk * 1024, SLAB_BYTES, 1024);
+            tcgen05_mma_tf32(tmem_base, ad, bd, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+          }
+          tcgen05_commit(smem_u32(&empty_bar[s]));       // frees the smem slot when these MMAs retire
+        }
+        tcgen05_commit(smem_u32(&tmem_full_bar));        // accumulator complete
+      }
+    } else {                                             // ===== epilogue warps =====
+      const int quarter = warp & 3;                      // TMEM lane quarter this warp may read
+      mbar_wait(smem_u32(&tmem_full_bar), 0);
+      tcgen05_fence_after();
+      const int row = m0 + quarter * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), v);
+        const int col = n0 + c * 32;
+        if (row < p.M && col < p.N) epi.template apply<32>(bz, row, col, min(32, p.N - col), v);
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------
+int encode_tensor_map(CUtensorMap* out, const float* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                      const uint32_t box[4]);
+bool eligible(const GemmDesc& g);
+
+template <bool A_K, bool B_K, int BN, int STAGES, class Epi>
+int launch(const GemmDesc& g, const Epi& epi, cudaStream_t st) {
+  CUtensorMap ta, tb;
+  const uint64_t big = 1;
+  {
+    uint64_t dims[4], str[3];
+    uint32_t box[4] = {32, 1, 1, 1};
+    if (A_K) { dims[0] = g.Kseg; dims[1] = g.M; str[0] = g.a_row * 4; box[1] = BM; }
+    else { dims[0] = g.M; dims[1] = g.Kseg; str[0] = g.a_k * 4; box[1] = BK; }
+    const int aseg = g.a_seg ? g.nseg_a() : 1;
+    dims[2] = aseg; str[1] = aseg > 1 ? g.a_seg * 4 : str[0] * dims[1];
+    const int ab = g.a_batch ? g.nbatch : 1;
+    dims[3] = ab; str[2] = ab > 1 ? g.a_batch * 4 : str[1] * dims[2];
+    (void)big;
+    MCRN_TRY(encode_tensor_map(&ta, g.A, dims, str, box));
+  }
+  {
+    uint64_t dims[4], str[3];
+    uint32_t box[4] = {32, 1, 1, 1};
+    if (B_K) { dims[0] = g.Kseg; dims[1] = g.N; str[0] = g.b_n * 4; box[1] = BN; }
+    else { dims[0] = g.N; dims[1] = g.Kseg; str[0] = g.b_k * 4; box[1] = BK; }
+    const int bseg = g.b_seg ? g.nseg_b() : 1;
+    dims[2] = bseg; str[1] = bseg > 1 ? g.b_seg * 4 : str[0] * dims[1];
+    const int bb = g.b_batch ? g.nbatch : 1;
+    dims[3] = bb; str[2] = bb > 1 ? g.b_batch * 4 : str[1] * dims[2];
+    MCRN_TRY(encode_tensor_map(&tb, g.B, dims, str, box));
+  }
+  TcParams p;
+  p.M = g.M; p.N = g.N; p.Kseg = g.Kseg; p.nseg = g.nseg;
+  p.a_seg_mod = g.a_seg ? g.nseg_a() : 1;
+  p.b_seg_mod = g.b_seg ? g.nseg_b() : 1;
+  p.nbatch = g.nbatch; p.splits = g.splits;
+  p.a_batched = g.a_batch ? 1 : 0;
+  p.b_batched = g.b_batch ? 1 : 0;
+  auto kern = gemm_tc_kernel<A_K, B_K, BN, STAGES, Epi>;
+  constexpr size_t smem = smem_bytes<BN, STAGES>();
+  static bool attr_set = false;
+  if (!attr_set) {
+    MCRN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM), g.nbatch * g.splits);
+  MCRN_LAUNCH(kern, grid, THREADS, smem, st, ta, tb, p, epi);
+  return MCRN_OK;
+}
+
+template <class Epi>
+int gemm_tc(const GemmDesc& g, const Epi& epi, cudaStream_t st) {
+  const bool a_k = (g.a_k == 1), b_k = (g.b_k == 1);
+  const bool wide = g.N > 64;
+  if (a_k && b_k) return wide ? launch<true, true, 128, 4, Epi>(g, epi, st) : launch<true, true, 64, 4, Epi>(g, epi, st);
+  if (a_k && !b_k) return wide ? launch<true, false, 128, 4, Epi>(g, epi, st) : launch<true, false, 64, 4, Epi>(g, epi, st);
+  if (!a_k && b_k) return wide ? launch<false, true, 128, 4, Epi>(g, epi, st) : launch<false, true, 64, 4, Epi>(g, epi, st);
+  return wide ? launch<false, false, 128, 4, Epi>(g, epi, st) : launch<false, false, 64, 4, Epi>(g, epi, st);
+}
+
+}  // namespace tc
+}  // namespace mcrn

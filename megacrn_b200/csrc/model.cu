@@ -57,40 +57,49 @@ int make_geo(const mcrn_dims* dm, Geo* g) {
 static inline int ew_grid(int64_t n) { int64_t b = (n + 255) / 256; return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b)); }
 
 // ---- one AGCRN cell -------------------------------------------------------------------
-struct CellW {           // folded weights of one cell (plan buffers)
+struct CellW {           // folded weights of one cell (plan buffers); wst = [hi | lo] when split
   const float *wg_st, *wg_in, *bg, *wu_st, *wu_in, *bu;
   int Hs, Cin;
 };
 struct CellBufs {        // per-step activations
   const float* xpin; int64_t xp_k, xp_n;
   float *xpg, *xpu, *z, *r, *hc;
+  float* hx;             // exact fp32 input state of the step (xpg block 0 is its tensor-core copy)
 };
+
+// Numerics mode of the run: with the tcgen05 engine every tensor-core operand is stored TF32-rounded
+// (round-to-nearest) by its producer and the state weights are split hi+lo; with the SIMT engine
+// everything stays exact fp32.
+extern int g_engine;
+static inline int tf32_mode() { return g_engine != 1 ? 1 : 0; }
 
 // propagation  XP[1..KS] = S * XP[0]      (model/MegaCRN.py:24-25 for the KS real supports)
 static int propagate(const Geo& g, const float* S, float* xp, int C, cudaStream_t st) {
   GemmDesc q;
   q.A = S; q.a_row = g.ldS; q.a_k = 1; q.M = g.KS * g.N; q.Kseg = g.N;
   q.B = xp; q.b_k = (int64_t)g.B * C; q.b_n = 1; q.N = g.B * C;
-  EpiStore e{xp + (int64_t)g.R * C, (int64_t)g.B * C, 0, 1.0f, nullptr, nullptr};
+  EpiStore e{xp + (int64_t)g.R * C, (int64_t)g.B * C, 0, 1.0f, nullptr, nullptr, tf32_mode()};
   return gemm(q, e, st);
 }
 
-static int cell_forward(const Geo& g, const float* S, const CellW& w, const CellBufs& b, float* h_out, cudaStream_t st) {
+static int cell_forward(const Geo& g, const float* S, const CellW& w, const CellBufs& b, float* h_out, float* h_mma,
+                        cudaStream_t st) {
   const int Hs = w.Hs;
+  const int rnd = tf32_mode(), wseg = rnd ? 2 * g.NB : g.NB;
   MCRN_TRY(propagate(g, S, b.xpg, Hs, st));
   {  // gate AGCN + sigmoid + z*h                                   model/MegaCRN.py:42-45
     GemmDesc q;
-    q.A = b.xpg; q.a_row = Hs; q.a_k = 1; q.a_seg = g.R * Hs; q.nseg = g.NB; q.Kseg = Hs; q.M = (int)g.R;
+    q.A = b.xpg; q.a_row = Hs; q.a_k = 1; q.a_seg = g.R * Hs; q.nseg = wseg; q.a_nseg = g.NB; q.Kseg = Hs; q.M = (int)g.R;
     q.B = w.wg_st; q.b_seg = (int64_t)Hs * 2 * Hs; q.b_k = 2 * Hs; q.b_n = 1; q.N = 2 * Hs;
-    EpiGate e{InTerm{b.xpin, b.xp_k, b.xp_n, w.wg_in, w.bg, g.NB, w.Cin, 2 * Hs, g.B}, Hs, b.xpg, b.z, b.r, b.xpu};
+    EpiGate e{InTerm{b.xpin, b.xp_k, b.xp_n, w.wg_in, w.bg, g.NB, w.Cin, 2 * Hs, g.B}, Hs, b.hx, b.z, b.r, b.xpu, rnd};
     MCRN_TRY(gemm(q, e, st));
   }
   MCRN_TRY(propagate(g, S, b.xpu, Hs, st));
   {  // update AGCN + tanh + blend                                  model/MegaCRN.py:46-47
     GemmDesc q;
-    q.A = b.xpu; q.a_row = Hs; q.a_k = 1; q.a_seg = g.R * Hs; q.nseg = g.NB; q.Kseg = Hs; q.M = (int)g.R;
+    q.A = b.xpu; q.a_row = Hs; q.a_k = 1; q.a_seg = g.R * Hs; q.nseg = wseg; q.a_nseg = g.NB; q.Kseg = Hs; q.M = (int)g.R;
     q.B = w.wu_st; q.b_seg = (int64_t)Hs * Hs; q.b_k = Hs; q.b_n = 1; q.N = Hs;
-    EpiUpdate e{InTerm{b.xpin, b.xp_k, b.xp_n, w.wu_in, w.bu, g.NB, w.Cin, Hs, g.B}, Hs, b.xpg, b.r, b.hc, h_out};
+    EpiUpdate e{InTerm{b.xpin, b.xp_k, b.xp_n, w.wu_in, w.bu, g.NB, w.Cin, Hs, g.B}, Hs, b.hx, b.r, b.hc, h_out, h_mma, rnd};
     MCRN_TRY(gemm(q, e, st));
   }
   return MCRN_OK;
@@ -101,6 +110,7 @@ static int propagate_in(const Geo& g, const float* S, float* xpin, int64_t xp_k,
   GemmDesc q;
   q.A = S; q.a_row = g.ldS; q.a_k = 1; q.M = g.N; q.Kseg = g.N; q.a_batch = (int64_t)g.N * g.ldS;
   q.B = xpin; q.b_k = xp_n; q.b_n = 1; q.N = cols; q.b_batch = 0; q.nbatch = g.KS;
+  q.prec_exact = 1;      // 1-2 raw input channels: tiny, keep exact fp32
   EpiStore e{xpin + xp_k, xp_n, xp_k, 1.0f, nullptr, nullptr};
   return gemm(q, e, st);
 }
@@ -112,12 +122,12 @@ struct Ptrs {            // resolved workspace pointers
 };
 
 static int supports_forward(const Geo& g, const Plan& p, float* ws, const float* mem, const float* we1, const float* we2,
-                            float* S, cudaStream_t st) {
+                            float* S, float* Sr, cudaStream_t st) {
   float *E1 = ws + p.E1, *E2 = ws + p.E2, *L1 = ws + p.L1, *L2 = ws + p.L2;
   for (int i = 0; i < 2; ++i) {  // E_i = We_i * Memory                         model/MegaCRN.py:169-170
     GemmDesc q;
     q.A = i ? we2 : we1; q.a_row = g.M; q.a_k = 1; q.M = g.N; q.Kseg = g.M;
-    q.B = mem; q.b_k = g.d; q.b_n = 1; q.N = g.d;
+    q.B = mem; q.b_k = g.d; q.b_n = 1; q.N = g.d; q.prec_exact = 1;
     EpiStore e{i ? E2 : E1, g.d, 0, 1.0f, nullptr, nullptr};
     MCRN_TRY(gemm(q, e, st));
   }
@@ -125,19 +135,20 @@ static int supports_forward(const Geo& g, const Plan& p, float* ws, const float*
   for (int i = 0; i < 2; ++i) {  // logits E1 E2^T / E2 E1^T, relu, row softmax   :171-172
     GemmDesc q;
     q.A = i ? E2 : E1; q.a_row = g.d; q.a_k = 1; q.M = g.N; q.Kseg = g.d;
-    q.B = i ? E1 : E2; q.b_k = 1; q.b_n = g.d; q.N = g.N;
+    q.B = i ? E1 : E2; q.b_k = 1; q.b_n = g.d; q.N = g.N; q.prec_exact = 1;
     EpiStore e{i ? L2 : L1, g.ldS, 0, 1.0f, nullptr, nullptr};
     MCRN_TRY(gemm(q, e, st));
     float* gi = S + (int64_t)i * per * g.N * g.ldS;
-    MCRN_LAUNCH(k_relu_softmax_rows, g.N, 256, 0, st, i ? L2 : L1, gi, g.N, g.ldS);
+    float* gri = Sr + (int64_t)i * per * g.N * g.ldS;
+    MCRN_LAUNCH(k_relu_softmax_rows, g.N, 256, 0, st, i ? L2 : L1, gi, gri, g.N, g.ldS);
     for (int k = 2; k < g.cheb_k; ++k) {  // T_k = 2 g T_{k-1} - T_{k-2}          :21-22 (hoisted)
       float* tk = gi + (int64_t)(k - 1) * g.N * g.ldS;
-      const float* tkm1 = gi + (int64_t)(k - 2) * g.N * g.ldS;
+      const float* tkm1 = gri + (int64_t)(k - 2) * g.N * g.ldS;      // tensor-core operands: rounded copies
       const float* tkm2 = (k >= 3) ? gi + (int64_t)(k - 3) * g.N * g.ldS : nullptr;
       GemmDesc c;
-      c.A = gi; c.a_row = g.ldS; c.a_k = 1; c.M = g.N; c.Kseg = g.N;
+      c.A = gri; c.a_row = g.ldS; c.a_k = 1; c.M = g.N; c.Kseg = g.N;
       c.B = tkm1; c.b_k = g.ldS; c.b_n = 1; c.N = g.N;
-      EpiCheb e{tk, g.ldS, tkm2};
+      EpiCheb e{tk, g.ldS, tkm2, gri + (int64_t)(k - 1) * g.N * g.ldS};
       MCRN_TRY(gemm(c, e, st));
     }
   }
@@ -145,10 +156,10 @@ static int supports_forward(const Geo& g, const Plan& p, float* ws, const float*
 }
 
 static int fold_all_weights(const Geo& g, const Plan& p, float* ws, const mcrn_params* prm, cudaStream_t st) {
-  MCRN_LAUNCH(k_fold_weights, 128, 256, 0, st, prm->enc_gate_w, ws + p.e_wg_st, ws + p.e_wg_in, g.Cin, g.H, 2 * g.H, g.cheb_k);
-  MCRN_LAUNCH(k_fold_weights, 128, 256, 0, st, prm->enc_update_w, ws + p.e_wu_st, ws + p.e_wu_in, g.Cin, g.H, g.H, g.cheb_k);
-  MCRN_LAUNCH(k_fold_weights, 128, 256, 0, st, prm->dec_gate_w, ws + p.d_wg_st, ws + p.d_wg_in, g.Cdec, g.D, 2 * g.D, g.cheb_k);
-  MCRN_LAUNCH(k_fold_weights, 128, 256, 0, st, prm->dec_update_w, ws + p.d_wu_st, ws + p.d_wu_in, g.Cdec, g.D, g.D, g.cheb_k);
+  MCRN_LAUNCH(k_fold_weights, 128, 256, 0, st, prm->enc_gate_w, ws + p.e_wg_st, ws + p.e_wg_in, g.Cin, g.H, 2 * g.H, g.cheb_k, tf32_mode());
+  MCRN_LAUNCH(k_fold_weights, 128, 256, 0, st, prm->enc_update_w, ws + p.e_wu_st, ws + p.e_wu_in, g.Cin, g.H, g.H, g.cheb_k, tf32_mode());
+  MCRN_LAUNCH(k_fold_weights, 128, 256, 0, st, prm->dec_gate_w, ws + p.d_wg_st, ws + p.d_wg_in, g.Cdec, g.D, 2 * g.D, g.cheb_k, tf32_mode());
+  MCRN_LAUNCH(k_fold_weights, 128, 256, 0, st, prm->dec_update_w, ws + p.d_wu_st, ws + p.d_wu_in, g.Cdec, g.D, g.D, g.cheb_k, tf32_mode());
   return MCRN_OK;
 }
 
@@ -163,6 +174,7 @@ static CellBufs enc_bufs(const Geo& g, const Plan& p, float* ws, int t) {
   b.z = p.save ? ws + p.enc_z + p.enc_v_sz * s : nullptr;
   b.r = ws + p.enc_r + p.enc_v_sz * s;
   b.hc = p.save ? ws + p.enc_hc + p.enc_v_sz * s : nullptr;
+  b.hx = ws + p.enc_hx + p.enc_v_sz * s;
   return b;
 }
 static CellBufs dec_bufs(const Geo& g, const Plan& p, float* ws, int t) {
@@ -176,6 +188,7 @@ static CellBufs dec_bufs(const Geo& g, const Plan& p, float* ws, int t) {
   b.z = p.save ? ws + p.dec_z + p.dec_v_sz * s : nullptr;
   b.r = ws + p.dec_r + p.dec_v_sz * s;
   b.hc = p.save ? ws + p.dec_hc + p.dec_v_sz * s : nullptr;
+  b.hx = ws + p.dec_hx + p.dec_v_sz * s;
   return b;
 }
 static CellW enc_w(const Geo& g, const Plan& p, float* ws, const mcrn_params* prm) {
@@ -191,8 +204,8 @@ static CellW dec_w(const Geo& g, const Plan& p, float* ws, const mcrn_params* pr
 int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const float* x, const float* y_cov,
                  const float* labels, const uint8_t* tf, float* output, float* h_att, float* query, float* pos,
                  float* neg, float* ws, cudaStream_t st) {
-  float* S = ws + p.S;
-  MCRN_TRY(supports_forward(g, p, ws, prm->memory, prm->we1, prm->we2, S, st));
+  float* S = ws + p.Sr;     // the recurrent GEMMs read the tensor-core copy of the supports
+  MCRN_TRY(supports_forward(g, p, ws, prm->memory, prm->we1, prm->we2, ws + p.S, ws + p.Sr, st));
   MCRN_TRY(fold_all_weights(g, p, ws, prm, st));
   // ---- encoder (ADCRNN_Encoder.forward :65-83; zero initial state :50-51, :174) ----
   {
@@ -201,11 +214,14 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
     MCRN_TRY(propagate_in(g, S, ws + p.enc_xpin, (int64_t)g.N * g.T_in * g.B * g.Cin, (int64_t)g.T_in * g.B * g.Cin,
                           g.T_in * g.B * g.Cin, st));
     MCRN_CUDA_OK(cudaMemsetAsync(ws + p.enc_xpg, 0, (size_t)g.R * g.H * sizeof(float), st));
+    MCRN_CUDA_OK(cudaMemsetAsync(ws + p.enc_hx, 0, (size_t)g.R * g.H * sizeof(float), st));
     CellW w = enc_w(g, p, ws, prm);
     for (int t = 0; t < g.T_in; ++t) {
       CellBufs b = enc_bufs(g, p, ws, t);
-      float* h_out = (t + 1 < g.T_in) ? enc_bufs(g, p, ws, t + 1).xpg : ws + p.h_enc;
-      MCRN_TRY(cell_forward(g, S, w, b, h_out, st));
+      const bool last = (t + 1 == g.T_in);
+      float* h_out = last ? ws + p.h_enc : enc_bufs(g, p, ws, t + 1).hx;
+      float* h_mma = last ? nullptr : enc_bufs(g, p, ws, t + 1).xpg;
+      MCRN_TRY(cell_forward(g, S, w, b, h_out, h_mma, st));
     }
   }
   // ---- memory query (:159-166) + decoder initial state (:179) ----
@@ -213,8 +229,8 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
     CellBufs b0 = dec_bufs(g, p, ws, 0);
     size_t shm = 8 * (g.d + g.M) * sizeof(float);
     MCRN_LAUNCH(k_memory_query, (int)ceil_div64(g.R, 8), 256, shm, st, ws + p.h_enc, prm->wq, prm->memory,
-                ws + p.mq_q, ws + p.mq_att, reinterpret_cast<int*>(ws + p.mq_ind), h_att, query, pos, neg, b0.xpg,
-                g.B, g.N, g.H, g.M, g.d);
+                ws + p.mq_q, ws + p.mq_att, reinterpret_cast<int*>(ws + p.mq_ind), h_att, query, pos, neg, b0.hx,
+                b0.xpg, tf32_mode(), g.B, g.N, g.H, g.M, g.d);
   }
   // ---- decoder loop (:181-192) ----
   {
@@ -227,8 +243,10 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
       MCRN_LAUNCH(k_stage_decoder_input, ew_grid(n_in), 256, 0, st, go_src, y_cov, const_cast<float*>(b.xpin), g.B,
                   g.T_out, g.N, g.Cout, g.Ycov, t);
       MCRN_TRY(propagate_in(g, S, const_cast<float*>(b.xpin), b.xp_k, b.xp_n, g.B * g.Cdec, st));
-      float* h_out = (t + 1 < g.T_out) ? dec_bufs(g, p, ws, t + 1).xpg : ws + p.h_dec_last;
-      MCRN_TRY(cell_forward(g, S, w, b, h_out, st));
+      const bool last = (t + 1 == g.T_out);
+      float* h_out = last ? ws + p.h_dec_last : dec_bufs(g, p, ws, t + 1).hx;
+      float* h_mma = last ? nullptr : dec_bufs(g, p, ws, t + 1).xpg;
+      MCRN_TRY(cell_forward(g, S, w, b, h_out, h_mma, st));
       MCRN_LAUNCH(k_proj_fwd, (int)ceil_div64(g.R, 8), 256, 0, st, h_out, prm->proj_w, prm->proj_b, output, g.B,
                   g.T_out, g.N, g.D, g.Cout, t);
     }
@@ -265,20 +283,25 @@ static int make_dxp(const Geo& g, const float* dv, int O, const float* wst, int 
   GemmDesc q;
   q.A = dv; q.a_row = O; q.a_k = 1; q.M = (int)g.R; q.Kseg = O;
   q.B = wst; q.b_k = 1; q.b_n = O; q.N = g.NB * Hs;
-  EpiBlocks e{dxp, Hs, g.R * Hs};
+  if (tf32_mode()) { q.nseg = 2; q.b_seg = (int64_t)g.NB * Hs * O; }     // W = hi + lo
+  EpiBlocks e{dxp, Hs, g.R * Hs, tf32_mode()};
   return gemm(q, e, st);
 }
 // out = add1 + add2 + dXP[0] + sum_k S_k^T dXP[1+k]    (M = N nodes, N = B*C, K = KS*N)
-static int propagate_T(const Geo& g, const float* S, const float* dxp, int C, const float* add2, float* out, cudaStream_t st) {
+static int propagate_T(const Geo& g, const float* S, const float* dxp, int C, const float* add2, float* out,
+                       cudaStream_t st, int exact = 0) {
   GemmDesc q;
+  q.prec_exact = exact;
   q.A = S; q.a_row = 1; q.a_k = g.ldS; q.M = g.N; q.Kseg = g.KS * g.N;
   q.B = dxp + g.R * C; q.b_k = (int64_t)g.B * C; q.b_n = 1; q.N = g.B * C;
   EpiStore e{out, (int64_t)g.B * C, 0, 1.0f, dxp, add2};
   return gemm(q, e, st);
 }
 // dS_k += dXP[1+k] * X^T       (M = KS*N, N = N nodes, K = B*C; X(node, col) = x + node*x_n + col)
-static int acc_ds(const Geo& g, const float* dp, int64_t dp_row, const float* x, int64_t x_n, int cols, float* dS, cudaStream_t st) {
+static int acc_ds(const Geo& g, const float* dp, int64_t dp_row, const float* x, int64_t x_n, int cols, float* dS,
+                  cudaStream_t st, int exact = 0) {
   GemmDesc q;
+  q.prec_exact = exact;
   q.A = dp; q.a_row = dp_row; q.a_k = 1; q.M = g.KS * g.N; q.Kseg = cols;
   q.B = x; q.b_k = 1; q.b_n = x_n; q.N = g.N;
   q.splits = split_for((int64_t)ceil_div(q.M, 64) * ceil_div(q.N, 64), cols / 16);
@@ -294,13 +317,13 @@ static int cell_backward(const Geo& g, const Plan& p, float* ws, const float* S,
   const int64_t nH = g.R * Hs;
   float *dU = ws + p.dU, *dG = ws + p.dG, *dXP = ws + p.dXP, *dZH = ws + p.dZH, *dHp = ws + p.dHp;
   float *dXPin = ws + p.dXPin, *dS = ws + p.dS;
-  MCRN_LAUNCH(k_bwd_du, ew_grid(nH), 256, 0, st, dH, b.r, b.hc, dU, nH);
+  MCRN_LAUNCH(k_bwd_du, ew_grid(nH), 256, 0, st, dH, b.r, b.hc, dU, nH, tf32_mode());
   // ---- update AGCN ----
   MCRN_TRY(make_dxp(g, dU, Hs, w.wu_st, Hs, dXP, st));
   MCRN_TRY(acc_dw(g, b.xpu, Hs, dU, Hs, a.wu_st, st));
   MCRN_TRY(propagate_T(g, S, dXP, Hs, nullptr, dZH, st));
   MCRN_TRY(acc_ds(g, dXP + nH, (int64_t)g.B * Hs, b.xpu, (int64_t)g.B * Hs, g.B * Hs, dS, st));
-  MCRN_LAUNCH(k_bwd_dg, ew_grid(nH), 256, 0, st, dZH, dH, b.xpg, b.z, b.r, b.hc, dG, dHp, g.R, Hs);
+  MCRN_LAUNCH(k_bwd_dg, ew_grid(nH), 256, 0, st, dZH, dH, b.hx, b.z, b.r, b.hc, dG, dHp, g.R, Hs, tf32_mode());
   // ---- gate AGCN ----
   MCRN_TRY(make_dxp(g, dG, 2 * Hs, w.wg_st, Hs, dXP, st));
   MCRN_TRY(acc_dw(g, b.xpg, Hs, dG, 2 * Hs, a.wg_st, st));
@@ -313,8 +336,8 @@ static int cell_backward(const Geo& g, const Plan& p, float* ws, const float* S,
   MCRN_LAUNCH(k_bwd_bias_win, rb, 256, shm, st, dG, 2 * Hs, b.xpin, b.xp_k, b.xp_n, g.NB, w.Cin, g.B, g.R, a.bg, a.wg_in);
   MCRN_LAUNCH(k_bwd_dxpin, (int)ceil_div64(g.R, 8), 256, 0, st, dU, w.wu_in, Hs, dG, w.wg_in, 2 * Hs, g.NB, w.Cin,
               g.R, dXPin);
-  MCRN_TRY(acc_ds(g, dXPin + g.R * w.Cin, (int64_t)g.B * w.Cin, b.xpin, b.xp_n, g.B * w.Cin, dS, st));
-  if (dxin) MCRN_TRY(propagate_T(g, S, dXPin, w.Cin, nullptr, dxin, st));
+  MCRN_TRY(acc_ds(g, dXPin + g.R * w.Cin, (int64_t)g.B * w.Cin, b.xpin, b.xp_n, g.B * w.Cin, dS, st, 1));
+  if (dxin) MCRN_TRY(propagate_T(g, S, dXPin, w.Cin, nullptr, dxin, st, 1));
   return MCRN_OK;
 }
 
@@ -325,15 +348,17 @@ static int supports_backward(const Geo& g, const Plan& p, float* ws, const mcrn_
   float* S = ws + p.S;
   float* dS = ws + p.dS;
   float* dg[2] = {ws + p.dg1, ws + p.dg2};
+  // N^3 work: exact fp32 on the SIMT engine for METR-LA/PEMS-BAY sizes (negligible FLOPs), tensor cores beyond.
+  const int big_exact = (g.N <= 1024) ? 1 : 0;
   for (int i = 0; i < 2; ++i) {
-    float* gi = S + (int64_t)i * per * mat;
+    float* gi = (big_exact ? S : ws + p.Sr) + (int64_t)i * per * mat;
     float* dt = dS + (int64_t)i * per * mat;                 // dt[k-1] = d T_k, k = 1..cheb_k-1
     for (int k = g.cheb_k - 1; k >= 2; --k) {
       float* dtk = dt + (int64_t)(k - 1) * mat;
       {  // dg += 2 * dT_k * T_{k-1}^T
         GemmDesc q;
         q.A = dtk; q.a_row = g.ldS; q.a_k = 1; q.M = g.N; q.Kseg = g.N;
-        q.B = gi + (int64_t)(k - 2) * mat; q.b_k = 1; q.b_n = g.ldS; q.N = g.N;
+        q.B = gi + (int64_t)(k - 2) * mat; q.b_k = 1; q.b_n = g.ldS; q.N = g.N; q.prec_exact = big_exact;
         EpiStore e{dg[i], g.ldS, 0, 2.0f, dg[i], nullptr};
         MCRN_TRY(gemm(q, e, st));
       }
@@ -341,7 +366,7 @@ static int supports_backward(const Geo& g, const Plan& p, float* ws, const mcrn_
         float* dtm1 = dt + (int64_t)(k - 2) * mat;
         GemmDesc q;
         q.A = gi; q.a_row = 1; q.a_k = g.ldS; q.M = g.N; q.Kseg = g.N;
-        q.B = dtk; q.b_k = g.ldS; q.b_n = 1; q.N = g.N;
+        q.B = dtk; q.b_k = g.ldS; q.b_n = 1; q.N = g.N; q.prec_exact = big_exact;
         EpiStore e{dtm1, g.ldS, 0, 2.0f, dtm1, nullptr};
         MCRN_TRY(gemm(q, e, st));
       }
@@ -359,7 +384,7 @@ static int supports_backward(const Geo& g, const Plan& p, float* ws, const mcrn_
   {  // dE1 = dL1 * E2 ; dE2 = dL1^T * E1
     GemmDesc q;
     q.A = dL1; q.a_row = g.ldS; q.a_k = 1; q.M = g.N; q.Kseg = g.N;
-    q.B = ws + p.E2; q.b_k = g.d; q.b_n = 1; q.N = g.d;
+    q.B = ws + p.E2; q.b_k = g.d; q.b_n = 1; q.N = g.d; q.prec_exact = 1;
     EpiStore e{dE1, g.d, 0, 1.0f, nullptr, nullptr};
     MCRN_TRY(gemm(q, e, st));
     q.A = dL1; q.a_row = 1; q.a_k = g.ldS; q.B = ws + p.E1;
@@ -371,14 +396,14 @@ static int supports_backward(const Geo& g, const Plan& p, float* ws, const mcrn_
     {  // dWe_i = dE_i * Memory^T                     [N x M]
       GemmDesc q;
       q.A = dE; q.a_row = g.d; q.a_k = 1; q.M = g.N; q.Kseg = g.d;
-      q.B = prm->memory; q.b_k = 1; q.b_n = g.d; q.N = g.M;
+      q.B = prm->memory; q.b_k = 1; q.b_n = g.d; q.N = g.M; q.prec_exact = 1;
       EpiStore e{i ? grads->we2 : grads->we1, g.M, 0, 1.0f, nullptr, nullptr};
       MCRN_TRY(gemm(q, e, st));
     }
     {  // dMemory += We_i^T * dE_i                    [M x d]
       GemmDesc q;
       q.A = i ? prm->we2 : prm->we1; q.a_row = 1; q.a_k = g.M; q.M = g.M; q.Kseg = g.N;
-      q.B = dE; q.b_k = g.d; q.b_n = 1; q.N = g.d;
+      q.B = dE; q.b_k = g.d; q.b_n = 1; q.N = g.d; q.prec_exact = 1;
       EpiStore e{grads->memory, g.d, 0, 1.0f, grads->memory, nullptr};
       MCRN_TRY(gemm(q, e, st));
     }
@@ -389,7 +414,7 @@ static int supports_backward(const Geo& g, const Plan& p, float* ws, const mcrn_
 int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uint8_t* tf, const float* d_output,
                   const float* d_hatt, const float* d_query, const float* d_pos, const float* d_neg,
                   const mcrn_params* grads, float* ws, cudaStream_t st) {
-  const float* S = ws + p.S;
+  const float* S = ws + p.Sr;     // tensor-core copy of the supports (equal to the exact ones in SIMT mode)
   // zero accumulators and the directly-accumulated outputs
   MCRN_CUDA_OK(cudaMemsetAsync(ws + p.acc_begin, 0, (p.acc_end - p.acc_begin) * sizeof(float), st));
   MCRN_CUDA_OK(cudaMemsetAsync(grads->memory, 0, (size_t)g.M * g.d * sizeof(float), st));
@@ -407,7 +432,7 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
     bool have_dgo = false;
     for (int t = g.T_out - 1; t >= 0; --t) {
       CellBufs b = dec_bufs(g, p, ws, t);
-      const float* h_t = (t + 1 < g.T_out) ? dec_bufs(g, p, ws, t + 1).xpg : ws + p.h_dec_last;
+      const float* h_t = (t + 1 < g.T_out) ? dec_bufs(g, p, ws, t + 1).hx : ws + p.h_dec_last;
       bool use_dgo = have_dgo && !(tf && tf[t]);
       size_t shm = (size_t)32 * g.Cout * sizeof(float);
       MCRN_LAUNCH(k_proj_bwd, (int)ceil_div64(g.R, 32), 256, shm, st, d_output, use_dgo ? dXin : nullptr, g.Cdec, h_t,
@@ -430,7 +455,7 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
     {  // dMemory += att^T dv + dsc^T query            [M x d], K = R
       GemmDesc q;
       q.A = ws + p.mq_att; q.a_row = 1; q.a_k = g.M; q.M = g.M; q.Kseg = (int)g.R;
-      q.B = dv; q.b_k = g.d; q.b_n = 1; q.N = g.d; q.splits = sp;
+      q.B = dv; q.b_k = g.d; q.b_n = 1; q.N = g.d; q.splits = sp; q.prec_exact = 1;
       EpiAtomicAdd e{grads->memory, g.d, 0};
       MCRN_TRY(gemm(q, e, st));
       q.A = dsc; q.B = ws + p.mq_q;
@@ -440,14 +465,14 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
       MCRN_CUDA_OK(cudaMemsetAsync(grads->wq, 0, (size_t)g.H * g.d * sizeof(float), st));
       GemmDesc q;
       q.A = ws + p.h_enc; q.a_row = 1; q.a_k = g.H; q.M = g.H; q.Kseg = (int)g.R;
-      q.B = dq; q.b_k = g.d; q.b_n = 1; q.N = g.d; q.splits = sp;
+      q.B = dq; q.b_k = g.d; q.b_n = 1; q.N = g.d; q.splits = sp; q.prec_exact = 1;
       EpiAtomicAdd e{grads->wq, g.d, 0};
       MCRN_TRY(gemm(q, e, st));
     }
     {  // dH_enc = dH0[:, :H] + dq Wq^T                [R x H], K = d
       GemmDesc q;
       q.A = dq; q.a_row = g.d; q.a_k = 1; q.M = (int)g.R; q.Kseg = g.d;
-      q.B = prm->wq; q.b_k = 1; q.b_n = g.d; q.N = g.H;
+      q.B = prm->wq; q.b_k = 1; q.b_n = g.d; q.N = g.H; q.prec_exact = 1;
       EpiStoreStrideAdd e{ws + p.dHenc, g.H, dH, g.D};
       MCRN_TRY(gemm(q, e, st));
     }
@@ -473,7 +498,9 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
 
 int supports_forward_entry(const Geo& g, const Plan& p, float* ws, const float* mem, const float* we1,
                            const float* we2, float* S, cudaStream_t st) {
-  return supports_forward(g, p, ws, mem, we1, we2, S, st);
+  MCRN_TRY(supports_forward(g, p, ws, mem, we1, we2, ws + p.S, ws + p.Sr, st));
+  MCRN_CUDA_OK(cudaMemcpyAsync(S, ws + p.S, (size_t)g.KS * g.N * g.ldS * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return MCRN_OK;
 }
 
 int trainer_loss_impl(const Geo& g, const float* output, const float* labels, const float* query, const float* pos,

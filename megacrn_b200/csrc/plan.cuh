@@ -13,13 +13,13 @@ struct Plan {
   int enc_slots, dec_slots;
   size_t bytes;
   // ---- offsets in floats --------------------------------------------------
-  size_t S, E1, E2, L1, L2;
+  size_t S, Sr, E1, E2, L1, L2;        // Sr: TF32-rounded copy of the supports (tensor-core operand)
   size_t e_wg_st, e_wg_in, e_wu_st, e_wu_in, d_wg_st, d_wg_in, d_wu_st, d_wu_in;   // folded weights
   size_t enc_xpin;                       // [NB][N][T_in][B][Cin]
-  size_t enc_xpg, enc_xpu, enc_z, enc_r, enc_hc;   // per slot strides below
+  size_t enc_xpg, enc_xpu, enc_z, enc_r, enc_hc, enc_hx;   // per slot; hx = exact fp32 input state of the step
   size_t h_enc;                          // [R][H]
   size_t mq_q, mq_att, mq_ind;           // [R][d], [R][M], int[R][2]
-  size_t dec_xpin, dec_xpg, dec_xpu, dec_z, dec_r, dec_hc;
+  size_t dec_xpin, dec_xpg, dec_xpu, dec_z, dec_r, dec_hc, dec_hx;
   size_t h_dec_last;                     // [R][D]
   // per-slot sizes (floats)
   size_t enc_xp_sz, enc_v_sz, dec_xpin_sz, dec_xp_sz, dec_v_sz;
@@ -45,17 +45,18 @@ static inline int make_plan(const Geo& g, bool save, Plan* p) {
   };
   const size_t R = (size_t)g.R, N = g.N, ldS = g.ldS, NB = g.NB, KS = g.KS;
   p->S = take(KS * N * ldS);
+  p->Sr = take(KS * N * ldS);
   p->E1 = take(N * g.d);
   p->E2 = take(N * g.d);
   p->L1 = take(N * ldS);
   p->L2 = take(N * ldS);
-  p->e_wg_st = take(NB * g.H * 2 * g.H);
+  p->e_wg_st = take(2 * NB * g.H * 2 * g.H);      // [hi | lo] TF32 split
   p->e_wg_in = take(NB * g.Cin * 2 * g.H);
-  p->e_wu_st = take(NB * g.H * g.H);
+  p->e_wu_st = take(2 * NB * g.H * g.H);      // [hi | lo] TF32 split
   p->e_wu_in = take(NB * g.Cin * g.H);
-  p->d_wg_st = take(NB * g.D * 2 * g.D);
+  p->d_wg_st = take(2 * NB * g.D * 2 * g.D);      // [hi | lo] TF32 split
   p->d_wg_in = take(NB * g.Cdec * 2 * g.D);
-  p->d_wu_st = take(NB * g.D * g.D);
+  p->d_wu_st = take(2 * NB * g.D * g.D);      // [hi | lo] TF32 split
   p->d_wu_in = take(NB * g.Cdec * g.D);
   p->enc_slots = save ? g.T_in : 2;
   p->dec_slots = save ? g.T_out : 2;
@@ -67,6 +68,7 @@ static inline int make_plan(const Geo& g, bool save, Plan* p) {
   p->enc_z = take(p->enc_v_sz * p->enc_slots);
   p->enc_r = take(p->enc_v_sz * p->enc_slots);
   p->enc_hc = take(p->enc_v_sz * p->enc_slots);
+  p->enc_hx = take(p->enc_v_sz * p->enc_slots);
   p->h_enc = take(R * g.H);
   p->mq_q = take(R * g.d);
   p->mq_att = take(R * g.M);
@@ -80,6 +82,7 @@ static inline int make_plan(const Geo& g, bool save, Plan* p) {
   p->dec_z = take(p->dec_v_sz * p->dec_slots);
   p->dec_r = take(p->dec_v_sz * p->dec_slots);
   p->dec_hc = take(p->dec_v_sz * p->dec_slots);
+  p->dec_hx = take(p->dec_v_sz * p->dec_slots);
   p->h_dec_last = take(R * g.D);
   p->loss_scratch = take(64);
   if (save) {

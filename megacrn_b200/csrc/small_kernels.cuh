@@ -24,7 +24,7 @@ __device__ __forceinline__ float block_sum_256(float v, float* sh) {
   __syncthreads();
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
   __syncthreads();
-  float t = (threadIdx.x < 8) ? sh[threadIdx.x] : 0.f;
+  float t = ((threadIdx.x & 31) < 8) ? sh[threadIdx.x & 31] : 0.f;
   t = warp_sum(t);
   return __shfl_sync(0xffffffffu, t, 0);
 }
@@ -33,7 +33,7 @@ __device__ __forceinline__ float block_max_256(float v, float* sh) {
   __syncthreads();
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
   __syncthreads();
-  float t = (threadIdx.x < 8) ? sh[threadIdx.x] : -INFINITY;
+  float t = ((threadIdx.x & 31) < 8) ? sh[threadIdx.x & 31] : -INFINITY;
   t = warp_max(t);
   return __shfl_sync(0xffffffffu, t, 0);
 }
@@ -41,10 +41,11 @@ __device__ __forceinline__ float block_max_256(float v, float* sh) {
 // ---- supports prologue ------------------------------------------------------------
 // g[row,:] = softmax(relu(L[row,:]))                     model/MegaCRN.py:171-172
 __global__ void __launch_bounds__(256) k_relu_softmax_rows(const float* __restrict__ L, float* __restrict__ G,
-                                                           int n, int ld) {
+                                                           float* __restrict__ Gr, int n, int ld) {
   __shared__ float sh[8];
   const float* l = L + (int64_t)blockIdx.x * ld;
   float* g = G + (int64_t)blockIdx.x * ld;
+  float* gr = Gr + (int64_t)blockIdx.x * ld;
   float mx = -INFINITY;
   for (int j = threadIdx.x; j < n; j += 256) mx = fmaxf(mx, fmaxf(l[j], 0.f));
   mx = block_max_256(mx, sh);
@@ -52,8 +53,12 @@ __global__ void __launch_bounds__(256) k_relu_softmax_rows(const float* __restri
   for (int j = threadIdx.x; j < n; j += 256) s += expf(fmaxf(l[j], 0.f) - mx);
   s = block_sum_256(s, sh);
   float inv = 1.0f / s;
-  for (int j = threadIdx.x; j < n; j += 256) g[j] = expf(fmaxf(l[j], 0.f) - mx) * inv;
-  for (int j = n + threadIdx.x; j < ld; j += 256) g[j] = 0.f;
+  for (int j = threadIdx.x; j < n; j += 256) {
+    float v = expf(fmaxf(l[j], 0.f) - mx) * inv;
+    g[j] = v;
+    gr[j] = tf32_rn(v);
+  }
+  for (int j = n + threadIdx.x; j < ld; j += 256) { g[j] = 0.f; gr[j] = 0.f; }
 }
 
 // dL[row,:] = g*(dg - sum(g*dg)) * (L > 0)      softmax + relu backward, one row per block
@@ -87,8 +92,10 @@ __global__ void k_add_transpose(const float* __restrict__ a, const float* __rest
 
 // ---- parameter re-packing (fold the two identity blocks; split input/state rows) ----
 // w [2*ck*(cin+hs), O] -> wst [NB][hs][O], win [NB][cin][O]       (tests/kernel_spec.py:fold_agcn_weights)
+// With split != 0, wst holds [2][NB][hs][O]: TF32 hi part then the TF32-rounded residual (lo); hi + lo carries
+// ~21 mantissa bits, which removes the (static, hence coherent over time and batch) weight-rounding error.
 __global__ void k_fold_weights(const float* __restrict__ w, float* __restrict__ wst, float* __restrict__ win,
-                               int cin, int hs, int O, int ck) {
+                               int cin, int hs, int O, int ck, int split) {
   int NB = 1 + 2 * (ck - 1), c = cin + hs;
   int64_t total = (int64_t)NB * c * O;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -102,8 +109,15 @@ __global__ void k_fold_weights(const float* __restrict__ w, float* __restrict__ 
       int g = (blk - 1) / (ck - 1), k = 1 + (blk - 1) % (ck - 1);
       v = w[((int64_t)(g * ck + k) * c + cc) * O + o];
     }
-    if (cc < cin) win[((int64_t)blk * cin + cc) * O + o] = v;
-    else wst[((int64_t)blk * hs + (cc - cin)) * O + o] = v;
+    if (cc < cin) {
+      win[((int64_t)blk * cin + cc) * O + o] = v;
+    } else if (!split) {
+      wst[((int64_t)blk * hs + (cc - cin)) * O + o] = v;
+    } else {
+      float hi = tf32_rn(v);
+      wst[((int64_t)blk * hs + (cc - cin)) * O + o] = hi;
+      wst[((int64_t)(NB + blk) * hs + (cc - cin)) * O + o] = tf32_rn(v - hi);
+    }
   }
 }
 
@@ -224,7 +238,8 @@ __global__ void __launch_bounds__(256) k_memory_query(const float* __restrict__ 
                                                       float* __restrict__ att, int* __restrict__ ind,
                                                       float* __restrict__ o_hatt, float* __restrict__ o_query,
                                                       float* __restrict__ o_pos, float* __restrict__ o_neg,
-                                                      float* __restrict__ dec_h0, int B, int N, int H, int M, int d) {
+                                                      float* __restrict__ dec_h0, float* __restrict__ dec_h0_mma,
+                                                      int rnd, int B, int N, int H, int M, int d) {
   extern __shared__ float shm[];                   // per warp: q[d] + sc[M]
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int64_t row = (int64_t)blockIdx.x * 8 + warp;
@@ -277,9 +292,13 @@ __global__ void __launch_bounds__(256) k_memory_query(const float* __restrict__ 
     o_pos[ob + j] = mem[(int64_t)i0 * d + j];      // :164
     o_neg[ob + j] = mem[(int64_t)i1 * d + j];      // :165
     dec_h0[row * (H + d) + H + j] = s;             // :179
+    dec_h0_mma[row * (H + d) + H + j] = rnd ? tf32_rn(s) : s;
     if (q_nm) q_nm[row * d + j] = q[j];
   }
-  for (int j = lane; j < H; j += 32) dec_h0[row * (H + d) + j] = hr[j];
+  for (int j = lane; j < H; j += 32) {
+    dec_h0[row * (H + d) + j] = hr[j];
+    dec_h0_mma[row * (H + d) + j] = rnd ? tf32_rn(hr[j]) : hr[j];
+  }
   if (att) for (int m = lane; m < M; m += 32) att[row * M + m] = sc[m];
   if (ind && lane == 0) { ind[row * 2] = i0; ind[row * 2 + 1] = i1; }
 }
@@ -336,24 +355,26 @@ __global__ void __launch_bounds__(256) k_memory_query_bwd_rows(
 // ---- cell backward, elementwise pieces (tests/kernel_spec.py:cell_bwd) ----------------------
 // dU = dH' * (1-r) * (1-hc^2)
 __global__ void k_bwd_du(const float* __restrict__ dH, const float* __restrict__ r, const float* __restrict__ hc,
-                         float* __restrict__ dU, int64_t n) {
+                         float* __restrict__ dU, int64_t n, int rnd) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float c = hc[i];
-    dU[i] = dH[i] * (1.0f - r[i]) * (1.0f - c * c);
+    float v = dH[i] * (1.0f - r[i]) * (1.0f - c * c);
+    dU[i] = rnd ? tf32_rn(v) : v;
   }
 }
 
 // dG[:, :H] = dZH*h*z(1-z); dG[:, H:] = dH'*(h-hc)*r(1-r); dh_part = dH'*r + dZH*z
 __global__ void k_bwd_dg(const float* __restrict__ dZH, const float* __restrict__ dH, const float* __restrict__ h,
                          const float* __restrict__ z, const float* __restrict__ r, const float* __restrict__ hc,
-                         float* __restrict__ dG, float* __restrict__ dh_part, int64_t R, int H) {
+                         float* __restrict__ dG, float* __restrict__ dh_part, int64_t R, int H, int rnd) {
   int64_t n = R * H;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t row = i / H;
     int c = (int)(i - row * H);
     float zz = z[i], rr = r[i], hh = h[i], dzh = dZH[i], dh = dH[i];
-    dG[row * 2 * H + c] = dzh * hh * zz * (1.0f - zz);
-    dG[row * 2 * H + H + c] = dh * (hh - hc[i]) * rr * (1.0f - rr);
+    float gz = dzh * hh * zz * (1.0f - zz), gr = dh * (hh - hc[i]) * rr * (1.0f - rr);
+    dG[row * 2 * H + c] = rnd ? tf32_rn(gz) : gz;
+    dG[row * 2 * H + H + c] = rnd ? tf32_rn(gr) : gr;
     dh_part[i] = dh * rr + dzh * zz;
   }
 }
