@@ -160,6 +160,11 @@ int mcrn_gemm(int M, int N, int K, const float* A, int lda, int trans_a,
               const float* B, int ldb, int trans_b, float* C, int ldc,
               int engine, void* stream);
 
+/* Debug aid: mcrn_gemm on the tcgen05 engine with shared-memory stage 0 of CTA (0,0,0) dumped to dbg
+ * (at least 16 K floats + 2). */
+int mcrn_debug_tc_gemm(int M, int N, int K, const float* A, int lda, int trans_a,
+                       const float* B, int ldb, int trans_b, float* C, int ldc, float* dbg, void* stream);
+
 /* Number of kernels the library launched since process start (for bench.py's
  * `gpu_launches`). */
 uint64_t mcrn_launch_count(void);

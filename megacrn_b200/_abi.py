@@ -83,6 +83,9 @@ def load() -> C.CDLL:
     lib.mcrn_gemm.restype = C.c_int
     lib.mcrn_gemm.argtypes = [C.c_int, C.c_int, C.c_int, fp, C.c_int, C.c_int, fp, C.c_int, C.c_int,
                               fp, C.c_int, C.c_int, vp]
+    lib.mcrn_debug_tc_gemm.restype = C.c_int
+    lib.mcrn_debug_tc_gemm.argtypes = [C.c_int, C.c_int, C.c_int, fp, C.c_int, C.c_int, fp, C.c_int, C.c_int,
+                                       fp, C.c_int, fp, vp]
     lib.mcrn_host_workspace_bytes.restype = C.c_size_t
     lib.mcrn_host_workspace_bytes.argtypes = [C.POINTER(Dims), C.c_uint32]
     lib.mcrn_forward_host.restype = C.c_int

@@ -170,6 +170,15 @@ int mcrn_gemm(int M, int N, int K, const float* A, int lda, int trans_a, const f
   return s;
 }
 
+// Debug aid (tools/tc_diag.py): one tcgen05 GEMM with the first shared-memory stage dumped to `dbg`.
+int mcrn_debug_tc_gemm(int M, int N, int K, const float* A, int lda, int trans_a, const float* B, int ldb, int trans_b,
+                       float* C, int ldc, float* dbg, void* stream) {
+  tc::g_dbg = dbg;
+  int s = mcrn_gemm(M, N, K, A, lda, trans_a, B, ldb, trans_b, C, ldc, 2, stream);
+  tc::g_dbg = nullptr;
+  return s;
+}
+
 int mcrn_trainer_loss(const mcrn_dims* dims, const float* output, const float* labels, const float* query,
                       const float* pos, const float* neg, float scaler_mean, float scaler_std, float lamb,
                       float lamb1, float* loss_out, float* d_output, float* d_query, void* workspace,

@@ -9,6 +9,7 @@
 namespace mcrn {
 namespace tc {
 
+float* g_dbg = nullptr;
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 static std::once_flag g_once;
 
@@ -21,7 +22,7 @@ static void resolve_encode() {
 }
 
 int encode_tensor_map(CUtensorMap* out, const float* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
-                      const uint32_t box[4]) {
+                      const uint32_t box[4], bool mn_major) {
   std::call_once(g_once, resolve_encode);
   if (!g_encode) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return MCRN_ERR_CUDA; }
   cuuint64_t gdim[4] = {dims[0], dims[1], dims[2], dims[3]};
@@ -29,7 +30,8 @@ int encode_tensor_map(CUtensorMap* out, const float* base, const uint64_t dims[4
   cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstr, bx, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): dims=[%llu,%llu,%llu,%llu] strides=[%llu,%llu,%llu] box=[%u,%u,%u,%u] base=%p",

@@ -23,7 +23,9 @@ constexpr uint32_t SLAB_BYTES = 32 * 128;       // [32 k-rows][128 B] slab of an
 
 struct TcParams {
   int M, N, Kseg, nseg, a_seg_mod, b_seg_mod, nbatch, splits, a_batched, b_batched;
+  float* dbg;            // debug dump (mcrn_debug_tc_gemm): [0, STAGE floats) = raw smem stage 0 after TMA
 };
+extern float* g_dbg;     // host-side: non-null only inside mcrn_debug_tc_gemm
 
 // ---- PTX wrappers -----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -79,13 +81,18 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, float (&v)[32
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   K-major fp32 : layout SWIZZLE_128B (2): rows of 128 B, 16-byte chunks XOR (row % 8); SBO = 1024 B per 8 rows.
+//   MN-major fp32: layout SWIZZLE_128B_BASE32B (1) -- the only MN-major layout the hardware accepts for 32-bit
+//                  operands: rows (k) of 128 B = 32 m, 32-byte chunks XOR (k % 4); atom = 4 k-rows (512 B);
+//                  LBO = stride between 32-wide M/N groups, SBO = stride between 4-row k groups.
+//                  The matching TMA mode is CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
 }
 
@@ -140,6 +147,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
+  if (p.dbg != nullptr && warp >= 2) {                   // debug: prefill the accumulator with a pattern
+    const int quarter = warp & 3;
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(-1000.0f - (float)(quarter * 32 + lane) - 0.001f * (c * 32 + j));
+      uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32);
+      asm volatile(
+          "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+          "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+          "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+          ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    tcgen05_fence_before();
+  }
+  if (p.dbg != nullptr) { __syncthreads(); tcgen05_fence_after(); }
+
   if (nit > 0) {
     if (warp == 0) {
       if (lane == 0) {                                   // ===== TMA producer =====
@@ -175,11 +203,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
           mbar_wait(smem_u32(&full_bar[s]), ph);
           tcgen05_fence_after();
+          if (p.dbg != nullptr && i == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+            const float* src = reinterpret_cast<const float*>(smem_raw + (smem_base - smem_u32(smem_raw)));
+            for (uint32_t q = 0; q < STAGE_BYTES / 4; ++q) p.dbg[q] = src[q];
+            p.dbg[STAGE_BYTES / 4] = __uint_as_float(tmem_base);
+            p.dbg[STAGE_BYTES / 4 + 1] = __uint_as_float(smem_base);
+          }
           const uint32_t a_addr = smem_base + (uint32_t)s * STAGE_BYTES, b_addr = a_addr + A_BYTES;
 #pragma unroll
           for (int kk = 0; kk < BK / 8; ++kk) {          // UMMA_K = 8 for tf32
-            const uint64_t ad = A_K ? make_smem_desc(a_addr + kk * 32, 16, 1024) : make_smem_desc(a_addr + kk * 1024, SLAB_BYTES, 1024);
-            const uint64_t bd = B_K ? make_smem_desc(b_addr + kk * 32, 16, 1024) : make_smem_desc(b_addr + kk * 1024, SLAB_BYTES, 1024);
+            const uint64_t ad = A_K ? make_smem_desc(a_addr + kk * 32, 16, 1024, 2) : make_smem_desc(a_addr + kk * 1024, SLAB_BYTES, 512, 1);
+            const uint64_t bd = B_K ? make_smem_desc(b_addr + kk * 32, 16, 1024, 2) : make_smem_desc(b_addr + kk * 1024, SLAB_BYTES, 512, 1);
             tcgen05_mma_tf32(tmem_base, ad, bd, idesc, (i > 0 || kk > 0) ? 1u : 0u);
           }
           tcgen05_commit(smem_u32(&empty_bar[s]));       // frees the smem slot when these MMAs retire
@@ -209,7 +243,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 // ---- host side ----------------------------------------------------------------------------
 int encode_tensor_map(CUtensorMap* out, const float* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
-                      const uint32_t box[4]);
+                      const uint32_t box[4], bool mn_major);
 bool eligible(const GemmDesc& g);
 
 template <bool A_K, bool B_K, int BN, int STAGES, class Epi>
@@ -226,7 +260,7 @@ int launch(const GemmDesc& g, const Epi& epi, cudaStream_t st) {
     const int ab = g.a_batch ? g.nbatch : 1;
     dims[3] = ab; str[2] = ab > 1 ? g.a_batch * 4 : str[1] * dims[2];
     (void)big;
-    MCRN_TRY(encode_tensor_map(&ta, g.A, dims, str, box));
+    MCRN_TRY(encode_tensor_map(&ta, g.A, dims, str, box, !A_K));
   }
   {
     uint64_t dims[4], str[3];
@@ -237,7 +271,7 @@ int launch(const GemmDesc& g, const Epi& epi, cudaStream_t st) {
     dims[2] = bseg; str[1] = bseg > 1 ? g.b_seg * 4 : str[0] * dims[1];
     const int bb = g.b_batch ? g.nbatch : 1;
     dims[3] = bb; str[2] = bb > 1 ? g.b_batch * 4 : str[1] * dims[2];
-    MCRN_TRY(encode_tensor_map(&tb, g.B, dims, str, box));
+    MCRN_TRY(encode_tensor_map(&tb, g.B, dims, str, box, !B_K));
   }
   TcParams p;
   p.M = g.M; p.N = g.N; p.Kseg = g.Kseg; p.nseg = g.nseg;
@@ -246,6 +280,7 @@ int launch(const GemmDesc& g, const Epi& epi, cudaStream_t st) {
   p.nbatch = g.nbatch; p.splits = g.splits;
   p.a_batched = g.a_batch ? 1 : 0;
   p.b_batched = g.b_batch ? 1 : 0;
+  p.dbg = g_dbg;
   auto kern = gemm_tc_kernel<A_K, B_K, BN, STAGES, Epi>;
   constexpr size_t smem = smem_bytes<BN, STAGES>();
   static bool attr_set = false;
