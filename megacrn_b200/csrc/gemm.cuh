@@ -21,8 +21,12 @@ struct GemmDesc {
   int M = 0, N = 0, Kseg = 0, nseg = 1, nbatch = 1, splits = 1;
   int a_nseg = 0, b_nseg = 0;   // distinct segments of A / B (0 = nseg); segment index wraps (hi/lo weight split)
   int prec_exact = 0;           // 1 = this contraction must run in exact fp32 (SIMT engine)
+  int use_map = 0;              // 1 = K-segment s reads A segment a_map[s] and B segment b_map[s] (3xTF32 products)
+  uint8_t a_map[16] = {0}, b_map[16] = {0};
   __host__ __device__ int nseg_a() const { return a_nseg ? a_nseg : nseg; }
   __host__ __device__ int nseg_b() const { return b_nseg ? b_nseg : nseg; }
+  __host__ __device__ int seg_a(int s) const { return use_map ? a_map[s] : s % nseg_a(); }
+  __host__ __device__ int seg_b(int s) const { return use_map ? b_map[s] : s % nseg_b(); }
 };
 
 // Round-to-nearest TF32 (cvt.rna): producers of tensor-core operands store rounded values so that the
@@ -105,13 +109,21 @@ struct EpiCheb {
 struct EpiBlocks {
   float* C; int W; int64_t blk_stride;
   int rnd = 0;                               // 1: blocks >= 1 (tensor-core operands downstream) are TF32-rounded
+  float* Clo = nullptr;                      // with rnd: TF32 residual of blocks >= 1 (same layout) for 3xTF32 products
   template <int V>
   __device__ __forceinline__ void apply(int, int m, int n0, int nv, const float (&acc)[V]) const {
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       if (j < nv) {
         int n = n0 + j, blk = n / W, c = n - blk * W;
-        C[(int64_t)blk * blk_stride + (int64_t)m * W + c] = (rnd && blk > 0) ? tf32_rn(acc[j]) : acc[j];
+        int64_t o = (int64_t)blk * blk_stride + (int64_t)m * W + c;
+        if (rnd && blk > 0) {
+          float hi = tf32_rn(acc[j]);
+          C[o] = hi;
+          if (Clo) Clo[o] = tf32_rn(acc[j] - hi);
+        } else {
+          C[o] = acc[j];
+        }
       }
     }
   }

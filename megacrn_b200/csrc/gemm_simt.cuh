@@ -33,8 +33,8 @@ __global__ void __launch_bounds__(SIMT_THREADS) gemm_simt_kernel(GemmDesc g, Epi
 
   for (int it = it0; it < it1; ++it) {
     const int seg = it / ktiles, k0 = (it - seg * ktiles) * SIMT_BK;
-    const float* As_g = A + (int64_t)(seg % g.nseg_a()) * g.a_seg;
-    const float* Bs_g = B + (int64_t)(seg % g.nseg_b()) * g.b_seg;
+    const float* As_g = A + (int64_t)g.seg_a(seg) * g.a_seg;
+    const float* Bs_g = B + (int64_t)g.seg_b(seg) * g.b_seg;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       int idx = tid + e * SIMT_THREADS;     // 0..1023

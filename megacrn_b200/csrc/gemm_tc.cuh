@@ -22,7 +22,8 @@ constexpr int BM = 128, BK = 32, THREADS = 192;
 constexpr uint32_t SLAB_BYTES = 32 * 128;       // [32 k-rows][128 B] slab of an MN-major operand
 
 struct TcParams {
-  int M, N, Kseg, nseg, a_seg_mod, b_seg_mod, nbatch, splits, a_batched, b_batched;
+  int M, N, Kseg, nseg, nbatch, splits, a_batched, b_batched;
+  uint8_t a_map[16], b_map[16];   // K-segment -> operand segment (hi/lo splits, block buffers)
   float* dbg;            // debug dump (mcrn_debug_tc_gemm): [0, STAGE floats) = raw smem stage 0 after TMA
 };
 extern float* g_dbg;     // host-side: non-null only inside mcrn_debug_tc_gemm
@@ -179,7 +180,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t fb = smem_u32(&full_bar[s]);
           mbar_expect_tx(fb, STAGE_BYTES);
           const int it = it0 + i, seg = it / kt, k0 = (it - seg * kt) * BK;
-          const int sa = seg % p.a_seg_mod, sb = seg % p.b_seg_mod;
+          const int sa = p.a_map[seg], sb = p.b_map[seg];
           const uint32_t a_dst = smem_base + (uint32_t)s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
           if (A_K) {
             tma_load_4d(a_dst, &tmA, fb, k0, m0, sa, bza);
@@ -224,13 +225,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int quarter = warp & 3;                      // TMEM lane quarter this warp may read
       mbar_wait(smem_u32(&tmem_full_bar), 0);
       tcgen05_fence_after();
-      const int row = m0 + quarter * 32 + lane;
+      // Each thread owns one accumulator ROW (TMEM lane).  Storing rows per thread would scatter every warp
+      // store over 32 cache lines, so each 32x32 chunk is transposed through shared memory (the pipeline
+      // stages are idle once the accumulator is complete) and the epilogue functor runs with the 32 lanes
+      // on 32 CONSECUTIVE COLUMNS of one row: all its global loads/stores are 128-byte coalesced.
+      float* scr = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))) + quarter * (32 * 33);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         float v[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), v);
-        const int col = n0 + c * 32;
-        if (row < p.M && col < p.N) epi.template apply<32>(bz, row, col, min(32, p.N - col), v);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) scr[lane * 33 + j] = v[j];
+        __syncwarp();
+        const int col = n0 + c * 32 + lane;
+        if (col < p.N) {
+#pragma unroll 4
+          for (int rr = 0; rr < 32; ++rr) {
+            const int row = m0 + quarter * 32 + rr;
+            if (row < p.M) {
+              float a1[1] = {scr[rr * 33 + lane]};
+              epi.template apply<1>(bz, row, col, 1, a1);
+            }
+          }
+        }
       }
     }
   }
@@ -255,7 +273,7 @@ int launch(const GemmDesc& g, const Epi& epi, cudaStream_t st) {
     uint32_t box[4] = {32, 1, 1, 1};
     if (A_K) { dims[0] = g.Kseg; dims[1] = g.M; str[0] = g.a_row * 4; box[1] = BM; }
     else { dims[0] = g.M; dims[1] = g.Kseg; str[0] = g.a_k * 4; box[1] = BK; }
-    const int aseg = g.a_seg ? g.nseg_a() : 1;
+    const int aseg = g.a_seg ? g.nseg_a() : 1;   // distinct A segments (with use_map: a_nseg must be set)
     dims[2] = aseg; str[1] = aseg > 1 ? g.a_seg * 4 : str[0] * dims[1];
     const int ab = g.a_batch ? g.nbatch : 1;
     dims[3] = ab; str[2] = ab > 1 ? g.a_batch * 4 : str[1] * dims[2];
@@ -275,8 +293,10 @@ int launch(const GemmDesc& g, const Epi& epi, cudaStream_t st) {
   }
   TcParams p;
   p.M = g.M; p.N = g.N; p.Kseg = g.Kseg; p.nseg = g.nseg;
-  p.a_seg_mod = g.a_seg ? g.nseg_a() : 1;
-  p.b_seg_mod = g.b_seg ? g.nseg_b() : 1;
+  for (int i = 0; i < 16; ++i) {
+    p.a_map[i] = (uint8_t)((i < g.nseg && g.a_seg) ? g.seg_a(i) : 0);
+    p.b_map[i] = (uint8_t)((i < g.nseg && g.b_seg) ? g.seg_b(i) : 0);
+  }
   p.nbatch = g.nbatch; p.splits = g.splits;
   p.a_batched = g.a_batch ? 1 : 0;
   p.b_batched = g.b_batch ? 1 : 0;

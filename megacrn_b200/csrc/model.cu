@@ -279,12 +279,13 @@ static int acc_dw(const Geo& g, const float* xp, int Hs, const float* dv, int O,
   return gemm(q, e, st);
 }
 // dXP[k] = dV * W_st[k]^T      (M = R, N = NB*Hs, K = O), stored block-wise
-static int make_dxp(const Geo& g, const float* dv, int O, const float* wst, int Hs, float* dxp, cudaStream_t st) {
+static int make_dxp(const Geo& g, const float* dv, int O, const float* wst, int Hs, float* dxp, float* dxp_lo,
+                    cudaStream_t st) {
   GemmDesc q;
   q.A = dv; q.a_row = O; q.a_k = 1; q.M = (int)g.R; q.Kseg = O;
   q.B = wst; q.b_k = 1; q.b_n = O; q.N = g.NB * Hs;
   if (tf32_mode()) { q.nseg = 2; q.b_seg = (int64_t)g.NB * Hs * O; }     // W = hi + lo
-  EpiBlocks e{dxp, Hs, g.R * Hs, tf32_mode()};
+  EpiBlocks e{dxp, Hs, g.R * Hs, tf32_mode(), tf32_mode() ? dxp_lo : nullptr};
   return gemm(q, e, st);
 }
 // out = add1 + add2 + dXP[0] + sum_k S_k^T dXP[1+k]    (M = N nodes, N = B*C, K = KS*N)
@@ -298,13 +299,25 @@ static int propagate_T(const Geo& g, const float* S, const float* dxp, int C, co
   return gemm(q, e, st);
 }
 // dS_k += dXP[1+k] * X^T       (M = KS*N, N = N nodes, K = B*C; X(node, col) = x + node*x_n + col)
-static int acc_ds(const Geo& g, const float* dp, int64_t dp_row, const float* x, int64_t x_n, int cols, float* dS,
-                  cudaStream_t st, int exact = 0) {
+// dS feeds the softmax backward, which cancels the (large) row-constant part of dg: TF32 products are not
+// accurate enough there, so in TF32 mode the product is formed as hi*hi + lo*hi + hi*lo (3xTF32, ~fp32).
+static int acc_ds(const Geo& g, const float* dp, const float* dp_lo, int64_t dp_row, const float* x, const float* x_lo,
+                  int64_t x_n, int cols, float* dS, cudaStream_t st, int exact = 0) {
   GemmDesc q;
   q.prec_exact = exact;
   q.A = dp; q.a_row = dp_row; q.a_k = 1; q.M = g.KS * g.N; q.Kseg = cols;
   q.B = x; q.b_k = 1; q.b_n = x_n; q.N = g.N;
-  q.splits = split_for((int64_t)ceil_div(q.M, 64) * ceil_div(q.N, 64), cols / 16);
+  if (!exact && tf32_mode() && dp_lo && x_lo) {
+    q.nseg = 3; q.use_map = 1; q.a_nseg = 2; q.b_nseg = 2;
+    const bool a_up = dp_lo > dp, b_up = x_lo > x;
+    q.A = a_up ? dp : dp_lo; q.a_seg = a_up ? (dp_lo - dp) : (dp - dp_lo);
+    q.B = b_up ? x : x_lo;   q.b_seg = b_up ? (x_lo - x) : (x - x_lo);
+    const uint8_t ah = a_up ? 0 : 1, al = 1 - ah, bh = b_up ? 0 : 1, bl = 1 - bh;
+    q.a_map[0] = ah; q.b_map[0] = bh;      // hi * hi
+    q.a_map[1] = al; q.b_map[1] = bh;      // lo * hi
+    q.a_map[2] = ah; q.b_map[2] = bl;      // hi * lo
+  }
+  q.splits = split_for((int64_t)ceil_div(q.M, 64) * ceil_div(q.N, 64), (int64_t)q.nseg * cols / 16);
   EpiAtomicAdd e{dS, g.ldS, 0};
   return gemm(q, e, st);
 }
@@ -316,19 +329,19 @@ static int cell_backward(const Geo& g, const Plan& p, float* ws, const float* S,
   const int Hs = w.Hs;
   const int64_t nH = g.R * Hs;
   float *dU = ws + p.dU, *dG = ws + p.dG, *dXP = ws + p.dXP, *dZH = ws + p.dZH, *dHp = ws + p.dHp;
-  float *dXPin = ws + p.dXPin, *dS = ws + p.dS;
-  MCRN_LAUNCH(k_bwd_du, ew_grid(nH), 256, 0, st, dH, b.r, b.hc, dU, nH, tf32_mode());
+  float *dXPin = ws + p.dXPin, *dS = ws + p.dS, *dXPlo = ws + p.dXPlo, *h_lo = ws + p.h_lo, *zh_lo = ws + p.zh_lo;
+  MCRN_LAUNCH(k_bwd_du, ew_grid(nH), 256, 0, st, dH, b.r, b.hc, dU, nH, tf32_mode(), b.z, b.hx, b.xpg, b.xpu, h_lo, zh_lo);
   // ---- update AGCN ----
-  MCRN_TRY(make_dxp(g, dU, Hs, w.wu_st, Hs, dXP, st));
+  MCRN_TRY(make_dxp(g, dU, Hs, w.wu_st, Hs, dXP, dXPlo, st));
   MCRN_TRY(acc_dw(g, b.xpu, Hs, dU, Hs, a.wu_st, st));
   MCRN_TRY(propagate_T(g, S, dXP, Hs, nullptr, dZH, st));
-  MCRN_TRY(acc_ds(g, dXP + nH, (int64_t)g.B * Hs, b.xpu, (int64_t)g.B * Hs, g.B * Hs, dS, st));
+  MCRN_TRY(acc_ds(g, dXP + nH, dXPlo + nH, (int64_t)g.B * Hs, b.xpu, zh_lo, (int64_t)g.B * Hs, g.B * Hs, dS, st));
   MCRN_LAUNCH(k_bwd_dg, ew_grid(nH), 256, 0, st, dZH, dH, b.hx, b.z, b.r, b.hc, dG, dHp, g.R, Hs, tf32_mode());
   // ---- gate AGCN ----
-  MCRN_TRY(make_dxp(g, dG, 2 * Hs, w.wg_st, Hs, dXP, st));
+  MCRN_TRY(make_dxp(g, dG, 2 * Hs, w.wg_st, Hs, dXP, dXPlo, st));
   MCRN_TRY(acc_dw(g, b.xpg, Hs, dG, 2 * Hs, a.wg_st, st));
   MCRN_TRY(propagate_T(g, S, dXP, Hs, dHp, dH_out, st));
-  MCRN_TRY(acc_ds(g, dXP + nH, (int64_t)g.B * Hs, b.xpg, (int64_t)g.B * Hs, g.B * Hs, dS, st));
+  MCRN_TRY(acc_ds(g, dXP + nH, dXPlo + nH, (int64_t)g.B * Hs, b.xpg, h_lo, (int64_t)g.B * Hs, g.B * Hs, dS, st));
   // ---- biases + input channels ----
   size_t shm = (size_t)64 * g.NB * w.Cin * sizeof(float);
   int rb = (int)ceil_div64(g.R, 64);
@@ -336,7 +349,7 @@ static int cell_backward(const Geo& g, const Plan& p, float* ws, const float* S,
   MCRN_LAUNCH(k_bwd_bias_win, rb, 256, shm, st, dG, 2 * Hs, b.xpin, b.xp_k, b.xp_n, g.NB, w.Cin, g.B, g.R, a.bg, a.wg_in);
   MCRN_LAUNCH(k_bwd_dxpin, (int)ceil_div64(g.R, 8), 256, 0, st, dU, w.wu_in, Hs, dG, w.wg_in, 2 * Hs, g.NB, w.Cin,
               g.R, dXPin);
-  MCRN_TRY(acc_ds(g, dXPin + g.R * w.Cin, (int64_t)g.B * w.Cin, b.xpin, b.xp_n, g.B * w.Cin, dS, st, 1));
+  MCRN_TRY(acc_ds(g, dXPin + g.R * w.Cin, nullptr, (int64_t)g.B * w.Cin, b.xpin, nullptr, b.xp_n, g.B * w.Cin, dS, st, 1));
   if (dxin) MCRN_TRY(propagate_T(g, S, dXPin, w.Cin, nullptr, dxin, st, 1));
   return MCRN_OK;
 }
