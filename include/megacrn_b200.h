@@ -152,6 +152,11 @@ int mcrn_support_ld(int num_nodes);
 int mcrn_supports_fwd(const mcrn_dims* dims, const float* memory, const float* we1, const float* we2,
                       float* supports_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same, also returning the TF32-rounded copy the tensor-core GEMMs read (tests). */
+int mcrn_supports_fwd2(const mcrn_dims* dims, const float* memory, const float* we1, const float* we2,
+                       float* supports_out, float* supports_tc_out, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
 /* Generic row-major GEMM  C[M,N] = A[M,K] * B[K,N]  on the library's GEMM engine
  * (the engine every stage uses).  trans_a / trans_b: the operand is stored
  * transposed ([K,M] / [N,K]).  engine: 0 = library default, 1 = SIMT fp32,
@@ -172,6 +177,8 @@ uint64_t mcrn_launch_count(void);
 /* 0 = default (tcgen05 TF32 where the shape allows, SIMT otherwise), 1 = force SIMT fp32. */
 int mcrn_set_engine(int engine);
 int mcrn_get_engine(void);
+/* Debug: bit i forces GEMM call-site class i onto the SIMT engine (see model.cu). */
+int mcrn_set_debug_mask(int mask);
 
 #ifdef __cplusplus
 }

@@ -80,6 +80,8 @@ def load() -> C.CDLL:
                                       C.c_float, fp, fp, fp, vp, C.c_size_t, vp]
     lib.mcrn_supports_fwd.restype = C.c_int
     lib.mcrn_supports_fwd.argtypes = [C.POINTER(Dims), fp, fp, fp, fp, vp, C.c_size_t, vp]
+    lib.mcrn_supports_fwd2.restype = C.c_int
+    lib.mcrn_supports_fwd2.argtypes = [C.POINTER(Dims), fp, fp, fp, fp, fp, vp, C.c_size_t, vp]
     lib.mcrn_gemm.restype = C.c_int
     lib.mcrn_gemm.argtypes = [C.c_int, C.c_int, C.c_int, fp, C.c_int, C.c_int, fp, C.c_int, C.c_int,
                               fp, C.c_int, C.c_int, vp]

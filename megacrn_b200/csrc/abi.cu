@@ -7,6 +7,7 @@
 
 namespace mcrn {
 int g_engine = 0;
+extern int g_simt_mask;
 const char* last_error();
 int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const float* x, const float* y_cov,
                  const float* labels, const uint8_t* tf, float* output, float* h_att, float* query, float* pos,
@@ -15,7 +16,7 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
                   const float* d_hatt, const float* d_query, const float* d_pos, const float* d_neg,
                   const mcrn_params* grads, float* ws, cudaStream_t st);
 int supports_forward_entry(const Geo& g, const Plan& p, float* ws, const float* mem, const float* we1,
-                           const float* we2, float* S, cudaStream_t st);
+                           const float* we2, float* S, float* Sr, cudaStream_t st);
 int trainer_loss_impl(const Geo& g, const float* output, const float* labels, const float* query, const float* pos,
                       const float* neg, float mean, float std, float lamb, float lamb1, float* loss_out,
                       float* d_output, float* d_query, float* scratch, cudaStream_t st);
@@ -71,6 +72,7 @@ int mcrn_set_engine(int engine) {
   return MCRN_OK;
 }
 int mcrn_get_engine(void) { return g_engine; }
+int mcrn_set_debug_mask(int mask) { g_simt_mask = mask; return MCRN_OK; }
 int mcrn_support_ld(int n) { return support_ld(n); }
 
 size_t mcrn_workspace_bytes(const mcrn_dims* dims, uint32_t flags) {
@@ -142,6 +144,12 @@ int mcrn_backward(const mcrn_dims* dims, const mcrn_params* params, const float*
 
 int mcrn_supports_fwd(const mcrn_dims* dims, const float* memory, const float* we1, const float* we2,
                       float* supports_out, void* workspace, size_t workspace_bytes, void* stream) {
+  return mcrn_supports_fwd2(dims, memory, we1, we2, supports_out, nullptr, workspace, workspace_bytes, stream);
+}
+
+int mcrn_supports_fwd2(const mcrn_dims* dims, const float* memory, const float* we1, const float* we2,
+                       float* supports_out, float* supports_tc_out, void* workspace, size_t workspace_bytes,
+                       void* stream) {
   Geo g;
   MCRN_TRY(make_geo(dims, &g));
   if (!memory || !we1 || !we2 || !supports_out || !workspace) { set_error("null pointer"); return MCRN_ERR_BAD_POINTER; }
@@ -150,7 +158,7 @@ int mcrn_supports_fwd(const mcrn_dims* dims, const float* memory, const float* w
   make_plan(g, false, &p);
   if (workspace_bytes < p.bytes) { set_error("workspace too small"); return MCRN_ERR_WORKSPACE; }
   return supports_forward_entry(g, p, static_cast<float*>(workspace), memory, we1, we2, supports_out,
-                                static_cast<cudaStream_t>(stream));
+                                supports_tc_out, static_cast<cudaStream_t>(stream));
 }
 
 int mcrn_gemm(int M, int N, int K, const float* A, int lda, int trans_a, const float* B, int ldb, int trans_b,

@@ -109,7 +109,6 @@ struct EpiCheb {
 struct EpiBlocks {
   float* C; int W; int64_t blk_stride;
   int rnd = 0;                               // 1: blocks >= 1 (tensor-core operands downstream) are TF32-rounded
-  float* Clo = nullptr;                      // with rnd: TF32 residual of blocks >= 1 (same layout) for 3xTF32 products
   template <int V>
   __device__ __forceinline__ void apply(int, int m, int n0, int nv, const float (&acc)[V]) const {
 #pragma unroll
@@ -117,13 +116,7 @@ struct EpiBlocks {
       if (j < nv) {
         int n = n0 + j, blk = n / W, c = n - blk * W;
         int64_t o = (int64_t)blk * blk_stride + (int64_t)m * W + c;
-        if (rnd && blk > 0) {
-          float hi = tf32_rn(acc[j]);
-          C[o] = hi;
-          if (Clo) Clo[o] = tf32_rn(acc[j] - hi);
-        } else {
-          C[o] = acc[j];
-        }
+        C[o] = (rnd && blk > 0) ? tf32_rn(acc[j]) : acc[j];
       }
     }
   }

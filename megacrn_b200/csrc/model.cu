@@ -72,12 +72,16 @@ struct CellBufs {        // per-step activations
 // everything stays exact fp32.
 extern int g_engine;
 static inline int tf32_mode() { return g_engine != 1 ? 1 : 0; }
+// Debug: bit i set -> GEMM call-site class i runs on the SIMT engine (operands stay as produced).
+// 0 propagate, 1 gate/update, 2 make_dxp, 3 acc_dw, 4 propagate_T, 5 acc_ds, 6 chebyshev
+int g_simt_mask = 0;
+static inline int dbg_exact(int bit) { return (g_simt_mask >> bit) & 1; }
 
 // propagation  XP[1..KS] = S * XP[0]      (model/MegaCRN.py:24-25 for the KS real supports)
 static int propagate(const Geo& g, const float* S, float* xp, int C, cudaStream_t st) {
   GemmDesc q;
   q.A = S; q.a_row = g.ldS; q.a_k = 1; q.M = g.KS * g.N; q.Kseg = g.N;
-  q.B = xp; q.b_k = (int64_t)g.B * C; q.b_n = 1; q.N = g.B * C;
+  q.B = xp; q.b_k = (int64_t)g.B * C; q.b_n = 1; q.N = g.B * C; q.prec_exact = dbg_exact(0);
   EpiStore e{xp + (int64_t)g.R * C, (int64_t)g.B * C, 0, 1.0f, nullptr, nullptr, tf32_mode()};
   return gemm(q, e, st);
 }
@@ -90,7 +94,7 @@ static int cell_forward(const Geo& g, const float* S, const CellW& w, const Cell
   {  // gate AGCN + sigmoid + z*h                                   model/MegaCRN.py:42-45
     GemmDesc q;
     q.A = b.xpg; q.a_row = Hs; q.a_k = 1; q.a_seg = g.R * Hs; q.nseg = wseg; q.a_nseg = g.NB; q.Kseg = Hs; q.M = (int)g.R;
-    q.B = w.wg_st; q.b_seg = (int64_t)Hs * 2 * Hs; q.b_k = 2 * Hs; q.b_n = 1; q.N = 2 * Hs;
+    q.B = w.wg_st; q.b_seg = (int64_t)Hs * 2 * Hs; q.b_k = 2 * Hs; q.b_n = 1; q.N = 2 * Hs; q.prec_exact = dbg_exact(1);
     EpiGate e{InTerm{b.xpin, b.xp_k, b.xp_n, w.wg_in, w.bg, g.NB, w.Cin, 2 * Hs, g.B}, Hs, b.hx, b.z, b.r, b.xpu, rnd};
     MCRN_TRY(gemm(q, e, st));
   }
@@ -98,7 +102,7 @@ static int cell_forward(const Geo& g, const float* S, const CellW& w, const Cell
   {  // update AGCN + tanh + blend                                  model/MegaCRN.py:46-47
     GemmDesc q;
     q.A = b.xpu; q.a_row = Hs; q.a_k = 1; q.a_seg = g.R * Hs; q.nseg = wseg; q.a_nseg = g.NB; q.Kseg = Hs; q.M = (int)g.R;
-    q.B = w.wu_st; q.b_seg = (int64_t)Hs * Hs; q.b_k = Hs; q.b_n = 1; q.N = Hs;
+    q.B = w.wu_st; q.b_seg = (int64_t)Hs * Hs; q.b_k = Hs; q.b_n = 1; q.N = Hs; q.prec_exact = dbg_exact(1);
     EpiUpdate e{InTerm{b.xpin, b.xp_k, b.xp_n, w.wu_in, w.bu, g.NB, w.Cin, Hs, g.B}, Hs, b.hx, b.r, b.hc, h_out, h_mma, rnd};
     MCRN_TRY(gemm(q, e, st));
   }
@@ -147,7 +151,7 @@ static int supports_forward(const Geo& g, const Plan& p, float* ws, const float*
       const float* tkm2 = (k >= 3) ? gi + (int64_t)(k - 3) * g.N * g.ldS : nullptr;
       GemmDesc c;
       c.A = gri; c.a_row = g.ldS; c.a_k = 1; c.M = g.N; c.Kseg = g.N;
-      c.B = tkm1; c.b_k = g.ldS; c.b_n = 1; c.N = g.N;
+      c.B = tkm1; c.b_k = g.ldS; c.b_n = 1; c.N = g.N; c.prec_exact = dbg_exact(6);
       EpiCheb e{tk, g.ldS, tkm2, gri + (int64_t)(k - 1) * g.N * g.ldS};
       MCRN_TRY(gemm(c, e, st));
     }
@@ -273,51 +277,38 @@ static int split_for(int64_t tiles, int64_t k_iters) {
 static int acc_dw(const Geo& g, const float* xp, int Hs, const float* dv, int O, float* dw, cudaStream_t st) {
   GemmDesc q;
   q.A = xp; q.a_row = 1; q.a_k = Hs; q.a_batch = g.R * Hs; q.M = Hs; q.Kseg = (int)g.R;
-  q.B = dv; q.b_k = O; q.b_n = 1; q.b_batch = 0; q.N = O; q.nbatch = g.NB;
+  q.B = dv; q.b_k = O; q.b_n = 1; q.b_batch = 0; q.N = O; q.nbatch = g.NB; q.prec_exact = dbg_exact(3);
   q.splits = split_for((int64_t)ceil_div(Hs, 64) * ceil_div(O, 64) * g.NB, g.R / 16);
   EpiAtomicAdd e{dw, O, (int64_t)Hs * O};
   return gemm(q, e, st);
 }
 // dXP[k] = dV * W_st[k]^T      (M = R, N = NB*Hs, K = O), stored block-wise
-static int make_dxp(const Geo& g, const float* dv, int O, const float* wst, int Hs, float* dxp, float* dxp_lo,
-                    cudaStream_t st) {
+static int make_dxp(const Geo& g, const float* dv, int O, const float* wst, int Hs, float* dxp, cudaStream_t st) {
   GemmDesc q;
   q.A = dv; q.a_row = O; q.a_k = 1; q.M = (int)g.R; q.Kseg = O;
-  q.B = wst; q.b_k = 1; q.b_n = O; q.N = g.NB * Hs;
+  q.B = wst; q.b_k = 1; q.b_n = O; q.N = g.NB * Hs; q.prec_exact = dbg_exact(2);
   if (tf32_mode()) { q.nseg = 2; q.b_seg = (int64_t)g.NB * Hs * O; }     // W = hi + lo
-  EpiBlocks e{dxp, Hs, g.R * Hs, tf32_mode(), tf32_mode() ? dxp_lo : nullptr};
+  EpiBlocks e{dxp, Hs, g.R * Hs, tf32_mode()};
   return gemm(q, e, st);
 }
 // out = add1 + add2 + dXP[0] + sum_k S_k^T dXP[1+k]    (M = N nodes, N = B*C, K = KS*N)
 static int propagate_T(const Geo& g, const float* S, const float* dxp, int C, const float* add2, float* out,
                        cudaStream_t st, int exact = 0) {
   GemmDesc q;
-  q.prec_exact = exact;
+  q.prec_exact = exact | dbg_exact(4);
   q.A = S; q.a_row = 1; q.a_k = g.ldS; q.M = g.N; q.Kseg = g.KS * g.N;
   q.B = dxp + g.R * C; q.b_k = (int64_t)g.B * C; q.b_n = 1; q.N = g.B * C;
   EpiStore e{out, (int64_t)g.B * C, 0, 1.0f, dxp, add2};
   return gemm(q, e, st);
 }
 // dS_k += dXP[1+k] * X^T       (M = KS*N, N = N nodes, K = B*C; X(node, col) = x + node*x_n + col)
-// dS feeds the softmax backward, which cancels the (large) row-constant part of dg: TF32 products are not
-// accurate enough there, so in TF32 mode the product is formed as hi*hi + lo*hi + hi*lo (3xTF32, ~fp32).
-static int acc_ds(const Geo& g, const float* dp, const float* dp_lo, int64_t dp_row, const float* x, const float* x_lo,
-                  int64_t x_n, int cols, float* dS, cudaStream_t st, int exact = 0) {
+static int acc_ds(const Geo& g, const float* dp, int64_t dp_row, const float* x, int64_t x_n, int cols, float* dS,
+                  cudaStream_t st, int exact = 0) {
   GemmDesc q;
-  q.prec_exact = exact;
+  q.prec_exact = exact | dbg_exact(5);
   q.A = dp; q.a_row = dp_row; q.a_k = 1; q.M = g.KS * g.N; q.Kseg = cols;
   q.B = x; q.b_k = 1; q.b_n = x_n; q.N = g.N;
-  if (!exact && tf32_mode() && dp_lo && x_lo) {
-    q.nseg = 3; q.use_map = 1; q.a_nseg = 2; q.b_nseg = 2;
-    const bool a_up = dp_lo > dp, b_up = x_lo > x;
-    q.A = a_up ? dp : dp_lo; q.a_seg = a_up ? (dp_lo - dp) : (dp - dp_lo);
-    q.B = b_up ? x : x_lo;   q.b_seg = b_up ? (x_lo - x) : (x - x_lo);
-    const uint8_t ah = a_up ? 0 : 1, al = 1 - ah, bh = b_up ? 0 : 1, bl = 1 - bh;
-    q.a_map[0] = ah; q.b_map[0] = bh;      // hi * hi
-    q.a_map[1] = al; q.b_map[1] = bh;      // lo * hi
-    q.a_map[2] = ah; q.b_map[2] = bl;      // hi * lo
-  }
-  q.splits = split_for((int64_t)ceil_div(q.M, 64) * ceil_div(q.N, 64), (int64_t)q.nseg * cols / 16);
+  q.splits = split_for((int64_t)ceil_div(q.M, 64) * ceil_div(q.N, 64), cols / 16);
   EpiAtomicAdd e{dS, g.ldS, 0};
   return gemm(q, e, st);
 }
@@ -329,19 +320,19 @@ static int cell_backward(const Geo& g, const Plan& p, float* ws, const float* S,
   const int Hs = w.Hs;
   const int64_t nH = g.R * Hs;
   float *dU = ws + p.dU, *dG = ws + p.dG, *dXP = ws + p.dXP, *dZH = ws + p.dZH, *dHp = ws + p.dHp;
-  float *dXPin = ws + p.dXPin, *dS = ws + p.dS, *dXPlo = ws + p.dXPlo, *h_lo = ws + p.h_lo, *zh_lo = ws + p.zh_lo;
-  MCRN_LAUNCH(k_bwd_du, ew_grid(nH), 256, 0, st, dH, b.r, b.hc, dU, nH, tf32_mode(), b.z, b.hx, b.xpg, b.xpu, h_lo, zh_lo);
+  float *dXPin = ws + p.dXPin, *dS = ws + p.dS;
+  MCRN_LAUNCH(k_bwd_du, ew_grid(nH), 256, 0, st, dH, b.r, b.hc, dU, nH, tf32_mode());
   // ---- update AGCN ----
-  MCRN_TRY(make_dxp(g, dU, Hs, w.wu_st, Hs, dXP, dXPlo, st));
+  MCRN_TRY(make_dxp(g, dU, Hs, w.wu_st, Hs, dXP, st));
   MCRN_TRY(acc_dw(g, b.xpu, Hs, dU, Hs, a.wu_st, st));
   MCRN_TRY(propagate_T(g, S, dXP, Hs, nullptr, dZH, st));
-  MCRN_TRY(acc_ds(g, dXP + nH, dXPlo + nH, (int64_t)g.B * Hs, b.xpu, zh_lo, (int64_t)g.B * Hs, g.B * Hs, dS, st));
+  MCRN_TRY(acc_ds(g, dXP + nH, (int64_t)g.B * Hs, b.xpu, (int64_t)g.B * Hs, g.B * Hs, dS, st));
   MCRN_LAUNCH(k_bwd_dg, ew_grid(nH), 256, 0, st, dZH, dH, b.hx, b.z, b.r, b.hc, dG, dHp, g.R, Hs, tf32_mode());
   // ---- gate AGCN ----
-  MCRN_TRY(make_dxp(g, dG, 2 * Hs, w.wg_st, Hs, dXP, dXPlo, st));
+  MCRN_TRY(make_dxp(g, dG, 2 * Hs, w.wg_st, Hs, dXP, st));
   MCRN_TRY(acc_dw(g, b.xpg, Hs, dG, 2 * Hs, a.wg_st, st));
   MCRN_TRY(propagate_T(g, S, dXP, Hs, dHp, dH_out, st));
-  MCRN_TRY(acc_ds(g, dXP + nH, dXPlo + nH, (int64_t)g.B * Hs, b.xpg, h_lo, (int64_t)g.B * Hs, g.B * Hs, dS, st));
+  MCRN_TRY(acc_ds(g, dXP + nH, (int64_t)g.B * Hs, b.xpg, (int64_t)g.B * Hs, g.B * Hs, dS, st));
   // ---- biases + input channels ----
   size_t shm = (size_t)64 * g.NB * w.Cin * sizeof(float);
   int rb = (int)ceil_div64(g.R, 64);
@@ -349,7 +340,7 @@ static int cell_backward(const Geo& g, const Plan& p, float* ws, const float* S,
   MCRN_LAUNCH(k_bwd_bias_win, rb, 256, shm, st, dG, 2 * Hs, b.xpin, b.xp_k, b.xp_n, g.NB, w.Cin, g.B, g.R, a.bg, a.wg_in);
   MCRN_LAUNCH(k_bwd_dxpin, (int)ceil_div64(g.R, 8), 256, 0, st, dU, w.wu_in, Hs, dG, w.wg_in, 2 * Hs, g.NB, w.Cin,
               g.R, dXPin);
-  MCRN_TRY(acc_ds(g, dXPin + g.R * w.Cin, nullptr, (int64_t)g.B * w.Cin, b.xpin, nullptr, b.xp_n, g.B * w.Cin, dS, st, 1));
+  MCRN_TRY(acc_ds(g, dXPin + g.R * w.Cin, (int64_t)g.B * w.Cin, b.xpin, b.xp_n, g.B * w.Cin, dS, st, 1));
   if (dxin) MCRN_TRY(propagate_T(g, S, dXPin, w.Cin, nullptr, dxin, st, 1));
   return MCRN_OK;
 }
@@ -510,9 +501,10 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
 }
 
 int supports_forward_entry(const Geo& g, const Plan& p, float* ws, const float* mem, const float* we1,
-                           const float* we2, float* S, cudaStream_t st) {
+                           const float* we2, float* S, float* Sr, cudaStream_t st) {
   MCRN_TRY(supports_forward(g, p, ws, mem, we1, we2, ws + p.S, ws + p.Sr, st));
   MCRN_CUDA_OK(cudaMemcpyAsync(S, ws + p.S, (size_t)g.KS * g.N * g.ldS * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (Sr) MCRN_CUDA_OK(cudaMemcpyAsync(Sr, ws + p.Sr, (size_t)g.KS * g.N * g.ldS * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return MCRN_OK;
 }
 

@@ -24,7 +24,7 @@ struct Plan {
   // per-slot sizes (floats)
   size_t enc_xp_sz, enc_v_sz, dec_xpin_sz, dec_xp_sz, dec_v_sz;
   // ---- backward temporaries -------------------------------------------------
-  size_t dH, dU, dG, dXP, dXPlo, dZH, dHp, dXPin, dXin, mq_dv, mq_dsc, mq_dq, dHenc, h_lo, zh_lo;
+  size_t dH, dU, dG, dXP, dZH, dHp, dXPin, dXin, mq_dv, mq_dsc, mq_dq, dHenc;
   size_t acc_begin, acc_end;             // zeroed at the start of backward
   size_t dS, a_e_wg_st, a_e_wg_in, a_e_wu_st, a_e_wu_in, a_d_wg_st, a_d_wg_in, a_d_wu_st, a_d_wu_in;
   size_t dg1, dg2;
@@ -91,9 +91,6 @@ static inline int make_plan(const Geo& g, bool save, Plan* p) {
     p->dU = take(R * g.D);
     p->dG = take(R * 2 * g.D);
     p->dXP = take(NB * R * g.D);
-    p->dXPlo = take(NB * R * g.D);     // TF32 residual of dXP blocks >= 1 (3xTF32 dS products)
-    p->h_lo = take(R * g.D);
-    p->zh_lo = take(R * g.D);
     p->dZH = take(R * g.D);
     p->dHp = take(R * g.D);
     p->dXPin = take(NB * R * Cm);

@@ -353,21 +353,13 @@ __global__ void __launch_bounds__(256) k_memory_query_bwd_rows(
 }
 
 // ---- cell backward, elementwise pieces (tests/kernel_spec.py:cell_bwd) ----------------------
-// dU = dH' * (1-r) * (1-hc^2).  In TF32 mode also emits the TF32 residuals of the two propagation inputs of
-// the step, h_lo = rn(h - rn(h)) and zh_lo = rn(z*h - rn(z*h)), used by the 3xTF32 dS products.
+// dU = dH' * (1-r) * (1-hc^2)
 __global__ void k_bwd_du(const float* __restrict__ dH, const float* __restrict__ r, const float* __restrict__ hc,
-                         float* __restrict__ dU, int64_t n, int rnd, const float* __restrict__ z,
-                         const float* __restrict__ hx, const float* __restrict__ h_hi, const float* __restrict__ zh_hi,
-                         float* __restrict__ h_lo, float* __restrict__ zh_lo) {
+                         float* __restrict__ dU, int64_t n, int rnd) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float c = hc[i];
     float v = dH[i] * (1.0f - r[i]) * (1.0f - c * c);
     dU[i] = rnd ? tf32_rn(v) : v;
-    if (rnd) {
-      float h = hx[i];
-      h_lo[i] = tf32_rn(h - h_hi[i]);
-      zh_lo[i] = tf32_rn(z[i] * h - zh_hi[i]);
-    }
   }
 }
 
