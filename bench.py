@@ -253,6 +253,13 @@ def main():
         dev_ms, launches = timed(step_device, args.steps)
         e2e_ms, _ = timed(step_e2e, args.steps)
     final_loss = float(step_e2e().item())
+    # host-side cost of enqueueing one step (no device wait inside): tells CPU-bound from GPU-bound
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        step_device()
+    enqueue_ms = (time.perf_counter() - t0) / 3 * 1e3
+    torch.cuda.synchronize(dev)
 
     if rank == 0:
         peaks = measured_peaks()
@@ -293,7 +300,7 @@ def main():
                        "final_loss": final_loss},
             "e2e": {"value": e2e_value, "unit": "sequences/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": int(4 * (hx.numel() + hy.numel() + hl.numel())), "d2h_bytes_per_step": 4},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "host_enqueue_ms_per_step": enqueue_ms,
             "clocks": clocks.summary(),
             "roofline": {"bound": "tensor", "kernel": f"propagation GEMM [{M_}x{K_}]x[{K_}x{N_}] (decoder S*[h])",
                          "achieved": k_tflops, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",

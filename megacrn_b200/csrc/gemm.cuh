@@ -108,42 +108,30 @@ struct EpiCheb {
 // Column n = blk*W + c is stored at C[blk][m][c]  (the dXP block buffers).
 struct EpiBlocks {
   float* C; int W; int64_t blk_stride;
-  int rnd = 0;                               // 1: blocks >= 1 (tensor-core operands downstream) are TF32-rounded
+  int rnd = 0;                               // 1: blocks 1..last-1 (tensor-core operands downstream) are TF32-rounded
+  int last = -1;                             // index of the input block (never rounded)
+  float* last_out = nullptr;                 // if set, block `last` is written here ([M][W]) instead of C[last]
   template <int V>
   __device__ __forceinline__ void apply(int, int m, int n0, int nv, const float (&acc)[V]) const {
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       if (j < nv) {
         int n = n0 + j, blk = n / W, c = n - blk * W;
-        int64_t o = (int64_t)blk * blk_stride + (int64_t)m * W + c;
-        C[o] = (rnd && blk > 0) ? tf32_rn(acc[j]) : acc[j];
+        if (blk == last && last_out) {
+          last_out[(int64_t)m * W + c] = acc[j];
+        } else {
+          int64_t o = (int64_t)blk * blk_stride + (int64_t)m * W + c;
+          C[o] = (rnd && blk > 0 && blk != last) ? tf32_rn(acc[j]) : acc[j];
+        }
       }
     }
   }
 };
 
-// Input-channel contribution of an AGCN (the 1-2 raw input channels):
-//   sum_{k<NB} sum_{ci<Cin} XPin[k][node][.][b][ci] * Win[k][ci][col]  + bias[col]
-struct InTerm {
-  const float* xpin; int64_t xp_k, xp_n;   // XPin(k, node, b, ci) = xpin + k*xp_k + node*xp_n + b*Cin + ci
-  const float* win;                        // [NB][Cin][O]
-  const float* bias;                       // [O]
-  int NB, Cin, O, Bsz;
-  __device__ __forceinline__ float eval(int m, int col) const {
-    int node = m / Bsz, b = m - node * Bsz;
-    const float* xp = xpin + (int64_t)node * xp_n + (int64_t)b * Cin;
-    float s = bias[col];
-    for (int k = 0; k < NB; ++k)
-      for (int ci = 0; ci < Cin; ++ci)
-        s = fmaf(xp[k * xp_k + ci], win[((int64_t)k * Cin + ci) * O + col], s);
-    return s;
-  }
-};
-
-// Gate AGCN epilogue (model/MegaCRN.py:43-45): zr = sigmoid(acc + in-term + bias);
-// columns [0,H) are z, [H,2H) are r;  writes z, r and z*h (the update AGCN's state input).
+// Gate AGCN epilogue (model/MegaCRN.py:43-45): zr = sigmoid(acc)  (input channels and bias are the
+// "input block" of the contraction); columns [0,H) are z, [H,2H) are r; writes z, r and z*h.
 struct EpiGate {
-  InTerm in; int H;
+  int H;
   const float* h;   // [R][H] current state, exact fp32
   float* z; float* r; float* zh;
   int rnd;          // 1: zh (a tensor-core operand only) is stored TF32-rounded
@@ -153,7 +141,7 @@ struct EpiGate {
     for (int j = 0; j < V; ++j) {
       if (j < nv) {
         int col = n0 + j;
-        float s = sigmoid_f(acc[j] + in.eval(m, col));
+        float s = sigmoid_f(acc[j]);
         if (col < H) {
           int64_t o = (int64_t)m * H + col;
           if (z) z[o] = s;
@@ -167,10 +155,9 @@ struct EpiGate {
   }
 };
 
-// Update AGCN epilogue (model/MegaCRN.py:46-47): hc = tanh(acc + in-term + bias);
-// h' = r*h + (1-r)*hc.
+// Update AGCN epilogue (model/MegaCRN.py:46-47): hc = tanh(acc); h' = r*h + (1-r)*hc.
 struct EpiUpdate {
-  InTerm in; int H;
+  int H;
   const float* h; const float* r;   // exact state, r gate
   float* hc; float* h_out;          // h_out: exact new state
   float* h_mma; int rnd;            // h_mma: the copy the next propagation / gate GEMM reads (TF32-rounded if rnd)
@@ -181,7 +168,7 @@ struct EpiUpdate {
       if (j < nv) {
         int col = n0 + j;
         int64_t o = (int64_t)m * H + col;
-        float c = tanhf(acc[j] + in.eval(m, col));
+        float c = tanhf(acc[j]);
         float rr = r[o];
         if (hc) hc[o] = c;
         float hn = rr * h[o] + (1.0f - rr) * c;

@@ -45,11 +45,13 @@ int make_geo(const mcrn_dims* dm, Geo* g) {
   g->Cdec = g->Cout + g->Ycov;
   g->ldS = support_ld(g->N);
   g->R = (int64_t)g->N * g->B;
-  int cm = g->Cin > g->Cdec ? g->Cin : g->Cdec;
-  if (g->NB * cm > 16) {
-    set_error("(1+2(cheb_k-1))*max(input_dim, output_dim+ycov_dim) = %d exceeds 16", g->NB * cm);
+  // the input channels and the bias ride in one extra K-block of width H (resp. D) of every AGCN contraction
+  if (g->NB * g->Cin + 1 > g->H || g->NB * g->Cdec + 1 > g->D) {
+    set_error("rnn_units=%d too small: need (1+2(cheb_k-1))*input_channels + 1 <= hidden width (enc %d<=%d, dec %d<=%d)",
+              g->H, g->NB * g->Cin + 1, g->H, g->NB * g->Cdec + 1, g->D);
     return MCRN_ERR_BAD_DIMS;
   }
+  if (2 * (g->NB + 1) > 16) { set_error("cheb_k=%d: 2*(2+2(cheb_k-1)) K-segments exceed 16", g->cheb_k); return MCRN_ERR_BAD_DIMS; }
   if (g->R * (int64_t)(2 * g->D) >= (int64_t)1 << 31) { set_error("N*B*2D overflows int32 row indexing"); return MCRN_ERR_BAD_DIMS; }
   return MCRN_OK;
 }
@@ -57,8 +59,8 @@ int make_geo(const mcrn_dims* dm, Geo* g) {
 static inline int ew_grid(int64_t n) { int64_t b = (n + 255) / 256; return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b)); }
 
 // ---- one AGCRN cell -------------------------------------------------------------------
-struct CellW {           // folded weights of one cell (plan buffers); wst = [hi | lo] when split
-  const float *wg_st, *wg_in, *bg, *wu_st, *wu_in, *bu;
+struct CellW {           // folded weights of one cell (plan buffers): [hi | lo][NB+1][Hs][O]
+  const float *wg, *wu;
   int Hs, Cin;
 };
 struct CellBufs {        // per-step activations
@@ -88,22 +90,26 @@ static int propagate(const Geo& g, const float* S, float* xp, int C, cudaStream_
 
 static int cell_forward(const Geo& g, const float* S, const CellW& w, const CellBufs& b, float* h_out, float* h_mma,
                         cudaStream_t st) {
-  const int Hs = w.Hs;
-  const int rnd = tf32_mode(), wseg = rnd ? 2 * g.NB : g.NB;
+  const int Hs = w.Hs, NBX = g.NB + 1;
+  const int rnd = tf32_mode(), wseg = rnd ? 2 * NBX : NBX;
+  const int64_t nH = g.R * Hs;
+  // input block (input channels + bias) of both AGCNs of this step
+  MCRN_LAUNCH(k_build_input_block, ew_grid(nH), 256, 0, st, b.xpin, b.xp_k, b.xp_n, g.NB, w.Cin, g.B, g.R, Hs, rnd,
+              b.xpg + (int64_t)g.NB * nH, b.xpu + (int64_t)g.NB * nH);
   MCRN_TRY(propagate(g, S, b.xpg, Hs, st));
   {  // gate AGCN + sigmoid + z*h                                   model/MegaCRN.py:42-45
     GemmDesc q;
-    q.A = b.xpg; q.a_row = Hs; q.a_k = 1; q.a_seg = g.R * Hs; q.nseg = wseg; q.a_nseg = g.NB; q.Kseg = Hs; q.M = (int)g.R;
-    q.B = w.wg_st; q.b_seg = (int64_t)Hs * 2 * Hs; q.b_k = 2 * Hs; q.b_n = 1; q.N = 2 * Hs; q.prec_exact = dbg_exact(1);
-    EpiGate e{InTerm{b.xpin, b.xp_k, b.xp_n, w.wg_in, w.bg, g.NB, w.Cin, 2 * Hs, g.B}, Hs, b.hx, b.z, b.r, b.xpu, rnd};
+    q.A = b.xpg; q.a_row = Hs; q.a_k = 1; q.a_seg = nH; q.nseg = wseg; q.a_nseg = NBX; q.Kseg = Hs; q.M = (int)g.R;
+    q.B = w.wg; q.b_seg = (int64_t)Hs * 2 * Hs; q.b_k = 2 * Hs; q.b_n = 1; q.N = 2 * Hs; q.prec_exact = dbg_exact(1);
+    EpiGate e{Hs, b.hx, b.z, b.r, b.xpu, rnd};
     MCRN_TRY(gemm(q, e, st));
   }
   MCRN_TRY(propagate(g, S, b.xpu, Hs, st));
   {  // update AGCN + tanh + blend                                  model/MegaCRN.py:46-47
     GemmDesc q;
-    q.A = b.xpu; q.a_row = Hs; q.a_k = 1; q.a_seg = g.R * Hs; q.nseg = wseg; q.a_nseg = g.NB; q.Kseg = Hs; q.M = (int)g.R;
-    q.B = w.wu_st; q.b_seg = (int64_t)Hs * Hs; q.b_k = Hs; q.b_n = 1; q.N = Hs; q.prec_exact = dbg_exact(1);
-    EpiUpdate e{InTerm{b.xpin, b.xp_k, b.xp_n, w.wu_in, w.bu, g.NB, w.Cin, Hs, g.B}, Hs, b.hx, b.r, b.hc, h_out, h_mma, rnd};
+    q.A = b.xpu; q.a_row = Hs; q.a_k = 1; q.a_seg = nH; q.nseg = wseg; q.a_nseg = NBX; q.Kseg = Hs; q.M = (int)g.R;
+    q.B = w.wu; q.b_seg = (int64_t)Hs * Hs; q.b_k = Hs; q.b_n = 1; q.N = Hs; q.prec_exact = dbg_exact(1);
+    EpiUpdate e{Hs, b.hx, b.r, b.hc, h_out, h_mma, rnd};
     MCRN_TRY(gemm(q, e, st));
   }
   return MCRN_OK;
@@ -160,10 +166,11 @@ static int supports_forward(const Geo& g, const Plan& p, float* ws, const float*
 }
 
 static int fold_all_weights(const Geo& g, const Plan& p, float* ws, const mcrn_params* prm, cudaStream_t st) {
-  MCRN_LAUNCH(k_fold_weights, 128, 256, 0, st, prm->enc_gate_w, ws + p.e_wg_st, ws + p.e_wg_in, g.Cin, g.H, 2 * g.H, g.cheb_k, tf32_mode());
-  MCRN_LAUNCH(k_fold_weights, 128, 256, 0, st, prm->enc_update_w, ws + p.e_wu_st, ws + p.e_wu_in, g.Cin, g.H, g.H, g.cheb_k, tf32_mode());
-  MCRN_LAUNCH(k_fold_weights, 128, 256, 0, st, prm->dec_gate_w, ws + p.d_wg_st, ws + p.d_wg_in, g.Cdec, g.D, 2 * g.D, g.cheb_k, tf32_mode());
-  MCRN_LAUNCH(k_fold_weights, 128, 256, 0, st, prm->dec_update_w, ws + p.d_wu_st, ws + p.d_wu_in, g.Cdec, g.D, g.D, g.cheb_k, tf32_mode());
+  const int sp = tf32_mode();
+  MCRN_LAUNCH(k_fold_weights, 128, 256, 0, st, prm->enc_gate_w, prm->enc_gate_b, ws + p.e_wg, g.Cin, g.H, 2 * g.H, g.cheb_k, sp);
+  MCRN_LAUNCH(k_fold_weights, 128, 256, 0, st, prm->enc_update_w, prm->enc_update_b, ws + p.e_wu, g.Cin, g.H, g.H, g.cheb_k, sp);
+  MCRN_LAUNCH(k_fold_weights, 128, 256, 0, st, prm->dec_gate_w, prm->dec_gate_b, ws + p.d_wg, g.Cdec, g.D, 2 * g.D, g.cheb_k, sp);
+  MCRN_LAUNCH(k_fold_weights, 128, 256, 0, st, prm->dec_update_w, prm->dec_update_b, ws + p.d_wu, g.Cdec, g.D, g.D, g.cheb_k, sp);
   return MCRN_OK;
 }
 
@@ -195,12 +202,8 @@ static CellBufs dec_bufs(const Geo& g, const Plan& p, float* ws, int t) {
   b.hx = ws + p.dec_hx + p.dec_v_sz * s;
   return b;
 }
-static CellW enc_w(const Geo& g, const Plan& p, float* ws, const mcrn_params* prm) {
-  return CellW{ws + p.e_wg_st, ws + p.e_wg_in, prm->enc_gate_b, ws + p.e_wu_st, ws + p.e_wu_in, prm->enc_update_b, g.H, g.Cin};
-}
-static CellW dec_w(const Geo& g, const Plan& p, float* ws, const mcrn_params* prm) {
-  return CellW{ws + p.d_wg_st, ws + p.d_wg_in, prm->dec_gate_b, ws + p.d_wu_st, ws + p.d_wu_in, prm->dec_update_b, g.D, g.Cdec};
-}
+static CellW enc_w(const Geo& g, const Plan& p, float* ws) { return CellW{ws + p.e_wg, ws + p.e_wu, g.H, g.Cin}; }
+static CellW dec_w(const Geo& g, const Plan& p, float* ws) { return CellW{ws + p.d_wg, ws + p.d_wu, g.D, g.Cdec}; }
 
 // ======================================================================================
 // forward                                                        model/MegaCRN.py:168-194
@@ -219,7 +222,7 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
                           g.T_in * g.B * g.Cin, st));
     MCRN_CUDA_OK(cudaMemsetAsync(ws + p.enc_xpg, 0, (size_t)g.R * g.H * sizeof(float), st));
     MCRN_CUDA_OK(cudaMemsetAsync(ws + p.enc_hx, 0, (size_t)g.R * g.H * sizeof(float), st));
-    CellW w = enc_w(g, p, ws, prm);
+    CellW w = enc_w(g, p, ws);
     for (int t = 0; t < g.T_in; ++t) {
       CellBufs b = enc_bufs(g, p, ws, t);
       const bool last = (t + 1 == g.T_in);
@@ -238,7 +241,7 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
   }
   // ---- decoder loop (:181-192) ----
   {
-    CellW w = dec_w(g, p, ws, prm);
+    CellW w = dec_w(g, p, ws);
     for (int t = 0; t < g.T_out; ++t) {
       CellBufs b = dec_bufs(g, p, ws, t);
       const float* go_src = nullptr;
@@ -261,7 +264,7 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
 // ======================================================================================
 // backward (BPTT)                                     tests/kernel_spec.py: cell_bwd, model_bwd
 // ======================================================================================
-struct CellAcc { float *wg_st, *wg_in, *bg, *wu_st, *wu_in, *bu; };
+struct CellAcc { float *wg, *wu; };     // accumulators [NB+1][Hs][O] (block NB: input-channel rows + bias row)
 
 static int split_for(int64_t tiles, int64_t k_iters) {
   // aim for ~4 waves of 148 CTAs, at least 4 k-iterations per split
@@ -273,22 +276,22 @@ static int split_for(int64_t tiles, int64_t k_iters) {
   return (int)s;
 }
 
-// dW_st[k] += XP[k]^T * dV     (M = Hs, N = O, K = R, batched over the NB blocks, split-K atomics)
+// dWall[k] += XP[k]^T * dV    (M = Hs, N = O, K = R, batched over the NB+1 blocks, split-K atomics)
 static int acc_dw(const Geo& g, const float* xp, int Hs, const float* dv, int O, float* dw, cudaStream_t st) {
   GemmDesc q;
   q.A = xp; q.a_row = 1; q.a_k = Hs; q.a_batch = g.R * Hs; q.M = Hs; q.Kseg = (int)g.R;
-  q.B = dv; q.b_k = O; q.b_n = 1; q.b_batch = 0; q.N = O; q.nbatch = g.NB; q.prec_exact = dbg_exact(3);
-  q.splits = split_for((int64_t)ceil_div(Hs, 64) * ceil_div(O, 64) * g.NB, g.R / 16);
+  q.B = dv; q.b_k = O; q.b_n = 1; q.b_batch = 0; q.N = O; q.nbatch = g.NB + 1; q.prec_exact = dbg_exact(3);
+  q.splits = split_for((int64_t)ceil_div(Hs, 64) * ceil_div(O, 64) * (g.NB + 1), g.R / 16);
   EpiAtomicAdd e{dw, O, (int64_t)Hs * O};
   return gemm(q, e, st);
 }
-// dXP[k] = dV * W_st[k]^T      (M = R, N = NB*Hs, K = O), stored block-wise
-static int make_dxp(const Geo& g, const float* dv, int O, const float* wst, int Hs, float* dxp, cudaStream_t st) {
+// dXP[k] = dV * Wall[k]^T     (M = R, N = (NB+1)*Hs, K = O), stored block-wise; the input block goes to dib
+static int make_dxp(const Geo& g, const float* dv, int O, const float* wall, int Hs, float* dxp, float* dib, cudaStream_t st) {
   GemmDesc q;
   q.A = dv; q.a_row = O; q.a_k = 1; q.M = (int)g.R; q.Kseg = O;
-  q.B = wst; q.b_k = 1; q.b_n = O; q.N = g.NB * Hs; q.prec_exact = dbg_exact(2);
-  if (tf32_mode()) { q.nseg = 2; q.b_seg = (int64_t)g.NB * Hs * O; }     // W = hi + lo
-  EpiBlocks e{dxp, Hs, g.R * Hs, tf32_mode()};
+  q.B = wall; q.b_k = 1; q.b_n = O; q.N = (g.NB + 1) * Hs; q.prec_exact = dbg_exact(2);
+  if (tf32_mode()) { q.nseg = 2; q.b_seg = (int64_t)(g.NB + 1) * Hs * O; }     // W = hi + lo
+  EpiBlocks e{dxp, Hs, g.R * Hs, tf32_mode(), g.NB, dib};
   return gemm(q, e, st);
 }
 // out = add1 + add2 + dXP[0] + sum_k S_k^T dXP[1+k]    (M = N nodes, N = B*C, K = KS*N)
@@ -323,23 +326,19 @@ static int cell_backward(const Geo& g, const Plan& p, float* ws, const float* S,
   float *dXPin = ws + p.dXPin, *dS = ws + p.dS;
   MCRN_LAUNCH(k_bwd_du, ew_grid(nH), 256, 0, st, dH, b.r, b.hc, dU, nH, tf32_mode());
   // ---- update AGCN ----
-  MCRN_TRY(make_dxp(g, dU, Hs, w.wu_st, Hs, dXP, st));
-  MCRN_TRY(acc_dw(g, b.xpu, Hs, dU, Hs, a.wu_st, st));
+  MCRN_TRY(make_dxp(g, dU, Hs, w.wu, Hs, dXP, ws + p.dIBu, st));
+  MCRN_TRY(acc_dw(g, b.xpu, Hs, dU, Hs, a.wu, st));
   MCRN_TRY(propagate_T(g, S, dXP, Hs, nullptr, dZH, st));
   MCRN_TRY(acc_ds(g, dXP + nH, (int64_t)g.B * Hs, b.xpu, (int64_t)g.B * Hs, g.B * Hs, dS, st));
   MCRN_LAUNCH(k_bwd_dg, ew_grid(nH), 256, 0, st, dZH, dH, b.hx, b.z, b.r, b.hc, dG, dHp, g.R, Hs, tf32_mode());
   // ---- gate AGCN ----
-  MCRN_TRY(make_dxp(g, dG, 2 * Hs, w.wg_st, Hs, dXP, st));
-  MCRN_TRY(acc_dw(g, b.xpg, Hs, dG, 2 * Hs, a.wg_st, st));
+  MCRN_TRY(make_dxp(g, dG, 2 * Hs, w.wg, Hs, dXP, nullptr, st));
+  MCRN_TRY(acc_dw(g, b.xpg, Hs, dG, 2 * Hs, a.wg, st));
   MCRN_TRY(propagate_T(g, S, dXP, Hs, dHp, dH_out, st));
   MCRN_TRY(acc_ds(g, dXP + nH, (int64_t)g.B * Hs, b.xpg, (int64_t)g.B * Hs, g.B * Hs, dS, st));
-  // ---- biases + input channels ----
-  size_t shm = (size_t)64 * g.NB * w.Cin * sizeof(float);
-  int rb = (int)ceil_div64(g.R, 64);
-  MCRN_LAUNCH(k_bwd_bias_win, rb, 256, shm, st, dU, Hs, b.xpin, b.xp_k, b.xp_n, g.NB, w.Cin, g.B, g.R, a.bu, a.wu_in);
-  MCRN_LAUNCH(k_bwd_bias_win, rb, 256, shm, st, dG, 2 * Hs, b.xpin, b.xp_k, b.xp_n, g.NB, w.Cin, g.B, g.R, a.bg, a.wg_in);
-  MCRN_LAUNCH(k_bwd_dxpin, (int)ceil_div64(g.R, 8), 256, 0, st, dU, w.wu_in, Hs, dG, w.wg_in, 2 * Hs, g.NB, w.Cin,
-              g.R, dXPin);
+  // ---- input channels: d(input block) of both AGCNs -> dXPin [NB][R][Cin] ----
+  const int64_t nIn = (int64_t)g.NB * g.R * w.Cin;
+  MCRN_LAUNCH(k_repack_dib, ew_grid(nIn), 256, 0, st, ws + p.dIBu, dXP + (int64_t)g.NB * nH, g.NB, w.Cin, g.R, Hs, dXPin);
   MCRN_TRY(acc_ds(g, dXPin + g.R * w.Cin, (int64_t)g.B * w.Cin, b.xpin, b.xp_n, g.B * w.Cin, dS, st, 1));
   if (dxin) MCRN_TRY(propagate_T(g, S, dXPin, w.Cin, nullptr, dxin, st, 1));
   return MCRN_OK;
@@ -422,17 +421,13 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
   // zero accumulators and the directly-accumulated outputs
   MCRN_CUDA_OK(cudaMemsetAsync(ws + p.acc_begin, 0, (p.acc_end - p.acc_begin) * sizeof(float), st));
   MCRN_CUDA_OK(cudaMemsetAsync(grads->memory, 0, (size_t)g.M * g.d * sizeof(float), st));
-  MCRN_CUDA_OK(cudaMemsetAsync(grads->enc_gate_b, 0, (size_t)2 * g.H * sizeof(float), st));
-  MCRN_CUDA_OK(cudaMemsetAsync(grads->enc_update_b, 0, (size_t)g.H * sizeof(float), st));
-  MCRN_CUDA_OK(cudaMemsetAsync(grads->dec_gate_b, 0, (size_t)2 * g.D * sizeof(float), st));
-  MCRN_CUDA_OK(cudaMemsetAsync(grads->dec_update_b, 0, (size_t)g.D * sizeof(float), st));
   MCRN_CUDA_OK(cudaMemsetAsync(grads->proj_w, 0, (size_t)g.Cout * g.D * sizeof(float), st));
   MCRN_CUDA_OK(cudaMemsetAsync(grads->proj_b, 0, (size_t)g.Cout * sizeof(float), st));
   float *dH = ws + p.dH, *dXin = ws + p.dXin;
   // ---- decoder, reverse time ----
   {
-    CellW w = dec_w(g, p, ws, prm);
-    CellAcc a{ws + p.a_d_wg_st, ws + p.a_d_wg_in, grads->dec_gate_b, ws + p.a_d_wu_st, ws + p.a_d_wu_in, grads->dec_update_b};
+    CellW w = dec_w(g, p, ws);
+    CellAcc a{ws + p.a_d_wg, ws + p.a_d_wu};
     bool have_dgo = false;
     for (int t = g.T_out - 1; t >= 0; --t) {
       CellBufs b = dec_bufs(g, p, ws, t);
@@ -483,8 +478,8 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
   }
   // ---- encoder, reverse time ----
   {
-    CellW w = enc_w(g, p, ws, prm);
-    CellAcc a{ws + p.a_e_wg_st, ws + p.a_e_wg_in, grads->enc_gate_b, ws + p.a_e_wu_st, ws + p.a_e_wu_in, grads->enc_update_b};
+    CellW w = enc_w(g, p, ws);
+    CellAcc a{ws + p.a_e_wg, ws + p.a_e_wu};
     float* dHe = ws + p.dHenc;
     for (int t = g.T_in - 1; t >= 0; --t) {
       CellBufs b = enc_bufs(g, p, ws, t);
@@ -493,10 +488,10 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
   }
   MCRN_TRY(supports_backward(g, p, ws, prm, grads, st));
   // ---- un-fold weight gradients into the reference layout ----
-  MCRN_LAUNCH(k_unfold_grads, 128, 256, 0, st, ws + p.a_e_wg_st, ws + p.a_e_wg_in, grads->enc_gate_w, g.Cin, g.H, 2 * g.H, g.cheb_k);
-  MCRN_LAUNCH(k_unfold_grads, 128, 256, 0, st, ws + p.a_e_wu_st, ws + p.a_e_wu_in, grads->enc_update_w, g.Cin, g.H, g.H, g.cheb_k);
-  MCRN_LAUNCH(k_unfold_grads, 128, 256, 0, st, ws + p.a_d_wg_st, ws + p.a_d_wg_in, grads->dec_gate_w, g.Cdec, g.D, 2 * g.D, g.cheb_k);
-  MCRN_LAUNCH(k_unfold_grads, 128, 256, 0, st, ws + p.a_d_wu_st, ws + p.a_d_wu_in, grads->dec_update_w, g.Cdec, g.D, g.D, g.cheb_k);
+  MCRN_LAUNCH(k_unfold_grads, 128, 256, 0, st, ws + p.a_e_wg, grads->enc_gate_w, grads->enc_gate_b, g.Cin, g.H, 2 * g.H, g.cheb_k);
+  MCRN_LAUNCH(k_unfold_grads, 128, 256, 0, st, ws + p.a_e_wu, grads->enc_update_w, grads->enc_update_b, g.Cin, g.H, g.H, g.cheb_k);
+  MCRN_LAUNCH(k_unfold_grads, 128, 256, 0, st, ws + p.a_d_wg, grads->dec_gate_w, grads->dec_gate_b, g.Cdec, g.D, 2 * g.D, g.cheb_k);
+  MCRN_LAUNCH(k_unfold_grads, 128, 256, 0, st, ws + p.a_d_wu, grads->dec_update_w, grads->dec_update_b, g.Cdec, g.D, g.D, g.cheb_k);
   return MCRN_OK;
 }
 

@@ -14,7 +14,7 @@ struct Plan {
   size_t bytes;
   // ---- offsets in floats --------------------------------------------------
   size_t S, Sr, E1, E2, L1, L2;        // Sr: TF32-rounded copy of the supports (tensor-core operand)
-  size_t e_wg_st, e_wg_in, e_wu_st, e_wu_in, d_wg_st, d_wg_in, d_wu_st, d_wu_in;   // folded weights
+  size_t e_wg, e_wu, d_wg, d_wu;         // folded weights [hi|lo][NB+1][Hs][O] (block NB = input channels + bias)
   size_t enc_xpin;                       // [NB][N][T_in][B][Cin]
   size_t enc_xpg, enc_xpu, enc_z, enc_r, enc_hc, enc_hx;   // per slot; hx = exact fp32 input state of the step
   size_t h_enc;                          // [R][H]
@@ -24,9 +24,9 @@ struct Plan {
   // per-slot sizes (floats)
   size_t enc_xp_sz, enc_v_sz, dec_xpin_sz, dec_xp_sz, dec_v_sz;
   // ---- backward temporaries -------------------------------------------------
-  size_t dH, dU, dG, dXP, dZH, dHp, dXPin, dXin, mq_dv, mq_dsc, mq_dq, dHenc;
+  size_t dH, dU, dG, dXP, dIBu, dZH, dHp, dXPin, dXin, mq_dv, mq_dsc, mq_dq, dHenc;
   size_t acc_begin, acc_end;             // zeroed at the start of backward
-  size_t dS, a_e_wg_st, a_e_wg_in, a_e_wu_st, a_e_wu_in, a_d_wg_st, a_d_wg_in, a_d_wu_st, a_d_wu_in;
+  size_t dS, a_e_wg, a_e_wu, a_d_wg, a_d_wu;
   size_t dg1, dg2;
   size_t dLa, dLb, dL1, dE1, dE2;
   // loss scratch
@@ -50,18 +50,14 @@ static inline int make_plan(const Geo& g, bool save, Plan* p) {
   p->E2 = take(N * g.d);
   p->L1 = take(N * ldS);
   p->L2 = take(N * ldS);
-  p->e_wg_st = take(2 * NB * g.H * 2 * g.H);      // [hi | lo] TF32 split
-  p->e_wg_in = take(NB * g.Cin * 2 * g.H);
-  p->e_wu_st = take(2 * NB * g.H * g.H);      // [hi | lo] TF32 split
-  p->e_wu_in = take(NB * g.Cin * g.H);
-  p->d_wg_st = take(2 * NB * g.D * 2 * g.D);      // [hi | lo] TF32 split
-  p->d_wg_in = take(NB * g.Cdec * 2 * g.D);
-  p->d_wu_st = take(2 * NB * g.D * g.D);      // [hi | lo] TF32 split
-  p->d_wu_in = take(NB * g.Cdec * g.D);
+  p->e_wg = take(2 * (NB + 1) * g.H * 2 * g.H);
+  p->e_wu = take(2 * (NB + 1) * g.H * g.H);
+  p->d_wg = take(2 * (NB + 1) * g.D * 2 * g.D);
+  p->d_wu = take(2 * (NB + 1) * g.D * g.D);
   p->enc_slots = save ? g.T_in : 2;
   p->dec_slots = save ? g.T_out : 2;
   p->enc_xpin = take(NB * N * g.T_in * g.B * g.Cin);
-  p->enc_xp_sz = (NB * R * g.H + 63) / 64 * 64;
+  p->enc_xp_sz = ((NB + 1) * R * g.H + 63) / 64 * 64;      // NB state blocks + the input block
   p->enc_v_sz = (R * g.H + 63) / 64 * 64;
   p->enc_xpg = take(p->enc_xp_sz * p->enc_slots);
   p->enc_xpu = take(p->enc_xp_sz * p->enc_slots);
@@ -74,7 +70,7 @@ static inline int make_plan(const Geo& g, bool save, Plan* p) {
   p->mq_att = take(R * g.M);
   p->mq_ind = take(R * 2);
   p->dec_xpin_sz = (NB * R * g.Cdec + 63) / 64 * 64;
-  p->dec_xp_sz = (NB * R * g.D + 63) / 64 * 64;
+  p->dec_xp_sz = ((NB + 1) * R * g.D + 63) / 64 * 64;
   p->dec_v_sz = (R * g.D + 63) / 64 * 64;
   p->dec_xpin = take(p->dec_xpin_sz * p->dec_slots);
   p->dec_xpg = take(p->dec_xp_sz * p->dec_slots);
@@ -90,7 +86,8 @@ static inline int make_plan(const Geo& g, bool save, Plan* p) {
     p->dH = take(R * g.D);
     p->dU = take(R * g.D);
     p->dG = take(R * 2 * g.D);
-    p->dXP = take(NB * R * g.D);
+    p->dXP = take((NB + 1) * R * g.D);
+    p->dIBu = take(R * g.D);
     p->dZH = take(R * g.D);
     p->dHp = take(R * g.D);
     p->dXPin = take(NB * R * Cm);
@@ -101,14 +98,10 @@ static inline int make_plan(const Geo& g, bool save, Plan* p) {
     p->dHenc = take(R * g.H);
     p->acc_begin = off;
     p->dS = take(KS * N * ldS);
-    p->a_e_wg_st = take(NB * g.H * 2 * g.H);
-    p->a_e_wg_in = take(NB * g.Cin * 2 * g.H);
-    p->a_e_wu_st = take(NB * g.H * g.H);
-    p->a_e_wu_in = take(NB * g.Cin * g.H);
-    p->a_d_wg_st = take(NB * g.D * 2 * g.D);
-    p->a_d_wg_in = take(NB * g.Cdec * 2 * g.D);
-    p->a_d_wu_st = take(NB * g.D * g.D);
-    p->a_d_wu_in = take(NB * g.Cdec * g.D);
+    p->a_e_wg = take((NB + 1) * g.H * 2 * g.H);
+    p->a_e_wu = take((NB + 1) * g.H * g.H);
+    p->a_d_wg = take((NB + 1) * g.D * 2 * g.D);
+    p->a_d_wu = take((NB + 1) * g.D * g.D);
     p->dg1 = take(N * ldS);
     p->dg2 = take(N * ldS);
     p->acc_end = off;

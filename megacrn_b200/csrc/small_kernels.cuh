@@ -90,49 +90,99 @@ __global__ void k_add_transpose(const float* __restrict__ a, const float* __rest
   }
 }
 
-// ---- parameter re-packing (fold the two identity blocks; split input/state rows) ----
-// w [2*ck*(cin+hs), O] -> wst [NB][hs][O], win [NB][cin][O]       (tests/kernel_spec.py:fold_agcn_weights)
-// With split != 0, wst holds [2][NB][hs][O]: TF32 hi part then the TF32-rounded residual (lo); hi + lo carries
-// ~21 mantissa bits, which removes the (static, hence coherent over time and batch) weight-rounding error.
-__global__ void k_fold_weights(const float* __restrict__ w, float* __restrict__ wst, float* __restrict__ win,
+// ---- parameter re-packing ---------------------------------------------------------------------
+// One AGCN's weights w [2*ck*(cin+hs), O] + bias [O]  ->  wall [S][NB+1][hs][O]  (tests/kernel_spec.py:
+// fold_agcn_weights), S = 2 when split (TF32 hi part, then the TF32-rounded residual lo; hi + lo carries ~21
+// mantissa bits, removing the static -- hence coherent over time and batch -- weight-rounding error), else 1.
+//   blocks 0..NB-1 : state-channel rows; block 0 = the two identity blocks summed (model/MegaCRN.py:20)
+//   block NB       : the "input block": row k*cin+ci = input-channel row ci of block k, row NB*cin = bias, rest 0
+__global__ void k_fold_weights(const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ wall,
                                int cin, int hs, int O, int ck, int split) {
-  int NB = 1 + 2 * (ck - 1), c = cin + hs;
-  int64_t total = (int64_t)NB * c * O;
+  const int NB = 1 + 2 * (ck - 1), c = cin + hs;
+  const int64_t total = (int64_t)(NB + 1) * hs * O;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int o = (int)(i % O);
-    int cc = (int)((i / O) % c);
-    int blk = (int)(i / ((int64_t)O * c));
-    float v;
-    if (blk == 0) {
-      v = w[((int64_t)0 * c + cc) * O + o] + w[((int64_t)ck * c + cc) * O + o];
-    } else {
-      int g = (blk - 1) / (ck - 1), k = 1 + (blk - 1) % (ck - 1);
-      v = w[((int64_t)(g * ck + k) * c + cc) * O + o];
+    const int o = (int)(i % O);
+    const int row = (int)((i / O) % hs);
+    const int blk = (int)(i / ((int64_t)O * hs));
+    int src_blk = blk, cc = cin + row;             // state row of block blk
+    float v = 0.f;
+    bool have = true;
+    if (blk == NB) {
+      if (row < NB * cin) { src_blk = row / cin; cc = row % cin; }
+      else { have = false; if (row == NB * cin) v = bias[o]; }
     }
-    if (cc < cin) {
-      win[((int64_t)blk * cin + cc) * O + o] = v;
-    } else if (!split) {
-      wst[((int64_t)blk * hs + (cc - cin)) * O + o] = v;
+    if (have) {
+      if (src_blk == 0) {
+        v = w[((int64_t)0 * c + cc) * O + o] + w[((int64_t)ck * c + cc) * O + o];
+      } else {
+        int g = (src_blk - 1) / (ck - 1), k = 1 + (src_blk - 1) % (ck - 1);
+        v = w[((int64_t)(g * ck + k) * c + cc) * O + o];
+      }
+    }
+    if (!split) {
+      wall[i] = v;
     } else {
       float hi = tf32_rn(v);
-      wst[((int64_t)blk * hs + (cc - cin)) * O + o] = hi;
-      wst[((int64_t)(NB + blk) * hs + (cc - cin)) * O + o] = tf32_rn(v - hi);
+      wall[i] = hi;
+      wall[total + i] = tf32_rn(v - hi);
     }
   }
 }
 
-// inverse for gradients: dw [2*ck*c, O] <- (dwst, dwin); both identity blocks get block 0
-__global__ void k_unfold_grads(const float* __restrict__ dwst, const float* __restrict__ dwin, float* __restrict__ dw,
+// inverse for gradients: dwall [NB+1][hs][O] -> dw [2*ck*c, O] (both identity blocks get block 0) and dbias [O]
+__global__ void k_unfold_grads(const float* __restrict__ dwall, float* __restrict__ dw, float* __restrict__ dbias,
                                int cin, int hs, int O, int ck) {
-  int c = cin + hs;
-  int64_t total = (int64_t)2 * ck * c * O;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+  const int NB = 1 + 2 * (ck - 1), c = cin + hs;
+  const int64_t total = (int64_t)2 * ck * c * O;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total + O; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i >= total) {
+      int o = (int)(i - total);
+      dbias[o] = dwall[((int64_t)NB * hs + NB * cin) * O + o];
+      continue;
+    }
     int o = (int)(i % O);
     int cc = (int)((i / O) % c);
     int kk = (int)(i / ((int64_t)O * c));      // 0..2ck-1
     int g = kk / ck, k = kk % ck;
     int blk = (k == 0) ? 0 : 1 + g * (ck - 1) + (k - 1);
-    dw[i] = (cc < cin) ? dwin[((int64_t)blk * cin + cc) * O + o] : dwst[((int64_t)blk * hs + (cc - cin)) * O + o];
+    dw[i] = (cc < cin) ? dwall[((int64_t)NB * hs + blk * cin + cc) * O + o]
+                       : dwall[((int64_t)blk * hs + (cc - cin)) * O + o];
+  }
+}
+
+// Input block of one step (block NB of both XP buffers of the step): column k*cin+ci = XPin[k][node][b][ci]
+// (TF32-rounded when rnd), column NB*cin = 1 (multiplies the bias row), remaining columns 0.
+__global__ void k_build_input_block(const float* __restrict__ xpin, int64_t xp_k, int64_t xp_n, int NB, int cin,
+                                    int B, int64_t R, int hs, int rnd, float* __restrict__ ib_g,
+                                    float* __restrict__ ib_u) {
+  const int64_t total = R * hs;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / hs;
+    const int j = (int)(i - row * hs);
+    float v = 0.f;
+    if (j < NB * cin) {
+      const int k = j / cin, ci = j - k * cin;
+      const int node = (int)(row / B), b = (int)(row - (int64_t)node * B);
+      v = xpin[(int64_t)k * xp_k + (int64_t)node * xp_n + (int64_t)b * cin + ci];
+      if (rnd) v = tf32_rn(v);
+    } else if (j == NB * cin) {
+      v = 1.0f;
+    }
+    ib_g[i] = v;
+    ib_u[i] = v;
+  }
+}
+
+// d(input block) [R][hs] (columns k*cin+ci) -> dXPin [NB][R][cin], summing the update- and gate-AGCN parts.
+__global__ void k_repack_dib(const float* __restrict__ dib_a, const float* __restrict__ dib_b, int NB, int cin,
+                             int64_t R, int hs, float* __restrict__ dxpin) {
+  const int64_t total = (int64_t)NB * R * cin;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin);
+    const int64_t row = (i / cin) % R;
+    const int k = (int)(i / ((int64_t)cin * R));
+    const int64_t src = row * hs + k * cin + ci;
+    dxpin[i] = dib_a[src] + dib_b[src];
   }
 }
 
@@ -376,66 +426,6 @@ __global__ void k_bwd_dg(const float* __restrict__ dZH, const float* __restrict_
     dG[row * 2 * H + c] = rnd ? tf32_rn(gz) : gz;
     dG[row * 2 * H + H + c] = rnd ? tf32_rn(gr) : gr;
     dh_part[i] = dh * rr + dzh * zz;
-  }
-}
-
-// Bias and input-channel weight gradients of one AGCN for one step:
-//   db[o] += sum_r dv[r][o] ;  dwin[k][ci][o] += sum_r XPin[k][r][ci] * dv[r][o].
-// Block = 64 rows; thread o owns output column o (strided if O > blockDim).  NB*Cin <= 16.
-__global__ void __launch_bounds__(256) k_bwd_bias_win(const float* __restrict__ dv, int O,
-                                                      const float* __restrict__ xpin, int64_t xp_k, int64_t xp_n,
-                                                      int NB, int Cin, int B, int64_t R,
-                                                      float* __restrict__ db, float* __restrict__ dwin) {
-  extern __shared__ float sxp[];                   // [64][NB*Cin]
-  int K = NB * Cin;
-  int64_t r0 = (int64_t)blockIdx.x * 64;
-  for (int i = threadIdx.x; i < 64 * K; i += blockDim.x) {
-    int64_t row = r0 + i / K;
-    int kc = i % K, k = kc / Cin, ci = kc % Cin;
-    float v = 0.f;
-    if (row < R) {
-      int node = (int)(row / B), b = (int)(row % B);
-      v = xpin[(int64_t)k * xp_k + (int64_t)node * xp_n + (int64_t)b * Cin + ci];
-    }
-    sxp[i] = v;
-  }
-  __syncthreads();
-  for (int o = threadIdx.x; o < O; o += blockDim.x) {
-    float accb = 0.f, accw[16];
-#pragma unroll
-    for (int q = 0; q < 16; ++q) accw[q] = 0.f;
-    for (int i = 0; i < 64; ++i) {
-      int64_t row = r0 + i;
-      if (row >= R) break;
-      float g = dv[row * O + o];
-      accb += g;
-#pragma unroll
-      for (int q = 0; q < 16; ++q)
-        if (q < K) accw[q] = fmaf(sxp[i * K + q], g, accw[q]);
-    }
-    atomicAdd(db + o, accb);
-#pragma unroll
-    for (int q = 0; q < 16; ++q)
-      if (q < K) atomicAdd(dwin + (int64_t)q * O + o, accw[q]);
-  }
-}
-
-// dXPin[k][r][ci] = sum_o dU[r][o]*Wu_in[k][ci][o] + sum_o dG[r][o]*Wg_in[k][ci][o]; one warp per row.
-__global__ void __launch_bounds__(256) k_bwd_dxpin(const float* __restrict__ dU, const float* __restrict__ wu_in, int Ou,
-                                                   const float* __restrict__ dG, const float* __restrict__ wg_in, int Og,
-                                                   int NB, int Cin, int64_t R, float* __restrict__ dxpin) {
-  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int64_t row = (int64_t)blockIdx.x * 8 + warp;
-  if (row >= R) return;
-  for (int kc = 0; kc < NB * Cin; ++kc) {
-    float s = 0.f;
-    for (int o = lane; o < Ou; o += 32) s = fmaf(dU[row * Ou + o], wu_in[(int64_t)kc * Ou + o], s);
-    for (int o = lane; o < Og; o += 32) s = fmaf(dG[row * Og + o], wg_in[(int64_t)kc * Og + o], s);
-    s = warp_sum(s);
-    if (lane == 0) {
-      int k = kc / Cin, ci = kc % Cin;
-      dxpin[((int64_t)k * R + row) * Cin + ci] = s;
-    }
   }
 }
 
