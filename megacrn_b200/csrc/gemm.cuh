@@ -55,8 +55,10 @@ struct EpiStore {
     for (int j = 0; j < V; ++j) {
       if (j < nv) {
         float v = alpha * acc[j];
-        if (add1) v += add1[off + j];
-        if (add2) v += add2[off + j];
+        // ld.global.nc for addends that are not the output itself: lets the compiler batch the loads of the
+        // unrolled row loop instead of serialising load -> store -> load on a possible alias
+        if (add1) v += (add1 != C) ? __ldg(add1 + off + j) : add1[off + j];
+        if (add2) v += (add2 != C) ? __ldg(add2 + off + j) : add2[off + j];
         C[off + j] = rnd ? tf32_rn(v) : v;
       }
     }
@@ -145,7 +147,7 @@ struct EpiGate {
         if (col < H) {
           int64_t o = (int64_t)m * H + col;
           if (z) z[o] = s;
-          float t = s * h[o];
+          float t = s * __ldg(h + o);
           zh[o] = rnd ? tf32_rn(t) : t;
         } else {
           r[(int64_t)m * H + (col - H)] = s;
@@ -169,9 +171,9 @@ struct EpiUpdate {
         int col = n0 + j;
         int64_t o = (int64_t)m * H + col;
         float c = tanhf(acc[j]);
-        float rr = r[o];
+        float rr = __ldg(r + o);
         if (hc) hc[o] = c;
-        float hn = rr * h[o] + (1.0f - rr) * c;
+        float hn = rr * __ldg(h + o) + (1.0f - rr) * c;
         h_out[o] = hn;
         if (h_mma) h_mma[o] = rnd ? tf32_rn(hn) : hn;
       }

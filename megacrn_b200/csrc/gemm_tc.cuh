@@ -109,7 +109,7 @@ template <int BN, int STAGES>
 constexpr size_t smem_bytes() { return (size_t)STAGES * (BM * BK * 4 + BN * BK * 4) + 1024; }
 
 template <bool A_K, bool B_K, int BN, int STAGES, class Epi>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p, Epi epi) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
@@ -240,7 +240,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         const int col = n0 + c * 32 + lane;
         if (col < p.N) {
-#pragma unroll 4
+#pragma unroll 8
           for (int rr = 0; rr < 32; ++rr) {
             const int row = m0 + quarter * 32 + rr;
             if (row < p.M) {
@@ -317,10 +317,10 @@ template <class Epi>
 int gemm_tc(const GemmDesc& g, const Epi& epi, cudaStream_t st) {
   const bool a_k = (g.a_k == 1), b_k = (g.b_k == 1);
   const bool wide = g.N > 64;
-  if (a_k && b_k) return wide ? launch<true, true, 128, 4, Epi>(g, epi, st) : launch<true, true, 64, 4, Epi>(g, epi, st);
-  if (a_k && !b_k) return wide ? launch<true, false, 128, 4, Epi>(g, epi, st) : launch<true, false, 64, 4, Epi>(g, epi, st);
-  if (!a_k && b_k) return wide ? launch<false, true, 128, 4, Epi>(g, epi, st) : launch<false, true, 64, 4, Epi>(g, epi, st);
-  return wide ? launch<false, false, 128, 4, Epi>(g, epi, st) : launch<false, false, 64, 4, Epi>(g, epi, st);
+  if (a_k && b_k) return wide ? launch<true, true, 128, 3, Epi>(g, epi, st) : launch<true, true, 64, 4, Epi>(g, epi, st);
+  if (a_k && !b_k) return wide ? launch<true, false, 128, 3, Epi>(g, epi, st) : launch<true, false, 64, 4, Epi>(g, epi, st);
+  if (!a_k && b_k) return wide ? launch<false, true, 128, 3, Epi>(g, epi, st) : launch<false, true, 64, 4, Epi>(g, epi, st);
+  return wide ? launch<false, false, 128, 3, Epi>(g, epi, st) : launch<false, false, 64, 4, Epi>(g, epi, st);
 }
 
 }  // namespace tc
