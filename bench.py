@@ -169,6 +169,7 @@ def main():
     ap.add_argument("--config", default="c2", choices=list(CONFIGS))
     ap.add_argument("--engine", default="default", choices=["default", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from the host instead of replaying CUDA graphs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
 
@@ -182,7 +183,7 @@ def main():
     import torch.distributed as dist
     from megacrn_b200 import MegaCRN, _abi
     from megacrn_b200.ddp import allreduce_gradients
-    from megacrn_b200.train_step import train_step
+    from megacrn_b200.train_step import GraphedTrainStep, train_step
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -208,15 +209,26 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
     stream = torch.cuda.current_stream(dev)
 
+    graphed = None if args.no_graph else GraphedTrainStep(model, B, t_in)
+    if graphed is not None:
+        graphed.load(dx, dy, dl)
+
     def step_device():
-        for p in params:
-            p.grad = None
-        loss = train_step(model, dx, dy, dl, batches_seen=0)
+        # public API: the drop-in module + the fused trainer loss; coin flips drawn on the host every step
+        if graphed is not None:
+            loss = graphed(batches_seen=0)
+        else:
+            for p in params:
+                p.grad = None
+            loss = train_step(model, dx, dy, dl, batches_seen=0)
         allreduce_gradients(params)
         return loss
 
     def step_e2e():
-        dx.copy_(hx, non_blocking=True); dy.copy_(hy, non_blocking=True); dl.copy_(hl, non_blocking=True)
+        if graphed is not None:
+            graphed.load(hx, hy, hl)               # pinned host -> static device buffers
+        else:
+            dx.copy_(hx, non_blocking=True); dy.copy_(hy, non_blocking=True); dl.copy_(hl, non_blocking=True)
         loss = step_device()
         loss_host.copy_(loss, non_blocking=True)
         stream.synchronize()
@@ -231,14 +243,14 @@ def main():
         """K steps, each bracketed by CUDA events on the launching stream, L2 flushed between steps."""
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         barrier()
-        l0 = lib.mcrn_launch_count()
+        l0 = lib.mcrn_launch_count() + (graphed.kernels_replayed if graphed is not None else 0)
         for s, e in evs:
             flush.zero_()
             s.record(stream)
             fn()
             e.record(stream)
         barrier()
-        launches = lib.mcrn_launch_count() - l0
+        launches = lib.mcrn_launch_count() + (graphed.kernels_replayed if graphed is not None else 0) - l0
         total_ms = sum(s.elapsed_time(e) for s, e in evs)
         t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         if world > 1:
@@ -296,6 +308,7 @@ def main():
                                    f"H={d.rnn_units} batch={B}/GPU, train step = forward + trainer loss + backward"
                                    + (" + 1 NCCL grad all-reduce" if world > 1 else ""),
                        "global_batch": gB, "parallelism": f"dp{world}", "engine": args.engine,
+                       "launch": "eager" if args.no_graph else "cuda-graph replay (one graph per teacher-forcing pattern)",
                        "l2": "256 MiB memset between timed steps (flush) + 1.2 GB/step activation working set",
                        "final_loss": final_loss},
             "e2e": {"value": e2e_value, "unit": "sequences/s", "ms_per_step": e2e_ms / args.steps,

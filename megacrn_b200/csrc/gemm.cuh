@@ -39,7 +39,14 @@ __device__ __forceinline__ float tf32_rn(float x) {
 
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+__device__ __forceinline__ bool is16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+
 // ---- epilogues ------------------------------------------------------------------
+// (V == 4 fragments take a 128-bit fast path when the addresses are 16-byte aligned.)
 // Protocol: op.template apply<V>(batch, m, n0, nv, acc) is called once per output row
 // fragment of V contiguous columns starting at n0 (nv <= V of them in range).
 
@@ -51,6 +58,16 @@ struct EpiStore {
   template <int V>
   __device__ __forceinline__ void apply(int bz, int m, int n0, int nv, const float (&acc)[V]) const {
     int64_t off = (int64_t)bz * c_batch + (int64_t)m * ldc + n0;
+    if constexpr (V == 4) {
+      if (nv == 4 && is16(C + off) && (!add1 || (add1 != C && is16(add1 + off))) && (!add2 || (add2 != C && is16(add2 + off)))) {
+        float v0 = alpha * acc[0], v1 = alpha * acc[1], v2 = alpha * acc[2], v3 = alpha * acc[3];
+        if (add1) { float4 t = ldg4(add1 + off); v0 += t.x; v1 += t.y; v2 += t.z; v3 += t.w; }
+        if (add2) { float4 t = ldg4(add2 + off); v0 += t.x; v1 += t.y; v2 += t.z; v3 += t.w; }
+        if (rnd) { v0 = tf32_rn(v0); v1 = tf32_rn(v1); v2 = tf32_rn(v2); v3 = tf32_rn(v3); }
+        st4(C + off, v0, v1, v2, v3);
+        return;
+      }
+    }
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       if (j < nv) {
@@ -82,6 +99,12 @@ struct EpiAtomicAdd {
   template <int V>
   __device__ __forceinline__ void apply(int bz, int m, int n0, int nv, const float (&acc)[V]) const {
     int64_t off = (int64_t)bz * c_batch + (int64_t)m * ldc + n0;
+    if constexpr (V == 4) {
+      if (nv == 4 && is16(C + off)) {                       // red.global.add.v4.f32 (sm_90+)
+        atomicAdd(reinterpret_cast<float4*>(C + off), make_float4(acc[0], acc[1], acc[2], acc[3]));
+        return;
+      }
+    }
 #pragma unroll
     for (int j = 0; j < V; ++j)
       if (j < nv) atomicAdd(C + off + j, acc[j]);
@@ -115,6 +138,19 @@ struct EpiBlocks {
   float* last_out = nullptr;                 // if set, block `last` is written here ([M][W]) instead of C[last]
   template <int V>
   __device__ __forceinline__ void apply(int, int m, int n0, int nv, const float (&acc)[V]) const {
+    if constexpr (V == 4) {
+      if (nv == 4 && (W & 3) == 0) {
+        const int blk = n0 / W, c = n0 - blk * W;
+        float* dst = (blk == last && last_out) ? last_out + (int64_t)m * W + c
+                                               : C + (int64_t)blk * blk_stride + (int64_t)m * W + c;
+        if (is16(dst)) {
+          const bool r_ = rnd && blk > 0 && blk != last;
+          st4(dst, r_ ? tf32_rn(acc[0]) : acc[0], r_ ? tf32_rn(acc[1]) : acc[1], r_ ? tf32_rn(acc[2]) : acc[2],
+              r_ ? tf32_rn(acc[3]) : acc[3]);
+          return;
+        }
+      }
+    }
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       if (j < nv) {
@@ -139,6 +175,22 @@ struct EpiGate {
   int rnd;          // 1: zh (a tensor-core operand only) is stored TF32-rounded
   template <int V>
   __device__ __forceinline__ void apply(int, int m, int n0, int nv, const float (&acc)[V]) const {
+    if constexpr (V == 4) {
+      if (nv == 4 && (H & 3) == 0 && is16(h) && is16(r) && is16(zh) && (!z || is16(z))) {
+        const float s0 = sigmoid_f(acc[0]), s1 = sigmoid_f(acc[1]), s2 = sigmoid_f(acc[2]), s3 = sigmoid_f(acc[3]);
+        if (n0 < H) {
+          const int64_t o = (int64_t)m * H + n0;
+          const float4 hv = ldg4(h + o);
+          if (z) st4(z + o, s0, s1, s2, s3);
+          float t0 = s0 * hv.x, t1 = s1 * hv.y, t2 = s2 * hv.z, t3 = s3 * hv.w;
+          if (rnd) { t0 = tf32_rn(t0); t1 = tf32_rn(t1); t2 = tf32_rn(t2); t3 = tf32_rn(t3); }
+          st4(zh + o, t0, t1, t2, t3);
+        } else {
+          st4(r + (int64_t)m * H + (n0 - H), s0, s1, s2, s3);
+        }
+        return;
+      }
+    }
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       if (j < nv) {
@@ -165,6 +217,22 @@ struct EpiUpdate {
   float* h_mma; int rnd;            // h_mma: the copy the next propagation / gate GEMM reads (TF32-rounded if rnd)
   template <int V>
   __device__ __forceinline__ void apply(int, int m, int n0, int nv, const float (&acc)[V]) const {
+    if constexpr (V == 4) {
+      if (nv == 4 && (H & 3) == 0 && is16(h) && is16(r) && is16(h_out) && (!hc || is16(hc)) && (!h_mma || is16(h_mma))) {
+        const int64_t o = (int64_t)m * H + n0;
+        const float4 hv = ldg4(h + o), rv = ldg4(r + o);
+        const float c0 = tanhf(acc[0]), c1 = tanhf(acc[1]), c2 = tanhf(acc[2]), c3 = tanhf(acc[3]);
+        if (hc) st4(hc + o, c0, c1, c2, c3);
+        const float n0_ = rv.x * hv.x + (1.0f - rv.x) * c0, n1_ = rv.y * hv.y + (1.0f - rv.y) * c1;
+        const float n2_ = rv.z * hv.z + (1.0f - rv.z) * c2, n3_ = rv.w * hv.w + (1.0f - rv.w) * c3;
+        st4(h_out + o, n0_, n1_, n2_, n3_);
+        if (h_mma) {
+          if (rnd) st4(h_mma + o, tf32_rn(n0_), tf32_rn(n1_), tf32_rn(n2_), tf32_rn(n3_));
+          else st4(h_mma + o, n0_, n1_, n2_, n3_);
+        }
+        return;
+      }
+    }
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       if (j < nv) {

@@ -228,24 +228,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // Each thread owns one accumulator ROW (TMEM lane).  Storing rows per thread would scatter every warp
       // store over 32 cache lines, so each 32x32 chunk is transposed through shared memory (the pipeline
       // stages are idle once the accumulator is complete) and the epilogue functor runs with the 32 lanes
-      // on 32 CONSECUTIVE COLUMNS of one row: all its global loads/stores are 128-byte coalesced.
-      float* scr = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))) + quarter * (32 * 33);
+      // on consecutive columns of a row (8 lanes x 4 columns = one 128-byte line per row, 4 rows per instruction):
+      // all its global loads/stores are 128-bit and fully coalesced.
+      float* scr = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))) + quarter * (32 * 36);
+      const int cq = (lane & 7) * 4, r0 = lane >> 3;       // this lane: 4 consecutive columns of rows r0, r0+4, ...
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         float v[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), v);
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) scr[lane * 33 + j] = v[j];
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(&scr[lane * 36 + j]) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         __syncwarp();
-        const int col = n0 + c * 32 + lane;
+        const int col = n0 + c * 32 + cq;
         if (col < p.N) {
-#pragma unroll 8
-          for (int rr = 0; rr < 32; ++rr) {
+          const int nv = min(4, p.N - col);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = r0 + 4 * i;
             const int row = m0 + quarter * 32 + rr;
             if (row < p.M) {
-              float a1[1] = {scr[rr * 33 + lane]};
-              epi.template apply<1>(bz, row, col, 1, a1);
+              const float4 t = *reinterpret_cast<const float4*>(&scr[rr * 36 + cq]);
+              float a4[4] = {t.x, t.y, t.z, t.w};
+              epi.template apply<4>(bz, row, col, nv, a4);
             }
           }
         }

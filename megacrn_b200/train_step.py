@@ -44,3 +44,82 @@ def train_step(model, x, y_cov, labels, batches_seen=0, teacher_forcing=None, **
     loss, d_out, d_q = fused_trainer_loss(model, output, labels, query, pos, neg, **loss_kw)
     torch.autograd.backward([output, query], [d_out, d_q])
     return loss
+
+
+class GraphedTrainStep:
+    """The training step (forward + fused trainer loss + backward) replayed from a CUDA graph.
+
+    The step is ~500 small kernel launches; enqueueing them from the host costs several ms, more than the
+    kernels need.  The whole step is captured once per teacher-forcing pattern (the coin flips of
+    model/MegaCRN.py:188-191 are host control flow: they are still drawn from ``np.random`` on every call, in the
+    reference's order, and select which captured graph is replayed) and replayed with one launch.
+
+    Inputs are copied into static device buffers (``load``), gradients land in static ``p.grad`` tensors that
+    alias one flat buffer (``flat_grad``), the loss in ``loss`` (a 1-element device tensor).
+    """
+
+    def __init__(self, model, batch, seq_len, max_graphs=16, **loss_kw):
+        self.model, self.loss_kw, self.max_graphs = model, loss_kw, max_graphs
+        dev = next(model.parameters()).device
+        self.x = torch.zeros(batch, seq_len, model.num_nodes, model.input_dim, device=dev)
+        self.y_cov = torch.zeros(batch, model.horizon, model.num_nodes, model.ycov_dim, device=dev)
+        self.labels = torch.zeros(batch, model.horizon, model.num_nodes, model.output_dim, device=dev)
+        self.graphs = {}
+        self.kernels_replayed = 0          # library kernels executed through graph replays so far
+        self.loss = None
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        self.pool = None
+
+    def load(self, x, y_cov, labels, non_blocking=True):
+        self.x.copy_(x, non_blocking=non_blocking)
+        self.y_cov.copy_(y_cov, non_blocking=non_blocking)
+        self.labels.copy_(labels, non_blocking=non_blocking)
+
+    def _eager(self, flags):
+        for p in self.params:
+            p.grad = None
+        return train_step(self.model, self.x, self.y_cov, self.labels, teacher_forcing=flags, **self.loss_kw)
+
+    def _capture(self, flags):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                  # warm-up outside capture (lazy inits, allocator)
+            for _ in range(2):
+                self._eager(flags)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        for p in self.params:
+            p.grad = None
+        lib = _abi.load()
+        n0 = lib.mcrn_launch_count()
+        with torch.cuda.graph(g, pool=self.pool):
+            loss = train_step(self.model, self.x, self.y_cov, self.labels, teacher_forcing=flags, **self.loss_kw)
+        kernels = int(lib.mcrn_launch_count() - n0)       # library kernels recorded in this graph
+        if self.pool is None:
+            self.pool = g.pool()
+        grads = [p.grad for p in self.params]
+        return g, loss, grads, kernels
+
+    def __call__(self, batches_seen=0, teacher_forcing=None):
+        m = self.model
+        flags = teacher_forcing if teacher_forcing is not None else m.draw_teacher_forcing(batches_seen)
+        m.last_teacher_forcing = flags
+        key = None if flags is None else tuple(bool(f) for f in flags)
+        entry = self.graphs.get(key)
+        if entry is None:
+            if len(self.graphs) >= self.max_graphs:        # too many distinct patterns: run this one eagerly
+                self.loss = self._eager(flags)
+                return self.loss
+            entry = self.graphs[key] = self._capture(flags)
+        g, loss, grads, kernels = entry
+        g.replay()
+        self.kernels_replayed += kernels
+        for p, gr in zip(self.params, grads):              # static gradient tensors of this graph
+            p.grad = gr
+        self.loss = loss
+        return loss
+
+    def flat_grad(self):
+        from .ddp import flat_grad_view
+        return flat_grad_view(self.params)
