@@ -120,7 +120,7 @@ static int propagate_in(const Geo& g, const float* S, float* xpin, int64_t xp_k,
   GemmDesc q;
   q.A = S; q.a_row = g.ldS; q.a_k = 1; q.M = g.N; q.Kseg = g.N; q.a_batch = (int64_t)g.N * g.ldS;
   q.B = xpin; q.b_k = xp_n; q.b_n = 1; q.N = cols; q.b_batch = 0; q.nbatch = g.KS;
-  q.prec_exact = 1;      // 1-2 raw input channels: tiny, keep exact fp32
+  // staged inputs are TF32-rounded in TF32 mode, so the tensor-core product is exact per term
   EpiStore e{xpin + xp_k, xp_n, xp_k, 1.0f, nullptr, nullptr};
   return gemm(q, e, st);
 }
@@ -217,7 +217,7 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
   // ---- encoder (ADCRNN_Encoder.forward :65-83; zero initial state :50-51, :174) ----
   {
     int64_t n_in = (int64_t)g.N * g.T_in * g.B * g.Cin;
-    MCRN_LAUNCH(k_stage_encoder_input, ew_grid(n_in), 256, 0, st, x, ws + p.enc_xpin, g.B, g.T_in, g.N, g.Cin);
+    MCRN_LAUNCH(k_stage_encoder_input, ew_grid(n_in), 256, 0, st, x, ws + p.enc_xpin, g.B, g.T_in, g.N, g.Cin, tf32_mode());
     MCRN_TRY(propagate_in(g, S, ws + p.enc_xpin, (int64_t)g.N * g.T_in * g.B * g.Cin, (int64_t)g.T_in * g.B * g.Cin,
                           g.T_in * g.B * g.Cin, st));
     MCRN_CUDA_OK(cudaMemsetAsync(ws + p.enc_xpg, 0, (size_t)g.R * g.H * sizeof(float), st));
@@ -248,7 +248,7 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
       if (t > 0) go_src = (tf && tf[t - 1]) ? labels : output;
       int64_t n_in = (int64_t)g.R * g.Cdec;
       MCRN_LAUNCH(k_stage_decoder_input, ew_grid(n_in), 256, 0, st, go_src, y_cov, const_cast<float*>(b.xpin), g.B,
-                  g.T_out, g.N, g.Cout, g.Ycov, t);
+                  g.T_out, g.N, g.Cout, g.Ycov, t, tf32_mode());
       MCRN_TRY(propagate_in(g, S, const_cast<float*>(b.xpin), b.xp_k, b.xp_n, g.B * g.Cdec, st));
       const bool last = (t + 1 == g.T_out);
       float* h_out = last ? ws + p.h_dec_last : dec_bufs(g, p, ws, t + 1).hx;
@@ -338,9 +338,10 @@ static int cell_backward(const Geo& g, const Plan& p, float* ws, const float* S,
   MCRN_TRY(acc_ds(g, dXP + nH, (int64_t)g.B * Hs, b.xpg, (int64_t)g.B * Hs, g.B * Hs, dS, st));
   // ---- input channels: d(input block) of both AGCNs -> dXPin [NB][R][Cin] ----
   const int64_t nIn = (int64_t)g.NB * g.R * w.Cin;
-  MCRN_LAUNCH(k_repack_dib, ew_grid(nIn), 256, 0, st, ws + p.dIBu, dXP + (int64_t)g.NB * nH, g.NB, w.Cin, g.R, Hs, dXPin);
-  MCRN_TRY(acc_ds(g, dXPin + g.R * w.Cin, (int64_t)g.B * w.Cin, b.xpin, b.xp_n, g.B * w.Cin, dS, st, 1));
-  if (dxin) MCRN_TRY(propagate_T(g, S, dXPin, w.Cin, nullptr, dxin, st, 1));
+  MCRN_LAUNCH(k_repack_dib, ew_grid(nIn), 256, 0, st, ws + p.dIBu, dXP + (int64_t)g.NB * nH, g.NB, w.Cin, g.R, Hs, dXPin,
+              tf32_mode());
+  MCRN_TRY(acc_ds(g, dXPin + g.R * w.Cin, (int64_t)g.B * w.Cin, b.xpin, b.xp_n, g.B * w.Cin, dS, st));
+  if (dxin) MCRN_TRY(propagate_T(g, S, dXPin, w.Cin, nullptr, dxin, st));
   return MCRN_OK;
 }
 

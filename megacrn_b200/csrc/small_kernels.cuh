@@ -175,34 +175,37 @@ __global__ void k_build_input_block(const float* __restrict__ xpin, int64_t xp_k
 
 // d(input block) [R][hs] (columns k*cin+ci) -> dXPin [NB][R][cin], summing the update- and gate-AGCN parts.
 __global__ void k_repack_dib(const float* __restrict__ dib_a, const float* __restrict__ dib_b, int NB, int cin,
-                             int64_t R, int hs, float* __restrict__ dxpin) {
+                             int64_t R, int hs, float* __restrict__ dxpin, int rnd) {
   const int64_t total = (int64_t)NB * R * cin;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int ci = (int)(i % cin);
     const int64_t row = (i / cin) % R;
     const int k = (int)(i / ((int64_t)cin * R));
     const int64_t src = row * hs + k * cin + ci;
-    dxpin[i] = dib_a[src] + dib_b[src];
+    float v = dib_a[src] + dib_b[src];
+    dxpin[i] = rnd ? tf32_rn(v) : v;
   }
 }
 
 // ---- input staging ------------------------------------------------------------------
 // Encoder inputs for all steps: x [B][T][N][Cin] -> XPin block 0, layout [N][T][B][Cin].
-__global__ void k_stage_encoder_input(const float* __restrict__ x, float* __restrict__ xp0, int B, int T, int N, int Cin) {
+__global__ void k_stage_encoder_input(const float* __restrict__ x, float* __restrict__ xp0, int B, int T, int N, int Cin,
+                                      int rnd) {
   int64_t total = (int64_t)N * T * B * Cin;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int ci = (int)(i % Cin);
     int b = (int)((i / Cin) % B);
     int t = (int)((i / ((int64_t)Cin * B)) % T);
     int n = (int)(i / ((int64_t)Cin * B * T));
-    xp0[i] = x[(((int64_t)b * T + t) * N + n) * Cin + ci];
+    float v = x[(((int64_t)b * T + t) * N + n) * Cin + ci];
+    xp0[i] = rnd ? tf32_rn(v) : v;
   }
 }
 
 // Decoder input of step t: [go | y_cov[:,t]] -> XPin block 0 [N][B][Cout+Ycov]  (model/MegaCRN.py:185).
 // go_src: nullptr (t == 0, zeros), or a [B][T][N][Cout] tensor (output or labels) read at step t-1.
 __global__ void k_stage_decoder_input(const float* __restrict__ go_src, const float* __restrict__ ycov,
-                                      float* __restrict__ xp0, int B, int T, int N, int Cout, int Ycov, int t) {
+                                      float* __restrict__ xp0, int B, int T, int N, int Cout, int Ycov, int t, int rnd) {
   int C = Cout + Ycov;
   int64_t total = (int64_t)N * B * C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -212,7 +215,7 @@ __global__ void k_stage_decoder_input(const float* __restrict__ go_src, const fl
     float v;
     if (c < Cout) v = go_src ? go_src[(((int64_t)b * T + (t - 1)) * N + n) * Cout + c] : 0.f;
     else v = ycov[(((int64_t)b * T + t) * N + n) * Ycov + (c - Cout)];
-    xp0[i] = v;
+    xp0[i] = rnd ? tf32_rn(v) : v;
   }
 }
 
