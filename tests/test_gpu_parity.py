@@ -206,6 +206,30 @@ def test_full_size_vs_oracle(cfg, engine):
         assert rel_l2(prm.grad.cpu(), ref_grads[pname]) < grad_tol(engine), (pname, rel_l2(prm.grad.cpu(), ref_grads[pname]))
 
 
+@pytest.mark.parametrize("cfg", ["c4_mini", "c5_mini"])
+def test_large_graph_shapes_vs_oracle(cfg):
+    """BASELINE.json configs[3] (EXPY-TKY N=1843) and configs[4] (N=2841, H=128) node counts at reduced batch / steps
+    (the CPU oracle re-runs the N^3 Chebyshev product in every AGCN call, model/MegaCRN.py:19-23)."""
+    if cfg == "c4_mini":
+        d, B, t_in = O.Dims(num_nodes=1843, horizon=2, rnn_units=64), 2, 2
+    else:
+        d, B, t_in = O.Dims(num_nodes=2841, horizon=1, rnn_units=128), 1, 1
+    p = O.init_params(d, seed=0)
+    x, y_cov, labels = O.synthetic_batch(d, B, t_in, seed=77)
+    flags = [False] * d.horizon
+    torch.set_num_threads(min(16, torch.get_num_threads()))
+    ref_loss, ref_outs, ref_grads = O.loss_and_grads(d, p, x, y_cov, labels, flags)
+    m = _model(d, p).train()
+    dv = _dev()
+    outs = m(x.to(dv), y_cov.to(dv), labels.to(dv), teacher_forcing=flags)
+    d_out, d_q = reference_upstream(ref_outs[0], ref_outs[2], ref_outs[3], ref_outs[4], labels)
+    torch.autograd.backward([outs[0], outs[2]], [d_out.to(dv), d_q.to(dv)])
+    for k, a, b in zip(OUT_NAMES[:3], outs[:3], ref_outs[:3]):
+        assert rel_l2(a.detach().cpu(), b) < FWD_TOL, (k, rel_l2(a.detach().cpu(), b))
+    for pname, prm in m.named_parameters():
+        assert rel_l2(prm.grad.cpu(), ref_grads[pname]) < GRAD_TOL, (pname, rel_l2(prm.grad.cpu(), ref_grads[pname]))
+
+
 def test_all_output_gradients_including_pos_neg(engine):
     """Upstream gradients on all five outputs (pos/neg are not detached by the model itself)."""
     d = O.Dims(num_nodes=40, horizon=3, rnn_units=16, mem_num=6, mem_dim=12)
