@@ -130,19 +130,33 @@ struct EpiCheb {
   }
 };
 
-// Column n = blk*W + c is stored at C[blk][m][c]  (the dXP block buffers).
+// Column n = blk*W + c is stored at C[blk][m][c]  (the dXP block buffers).  Block `last` is the input block: its
+// first nin = NB*Cin columns are d(XPin) and go straight to dxpin [NB][R][Cin] (accumulating the second AGCN's part
+// on top of the first's when `accumulate`); its remaining columns (bias / padding) are not needed.
 struct EpiBlocks {
   float* C; int W; int64_t blk_stride;
   int rnd = 0;                               // 1: blocks 1..last-1 (tensor-core operands downstream) are TF32-rounded
-  int last = -1;                             // index of the input block (never rounded)
-  float* last_out = nullptr;                 // if set, block `last` is written here ([M][W]) instead of C[last]
+  int last = -1;
+  float* dxpin = nullptr; int cin = 1, nin = 0; int64_t R = 0; int accumulate = 0;
+  __device__ __forceinline__ void input_col(int m, int c, float v) const {
+    if (c < nin) {
+      const int k = c / cin, ci = c - k * cin;
+      float* dst = dxpin + ((int64_t)k * R + m) * cin + ci;
+      if (accumulate) { v += *dst; if (rnd) v = tf32_rn(v); }
+      *dst = v;
+    }
+  }
   template <int V>
   __device__ __forceinline__ void apply(int, int m, int n0, int nv, const float (&acc)[V]) const {
     if constexpr (V == 4) {
       if (nv == 4 && (W & 3) == 0) {
         const int blk = n0 / W, c = n0 - blk * W;
-        float* dst = (blk == last && last_out) ? last_out + (int64_t)m * W + c
-                                               : C + (int64_t)blk * blk_stride + (int64_t)m * W + c;
+        if (blk == last && dxpin) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) input_col(m, c + j, acc[j]);
+          return;
+        }
+        float* dst = C + (int64_t)blk * blk_stride + (int64_t)m * W + c;
         if (is16(dst)) {
           const bool r_ = rnd && blk > 0 && blk != last;
           st4(dst, r_ ? tf32_rn(acc[0]) : acc[0], r_ ? tf32_rn(acc[1]) : acc[1], r_ ? tf32_rn(acc[2]) : acc[2],
@@ -155,12 +169,67 @@ struct EpiBlocks {
     for (int j = 0; j < V; ++j) {
       if (j < nv) {
         int n = n0 + j, blk = n / W, c = n - blk * W;
-        if (blk == last && last_out) {
-          last_out[(int64_t)m * W + c] = acc[j];
+        if (blk == last && dxpin) {
+          input_col(m, c, acc[j]);
         } else {
           int64_t o = (int64_t)blk * blk_stride + (int64_t)m * W + c;
           C[o] = (rnd && blk > 0 && blk != last) ? tf32_rn(acc[j]) : acc[j];
         }
+      }
+    }
+  }
+};
+
+// Backward of the update-side propagation fused with the gate backward (tests/kernel_spec.py:cell_bwd):
+//   dZH = acc + dXP0 ; dG[:, :H] = dZH*h*z(1-z) ; dG[:, H:] = dH'*(h-hc)*r(1-r) ; dh_part = dH'*r + dZH*z.
+// The GEMM output is [N nodes][B*H] == flat [R][H]; dG is [R][2H].
+struct EpiDG {
+  const float *dxp0, *dH, *h, *z, *r, *hc;
+  float *dG, *dh_part;
+  int H; int64_t ld; int rnd;
+  __device__ __forceinline__ void one(int64_t flat, float acc, float& gz, float& gr, float& hp) const {
+    const float dzh = acc + __ldg(dxp0 + flat), zz = __ldg(z + flat), rr = __ldg(r + flat), hh = __ldg(h + flat);
+    const float dh = __ldg(dH + flat);
+    gz = dzh * hh * zz * (1.0f - zz);
+    gr = dh * (hh - __ldg(hc + flat)) * rr * (1.0f - rr);
+    hp = dh * rr + dzh * zz;
+    if (rnd) { gz = tf32_rn(gz); gr = tf32_rn(gr); }
+  }
+  template <int V>
+  __device__ __forceinline__ void apply(int, int m, int n0, int nv, const float (&acc)[V]) const {
+    const int64_t flat0 = (int64_t)m * ld + n0;
+    if constexpr (V == 4) {
+      if (nv == 4 && (H & 3) == 0 && (ld & 3) == 0 && is16(dxp0) && is16(dH) && is16(h) && is16(z) && is16(r) &&
+          is16(hc) && is16(dG) && is16(dh_part)) {
+        const float4 a = ldg4(dxp0 + flat0), zz = ldg4(z + flat0), rr = ldg4(r + flat0), hh = ldg4(h + flat0);
+        const float4 dh = ldg4(dH + flat0), cc = ldg4(hc + flat0);
+        const float d0 = acc[0] + a.x, d1 = acc[1] + a.y, d2 = acc[2] + a.z, d3 = acc[3] + a.w;
+        float g0 = d0 * hh.x * zz.x * (1.0f - zz.x), g1 = d1 * hh.y * zz.y * (1.0f - zz.y);
+        float g2 = d2 * hh.z * zz.z * (1.0f - zz.z), g3 = d3 * hh.w * zz.w * (1.0f - zz.w);
+        float q0 = dh.x * (hh.x - cc.x) * rr.x * (1.0f - rr.x), q1 = dh.y * (hh.y - cc.y) * rr.y * (1.0f - rr.y);
+        float q2 = dh.z * (hh.z - cc.z) * rr.z * (1.0f - rr.z), q3 = dh.w * (hh.w - cc.w) * rr.w * (1.0f - rr.w);
+        if (rnd) {
+          g0 = tf32_rn(g0); g1 = tf32_rn(g1); g2 = tf32_rn(g2); g3 = tf32_rn(g3);
+          q0 = tf32_rn(q0); q1 = tf32_rn(q1); q2 = tf32_rn(q2); q3 = tf32_rn(q3);
+        }
+        const int64_t row = flat0 / H;
+        const int c = (int)(flat0 - row * H);
+        st4(dG + row * 2 * H + c, g0, g1, g2, g3);
+        st4(dG + row * 2 * H + H + c, q0, q1, q2, q3);
+        st4(dh_part + flat0, dh.x * rr.x + d0 * zz.x, dh.y * rr.y + d1 * zz.y, dh.z * rr.z + d2 * zz.z, dh.w * rr.w + d3 * zz.w);
+        return;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      if (j < nv) {
+        const int64_t flat = flat0 + j, row = flat / H;
+        const int c = (int)(flat - row * H);
+        float gz, gr, hp;
+        one(flat, acc[j], gz, gr, hp);
+        dG[row * 2 * H + c] = gz;
+        dG[row * 2 * H + H + c] = gr;
+        dh_part[flat] = hp;
       }
     }
   }

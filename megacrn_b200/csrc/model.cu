@@ -264,7 +264,6 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
 // ======================================================================================
 // backward (BPTT)                                     tests/kernel_spec.py: cell_bwd, model_bwd
 // ======================================================================================
-struct CellAcc { float *wg, *wu; };     // accumulators [NB+1][Hs][O] (block NB: input-channel rows + bias row)
 
 static int split_for(int64_t tiles, int64_t k_iters) {
   // aim for ~4 waves of 148 CTAs, at least 4 k-iterations per split
@@ -276,22 +275,31 @@ static int split_for(int64_t tiles, int64_t k_iters) {
   return (int)s;
 }
 
-// dWall[k] += XP[k]^T * dV    (M = Hs, N = O, K = R, batched over the NB+1 blocks, split-K atomics)
-static int acc_dw(const Geo& g, const float* xp, int Hs, const float* dv, int O, float* dw, cudaStream_t st) {
-  GemmDesc q;
-  q.A = xp; q.a_row = 1; q.a_k = Hs; q.a_batch = g.R * Hs; q.M = Hs; q.Kseg = (int)g.R;
-  q.B = dv; q.b_k = O; q.b_n = 1; q.b_batch = 0; q.N = O; q.nbatch = g.NB + 1; q.prec_exact = dbg_exact(3);
-  q.splits = split_for((int64_t)ceil_div(Hs, 64) * ceil_div(O, 64) * (g.NB + 1), g.R / 16);
-  EpiAtomicAdd e{dw, O, (int64_t)Hs * O};
-  return gemm(q, e, st);
+// dWall[k] = sum_t XP_t[k]^T * dV_t   (M = Hs, N = O, K = T*R as T segments of R, batched over the NB+1 blocks,
+// split-K atomics).  One launch per AGCN for the whole sequence instead of one per step.
+static int acc_dw_all(const Geo& g, const float* xp0, int64_t xp_step, int T, int Hs, const float* dv_all, int O,
+                      float* dw, cudaStream_t st) {
+  for (int t0 = 0; t0 < T; t0 += 16) {            // at most 16 K-segments per launch
+    const int nt = T - t0 < 16 ? T - t0 : 16;
+    GemmDesc q;
+    q.A = xp0 + (int64_t)t0 * xp_step; q.a_row = 1; q.a_k = Hs; q.a_batch = g.R * Hs; q.a_seg = xp_step;
+    q.M = Hs; q.Kseg = (int)g.R; q.nseg = nt;
+    q.B = dv_all + (int64_t)t0 * g.R * O; q.b_k = O; q.b_n = 1; q.b_batch = 0; q.b_seg = g.R * O; q.N = O;
+    q.nbatch = g.NB + 1; q.prec_exact = dbg_exact(3);
+    q.splits = split_for((int64_t)ceil_div(Hs, 128) * ceil_div(O, 128) * (g.NB + 1), (int64_t)nt * g.R / 32);
+    EpiAtomicAdd e{dw, O, (int64_t)Hs * O};
+    MCRN_TRY(gemm(q, e, st));
+  }
+  return MCRN_OK;
 }
 // dXP[k] = dV * Wall[k]^T     (M = R, N = (NB+1)*Hs, K = O), stored block-wise; the input block goes to dib
-static int make_dxp(const Geo& g, const float* dv, int O, const float* wall, int Hs, float* dxp, float* dib, cudaStream_t st) {
+static int make_dxp(const Geo& g, const float* dv, int O, const float* wall, int Hs, float* dxp, float* dxpin, int cin,
+                    int accumulate, cudaStream_t st) {
   GemmDesc q;
   q.A = dv; q.a_row = O; q.a_k = 1; q.M = (int)g.R; q.Kseg = O;
   q.B = wall; q.b_k = 1; q.b_n = O; q.N = (g.NB + 1) * Hs; q.prec_exact = dbg_exact(2);
   if (tf32_mode()) { q.nseg = 2; q.b_seg = (int64_t)(g.NB + 1) * Hs * O; }     // W = hi + lo
-  EpiBlocks e{dxp, Hs, g.R * Hs, tf32_mode(), g.NB, dib};
+  EpiBlocks e{dxp, Hs, g.R * Hs, tf32_mode(), g.NB, dxpin, cin, g.NB * cin, g.R, accumulate};
   return gemm(q, e, st);
 }
 // out = add1 + add2 + dXP[0] + sum_k S_k^T dXP[1+k]    (M = N nodes, N = B*C, K = KS*N)
@@ -319,27 +327,28 @@ static int acc_ds(const Geo& g, const float* dp, int64_t dp_row, const float* x,
 // One cell backward.  dH (in) = grad of h'; dH_out (out) = grad of h; if dxin != null also writes
 // d(xin)[N][B][Cin].
 static int cell_backward(const Geo& g, const Plan& p, float* ws, const float* S, const CellW& w, const CellBufs& b,
-                         const CellAcc& a, const float* dH, float* dH_out, float* dxin, cudaStream_t st) {
+                         float* dU, float* dG, const float* dH, float* dH_out, float* dxin, cudaStream_t st) {
   const int Hs = w.Hs;
   const int64_t nH = g.R * Hs;
-  float *dU = ws + p.dU, *dG = ws + p.dG, *dXP = ws + p.dXP, *dZH = ws + p.dZH, *dHp = ws + p.dHp;
+  float *dXP = ws + p.dXP, *dHp = ws + p.dHp;
   float *dXPin = ws + p.dXPin, *dS = ws + p.dS;
   MCRN_LAUNCH(k_bwd_du, ew_grid(nH), 256, 0, st, dH, b.r, b.hc, dU, nH, tf32_mode());
-  // ---- update AGCN ----
-  MCRN_TRY(make_dxp(g, dU, Hs, w.wu, Hs, dXP, ws + p.dIBu, st));
-  MCRN_TRY(acc_dw(g, b.xpu, Hs, dU, Hs, a.wu, st));
-  MCRN_TRY(propagate_T(g, S, dXP, Hs, nullptr, dZH, st));
+  // ---- update AGCN: dXP = dU Wu^T ; dZH = dXP0 + S^T dXP[1..] fused with the gate backward -> dG, dh_part ----
+  MCRN_TRY(make_dxp(g, dU, Hs, w.wu, Hs, dXP, dXPin, w.Cin, 0, st));
+  {
+    GemmDesc q;
+    q.prec_exact = dbg_exact(4);
+    q.A = S; q.a_row = 1; q.a_k = g.ldS; q.M = g.N; q.Kseg = g.KS * g.N;
+    q.B = dXP + nH; q.b_k = (int64_t)g.B * Hs; q.b_n = 1; q.N = g.B * Hs;
+    EpiDG e{dXP, dH, b.hx, b.z, b.r, b.hc, dG, dHp, Hs, (int64_t)g.B * Hs, tf32_mode()};
+    MCRN_TRY(gemm(q, e, st));
+  }
   MCRN_TRY(acc_ds(g, dXP + nH, (int64_t)g.B * Hs, b.xpu, (int64_t)g.B * Hs, g.B * Hs, dS, st));
-  MCRN_LAUNCH(k_bwd_dg, ew_grid(nH), 256, 0, st, dZH, dH, b.hx, b.z, b.r, b.hc, dG, dHp, g.R, Hs, tf32_mode());
   // ---- gate AGCN ----
-  MCRN_TRY(make_dxp(g, dG, 2 * Hs, w.wg, Hs, dXP, nullptr, st));
-  MCRN_TRY(acc_dw(g, b.xpg, Hs, dG, 2 * Hs, a.wg, st));
+  MCRN_TRY(make_dxp(g, dG, 2 * Hs, w.wg, Hs, dXP, dXPin, w.Cin, 1, st));
   MCRN_TRY(propagate_T(g, S, dXP, Hs, dHp, dH_out, st));
   MCRN_TRY(acc_ds(g, dXP + nH, (int64_t)g.B * Hs, b.xpg, (int64_t)g.B * Hs, g.B * Hs, dS, st));
-  // ---- input channels: d(input block) of both AGCNs -> dXPin [NB][R][Cin] ----
-  const int64_t nIn = (int64_t)g.NB * g.R * w.Cin;
-  MCRN_LAUNCH(k_repack_dib, ew_grid(nIn), 256, 0, st, ws + p.dIBu, dXP + (int64_t)g.NB * nH, g.NB, w.Cin, g.R, Hs, dXPin,
-              tf32_mode());
+  // ---- input channels (dXPin [NB][R][Cin] was scattered by the two make_dxp epilogues) ----
   MCRN_TRY(acc_ds(g, dXPin + g.R * w.Cin, (int64_t)g.B * w.Cin, b.xpin, b.xp_n, g.B * w.Cin, dS, st));
   if (dxin) MCRN_TRY(propagate_T(g, S, dXPin, w.Cin, nullptr, dxin, st));
   return MCRN_OK;
@@ -428,7 +437,7 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
   // ---- decoder, reverse time ----
   {
     CellW w = dec_w(g, p, ws);
-    CellAcc a{ws + p.a_d_wg, ws + p.a_d_wu};
+    float *dU_all = ws + p.d_dU, *dG_all = ws + p.d_dG;
     bool have_dgo = false;
     for (int t = g.T_out - 1; t >= 0; --t) {
       CellBufs b = dec_bufs(g, p, ws, t);
@@ -440,9 +449,12 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
                   g.Cout, t);
       // d(go_t) is needed only when go_t was the model's own prediction of step t-1
       bool need_dxin = (t > 0) && !(tf && tf[t - 1]);
-      MCRN_TRY(cell_backward(g, p, ws, S, w, b, a, dH, dH, need_dxin ? dXin : nullptr, st));
+      MCRN_TRY(cell_backward(g, p, ws, S, w, b, dU_all + (int64_t)t * g.R * g.D, dG_all + (int64_t)t * g.R * 2 * g.D, dH, dH,
+                             need_dxin ? dXin : nullptr, st));
       have_dgo = need_dxin;
     }
+    MCRN_TRY(acc_dw_all(g, ws + p.dec_xpu, (int64_t)p.dec_xp_sz, g.T_out, g.D, dU_all, g.D, ws + p.a_d_wu, st));
+    MCRN_TRY(acc_dw_all(g, ws + p.dec_xpg, (int64_t)p.dec_xp_sz, g.T_out, g.D, dG_all, 2 * g.D, ws + p.a_d_wg, st));
   }
   // ---- memory query ----
   {
@@ -480,12 +492,15 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
   // ---- encoder, reverse time ----
   {
     CellW w = enc_w(g, p, ws);
-    CellAcc a{ws + p.a_e_wg, ws + p.a_e_wu};
+    float *dU_all = ws + p.e_dU, *dG_all = ws + p.e_dG;
     float* dHe = ws + p.dHenc;
     for (int t = g.T_in - 1; t >= 0; --t) {
       CellBufs b = enc_bufs(g, p, ws, t);
-      MCRN_TRY(cell_backward(g, p, ws, S, w, b, a, dHe, dHe, nullptr, st));
+      MCRN_TRY(cell_backward(g, p, ws, S, w, b, dU_all + (int64_t)t * g.R * g.H, dG_all + (int64_t)t * g.R * 2 * g.H, dHe, dHe,
+                             nullptr, st));
     }
+    MCRN_TRY(acc_dw_all(g, ws + p.enc_xpu, (int64_t)p.enc_xp_sz, g.T_in, g.H, dU_all, g.H, ws + p.a_e_wu, st));
+    MCRN_TRY(acc_dw_all(g, ws + p.enc_xpg, (int64_t)p.enc_xp_sz, g.T_in, g.H, dG_all, 2 * g.H, ws + p.a_e_wg, st));
   }
   MCRN_TRY(supports_backward(g, p, ws, prm, grads, st));
   // ---- un-fold weight gradients into the reference layout ----

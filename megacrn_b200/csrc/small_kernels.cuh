@@ -173,20 +173,6 @@ __global__ void k_build_input_block(const float* __restrict__ xpin, int64_t xp_k
   }
 }
 
-// d(input block) [R][hs] (columns k*cin+ci) -> dXPin [NB][R][cin], summing the update- and gate-AGCN parts.
-__global__ void k_repack_dib(const float* __restrict__ dib_a, const float* __restrict__ dib_b, int NB, int cin,
-                             int64_t R, int hs, float* __restrict__ dxpin, int rnd) {
-  const int64_t total = (int64_t)NB * R * cin;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int ci = (int)(i % cin);
-    const int64_t row = (i / cin) % R;
-    const int k = (int)(i / ((int64_t)cin * R));
-    const int64_t src = row * hs + k * cin + ci;
-    float v = dib_a[src] + dib_b[src];
-    dxpin[i] = rnd ? tf32_rn(v) : v;
-  }
-}
-
 // ---- input staging ------------------------------------------------------------------
 // Encoder inputs for all steps: x [B][T][N][Cin] -> XPin block 0, layout [N][T][B][Cin].
 __global__ void k_stage_encoder_input(const float* __restrict__ x, float* __restrict__ xp0, int B, int T, int N, int Cin,
@@ -413,22 +399,6 @@ __global__ void k_bwd_du(const float* __restrict__ dH, const float* __restrict__
     float c = hc[i];
     float v = dH[i] * (1.0f - r[i]) * (1.0f - c * c);
     dU[i] = rnd ? tf32_rn(v) : v;
-  }
-}
-
-// dG[:, :H] = dZH*h*z(1-z); dG[:, H:] = dH'*(h-hc)*r(1-r); dh_part = dH'*r + dZH*z
-__global__ void k_bwd_dg(const float* __restrict__ dZH, const float* __restrict__ dH, const float* __restrict__ h,
-                         const float* __restrict__ z, const float* __restrict__ r, const float* __restrict__ hc,
-                         float* __restrict__ dG, float* __restrict__ dh_part, int64_t R, int H, int rnd) {
-  int64_t n = R * H;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t row = i / H;
-    int c = (int)(i - row * H);
-    float zz = z[i], rr = r[i], hh = h[i], dzh = dZH[i], dh = dH[i];
-    float gz = dzh * hh * zz * (1.0f - zz), gr = dh * (hh - hc[i]) * rr * (1.0f - rr);
-    dG[row * 2 * H + c] = rnd ? tf32_rn(gz) : gz;
-    dG[row * 2 * H + H + c] = rnd ? tf32_rn(gr) : gr;
-    dh_part[i] = dh * rr + dzh * zz;
   }
 }
 
