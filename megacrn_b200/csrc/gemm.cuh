@@ -130,33 +130,20 @@ struct EpiCheb {
   }
 };
 
-// Column n = blk*W + c is stored at C[blk][m][c]  (the dXP block buffers).  Block `last` is the input block: its
-// first nin = NB*Cin columns are d(XPin) and go straight to dxpin [NB][R][Cin] (accumulating the second AGCN's part
-// on top of the first's when `accumulate`); its remaining columns (bias / padding) are not needed.
+// Column n = blk*W + c is stored at C[blk][m][c]  (the dXP block buffers); block `last` (the input block) may be
+// redirected to last_out [M][W].
 struct EpiBlocks {
   float* C; int W; int64_t blk_stride;
   int rnd = 0;                               // 1: blocks 1..last-1 (tensor-core operands downstream) are TF32-rounded
   int last = -1;
-  float* dxpin = nullptr; int cin = 1, nin = 0; int64_t R = 0; int accumulate = 0;
-  __device__ __forceinline__ void input_col(int m, int c, float v) const {
-    if (c < nin) {
-      const int k = c / cin, ci = c - k * cin;
-      float* dst = dxpin + ((int64_t)k * R + m) * cin + ci;
-      if (accumulate) { v += *dst; if (rnd) v = tf32_rn(v); }
-      *dst = v;
-    }
-  }
+  float* last_out = nullptr;
   template <int V>
   __device__ __forceinline__ void apply(int, int m, int n0, int nv, const float (&acc)[V]) const {
     if constexpr (V == 4) {
       if (nv == 4 && (W & 3) == 0) {
         const int blk = n0 / W, c = n0 - blk * W;
-        if (blk == last && dxpin) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) input_col(m, c + j, acc[j]);
-          return;
-        }
-        float* dst = C + (int64_t)blk * blk_stride + (int64_t)m * W + c;
+        float* dst = (blk == last && last_out) ? last_out + (int64_t)m * W + c
+                                               : C + (int64_t)blk * blk_stride + (int64_t)m * W + c;
         if (is16(dst)) {
           const bool r_ = rnd && blk > 0 && blk != last;
           st4(dst, r_ ? tf32_rn(acc[0]) : acc[0], r_ ? tf32_rn(acc[1]) : acc[1], r_ ? tf32_rn(acc[2]) : acc[2],
@@ -169,8 +156,8 @@ struct EpiBlocks {
     for (int j = 0; j < V; ++j) {
       if (j < nv) {
         int n = n0 + j, blk = n / W, c = n - blk * W;
-        if (blk == last && dxpin) {
-          input_col(m, c, acc[j]);
+        if (blk == last && last_out) {
+          last_out[(int64_t)m * W + c] = acc[j];
         } else {
           int64_t o = (int64_t)blk * blk_stride + (int64_t)m * W + c;
           C[o] = (rnd && blk > 0 && blk != last) ? tf32_rn(acc[j]) : acc[j];

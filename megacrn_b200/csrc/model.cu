@@ -293,13 +293,14 @@ static int acc_dw_all(const Geo& g, const float* xp0, int64_t xp_step, int T, in
   return MCRN_OK;
 }
 // dXP[k] = dV * Wall[k]^T     (M = R, N = (NB+1)*Hs, K = O), stored block-wise; the input block goes to dib
-static int make_dxp(const Geo& g, const float* dv, int O, const float* wall, int Hs, float* dxp, float* dxpin, int cin,
-                    int accumulate, cudaStream_t st) {
+static int make_dxp(const Geo& g, const float* dv, int O, const float* wall, int Hs, float* dxp, float* dib, cudaStream_t st) {
   GemmDesc q;
   q.A = dv; q.a_row = O; q.a_k = 1; q.M = (int)g.R; q.Kseg = O;
   q.B = wall; q.b_k = 1; q.b_n = O; q.N = (g.NB + 1) * Hs; q.prec_exact = dbg_exact(2);
-  if (tf32_mode()) { q.nseg = 2; q.b_seg = (int64_t)(g.NB + 1) * Hs * O; }     // W = hi + lo
-  EpiBlocks e{dxp, Hs, g.R * Hs, tf32_mode(), g.NB, dxpin, cin, g.NB * cin, g.R, accumulate};
+  // Backward uses the TF32 hi part of the weights only (the lo residual halves the K loop for a 2^-11 relative change of
+  // dXP, far inside the gradient tolerance); mcrn_set_debug_mask bit 8 restores hi + lo.
+  if (tf32_mode() && dbg_exact(8)) { q.nseg = 2; q.b_seg = (int64_t)(g.NB + 1) * Hs * O; }
+  EpiBlocks e{dxp, Hs, g.R * Hs, tf32_mode(), g.NB, dib};
   return gemm(q, e, st);
 }
 // out = add1 + add2 + dXP[0] + sum_k S_k^T dXP[1+k]    (M = N nodes, N = B*C, K = KS*N)
@@ -334,7 +335,7 @@ static int cell_backward(const Geo& g, const Plan& p, float* ws, const float* S,
   float *dXPin = ws + p.dXPin, *dS = ws + p.dS;
   MCRN_LAUNCH(k_bwd_du, ew_grid(nH), 256, 0, st, dH, b.r, b.hc, dU, nH, tf32_mode());
   // ---- update AGCN: dXP = dU Wu^T ; dZH = dXP0 + S^T dXP[1..] fused with the gate backward -> dG, dh_part ----
-  MCRN_TRY(make_dxp(g, dU, Hs, w.wu, Hs, dXP, dXPin, w.Cin, 0, st));
+  MCRN_TRY(make_dxp(g, dU, Hs, w.wu, Hs, dXP, ws + p.dIBu, st));
   {
     GemmDesc q;
     q.prec_exact = dbg_exact(4);
@@ -345,10 +346,13 @@ static int cell_backward(const Geo& g, const Plan& p, float* ws, const float* S,
   }
   MCRN_TRY(acc_ds(g, dXP + nH, (int64_t)g.B * Hs, b.xpu, (int64_t)g.B * Hs, g.B * Hs, dS, st));
   // ---- gate AGCN ----
-  MCRN_TRY(make_dxp(g, dG, 2 * Hs, w.wg, Hs, dXP, dXPin, w.Cin, 1, st));
+  MCRN_TRY(make_dxp(g, dG, 2 * Hs, w.wg, Hs, dXP, nullptr, st));
   MCRN_TRY(propagate_T(g, S, dXP, Hs, dHp, dH_out, st));
   MCRN_TRY(acc_ds(g, dXP + nH, (int64_t)g.B * Hs, b.xpg, (int64_t)g.B * Hs, g.B * Hs, dS, st));
-  // ---- input channels (dXPin [NB][R][Cin] was scattered by the two make_dxp epilogues) ----
+  // ---- input channels: d(input block) of both AGCNs -> dXPin [NB][R][Cin] ----
+  const int64_t nIn = (int64_t)g.NB * g.R * w.Cin;
+  MCRN_LAUNCH(k_repack_dib, ew_grid(nIn), 256, 0, st, ws + p.dIBu, dXP + (int64_t)g.NB * nH, g.NB, w.Cin, g.R, Hs, dXPin,
+              tf32_mode());
   MCRN_TRY(acc_ds(g, dXPin + g.R * w.Cin, (int64_t)g.B * w.Cin, b.xpin, b.xp_n, g.B * w.Cin, dS, st));
   if (dxin) MCRN_TRY(propagate_T(g, S, dXPin, w.Cin, nullptr, dxin, st));
   return MCRN_OK;

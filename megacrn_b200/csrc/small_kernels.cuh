@@ -173,6 +173,20 @@ __global__ void k_build_input_block(const float* __restrict__ xpin, int64_t xp_k
   }
 }
 
+// d(input block) [R][hs] (columns k*cin+ci) of the update and gate AGCNs -> dXPin [NB][R][cin] (their sum).
+__global__ void k_repack_dib(const float* __restrict__ dib_a, const float* __restrict__ dib_b, int NB, int cin,
+                             int64_t R, int hs, float* __restrict__ dxpin, int rnd) {
+  const int64_t total = (int64_t)NB * R * cin;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin);
+    const int64_t row = (i / cin) % R;
+    const int k = (int)(i / ((int64_t)cin * R));
+    const int64_t src = row * hs + k * cin + ci;
+    float v = dib_a[src] + dib_b[src];
+    dxpin[i] = rnd ? tf32_rn(v) : v;
+  }
+}
+
 // ---- input staging ------------------------------------------------------------------
 // Encoder inputs for all steps: x [B][T][N][Cin] -> XPin block 0, layout [N][T][B][Cin].
 __global__ void k_stage_encoder_input(const float* __restrict__ x, float* __restrict__ xp0, int B, int T, int N, int Cin,
