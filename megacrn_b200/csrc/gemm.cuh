@@ -55,6 +55,23 @@ struct EpiStore {
   float* C; int64_t ldc, c_batch; float alpha;
   const float* add1; const float* add2;     // optional, same layout as C
   int rnd = 0;                              // 1: store TF32-rounded (the output is a tensor-core operand)
+  // two-phase protocol of the tensor-core epilogue: all loads of a batch of rows are issued before any store
+  static constexpr int NP = 2;
+  __device__ __forceinline__ bool fast4(int, int, int n0) const {
+    return ((ldc | c_batch | n0) & 3) == 0 && is16(C) && (!add1 || (add1 != C && is16(add1))) && (!add2 || (add2 != C && is16(add2)));
+  }
+  __device__ __forceinline__ void load4(int bz, int m, int n0, float4 (&p)[NP]) const {
+    const int64_t off = (int64_t)bz * c_batch + (int64_t)m * ldc + n0;
+    p[0] = add1 ? ldg4(add1 + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+    p[1] = add2 ? ldg4(add2 + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __device__ __forceinline__ void fin4(int bz, int m, int n0, const float4 (&p)[NP], const float (&acc)[4]) const {
+    const int64_t off = (int64_t)bz * c_batch + (int64_t)m * ldc + n0;
+    float v0 = alpha * acc[0] + p[0].x + p[1].x, v1 = alpha * acc[1] + p[0].y + p[1].y;
+    float v2 = alpha * acc[2] + p[0].z + p[1].z, v3 = alpha * acc[3] + p[0].w + p[1].w;
+    if (rnd) { v0 = tf32_rn(v0); v1 = tf32_rn(v1); v2 = tf32_rn(v2); v3 = tf32_rn(v3); }
+    st4(C + off, v0, v1, v2, v3);
+  }
   template <int V>
   __device__ __forceinline__ void apply(int bz, int m, int n0, int nv, const float (&acc)[V]) const {
     int64_t off = (int64_t)bz * c_batch + (int64_t)m * ldc + n0;
@@ -84,6 +101,7 @@ struct EpiStore {
 
 // C[m][n] = acc + add[m*ld_add + n]   (add has a different row stride, e.g. a column slice)
 struct EpiStoreStrideAdd {
+  static constexpr int NP = 0;
   float* C; int64_t ldc; const float* add; int64_t ld_add;
   template <int V>
   __device__ __forceinline__ void apply(int, int m, int n0, int nv, const float (&acc)[V]) const {
@@ -95,6 +113,7 @@ struct EpiStoreStrideAdd {
 
 // C += acc with atomics (split-K / accumulation over timesteps).
 struct EpiAtomicAdd {
+  static constexpr int NP = 0;
   float* C; int64_t ldc, c_batch;
   template <int V>
   __device__ __forceinline__ void apply(int bz, int m, int n0, int nv, const float (&acc)[V]) const {
@@ -114,6 +133,7 @@ struct EpiAtomicAdd {
 // Chebyshev recursion  T_k = 2*(S*T_{k-1}) - T_{k-2}  (model/MegaCRN.py:21-22);
 // prev == nullptr means T_{k-2} = I.
 struct EpiCheb {
+  static constexpr int NP = 0;
   float* C; int64_t ldc; const float* prev;
   float* Cr;                                 // TF32-rounded copy (tensor-core operand), may alias nothing
   template <int V>
@@ -133,6 +153,7 @@ struct EpiCheb {
 // Column n = blk*W + c is stored at C[blk][m][c]  (the dXP block buffers); block `last` (the input block) may be
 // redirected to last_out [M][W].
 struct EpiBlocks {
+  static constexpr int NP = 0;
   float* C; int W; int64_t blk_stride;
   int rnd = 0;                               // 1: blocks 1..last-1 (tensor-core operands downstream) are TF32-rounded
   int last = -1;
@@ -174,6 +195,33 @@ struct EpiDG {
   const float *dxp0, *dH, *h, *z, *r, *hc;
   float *dG, *dh_part;
   int H; int64_t ld; int rnd;
+  static constexpr int NP = 6;
+  __device__ __forceinline__ bool fast4(int, int, int n0) const {
+    return ((H | n0) & 3) == 0 && (ld & 3) == 0 && is16(dxp0) && is16(dH) && is16(h) && is16(z) && is16(r) && is16(hc) &&
+           is16(dG) && is16(dh_part);
+  }
+  __device__ __forceinline__ void load4(int, int m, int n0, float4 (&p)[NP]) const {
+    const int64_t f = (int64_t)m * ld + n0;
+    p[0] = ldg4(dxp0 + f); p[1] = ldg4(z + f); p[2] = ldg4(r + f); p[3] = ldg4(h + f); p[4] = ldg4(dH + f); p[5] = ldg4(hc + f);
+  }
+  __device__ __forceinline__ void fin4(int, int m, int n0, const float4 (&p)[NP], const float (&acc)[4]) const {
+    const int64_t flat0 = (int64_t)m * ld + n0;
+    const float4 a = p[0], zz = p[1], rr = p[2], hh = p[3], dh = p[4], cc = p[5];
+    const float d0 = acc[0] + a.x, d1 = acc[1] + a.y, d2 = acc[2] + a.z, d3 = acc[3] + a.w;
+    float g0 = d0 * hh.x * zz.x * (1.0f - zz.x), g1 = d1 * hh.y * zz.y * (1.0f - zz.y);
+    float g2 = d2 * hh.z * zz.z * (1.0f - zz.z), g3 = d3 * hh.w * zz.w * (1.0f - zz.w);
+    float q0 = dh.x * (hh.x - cc.x) * rr.x * (1.0f - rr.x), q1 = dh.y * (hh.y - cc.y) * rr.y * (1.0f - rr.y);
+    float q2 = dh.z * (hh.z - cc.z) * rr.z * (1.0f - rr.z), q3 = dh.w * (hh.w - cc.w) * rr.w * (1.0f - rr.w);
+    if (rnd) {
+      g0 = tf32_rn(g0); g1 = tf32_rn(g1); g2 = tf32_rn(g2); g3 = tf32_rn(g3);
+      q0 = tf32_rn(q0); q1 = tf32_rn(q1); q2 = tf32_rn(q2); q3 = tf32_rn(q3);
+    }
+    const int64_t row = flat0 / H;
+    const int c = (int)(flat0 - row * H);
+    st4(dG + row * 2 * H + c, g0, g1, g2, g3);
+    st4(dG + row * 2 * H + H + c, q0, q1, q2, q3);
+    st4(dh_part + flat0, dh.x * rr.x + d0 * zz.x, dh.y * rr.y + d1 * zz.y, dh.z * rr.z + d2 * zz.z, dh.w * rr.w + d3 * zz.w);
+  }
   __device__ __forceinline__ void one(int64_t flat, float acc, float& gz, float& gr, float& hp) const {
     const float dzh = acc + __ldg(dxp0 + flat), zz = __ldg(z + flat), rr = __ldg(r + flat), hh = __ldg(h + flat);
     const float dh = __ldg(dH + flat);
@@ -229,6 +277,25 @@ struct EpiGate {
   const float* h;   // [R][H] current state, exact fp32
   float* z; float* r; float* zh;
   int rnd;          // 1: zh (a tensor-core operand only) is stored TF32-rounded
+  static constexpr int NP = 1;
+  __device__ __forceinline__ bool fast4(int, int, int n0) const {
+    return ((H | n0) & 3) == 0 && is16(h) && is16(r) && is16(zh) && (!z || is16(z));
+  }
+  __device__ __forceinline__ void load4(int, int m, int n0, float4 (&p)[NP]) const {
+    p[0] = (n0 < H) ? ldg4(h + (int64_t)m * H + n0) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __device__ __forceinline__ void fin4(int, int m, int n0, const float4 (&p)[NP], const float (&acc)[4]) const {
+    const float s0 = sigmoid_f(acc[0]), s1 = sigmoid_f(acc[1]), s2 = sigmoid_f(acc[2]), s3 = sigmoid_f(acc[3]);
+    if (n0 < H) {
+      const int64_t o = (int64_t)m * H + n0;
+      if (z) st4(z + o, s0, s1, s2, s3);
+      float t0 = s0 * p[0].x, t1 = s1 * p[0].y, t2 = s2 * p[0].z, t3 = s3 * p[0].w;
+      if (rnd) { t0 = tf32_rn(t0); t1 = tf32_rn(t1); t2 = tf32_rn(t2); t3 = tf32_rn(t3); }
+      st4(zh + o, t0, t1, t2, t3);
+    } else {
+      st4(r + (int64_t)m * H + (n0 - H), s0, s1, s2, s3);
+    }
+  }
   template <int V>
   __device__ __forceinline__ void apply(int, int m, int n0, int nv, const float (&acc)[V]) const {
     if constexpr (V == 4) {
@@ -271,6 +338,28 @@ struct EpiUpdate {
   const float* h; const float* r;   // exact state, r gate
   float* hc; float* h_out;          // h_out: exact new state
   float* h_mma; int rnd;            // h_mma: the copy the next propagation / gate GEMM reads (TF32-rounded if rnd)
+  static constexpr int NP = 2;
+  __device__ __forceinline__ bool fast4(int, int, int n0) const {
+    return ((H | n0) & 3) == 0 && is16(h) && is16(r) && is16(h_out) && (!hc || is16(hc)) && (!h_mma || is16(h_mma));
+  }
+  __device__ __forceinline__ void load4(int, int m, int n0, float4 (&p)[NP]) const {
+    const int64_t o = (int64_t)m * H + n0;
+    p[0] = ldg4(h + o);
+    p[1] = ldg4(r + o);
+  }
+  __device__ __forceinline__ void fin4(int, int m, int n0, const float4 (&p)[NP], const float (&acc)[4]) const {
+    const int64_t o = (int64_t)m * H + n0;
+    const float4 hv = p[0], rv = p[1];
+    const float c0 = tanhf(acc[0]), c1 = tanhf(acc[1]), c2 = tanhf(acc[2]), c3 = tanhf(acc[3]);
+    if (hc) st4(hc + o, c0, c1, c2, c3);
+    const float n0_ = rv.x * hv.x + (1.0f - rv.x) * c0, n1_ = rv.y * hv.y + (1.0f - rv.y) * c1;
+    const float n2_ = rv.z * hv.z + (1.0f - rv.z) * c2, n3_ = rv.w * hv.w + (1.0f - rv.w) * c3;
+    st4(h_out + o, n0_, n1_, n2_, n3_);
+    if (h_mma) {
+      if (rnd) st4(h_mma + o, tf32_rn(n0_), tf32_rn(n1_), tf32_rn(n2_), tf32_rn(n3_));
+      else st4(h_mma + o, n0_, n1_, n2_, n3_);
+    }
+  }
   template <int V>
   __device__ __forceinline__ void apply(int, int m, int n0, int nv, const float (&acc)[V]) const {
     if constexpr (V == 4) {

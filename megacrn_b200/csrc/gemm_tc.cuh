@@ -243,14 +243,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int col = n0 + c * 32 + cq;
         if (col < p.N) {
           const int nv = min(4, p.N - col);
+          const int rbase = m0 + quarter * 32 + r0;
+          bool done = false;
+          if constexpr (Epi::NP > 0) {
+            // two-phase fast path: issue the global loads of a whole batch of rows, then compute and store
+            if (nv == 4 && epi.fast4(bz, rbase, col)) {
+              constexpr int RB = Epi::NP <= 2 ? 8 : (Epi::NP <= 4 ? 4 : 2);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = r0 + 4 * i;
-            const int row = m0 + quarter * 32 + rr;
-            if (row < p.M) {
-              const float4 t = *reinterpret_cast<const float4*>(&scr[rr * 36 + cq]);
-              float a4[4] = {t.x, t.y, t.z, t.w};
-              epi.template apply<4>(bz, row, col, nv, a4);
+              for (int b0 = 0; b0 < 8; b0 += RB) {
+                float4 pre[RB][Epi::NP];
+#pragma unroll
+                for (int i = 0; i < RB; ++i) {
+                  const int row = rbase + 4 * (b0 + i);
+                  if (row < p.M) epi.load4(bz, row, col, pre[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < RB; ++i) {
+                  const int rr = r0 + 4 * (b0 + i);
+                  const int row = m0 + quarter * 32 + rr;
+                  if (row < p.M) {
+                    const float4 t = *reinterpret_cast<const float4*>(&scr[rr * 36 + cq]);
+                    const float a4[4] = {t.x, t.y, t.z, t.w};
+                    epi.fin4(bz, row, col, pre[i], a4);
+                  }
+                }
+              }
+              done = true;
+            }
+          }
+          if (!done) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = r0 + 4 * i;
+              const int row = m0 + quarter * 32 + rr;
+              if (row < p.M) {
+                const float4 t = *reinterpret_cast<const float4*>(&scr[rr * 36 + cq]);
+                float a4[4] = {t.x, t.y, t.z, t.w};
+                epi.template apply<4>(bz, row, col, nv, a4);
+              }
             }
           }
         }
