@@ -21,12 +21,19 @@ struct GemmDesc {
   int M = 0, N = 0, Kseg = 0, nseg = 1, nbatch = 1, splits = 1;
   int a_nseg = 0, b_nseg = 0;   // distinct segments of A / B (0 = nseg); segment index wraps (hi/lo weight split)
   int prec_exact = 0;           // 1 = this contraction must run in exact fp32 (SIMT engine)
-  int use_map = 0;              // 1 = K-segment s reads A segment a_map[s] and B segment b_map[s] (3xTF32 products)
+  int use_map = 0;              // 1 = K-segment s reads A segment a_map[s] and B segment b_map[s]
   uint8_t a_map[16] = {0}, b_map[16] = {0};
+  // b_sub = 2: every A segment multiplies TWO B segments (s and s + b_sub_seg: the TF32 hi and lo weight parts).
+  // The tensor-core engine stages A once for both (gemm_tc_hilo); the SIMT engine walks 2*nseg segments.
+  int b_sub = 1, b_sub_seg = 0;
   __host__ __device__ int nseg_a() const { return a_nseg ? a_nseg : nseg; }
   __host__ __device__ int nseg_b() const { return b_nseg ? b_nseg : nseg; }
-  __host__ __device__ int seg_a(int s) const { return use_map ? a_map[s] : s % nseg_a(); }
-  __host__ __device__ int seg_b(int s) const { return use_map ? b_map[s] : s % nseg_b(); }
+  __host__ __device__ int total_segs() const { return nseg * b_sub; }
+  __host__ __device__ int seg_a(int s) const { s = s % nseg; return use_map ? a_map[s] : s % nseg_a(); }
+  __host__ __device__ int seg_b(int s) const {
+    const int sub = s / nseg; s = s % nseg;
+    return (use_map ? b_map[s] : s % nseg_b()) + sub * b_sub_seg;
+  }
 };
 
 // Round-to-nearest TF32 (cvt.rna): producers of tensor-core operands store rounded values so that the

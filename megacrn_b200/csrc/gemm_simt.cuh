@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) gemm_simt_kernel(GemmDesc g, Epi
   const float* A = g.A + (int64_t)bz * g.a_batch;
   const float* B = g.B + (int64_t)bz * g.b_batch;
   const int ktiles = (g.Kseg + SIMT_BK - 1) / SIMT_BK;
-  const int total = g.nseg * ktiles;
+  const int total = g.total_segs() * ktiles;
   const int per = (total + g.splits - 1) / g.splits;
   const int it0 = split * per, it1 = min(total, it0 + per);
   const bool a_kc = (g.a_k == 1), b_nc = (g.b_n == 1);

@@ -49,6 +49,8 @@ bool eligible(const GemmDesc& g) {
   if (g.prec_exact) return false;
   if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.B) & 15)) return false;
   if (g.M < 1 || g.N < 1 || g.Kseg < 1 || g.nseg > 16) return false;
+  if (g.b_sub == 2 && !(g.a_k == 1 && g.b_n == 1 && g.b_seg && !g.use_map && g.splits == 1)) return false;
+  if (g.b_sub > 2) return false;
   // A: exactly one of (K contiguous, M contiguous); the other stride 16-byte aligned
   if (g.a_k == 1) { if (!ok_stride(g.a_row)) return false; }
   else if (g.a_row == 1) { if (!ok_stride(g.a_k)) return false; }

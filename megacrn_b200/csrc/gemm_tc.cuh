@@ -24,6 +24,7 @@ constexpr uint32_t SLAB_BYTES = 32 * 128;       // [32 k-rows][128 B] slab of an
 struct TcParams {
   int M, N, Kseg, nseg, nbatch, splits, a_batched, b_batched;
   uint8_t a_map[16], b_map[16];   // K-segment -> operand segment (hi/lo splits, block buffers)
+  int b_sub_seg;                  // BSUB > 1: B sub-tile j reads segment b_map[seg] + j * b_sub_seg
   float* dbg;            // debug dump (mcrn_debug_tc_gemm): [0, STAGE floats) = raw smem stage 0 after TMA
 };
 extern float* g_dbg;     // host-side: non-null only inside mcrn_debug_tc_gemm
@@ -105,22 +106,29 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
          ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-template <int BN, int STAGES>
-constexpr size_t smem_bytes() { return (size_t)STAGES * (BM * BK * 4 + BN * BK * 4) + 1024; }
+// Sub-tiling (CTA-level register blocking of the shared-memory traffic, which is what bounds these GEMMs:
+// fp32 operands give a 128x128 tile only 32 FLOP per byte staged):
+//   MSUB = 2 : two 128-row A sub-tiles share every B stage (CTA tile 256 x BN, two accumulators)
+//   BSUB = 2 : two B sub-tiles (the TF32 hi and lo parts of the weights, `b_sub_seg` segments apart) multiply the
+//              same A stage and accumulate into the same accumulator, so A is staged once for hi+lo.
+template <int BN, int STAGES, int MSUB, int BSUB>
+constexpr size_t smem_bytes() { return (size_t)STAGES * (MSUB * BM * BK * 4 + BSUB * BN * BK * 4) + 1024; }
 
-template <bool A_K, bool B_K, int BN, int STAGES, class Epi>
-__global__ void __launch_bounds__(THREADS, 2)
+template <bool A_K, bool B_K, int BN, int STAGES, int MSUB, int BSUB, class Epi>
+__global__ void __launch_bounds__(THREADS, (smem_bytes<BN, STAGES, MSUB, BSUB>() <= 113 * 1024) ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p, Epi epi) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_slot;
-  constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = MSUB * A_BYTES + BSUB * B_BYTES;
+  constexpr uint32_t TMEM_COLS = MSUB * BN;
+  static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns: power of two");
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bz = blockIdx.z / p.splits, split = blockIdx.z - bz * p.splits;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * (BM * MSUB), n0 = blockIdx.x * BN;
   const int kt = (p.Kseg + BK - 1) / BK;
   const int total = p.nseg * kt;
   const int per = (total + p.splits - 1) / p.splits;
@@ -140,34 +148,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_slot;
-
-  if (p.dbg != nullptr && warp >= 2) {                   // debug: prefill the accumulator with a pattern
-    const int quarter = warp & 3;
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(-1000.0f - (float)(quarter * 32 + lane) - 0.001f * (c * 32 + j));
-      uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32);
-      asm volatile(
-          "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-          "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-          "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-          ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
-          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
-          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
-    }
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    tcgen05_fence_before();
-  }
-  if (p.dbg != nullptr) { __syncthreads(); tcgen05_fence_after(); }
 
   if (nit > 0) {
     if (warp == 0) {
@@ -181,18 +168,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_expect_tx(fb, STAGE_BYTES);
           const int it = it0 + i, seg = it / kt, k0 = (it - seg * kt) * BK;
           const int sa = p.a_map[seg], sb = p.b_map[seg];
-          const uint32_t a_dst = smem_base + (uint32_t)s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
-          if (A_K) {
-            tma_load_4d(a_dst, &tmA, fb, k0, m0, sa, bza);
-          } else {
+          const uint32_t a_dst = smem_base + (uint32_t)s * STAGE_BYTES, b_dst = a_dst + MSUB * A_BYTES;
 #pragma unroll
-            for (int j = 0; j < BM / 32; ++j) tma_load_4d(a_dst + j * SLAB_BYTES, &tmA, fb, m0 + 32 * j, k0, sa, bza);
+          for (int ms = 0; ms < MSUB; ++ms) {
+            if (A_K) {
+              tma_load_4d(a_dst + ms * A_BYTES, &tmA, fb, k0, m0 + ms * BM, sa, bza);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BM / 32; ++j)
+                tma_load_4d(a_dst + ms * A_BYTES + j * SLAB_BYTES, &tmA, fb, m0 + ms * BM + 32 * j, k0, sa, bza);
+            }
           }
-          if (B_K) {
-            tma_load_4d(b_dst, &tmB, fb, k0, n0, sb, bzb);
-          } else {
 #pragma unroll
-            for (int j = 0; j < BN / 32; ++j) tma_load_4d(b_dst + j * SLAB_BYTES, &tmB, fb, n0 + 32 * j, k0, sb, bzb);
+          for (int bs = 0; bs < BSUB; ++bs) {
+            const int sbb = sb + bs * p.b_sub_seg;
+            if (B_K) {
+              tma_load_4d(b_dst + bs * B_BYTES, &tmB, fb, k0, n0, sbb, bzb);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 32; ++j)
+                tma_load_4d(b_dst + bs * B_BYTES + j * SLAB_BYTES, &tmB, fb, n0 + 32 * j, k0, sbb, bzb);
+            }
           }
         }
       }
@@ -210,16 +206,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             p.dbg[STAGE_BYTES / 4] = __uint_as_float(tmem_base);
             p.dbg[STAGE_BYTES / 4 + 1] = __uint_as_float(smem_base);
           }
-          const uint32_t a_addr = smem_base + (uint32_t)s * STAGE_BYTES, b_addr = a_addr + A_BYTES;
+          const uint32_t a_addr = smem_base + (uint32_t)s * STAGE_BYTES, b_addr = a_addr + MSUB * A_BYTES;
 #pragma unroll
-          for (int kk = 0; kk < BK / 8; ++kk) {          // UMMA_K = 8 for tf32
-            const uint64_t ad = A_K ? make_smem_desc(a_addr + kk * 32, 16, 1024, 2) : make_smem_desc(a_addr + kk * 1024, SLAB_BYTES, 512, 1);
-            const uint64_t bd = B_K ? make_smem_desc(b_addr + kk * 32, 16, 1024, 2) : make_smem_desc(b_addr + kk * 1024, SLAB_BYTES, 512, 1);
-            tcgen05_mma_tf32(tmem_base, ad, bd, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+          for (int ms = 0; ms < MSUB; ++ms) {
+#pragma unroll
+            for (int bs = 0; bs < BSUB; ++bs) {
+#pragma unroll
+              for (int kk = 0; kk < BK / 8; ++kk) {      // UMMA_K = 8 for tf32
+                const uint32_t aa = a_addr + ms * A_BYTES, bb = b_addr + bs * B_BYTES;
+                const uint64_t ad = A_K ? make_smem_desc(aa + kk * 32, 16, 1024, 2) : make_smem_desc(aa + kk * 1024, SLAB_BYTES, 512, 1);
+                const uint64_t bd = B_K ? make_smem_desc(bb + kk * 32, 16, 1024, 2) : make_smem_desc(bb + kk * 1024, SLAB_BYTES, 512, 1);
+                tcgen05_mma_tf32(tmem_base + (uint32_t)(ms * BN), ad, bd, idesc, (i > 0 || kk > 0 || bs > 0) ? 1u : 0u);
+              }
+            }
           }
           tcgen05_commit(smem_u32(&empty_bar[s]));       // frees the smem slot when these MMAs retire
         }
-        tcgen05_commit(smem_u32(&tmem_full_bar));        // accumulator complete
+        tcgen05_commit(smem_u32(&tmem_full_bar));        // accumulator(s) complete
       }
     } else {                                             // ===== epilogue warps =====
       const int quarter = warp & 3;                      // TMEM lane quarter this warp may read
@@ -227,59 +230,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tcgen05_fence_after();
       // Each thread owns one accumulator ROW (TMEM lane).  Storing rows per thread would scatter every warp
       // store over 32 cache lines, so each 32x32 chunk is transposed through shared memory (the pipeline
-      // stages are idle once the accumulator is complete) and the epilogue functor runs with the 32 lanes
-      // on consecutive columns of a row (8 lanes x 4 columns = one 128-byte line per row, 4 rows per instruction):
+      // stages are idle once the accumulator is complete) and the epilogue functor runs with the lanes on
+      // consecutive columns of a row (8 lanes x 4 columns = one 128-byte line per row, 4 rows per instruction):
       // all its global loads/stores are 128-bit and fully coalesced.
       float* scr = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))) + quarter * (32 * 36);
       const int cq = (lane & 7) * 4, r0 = lane >> 3;       // this lane: 4 consecutive columns of rows r0, r0+4, ...
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        float v[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), v);
-        __syncwarp();
+      for (int ms = 0; ms < MSUB; ++ms) {
+        const int mrow0 = m0 + ms * BM + quarter * 32;
+        if (mrow0 >= p.M) break;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          float v[32];
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ms * BN + c * 32), v);
+          __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(&scr[lane * 36 + j]) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        __syncwarp();
-        const int col = n0 + c * 32 + cq;
-        if (col < p.N) {
-          const int nv = min(4, p.N - col);
-          const int rbase = m0 + quarter * 32 + r0;
-          bool done = false;
-          if constexpr (Epi::NP > 0) {
-            // two-phase fast path: issue the global loads of a whole batch of rows, then compute and store
-            if (nv == 4 && epi.fast4(bz, rbase, col)) {
-              constexpr int RB = Epi::NP <= 2 ? 8 : (Epi::NP <= 4 ? 4 : 2);
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(&scr[lane * 36 + j]) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          __syncwarp();
+          const int col = n0 + c * 32 + cq;
+          if (col < p.N) {
+            const int nv = min(4, p.N - col);
+            const int rbase = mrow0 + r0;
+            bool done = false;
+            if constexpr (Epi::NP > 0) {
+              // two-phase fast path: issue the global loads of a whole batch of rows, then compute and store
+              if (nv == 4 && epi.fast4(bz, rbase, col)) {
+                constexpr int RB = Epi::NP <= 2 ? 8 : (Epi::NP <= 4 ? 4 : 2);
 #pragma unroll
-              for (int b0 = 0; b0 < 8; b0 += RB) {
-                float4 pre[RB][Epi::NP];
+                for (int b0 = 0; b0 < 8; b0 += RB) {
+                  float4 pre[RB][Epi::NP];
 #pragma unroll
-                for (int i = 0; i < RB; ++i) {
-                  const int row = rbase + 4 * (b0 + i);
-                  if (row < p.M) epi.load4(bz, row, col, pre[i]);
-                }
+                  for (int i = 0; i < RB; ++i) {
+                    const int row = rbase + 4 * (b0 + i);
+                    if (row < p.M) epi.load4(bz, row, col, pre[i]);
+                  }
 #pragma unroll
-                for (int i = 0; i < RB; ++i) {
-                  const int rr = r0 + 4 * (b0 + i);
-                  const int row = m0 + quarter * 32 + rr;
-                  if (row < p.M) {
-                    const float4 t = *reinterpret_cast<const float4*>(&scr[rr * 36 + cq]);
-                    const float a4[4] = {t.x, t.y, t.z, t.w};
-                    epi.fin4(bz, row, col, pre[i], a4);
+                  for (int i = 0; i < RB; ++i) {
+                    const int rr = r0 + 4 * (b0 + i);
+                    const int row = mrow0 + rr;
+                    if (row < p.M) {
+                      const float4 t = *reinterpret_cast<const float4*>(&scr[rr * 36 + cq]);
+                      const float a4[4] = {t.x, t.y, t.z, t.w};
+                      epi.fin4(bz, row, col, pre[i], a4);
+                    }
                   }
                 }
+                done = true;
               }
-              done = true;
             }
-          }
-          if (!done) {
+            if (!done) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = r0 + 4 * i;
-              const int row = m0 + quarter * 32 + rr;
-              if (row < p.M) {
-                const float4 t = *reinterpret_cast<const float4*>(&scr[rr * 36 + cq]);
-                float a4[4] = {t.x, t.y, t.z, t.w};
-                epi.template apply<4>(bz, row, col, nv, a4);
+              for (int i = 0; i < 8; ++i) {
+                const int rr = r0 + 4 * i;
+                const int row = mrow0 + rr;
+                if (row < p.M) {
+                  const float4 t = *reinterpret_cast<const float4*>(&scr[rr * 36 + cq]);
+                  float a4[4] = {t.x, t.y, t.z, t.w};
+                  epi.template apply<4>(bz, row, col, nv, a4);
+                }
               }
             }
           }
@@ -290,7 +298,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
 }
 
@@ -299,10 +307,9 @@ int encode_tensor_map(CUtensorMap* out, const float* base, const uint64_t dims[4
                       const uint32_t box[4], bool mn_major);
 bool eligible(const GemmDesc& g);
 
-template <bool A_K, bool B_K, int BN, int STAGES, class Epi>
+template <bool A_K, bool B_K, int BN, int STAGES, int MSUB, int BSUB, class Epi>
 int launch(const GemmDesc& g, const Epi& epi, cudaStream_t st) {
   CUtensorMap ta, tb;
-  const uint64_t big = 1;
   {
     uint64_t dims[4], str[3];
     uint32_t box[4] = {32, 1, 1, 1};
@@ -312,7 +319,6 @@ int launch(const GemmDesc& g, const Epi& epi, cudaStream_t st) {
     dims[2] = aseg; str[1] = aseg > 1 ? g.a_seg * 4 : str[0] * dims[1];
     const int ab = g.a_batch ? g.nbatch : 1;
     dims[3] = ab; str[2] = ab > 1 ? g.a_batch * 4 : str[1] * dims[2];
-    (void)big;
     MCRN_TRY(encode_tensor_map(&ta, g.A, dims, str, box, !A_K));
   }
   {
@@ -320,7 +326,7 @@ int launch(const GemmDesc& g, const Epi& epi, cudaStream_t st) {
     uint32_t box[4] = {32, 1, 1, 1};
     if (B_K) { dims[0] = g.Kseg; dims[1] = g.N; str[0] = g.b_n * 4; box[1] = BN; }
     else { dims[0] = g.N; dims[1] = g.Kseg; str[0] = g.b_k * 4; box[1] = BK; }
-    const int bseg = g.b_seg ? g.nseg_b() : 1;
+    const int bseg = g.b_seg ? g.nseg_b() * (BSUB > 1 ? BSUB : 1) : 1;
     dims[2] = bseg; str[1] = bseg > 1 ? g.b_seg * 4 : str[0] * dims[1];
     const int bb = g.b_batch ? g.nbatch : 1;
     dims[3] = bb; str[2] = bb > 1 ? g.b_batch * 4 : str[1] * dims[2];
@@ -335,15 +341,16 @@ int launch(const GemmDesc& g, const Epi& epi, cudaStream_t st) {
   p.nbatch = g.nbatch; p.splits = g.splits;
   p.a_batched = g.a_batch ? 1 : 0;
   p.b_batched = g.b_batch ? 1 : 0;
+  p.b_sub_seg = g.b_sub_seg;
   p.dbg = g_dbg;
-  auto kern = gemm_tc_kernel<A_K, B_K, BN, STAGES, Epi>;
-  constexpr size_t smem = smem_bytes<BN, STAGES>();
+  auto kern = gemm_tc_kernel<A_K, B_K, BN, STAGES, MSUB, BSUB, Epi>;
+  constexpr size_t smem = smem_bytes<BN, STAGES, MSUB, BSUB>();
   static bool attr_set = false;
   if (!attr_set) {
     MCRN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM), g.nbatch * g.splits);
+  dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM * MSUB), g.nbatch * g.splits);
   MCRN_LAUNCH(kern, grid, THREADS, smem, st, ta, tb, p, epi);
   return MCRN_OK;
 }
@@ -352,10 +359,18 @@ template <class Epi>
 int gemm_tc(const GemmDesc& g, const Epi& epi, cudaStream_t st) {
   const bool a_k = (g.a_k == 1), b_k = (g.b_k == 1);
   const bool wide = g.N > 64;
-  if (a_k && b_k) return wide ? launch<true, true, 128, 3, Epi>(g, epi, st) : launch<true, true, 64, 4, Epi>(g, epi, st);
-  if (a_k && !b_k) return wide ? launch<true, false, 128, 3, Epi>(g, epi, st) : launch<true, false, 64, 4, Epi>(g, epi, st);
-  if (!a_k && b_k) return wide ? launch<false, true, 128, 3, Epi>(g, epi, st) : launch<false, true, 64, 4, Epi>(g, epi, st);
-  return wide ? launch<false, false, 128, 3, Epi>(g, epi, st) : launch<false, false, 64, 4, Epi>(g, epi, st);
+  if (a_k && b_k) return wide ? launch<true, true, 128, 3, 1, 1, Epi>(g, epi, st) : launch<true, true, 64, 4, 1, 1, Epi>(g, epi, st);
+  if (a_k && !b_k) return wide ? launch<true, false, 128, 3, 1, 1, Epi>(g, epi, st) : launch<true, false, 64, 4, 1, 1, Epi>(g, epi, st);
+  if (!a_k && b_k) return wide ? launch<false, true, 128, 3, 1, 1, Epi>(g, epi, st) : launch<false, true, 64, 4, 1, 1, Epi>(g, epi, st);
+  return wide ? launch<false, false, 128, 3, 1, 1, Epi>(g, epi, st) : launch<false, false, 64, 4, 1, 1, Epi>(g, epi, st);
+}
+
+// Weight contraction of the AGCN forward (A K-major = XP blocks, B MN-major = [hi | lo] weights, b_sub = 2):
+// 256 x BN CTA tiles, the hi and lo weight tiles share each A stage.
+template <class Epi>
+int gemm_tc_hilo(const GemmDesc& g, const Epi& epi, cudaStream_t st) {
+  if (g.N > 64) return launch<true, false, 128, 3, 2, 2, Epi>(g, epi, st);
+  return launch<true, false, 64, 4, 2, 2, Epi>(g, epi, st);
 }
 
 }  // namespace tc

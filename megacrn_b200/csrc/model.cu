@@ -91,7 +91,7 @@ static int propagate(const Geo& g, const float* S, float* xp, int C, cudaStream_
 static int cell_forward(const Geo& g, const float* S, const CellW& w, const CellBufs& b, float* h_out, float* h_mma,
                         cudaStream_t st) {
   const int Hs = w.Hs, NBX = g.NB + 1;
-  const int rnd = tf32_mode(), wseg = rnd ? 2 * NBX : NBX;
+  const int rnd = tf32_mode();
   const int64_t nH = g.R * Hs;
   // input block (input channels + bias) of both AGCNs of this step
   MCRN_LAUNCH(k_build_input_block, ew_grid(nH), 256, 0, st, b.xpin, b.xp_k, b.xp_n, g.NB, w.Cin, g.B, g.R, Hs, rnd,
@@ -99,7 +99,8 @@ static int cell_forward(const Geo& g, const float* S, const CellW& w, const Cell
   MCRN_TRY(propagate(g, S, b.xpg, Hs, st));
   {  // gate AGCN + sigmoid + z*h                                   model/MegaCRN.py:42-45
     GemmDesc q;
-    q.A = b.xpg; q.a_row = Hs; q.a_k = 1; q.a_seg = nH; q.nseg = wseg; q.a_nseg = NBX; q.Kseg = Hs; q.M = (int)g.R;
+    q.A = b.xpg; q.a_row = Hs; q.a_k = 1; q.a_seg = nH; q.nseg = NBX; q.Kseg = Hs; q.M = (int)g.R;
+    if (rnd) { q.b_sub = 2; q.b_sub_seg = NBX; }           // W = hi + lo, both applied to each A stage
     q.B = w.wg; q.b_seg = (int64_t)Hs * 2 * Hs; q.b_k = 2 * Hs; q.b_n = 1; q.N = 2 * Hs; q.prec_exact = dbg_exact(1);
     EpiGate e{Hs, b.hx, b.z, b.r, b.xpu, rnd};
     MCRN_TRY(gemm(q, e, st));
@@ -107,7 +108,8 @@ static int cell_forward(const Geo& g, const float* S, const CellW& w, const Cell
   MCRN_TRY(propagate(g, S, b.xpu, Hs, st));
   {  // update AGCN + tanh + blend                                  model/MegaCRN.py:46-47
     GemmDesc q;
-    q.A = b.xpu; q.a_row = Hs; q.a_k = 1; q.a_seg = nH; q.nseg = wseg; q.a_nseg = NBX; q.Kseg = Hs; q.M = (int)g.R;
+    q.A = b.xpu; q.a_row = Hs; q.a_k = 1; q.a_seg = nH; q.nseg = NBX; q.Kseg = Hs; q.M = (int)g.R;
+    if (rnd) { q.b_sub = 2; q.b_sub_seg = NBX; }
     q.B = w.wu; q.b_seg = (int64_t)Hs * Hs; q.b_k = Hs; q.b_n = 1; q.N = Hs; q.prec_exact = dbg_exact(1);
     EpiUpdate e{Hs, b.hx, b.r, b.hc, h_out, h_mma, rnd};
     MCRN_TRY(gemm(q, e, st));
