@@ -367,10 +367,15 @@ int gemm_tc(const GemmDesc& g, const Epi& epi, cudaStream_t st) {
 
 // Weight contraction of the AGCN forward (A K-major = XP blocks, B MN-major = [hi | lo] weights, b_sub = 2):
 // 256 x BN CTA tiles, the hi and lo weight tiles share each A stage.
+extern int g_hilo_cfg;    // tuning knob (MCRN_HILO_CFG): which sub-tiling the hi/lo contraction uses
 template <class Epi>
 int gemm_tc_hilo(const GemmDesc& g, const Epi& epi, cudaStream_t st) {
-  if (g.N > 64) return launch<true, false, 128, 3, 2, 2, Epi>(g, epi, st);
-  return launch<true, false, 64, 4, 2, 2, Epi>(g, epi, st);
+  if (g.N <= 64) return launch<true, false, 64, 4, 2, 2, Epi>(g, epi, st);
+  switch (g_hilo_cfg) {
+    case 1: return launch<true, false, 128, 2, 1, 2, Epi>(g, epi, st);   // 128 x 128, A shared by hi/lo, 2 CTAs/SM
+    case 2: return launch<true, false, 128, 4, 1, 2, Epi>(g, epi, st);   // same, 4 stages, 1 CTA/SM
+    default: return launch<true, false, 128, 3, 2, 2, Epi>(g, epi, st);  // 256 x 128, 1 CTA/SM
+  }
 }
 
 }  // namespace tc

@@ -88,6 +88,13 @@ static int propagate(const Geo& g, const float* S, float* xp, int C, cudaStream_
   return gemm(q, e, st);
 }
 
+// hi + lo weights: either both applied to each staged A tile (b_sub = 2) or as 2*NBX K-segments (MCRN_HILO_CFG=3)
+namespace tc { extern int g_hilo_cfg; }
+static inline void hilo(GemmDesc& q, int NBX) {
+  if (tc::g_hilo_cfg == 3) { q.nseg = 2 * NBX; q.a_nseg = NBX; }
+  else { q.b_sub = 2; q.b_sub_seg = NBX; }
+}
+
 static int cell_forward(const Geo& g, const float* S, const CellW& w, const CellBufs& b, float* h_out, float* h_mma,
                         cudaStream_t st) {
   const int Hs = w.Hs, NBX = g.NB + 1;
@@ -100,7 +107,7 @@ static int cell_forward(const Geo& g, const float* S, const CellW& w, const Cell
   {  // gate AGCN + sigmoid + z*h                                   model/MegaCRN.py:42-45
     GemmDesc q;
     q.A = b.xpg; q.a_row = Hs; q.a_k = 1; q.a_seg = nH; q.nseg = NBX; q.Kseg = Hs; q.M = (int)g.R;
-    if (rnd) { q.b_sub = 2; q.b_sub_seg = NBX; }           // W = hi + lo, both applied to each A stage
+    if (rnd) hilo(q, NBX);                                   // W = hi + lo
     q.B = w.wg; q.b_seg = (int64_t)Hs * 2 * Hs; q.b_k = 2 * Hs; q.b_n = 1; q.N = 2 * Hs; q.prec_exact = dbg_exact(1);
     EpiGate e{Hs, b.hx, b.z, b.r, b.xpu, rnd};
     MCRN_TRY(gemm(q, e, st));
@@ -109,7 +116,7 @@ static int cell_forward(const Geo& g, const float* S, const CellW& w, const Cell
   {  // update AGCN + tanh + blend                                  model/MegaCRN.py:46-47
     GemmDesc q;
     q.A = b.xpu; q.a_row = Hs; q.a_k = 1; q.a_seg = nH; q.nseg = NBX; q.Kseg = Hs; q.M = (int)g.R;
-    if (rnd) { q.b_sub = 2; q.b_sub_seg = NBX; }
+    if (rnd) hilo(q, NBX);
     q.B = w.wu; q.b_seg = (int64_t)Hs * Hs; q.b_k = Hs; q.b_n = 1; q.N = Hs; q.prec_exact = dbg_exact(1);
     EpiUpdate e{Hs, b.hx, b.r, b.hc, h_out, h_mma, rnd};
     MCRN_TRY(gemm(q, e, st));
@@ -327,17 +334,68 @@ static int acc_ds(const Geo& g, const float* dp, int64_t dp_row, const float* x,
   return gemm(q, e, st);
 }
 
+// ---- side stream: the dS accumulations only feed the supports backward at the very end, so they run on a second
+// stream concurrently with the recurrent chain (each of these GEMMs fills only part of the GPU).  Works eagerly
+// and under stream capture (the fork/join events become graph edges).
+struct Side {
+  cudaStream_t s = nullptr;
+  cudaEvent_t ready[3] = {nullptr, nullptr, nullptr};   // main -> side: buffer i has been written
+  cudaEvent_t freed[3] = {nullptr, nullptr, nullptr};   // side -> main: buffer i has been consumed
+  bool pending[3] = {false, false, false};
+  cudaEvent_t join = nullptr;
+};
+static Side g_side;
+static int side_init() {
+  if (g_side.s) return MCRN_OK;
+  MCRN_CUDA_OK(cudaStreamCreateWithFlags(&g_side.s, cudaStreamNonBlocking));
+  for (int i = 0; i < 3; ++i) {
+    MCRN_CUDA_OK(cudaEventCreateWithFlags(&g_side.ready[i], cudaEventDisableTiming));
+    MCRN_CUDA_OK(cudaEventCreateWithFlags(&g_side.freed[i], cudaEventDisableTiming));
+  }
+  MCRN_CUDA_OK(cudaEventCreateWithFlags(&g_side.join, cudaEventDisableTiming));
+  return MCRN_OK;
+}
+// main stream has just produced buffer i: let the side stream start on it
+static int side_begin(int i, cudaStream_t mainst) {
+  MCRN_CUDA_OK(cudaEventRecord(g_side.ready[i], mainst));
+  MCRN_CUDA_OK(cudaStreamWaitEvent(g_side.s, g_side.ready[i], 0));
+  return MCRN_OK;
+}
+// side stream is done with buffer i
+static int side_end(int i) {
+  MCRN_CUDA_OK(cudaEventRecord(g_side.freed[i], g_side.s));
+  g_side.pending[i] = true;
+  return MCRN_OK;
+}
+// main stream is about to overwrite buffer i
+static int side_wait(int i, cudaStream_t mainst) {
+  if (g_side.pending[i]) {
+    MCRN_CUDA_OK(cudaStreamWaitEvent(mainst, g_side.freed[i], 0));
+    g_side.pending[i] = false;
+  }
+  return MCRN_OK;
+}
+static int side_join(cudaStream_t mainst) {
+  for (int i = 0; i < 3; ++i) MCRN_TRY(side_wait(i, mainst));
+  return MCRN_OK;
+}
+
 // One cell backward.  dH (in) = grad of h'; dH_out (out) = grad of h; if dxin != null also writes
 // d(xin)[N][B][Cin].
 static int cell_backward(const Geo& g, const Plan& p, float* ws, const float* S, const CellW& w, const CellBufs& b,
                          float* dU, float* dG, const float* dH, float* dH_out, float* dxin, cudaStream_t st) {
   const int Hs = w.Hs;
   const int64_t nH = g.R * Hs;
-  float *dXP = ws + p.dXP, *dHp = ws + p.dHp;
+  float *dXP = ws + p.dXP, *dXP2 = ws + p.dXP2, *dHp = ws + p.dHp;
   float *dXPin = ws + p.dXPin, *dS = ws + p.dS;
+  cudaStream_t sd = g_side.s;
   MCRN_LAUNCH(k_bwd_du, ew_grid(nH), 256, 0, st, dH, b.r, b.hc, dU, nH, tf32_mode());
   // ---- update AGCN: dXP = dU Wu^T ; dZH = dXP0 + S^T dXP[1..] fused with the gate backward -> dG, dh_part ----
+  MCRN_TRY(side_wait(0, st));
   MCRN_TRY(make_dxp(g, dU, Hs, w.wu, Hs, dXP, ws + p.dIBu, st));
+  MCRN_TRY(side_begin(0, st));
+  MCRN_TRY(acc_ds(g, dXP + nH, (int64_t)g.B * Hs, b.xpu, (int64_t)g.B * Hs, g.B * Hs, dS, sd));
+  MCRN_TRY(side_end(0));
   {
     GemmDesc q;
     q.prec_exact = dbg_exact(4);
@@ -346,16 +404,21 @@ static int cell_backward(const Geo& g, const Plan& p, float* ws, const float* S,
     EpiDG e{dXP, dH, b.hx, b.z, b.r, b.hc, dG, dHp, Hs, (int64_t)g.B * Hs, tf32_mode()};
     MCRN_TRY(gemm(q, e, st));
   }
-  MCRN_TRY(acc_ds(g, dXP + nH, (int64_t)g.B * Hs, b.xpu, (int64_t)g.B * Hs, g.B * Hs, dS, st));
   // ---- gate AGCN ----
-  MCRN_TRY(make_dxp(g, dG, 2 * Hs, w.wg, Hs, dXP, nullptr, st));
-  MCRN_TRY(propagate_T(g, S, dXP, Hs, dHp, dH_out, st));
-  MCRN_TRY(acc_ds(g, dXP + nH, (int64_t)g.B * Hs, b.xpg, (int64_t)g.B * Hs, g.B * Hs, dS, st));
+  MCRN_TRY(side_wait(1, st));
+  MCRN_TRY(make_dxp(g, dG, 2 * Hs, w.wg, Hs, dXP2, nullptr, st));
+  MCRN_TRY(side_begin(1, st));
+  MCRN_TRY(acc_ds(g, dXP2 + nH, (int64_t)g.B * Hs, b.xpg, (int64_t)g.B * Hs, g.B * Hs, dS, sd));
+  MCRN_TRY(side_end(1));
+  MCRN_TRY(propagate_T(g, S, dXP2, Hs, dHp, dH_out, st));
   // ---- input channels: d(input block) of both AGCNs -> dXPin [NB][R][Cin] ----
   const int64_t nIn = (int64_t)g.NB * g.R * w.Cin;
-  MCRN_LAUNCH(k_repack_dib, ew_grid(nIn), 256, 0, st, ws + p.dIBu, dXP + (int64_t)g.NB * nH, g.NB, w.Cin, g.R, Hs, dXPin,
+  MCRN_TRY(side_wait(2, st));
+  MCRN_LAUNCH(k_repack_dib, ew_grid(nIn), 256, 0, st, ws + p.dIBu, dXP2 + (int64_t)g.NB * nH, g.NB, w.Cin, g.R, Hs, dXPin,
               tf32_mode());
-  MCRN_TRY(acc_ds(g, dXPin + g.R * w.Cin, (int64_t)g.B * w.Cin, b.xpin, b.xp_n, g.B * w.Cin, dS, st));
+  MCRN_TRY(side_begin(2, st));
+  MCRN_TRY(acc_ds(g, dXPin + g.R * w.Cin, (int64_t)g.B * w.Cin, b.xpin, b.xp_n, g.B * w.Cin, dS, sd));
+  MCRN_TRY(side_end(2));
   if (dxin) MCRN_TRY(propagate_T(g, S, dXPin, w.Cin, nullptr, dxin, st));
   return MCRN_OK;
 }
@@ -434,6 +497,7 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
                   const float* d_hatt, const float* d_query, const float* d_pos, const float* d_neg,
                   const mcrn_params* grads, float* ws, cudaStream_t st) {
   const float* S = ws + p.Sr;     // tensor-core copy of the supports (equal to the exact ones in SIMT mode)
+  MCRN_TRY(side_init());
   // zero accumulators and the directly-accumulated outputs
   MCRN_CUDA_OK(cudaMemsetAsync(ws + p.acc_begin, 0, (p.acc_end - p.acc_begin) * sizeof(float), st));
   MCRN_CUDA_OK(cudaMemsetAsync(grads->memory, 0, (size_t)g.M * g.d * sizeof(float), st));
@@ -508,6 +572,7 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
     MCRN_TRY(acc_dw_all(g, ws + p.enc_xpu, (int64_t)p.enc_xp_sz, g.T_in, g.H, dU_all, g.H, ws + p.a_e_wu, st));
     MCRN_TRY(acc_dw_all(g, ws + p.enc_xpg, (int64_t)p.enc_xp_sz, g.T_in, g.H, dG_all, 2 * g.H, ws + p.a_e_wg, st));
   }
+  MCRN_TRY(side_join(st));        // all dS contributions have landed
   MCRN_TRY(supports_backward(g, p, ws, prm, grads, st));
   // ---- un-fold weight gradients into the reference layout ----
   MCRN_LAUNCH(k_unfold_grads, 128, 256, 0, st, ws + p.a_e_wg, grads->enc_gate_w, grads->enc_gate_b, g.Cin, g.H, 2 * g.H, g.cheb_k);

@@ -24,7 +24,7 @@ struct Plan {
   // per-slot sizes (floats)
   size_t enc_xp_sz, enc_v_sz, dec_xpin_sz, dec_xp_sz, dec_v_sz;
   // ---- backward temporaries -------------------------------------------------
-  size_t dH, dXP, dIBu, dHp, dXPin, dXin, mq_dv, mq_dsc, mq_dq, dHenc;
+  size_t dH, dXP, dXP2, dIBu, dHp, dXPin, dXin, mq_dv, mq_dsc, mq_dq, dHenc;   // dXP: update-AGCN blocks, dXP2: gate-AGCN blocks
   size_t e_dU, e_dG, d_dU, d_dG;         // dU_t / dG_t of every step ([T][R][Hs] / [T][R][2Hs]): weight gradients are one GEMM per AGCN over all steps
   size_t acc_begin, acc_end;             // zeroed at the start of backward
   size_t dS, a_e_wg, a_e_wu, a_d_wg, a_d_wu;
@@ -90,6 +90,7 @@ static inline int make_plan(const Geo& g, bool save, Plan* p) {
     p->d_dU = take((size_t)g.T_out * R * g.D);
     p->d_dG = take((size_t)g.T_out * R * 2 * g.D);
     p->dXP = take((NB + 1) * R * g.D);
+    p->dXP2 = take((NB + 1) * R * g.D);
     p->dIBu = take(R * g.D);
     p->dHp = take(R * g.D);
     p->dXPin = take(NB * R * Cm);
