@@ -12,6 +12,7 @@ namespace mcrn {
 namespace tc {
 
 float* g_dbg = nullptr;
+int g_pdl = getenv("MCRN_PDL") ? atoi(getenv("MCRN_PDL")) : 0;
 // 3 = hi/lo as 2*NBX K-segments on 128x128 tiles, 2 CTAs/SM: measured fastest at C2 (7.68 ms/step vs 7.86 / 7.94 / 8.07
 // for the A-sharing variants 1 / 2 / 0): these GEMMs are bound by per-CTA latency, not by staged bytes.
 int g_hilo_cfg = getenv("MCRN_HILO_CFG") ? atoi(getenv("MCRN_HILO_CFG")) : 3;

@@ -28,6 +28,7 @@ struct TcParams {
   float* dbg;            // debug dump (mcrn_debug_tc_gemm): [0, STAGE floats) = raw smem stage 0 after TMA
 };
 extern float* g_dbg;     // host-side: non-null only inside mcrn_debug_tc_gemm
+extern int g_pdl;        // MCRN_PDL=1: launch the GEMM kernels with programmatic dependent launch
 
 // ---- PTX wrappers -----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -135,6 +136,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int it0 = split * per;
   const int nit = max(0, min(total, it0 + per) - it0);
 
+  // One pipeline stage of TMA loads for local k-iteration i (executed by the producer thread only).
+  auto produce = [&](int i) {
+    const int s = i % STAGES;
+    const uint32_t fb = smem_u32(&full_bar[s]);
+    mbar_expect_tx(fb, STAGE_BYTES);
+    const int bza = bz * p.a_batched, bzb = bz * p.b_batched;
+    const int it = it0 + i, seg = it / kt, k0 = (it - seg * kt) * BK;
+    const int sa = p.a_map[seg], sb = p.b_map[seg];
+    const uint32_t a_dst = smem_base + (uint32_t)s * STAGE_BYTES, b_dst = a_dst + MSUB * A_BYTES;
+#pragma unroll
+    for (int ms = 0; ms < MSUB; ++ms) {
+      if (A_K) {
+        tma_load_4d(a_dst + ms * A_BYTES, &tmA, fb, k0, m0 + ms * BM, sa, bza);
+      } else {
+#pragma unroll
+        for (int j = 0; j < BM / 32; ++j)
+          tma_load_4d(a_dst + ms * A_BYTES + j * SLAB_BYTES, &tmA, fb, m0 + ms * BM + 32 * j, k0, sa, bza);
+      }
+    }
+#pragma unroll
+    for (int bs = 0; bs < BSUB; ++bs) {
+      const int sbb = sb + bs * p.b_sub_seg;
+      if (B_K) {
+        tma_load_4d(b_dst + bs * B_BYTES, &tmB, fb, k0, n0, sbb, bzb);
+      } else {
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j)
+          tma_load_4d(b_dst + bs * B_BYTES + j * SLAB_BYTES, &tmB, fb, n0 + 32 * j, k0, sbb, bzb);
+      }
+    }
+  };
+
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -146,6 +179,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_init(smem_u32(&tmem_full_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // Programmatic dependent launch: everything above overlapped the previous kernel's tail; its results are
+    // needed from here on (no-op when the kernel was launched without the PDL attribute).
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // The first STAGES loads need no free-slot handshake: issue them before the TMEM allocation / CTA barrier.
+    const int pre = nit < STAGES ? nit : STAGES;
+    for (int i = 0; i < pre; ++i) produce(i);
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(TMEM_COLS) : "memory");
@@ -155,41 +194,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // every CTA of this grid is resident or done once all have reached this point: let the next kernel's CTAs start
+  // their own prologue (they block in griddepcontrol.wait until this grid has completed and flushed)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (nit > 0) {
     if (warp == 0) {
-      if (lane == 0) {                                   // ===== TMA producer =====
-        const int bza = bz * p.a_batched, bzb = bz * p.b_batched;
-        for (int i = 0; i < nit; ++i) {
-          const int s = i % STAGES;
+      if (lane == 0) {                                   // ===== TMA producer (stages 0..STAGES-1 already in flight) =====
+        for (int i = STAGES; i < nit; ++i) {
           const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
-          const uint32_t fb = smem_u32(&full_bar[s]);
-          mbar_expect_tx(fb, STAGE_BYTES);
-          const int it = it0 + i, seg = it / kt, k0 = (it - seg * kt) * BK;
-          const int sa = p.a_map[seg], sb = p.b_map[seg];
-          const uint32_t a_dst = smem_base + (uint32_t)s * STAGE_BYTES, b_dst = a_dst + MSUB * A_BYTES;
-#pragma unroll
-          for (int ms = 0; ms < MSUB; ++ms) {
-            if (A_K) {
-              tma_load_4d(a_dst + ms * A_BYTES, &tmA, fb, k0, m0 + ms * BM, sa, bza);
-            } else {
-#pragma unroll
-              for (int j = 0; j < BM / 32; ++j)
-                tma_load_4d(a_dst + ms * A_BYTES + j * SLAB_BYTES, &tmA, fb, m0 + ms * BM + 32 * j, k0, sa, bza);
-            }
-          }
-#pragma unroll
-          for (int bs = 0; bs < BSUB; ++bs) {
-            const int sbb = sb + bs * p.b_sub_seg;
-            if (B_K) {
-              tma_load_4d(b_dst + bs * B_BYTES, &tmB, fb, k0, n0, sbb, bzb);
-            } else {
-#pragma unroll
-              for (int j = 0; j < BN / 32; ++j)
-                tma_load_4d(b_dst + bs * B_BYTES + j * SLAB_BYTES, &tmB, fb, n0 + 32 * j, k0, sbb, bzb);
-            }
-          }
+          mbar_wait(smem_u32(&empty_bar[i % STAGES]), ph ^ 1u);
+          produce(i);
         }
       }
     } else if (warp == 1) {
@@ -351,7 +367,19 @@ int launch(const GemmDesc& g, const Epi& epi, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM * MSUB), g.nbatch * g.splits);
-  MCRN_LAUNCH(kern, grid, THREADS, smem, st, ta, tb, p, epi);
+  if (!g_pdl) {
+    MCRN_LAUNCH(kern, grid, THREADS, smem, st, ta, tb, p, epi);
+    return MCRN_OK;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ta, tb, p, epi);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (le != cudaSuccess) { set_error("cudaLaunchKernelEx(gemm_tc_kernel) failed: %s", cudaGetErrorString(le)); return MCRN_ERR_CUDA; }
   return MCRN_OK;
 }
 
