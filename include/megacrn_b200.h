@@ -179,6 +179,10 @@ int mcrn_set_engine(int engine);
 int mcrn_get_engine(void);
 /* Debug: bit i forces GEMM call-site class i onto the SIMT engine (see model.cu). */
 int mcrn_set_debug_mask(int mask);
+/* Forward AGCN as ONE fused kernel per AGCN call (graph convolution + weight contraction + gate/update tail;
+ * csrc/agcn_fused.cuh) where the hidden width is 64 or 128: fused = 1 (default) / 0 = per-stage GEMM kernels.
+ * weight_parts: 2 = TF32 hi + lo residual of the weights (default), 1 = hi only. */
+int mcrn_set_fused(int fused, int weight_parts);
 
 #ifdef __cplusplus
 }

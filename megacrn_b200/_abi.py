@@ -66,6 +66,8 @@ def load() -> C.CDLL:
     lib.mcrn_launch_count.restype = C.c_uint64
     lib.mcrn_set_engine.argtypes = [C.c_int]
     lib.mcrn_get_engine.restype = C.c_int
+    lib.mcrn_set_fused.restype = C.c_int
+    lib.mcrn_set_fused.argtypes = [C.c_int, C.c_int]
     lib.mcrn_support_ld.argtypes = [C.c_int]
     lib.mcrn_workspace_bytes.restype = C.c_size_t
     lib.mcrn_workspace_bytes.argtypes = [C.POINTER(Dims), C.c_uint32]

@@ -3,11 +3,13 @@
 // fused epilogues plus the small HBM-bound kernels.  The decomposition is the one proven in
 // tests/kernel_spec.py; reference lines are cited per stage.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <unordered_map>
 
 #include "engine.cuh"
+#include "agcn_fused.cuh"
 #include "plan.cuh"
 #include "loss.cuh"
 #include "small_kernels.cuh"
@@ -95,6 +97,22 @@ static inline void hilo(GemmDesc& q, int NBX) {
   else { q.b_sub = 2; q.b_sub_seg = NBX; }
 }
 
+// Fused AGCN kernel (agcn_fused.cuh): propagation + weight contraction + gate/update tail in one launch per AGCN.
+// g_fused: 0 = off (per-stage GEMMs), 1 = on where the shape is instantiated.  g_fused_parts: 2 = hi + lo weights, 1 = hi only.
+int g_fused = getenv("MCRN_FUSED") ? atoi(getenv("MCRN_FUSED")) : 1;
+int g_fused_parts = getenv("MCRN_FUSED_PARTS") ? atoi(getenv("MCRN_FUSED_PARTS")) : 2;
+
+template <int HS>
+static int cell_forward_fused(const Geo& g, const float* S, const CellW& w, const CellBufs& b, float* h_out, float* h_mma,
+                              cudaStream_t st) {
+  const int save = b.z != nullptr ? 1 : 0;
+  EpiGate eg{HS, b.hx, b.z, b.r, b.xpu, 1};
+  MCRN_TRY((fused::launch_agcn_fused<HS, 2 * HS>(g.N, g.B, g.KS, g.ldS, S, b.xpg, w.wg, g_fused_parts, save, eg, st)));
+  EpiUpdate eu{HS, b.hx, b.r, b.hc, h_out, h_mma, 1};
+  MCRN_TRY((fused::launch_agcn_fused<HS, HS>(g.N, g.B, g.KS, g.ldS, S, b.xpu, w.wu, g_fused_parts, save, eu, st)));
+  return MCRN_OK;
+}
+
 static int cell_forward(const Geo& g, const float* S, const CellW& w, const CellBufs& b, float* h_out, float* h_mma,
                         cudaStream_t st) {
   const int Hs = w.Hs, NBX = g.NB + 1;
@@ -103,6 +121,10 @@ static int cell_forward(const Geo& g, const float* S, const CellW& w, const Cell
   // input block (input channels + bias) of both AGCNs of this step
   MCRN_LAUNCH(k_build_input_block, ew_grid(nH), 256, 0, st, b.xpin, b.xp_k, b.xp_n, g.NB, w.Cin, g.B, g.R, Hs, rnd,
               b.xpg + (int64_t)g.NB * nH, b.xpu + (int64_t)g.NB * nH);
+  if (rnd && g_fused && !(g_simt_mask & 3) && fused::fused_eligible(g.N, g.B, Hs, 2 * Hs, S, b.xpg, w.wg) &&
+      fused::fused_eligible(g.N, g.B, Hs, Hs, S, b.xpu, w.wu)) {
+    return Hs == 64 ? cell_forward_fused<64>(g, S, w, b, h_out, h_mma, st) : cell_forward_fused<128>(g, S, w, b, h_out, h_mma, st);
+  }
   MCRN_TRY(propagate(g, S, b.xpg, Hs, st));
   {  // gate AGCN + sigmoid + z*h                                   model/MegaCRN.py:42-45
     GemmDesc q;

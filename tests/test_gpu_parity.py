@@ -266,6 +266,40 @@ def test_batch_split_invariance(engine):
         assert rel_l2(torch.cat([u, v]).cpu(), f.cpu()) < 1e-5
 
 
+@pytest.mark.parametrize("N,H,dm,B,T", [(207, 64, 64, 4, 3), (300, 64, 64, 3, 2), (130, 32, 32, 2, 2), (100, 128, 64, 2, 2)])
+def test_fused_agcn_kernel_matches_per_stage_path(N, H, dm, B, T):
+    """csrc/agcn_fused.cuh (graph conv + weight contraction + gate tail in one kernel, P_k kept in TMEM) against the
+    per-stage tcgen05 GEMM path of the same library: same TF32 rounding points, different accumulation order only.
+    (130, 32, 32): encoder per-stage (H=32), decoder fused (D=64); (100, 128, 64): encoder fused, decoder per-stage."""
+    from megacrn_b200 import _abi
+    lib = _abi.load()
+    d = O.Dims(num_nodes=N, horizon=T, rnn_units=H, mem_dim=dm)
+    p = O.init_params(d, seed=1)
+    x, y_cov, labels = O.synthetic_batch(d, B, T, seed=8)
+    flags = [t % 2 == 0 for t in range(T)]
+    dv = _dev()
+    gen = torch.Generator().manual_seed(3)
+    res = {}
+    try:
+        for fused, parts in ((0, 2), (1, 2), (1, 1)):
+            assert lib.mcrn_set_fused(fused, parts) == 0
+            m = _model(d, p).train()
+            outs = m(x.to(dv), y_cov.to(dv), labels.to(dv), teacher_forcing=flags)
+            if (fused, parts) == (0, 2):
+                ups = [torch.randn(outs[0].shape, generator=gen).to(dv), torch.randn(outs[2].shape, generator=gen).to(dv)]
+            torch.autograd.backward([outs[0], outs[2]], ups)
+            res[(fused, parts)] = ([o.detach().cpu() for o in outs[:3]], {k: v.grad.cpu() for k, v in m.named_parameters()})
+    finally:
+        lib.mcrn_set_fused(1, 2)
+    ref_o, ref_g = res[(0, 2)]
+    for (fused, parts), tol_o, tol_g in (((1, 2), 1e-4, 1e-3), ((1, 1), 1e-3, 4e-3)):
+        got_o, got_g = res[(fused, parts)]
+        for k, a, b in zip(OUT_NAMES[:3], got_o, ref_o):
+            assert rel_l2(a, b) < tol_o, (parts, k, rel_l2(a, b))
+        for k in ref_g:
+            assert rel_l2(got_g[k], ref_g[k]) < tol_g, (parts, k, rel_l2(got_g[k], ref_g[k]))
+
+
 def test_fused_trainer_loss_matches_torch():
     from megacrn_b200 import _abi
     from megacrn_b200.train_step import fused_trainer_loss
