@@ -179,10 +179,15 @@ int mcrn_set_engine(int engine);
 int mcrn_get_engine(void);
 /* Debug: bit i forces GEMM call-site class i onto the SIMT engine (see model.cu). */
 int mcrn_set_debug_mask(int mask);
-/* Forward AGCN as ONE fused kernel per AGCN call (graph convolution + weight contraction + gate/update tail;
- * csrc/agcn_fused.cuh) where the hidden width is 64 or 128: fused = 1 (default) / 0 = per-stage GEMM kernels.
- * weight_parts: 2 = TF32 hi + lo residual of the weights (default), 1 = hi only. */
+/* Forward AGCN as ONE fused kernel per AGCN call (graph convolution + weight contraction + gate/update tail) where the
+ * hidden width is 64 or 128: fused = 2 (default) fp16 operands / fp32 accumulate (csrc/agcn_fused_h.cuh), 1 = TF32
+ * operands (csrc/agcn_fused.cuh), 0 = per-stage GEMM kernels.
+ * weight_parts: 2 = hi + lo residual of the weights (default), 1 = hi only. */
 int mcrn_set_fused(int fused, int weight_parts);
+/* Debug aid (tools/fused_timeline.py): while device_slots != NULL the `which`-th fused AGCN launch after this call
+ * (-1 = every launch) records clock64 timestamps of CTA (0,0) into it (512 x int64; slot map in csrc/agcn_fused.cuh).
+ * NULL switches the recording off. */
+int mcrn_debug_fused_timeline(long long* device_slots, int which);
 
 #ifdef __cplusplus
 }

@@ -66,6 +66,8 @@ def load() -> C.CDLL:
     lib.mcrn_launch_count.restype = C.c_uint64
     lib.mcrn_set_engine.argtypes = [C.c_int]
     lib.mcrn_get_engine.restype = C.c_int
+    lib.mcrn_debug_fused_timeline.restype = C.c_int
+    lib.mcrn_debug_fused_timeline.argtypes = [C.c_void_p, C.c_int]
     lib.mcrn_set_fused.restype = C.c_int
     lib.mcrn_set_fused.argtypes = [C.c_int, C.c_int]
     lib.mcrn_support_ld.argtypes = [C.c_int]

@@ -29,7 +29,18 @@ struct FusedParams {
   int nparts;          // 1 = TF32 hi weights only, 2 = hi + lo residual
   float* xp_save;      // training: base of the XP buffer [NB+1][R][HS]; P_k is stored to block 1+k.  null = eval
   int64_t blk_stride;  // R * HS
+  long long* dbg;      // debug: clock64 timestamps of CTA (0,0) (mcrn_debug_fused_timeline); null in production
 };
+extern long long* g_dbg_timeline;   // host side: non-null only while mcrn_debug_fused_timeline is armed
+extern int g_dbg_which, g_dbg_count;
+
+// timeline slots: [0] start, [1] after prologue, [2 + it] MMA issuer: operands of item `it` landed (up to 200 items),
+// [210 + 4k .. ] rounding warp 2: p_full seen / rounded+stored / (2 unused), [230] acc_full seen, [231] epilogue done,
+// [232] producer done issuing, [233] MMA issuer done issuing, [240 + it] producer: slot free for item `it`
+#define MCRN_TL(slot)                                                      \
+  do {                                                                     \
+    if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0) p.dbg[(slot)] = clock64(); \
+  } while (0)
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -137,6 +148,7 @@ agcn_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant
   const int m0 = blockIdx.x * BM, b = blockIdx.y;
   const int kb1 = (p.N + BK - 1) / BK;
   const int NBLK = p.KS + 1;                         // weight segments per part: NB + 1 = KS + 2; NBLK = index of the input block
+  if (threadIdx.x == 0) MCRN_TL(0);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmS) : "memory");
@@ -164,6 +176,7 @@ agcn_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  if (threadIdx.x == 0) MCRN_TL(1);
 
   if (warp == 0) {
     if (lane == 0) {                                     // ===== TMA producer =====
@@ -171,6 +184,7 @@ agcn_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant
       for_each_item<C::KB2>(p.KS, kb1, p.nparts, [&](int type, int k, int j, int part) {
         const int s = it % NST;
         if (it >= NST) mbar_wait_b(smem_u32(&empty_bar[s]), (((uint32_t)(it / NST)) & 1u) ^ 1u);
+        if (it < 200) MCRN_TL(240 + it);
         const uint32_t fb = smem_u32(&full_bar[s]);
         const uint32_t a_dst = smem_base + (uint32_t)s * C::STAGE, b_dst = a_dst + C::A_SLOT;
         if (type == ITEM_P) {
@@ -193,6 +207,7 @@ agcn_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant
         }
         ++it;
       });
+      MCRN_TL(232);
     }
   } else if (warp == 1) {
     if (lane == 0) {                                     // ===== MMA issuer =====
@@ -204,6 +219,7 @@ agcn_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant
         const int s = it % NST;
         mbar_wait_b(smem_u32(&full_bar[s]), ((uint32_t)(it / NST)) & 1u);
         tcgen05_fence_after();
+        if (it < 200) MCRN_TL(2 + it);
         const uint32_t a_addr = smem_base + (uint32_t)s * C::STAGE, b_addr = a_addr + C::A_SLOT;
         const uint32_t pbuf = tmem_base + ((k & 1) ? C::TM_P1 : C::TM_P0);
         if (type == ITEM_P) {
@@ -240,6 +256,7 @@ agcn_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant
         ++it;
       });
       tcgen05_commit(smem_u32(&acc_full_bar));
+      MCRN_TL(233);
     }
   } else {                                               // ===== rounding + epilogue warps =====
     const int quarter = warp & 3;                        // TMEM lane quarter this warp may access
@@ -251,6 +268,7 @@ agcn_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant
     for (int k = 0; k < p.KS; ++k) {
       mbar_wait_b(smem_u32(&p_full_bar[k & 1]), ((uint32_t)(k >> 1)) & 1u);
       tcgen05_fence_after();
+      if (warp == 2 && lane == 0 && k < 5) MCRN_TL(210 + 4 * k);
       const uint32_t pbuf = tmem_base + ((k & 1) ? C::TM_P1 : C::TM_P0) + lane_off;
 #pragma unroll 1
       for (int c = 0; c < HS / 32; ++c) {
@@ -277,10 +295,12 @@ agcn_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&p_ready_bar[k & 1]));
+      if (warp == 2 && lane == 0 && k < 5) MCRN_TL(211 + 4 * k);
     }
     // ---- epilogue: accumulator -> gate / update math (rows = (node, b), all O columns) ----
     mbar_wait_b(smem_u32(&acc_full_bar), 0);
     tcgen05_fence_after();
+    if (warp == 2 && lane == 0) MCRN_TL(230);
     if (node0 < p.N) {
 #pragma unroll 1
       for (int c = 0; c < O / 32; ++c) {
@@ -330,6 +350,7 @@ agcn_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant
       }
     }
   }
+  if (warp == 2 && lane == 0) MCRN_TL(231);
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -377,6 +398,11 @@ int launch_agcn_fused(int N, int B, int KS, int ldS, const float* S, float* xp, 
   p.N = N; p.B = B; p.KS = KS; p.nparts = nparts;
   p.xp_save = save ? xp : nullptr;
   p.blk_stride = R * HS;
+  p.dbg = nullptr;
+  if (g_dbg_timeline != nullptr) {
+    if (g_dbg_which < 0 || g_dbg_count == g_dbg_which) p.dbg = g_dbg_timeline;
+    ++g_dbg_count;
+  }
   auto kern = agcn_fused_kernel<HS, O, Epi>;
   static bool attr_set = false;
   if (!attr_set) {

@@ -1,0 +1,506 @@
+// Fused AGCN forward, fp16-operand version (the default forward path for hidden widths 64 / 128).
+//
+// Same structure as agcn_fused.cuh -- per CTA (128-node tile, batch element b):
+//     MMA1   P_k[128 x HS] = S_k[tile rows, :] * X[:, b, :]                 (tcgen05.mma.kind::f16, fp32 accumulate, TMEM)
+//     round  P_k -> fp16 pairs, packed IN PLACE in TMEM (tcgen05.ld / cvt.rn.f16x2 / tcgen05.st)
+//     MMA2   acc[128 x O] += P_k * W_k   (A = packed P_k straight from TMEM)  + X_tile * W_0 + IB_tile * W_NB  (A in smem)
+//     epilogue: sigmoid / tanh / GRU algebra (model/MegaCRN.py:43-47), writes the fp32 tensors the backward needs and the
+//               fp16 operand copies (row-major and node-transposed) the next fused launch reads
+// -- but every tensor-core operand is stored in HALF precision.  fp16 has the same 11-bit significand as TF32, so the
+// numerics match the TF32 path (all forward operands are O(1): softmax supports, states in (-1,1), inputs, weights), while
+// each operand byte carries twice the work: the kernel is bound by the L2 -> shared-memory fill rate (~32 B/clk/SM
+// measured), and kind::f16 also runs at twice the kind::tf32 MMA rate.  The weights keep the hi + lo split
+// (hi = fp16(W), lo = fp16(W - hi)).  All operands are K-major with the 128-byte swizzle:
+//     S16  [KS][N][ld16]        supports                       A of MMA1   box [64 k][128 m]
+//     X16T [B][HS][ldT]         state, node index contiguous   B of MMA1   box [64 k][HS n]
+//     X16  [R][HS], IB16 [R][HS] state / input block rows      A of MMA2 (identity + input segments)  box [64 k][1][128 m]
+//     W16  [parts][KS+2][O][HS] folded weights, transposed     B of MMA2   box [64 k][O n]
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = P rounding + epilogue,
+// warps 6..9 = epilogue only (each TMEM lane quarter is served by two warps that split the column chunks).
+#pragma once
+
+#include <cuda_fp16.h>
+
+#include "agcn_fused.cuh"
+
+namespace mcrn {
+namespace fusedh {
+
+using namespace tc;
+using fused::mbar_arrive;
+using fused::mbar_wait_b;
+using fused::pow2_cols;
+using fused::tmem_wait_st;
+using fused::ITEM_P;
+using fused::ITEM_SS;
+using fused::ITEM_TS;
+
+constexpr int FTHREADS = 320;
+constexpr int BKH = 64;                         // halves per k-block = one 128-byte swizzle row
+
+struct HParams {
+  int N, B, KS, nparts;
+  float* xp_save;       // training: fp32 XP buffer [KS+2][R][HS]; the (fp16-rounded) P_k goes to block 1+k.  null = eval
+  int64_t blk_stride;   // R * HS
+  long long* dbg;       // debug timeline (see agcn_fused.cuh)
+};
+
+__device__ __forceinline__ void tcgen05_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+// Instruction descriptor, kind::f16: D = F32 (bits [4,6) = 1), A = B = F16 (format 0), both K-major, N>>3 [17,23), M>>4 [24,29).
+template <int N_>
+__device__ __forceinline__ constexpr uint32_t make_idesc_f16() {
+  return (1u << 4) | ((uint32_t)(N_ >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);       // .x (low 16 bits) = lo
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float round_h(float v) { return __half2float(__float2half_rn(v)); }
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float t = __expf(-2.0f * fabsf(x));
+  return copysignf(__fdividef(1.0f - t, 1.0f + t), x);
+}
+
+template <int HS, int O>
+struct CfgH {
+  static_assert(HS == 64 || HS == 128, "hidden width of the fused AGCN kernel: 64 or 128");
+  static_assert(O == HS || O == 2 * HS, "output width: HS (update) or 2*HS (gate)");
+  static constexpr uint32_t A_SLOT = BM * 128;                    // 16 KB: [128 rows][64 halves]
+  static constexpr uint32_t B_SLOT = (uint32_t)O * 128;           // [O rows][64 halves]  (>= the [HS rows] tile of MMA1)
+  static constexpr uint32_t STAGE = A_SLOT + B_SLOT;
+  static constexpr int NST = O >= 256 ? 4 : (O >= 128 ? 6 : 8);
+  static constexpr uint32_t SCRATCH = 4 * 32 * 36 * 4;            // rounding warps: 32 x 36 floats each
+  static constexpr size_t SMEM = (size_t)NST * STAGE + SCRATCH + 1024;
+  static_assert((size_t)NST * STAGE >= 8 * 32 * 36 * 4, "the epilogue stages through the (idle) ring");
+  static constexpr uint32_t TM_ACC = 0, TM_P0 = O, TM_P1 = O + HS;
+  static constexpr uint32_t TMEM_COLS = pow2_cols(O + 2 * HS);
+  static constexpr int KB2 = HS / BKH;                            // k-blocks of the weight contraction per segment
+};
+
+// ---- epilogue functors ------------------------------------------------------------------------
+// load4 / fin4 work on 4 consecutive columns of one (node, b) row.  fin4 returns in `st` the value the next fused
+// launch consumes as a tensor-core operand (already fp16-rounded), or leaves it untouched for columns without one.
+
+// Gate AGCN (model/MegaCRN.py:43-45): zr = sigmoid(acc); columns [0,H) = z, [H,2H) = r; writes z, r, z*h.
+struct EpiGateH {
+  static constexpr int NP = 1;
+  int H;
+  const float* h;       // [R][H] exact state
+  float* z;             // null in eval
+  float* r;
+  float* zh32;          // fp32 copy of the fp16-rounded z*h (XPu block 0, read by the backward); null in eval
+  __half* x16;          // [R][H]        z*h, A operand of the update AGCN's identity segment
+  __half* x16T;         // [B][H][ldT]   z*h, B operand of the update AGCN's propagation
+  int ldT;
+  __device__ __forceinline__ bool has_state(int n0) const { return n0 < H; }
+  __device__ __forceinline__ void load4(int row, int n0, float4 (&p)[NP]) const {
+    p[0] = (n0 < H) ? ldg4(h + (int64_t)row * H + n0) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __device__ __forceinline__ void fin4(int row, int n0, const float4 (&p)[NP], const float (&acc)[4], float (&st)[4]) const {
+    const float s0 = sigmoid_fast(acc[0]), s1 = sigmoid_fast(acc[1]), s2 = sigmoid_fast(acc[2]), s3 = sigmoid_fast(acc[3]);
+    if (n0 < H) {
+      const int64_t o = (int64_t)row * H + n0;
+      if (z) st4(z + o, s0, s1, s2, s3);
+      st[0] = round_h(s0 * p[0].x); st[1] = round_h(s1 * p[0].y); st[2] = round_h(s2 * p[0].z); st[3] = round_h(s3 * p[0].w);
+      if (zh32) st4(zh32 + o, st[0], st[1], st[2], st[3]);
+      *reinterpret_cast<uint2*>(x16 + o) = make_uint2(pack_h2(st[0], st[1]), pack_h2(st[2], st[3]));
+    } else {
+      st4(r + (int64_t)row * H + (n0 - H), s0, s1, s2, s3);
+    }
+  }
+};
+
+// Update AGCN (model/MegaCRN.py:46-47): hc = tanh(acc); h' = r*h + (1-r)*hc.
+struct EpiUpdateH {
+  static constexpr int NP = 2;
+  int H;
+  const float* h; const float* r;
+  float* hc;            // null in eval
+  float* h_out;         // exact new state
+  float* h32;           // fp32 copy of the fp16-rounded new state (next step's XPg block 0); null in eval / last step
+  __half* x16;          // next step's operand copies; null after the last step
+  __half* x16T;
+  int ldT;
+  __device__ __forceinline__ bool has_state(int) const { return x16 != nullptr; }
+  __device__ __forceinline__ void load4(int row, int n0, float4 (&p)[NP]) const {
+    const int64_t o = (int64_t)row * H + n0;
+    p[0] = ldg4(h + o);
+    p[1] = ldg4(r + o);
+  }
+  __device__ __forceinline__ void fin4(int row, int n0, const float4 (&p)[NP], const float (&acc)[4], float (&st)[4]) const {
+    const int64_t o = (int64_t)row * H + n0;
+    const float4 hv = p[0], rv = p[1];
+    const float c0 = tanh_fast(acc[0]), c1 = tanh_fast(acc[1]), c2 = tanh_fast(acc[2]), c3 = tanh_fast(acc[3]);
+    if (hc) st4(hc + o, c0, c1, c2, c3);
+    const float n0_ = rv.x * hv.x + (1.0f - rv.x) * c0, n1_ = rv.y * hv.y + (1.0f - rv.y) * c1;
+    const float n2_ = rv.z * hv.z + (1.0f - rv.z) * c2, n3_ = rv.w * hv.w + (1.0f - rv.w) * c3;
+    st4(h_out + o, n0_, n1_, n2_, n3_);
+    st[0] = round_h(n0_); st[1] = round_h(n1_); st[2] = round_h(n2_); st[3] = round_h(n3_);
+    if (h32) st4(h32 + o, st[0], st[1], st[2], st[3]);
+    if (x16) *reinterpret_cast<uint2*>(x16 + o) = make_uint2(pack_h2(st[0], st[1]), pack_h2(st[2], st[3]));
+  }
+};
+
+#define MCRN_TLH(slot)                                                     \
+  do {                                                                     \
+    if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0) p.dbg[(slot)] = clock64(); \
+  } while (0)
+
+template <int HS, int O, class Epi>
+__global__ void __launch_bounds__(FTHREADS, 1)
+agcn_fused_h_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmXT,
+                    const __grid_constant__ CUtensorMap tmXA, const __grid_constant__ CUtensorMap tmIB,
+                    const __grid_constant__ CUtensorMap tmW, HParams p, Epi epi) {
+  using C = CfgH<HS, O>;
+  constexpr int NST = C::NST;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[NST];
+  __shared__ __align__(8) uint64_t empty_bar[NST];
+  __shared__ __align__(8) uint64_t p_full_bar[2];    // MMA1 of a P buffer retired (tcgen05.commit)
+  __shared__ __align__(8) uint64_t p_ready_bar[2];   // the 4 rounding warps have packed the P buffer
+  __shared__ __align__(8) uint64_t acc_full_bar;
+  __shared__ uint32_t tmem_slot;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, b = blockIdx.y;
+  const int kb1 = (p.N + BKH - 1) / BKH;
+  const int NSEG = p.KS + 2;                         // weight segments per part
+  if (threadIdx.x == 0) MCRN_TLH(0);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmS) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmXT) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmXA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmIB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+#pragma unroll
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&p_full_bar[0]), 1);
+    mbar_init(smem_u32(&p_full_bar[1]), 1);
+    mbar_init(smem_u32(&p_ready_bar[0]), 4);
+    mbar_init(smem_u32(&p_ready_bar[1]), 4);
+    mbar_init(smem_u32(&acc_full_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (threadIdx.x == 0) MCRN_TLH(1);
+
+  if (warp == 0) {
+    if (lane == 0) {                                     // ===== TMA producer =====
+      int it = 0;
+      fused::for_each_item<C::KB2>(p.KS, kb1, p.nparts, [&](int type, int k, int j, int part) {
+        const int s = it % NST;
+        if (it >= NST) mbar_wait_b(smem_u32(&empty_bar[s]), (((uint32_t)(it / NST)) & 1u) ^ 1u);
+        if (it < 200) MCRN_TLH(240 + it);
+        const uint32_t fb = smem_u32(&full_bar[s]);
+        const uint32_t a_dst = smem_base + (uint32_t)s * C::STAGE, b_dst = a_dst + C::A_SLOT;
+        if (type == ITEM_P) {
+          mbar_expect_tx(fb, C::A_SLOT + (uint32_t)HS * 128);
+          tma_load_4d(a_dst, &tmS, fb, j * BKH, m0, k, 0);                      // S_k[m0.., 64 j..]
+          tma_load_4d(b_dst, &tmXT, fb, j * BKH, 0, b, 0);                      // X^T[b][0..HS][64 j..]
+        } else {
+          const int wseg = (type == ITEM_SS ? k : 1 + k) + part * NSEG;
+          if (type == ITEM_SS) {
+            mbar_expect_tx(fb, C::A_SLOT + C::B_SLOT);
+            tma_load_4d(a_dst, k == 0 ? &tmXA : &tmIB, fb, j * BKH, b, m0, 0);  // X / IB rows (m0.., b), channels 64 j..
+          } else {
+            mbar_expect_tx(fb, C::B_SLOT);
+          }
+          tma_load_4d(b_dst, &tmW, fb, j * BKH, 0, wseg, 0);                    // W^T[wseg][0..O][64 j..]
+        }
+        ++it;
+      });
+      MCRN_TLH(232);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {                                     // ===== MMA issuer =====
+      constexpr uint32_t idesc1 = make_idesc_f16<HS>();
+      constexpr uint32_t idesc2 = make_idesc_f16<O>();
+      int it = 0;
+      bool acc_on = false;
+      fused::for_each_item<C::KB2>(p.KS, kb1, p.nparts, [&](int type, int k, int j, int part) {
+        const int s = it % NST;
+        mbar_wait_b(smem_u32(&full_bar[s]), ((uint32_t)(it / NST)) & 1u);
+        tcgen05_fence_after();
+        if (it < 200) MCRN_TLH(2 + it);
+        const uint32_t a_addr = smem_base + (uint32_t)s * C::STAGE, b_addr = a_addr + C::A_SLOT;
+        const uint32_t pbuf = tmem_base + ((k & 1) ? C::TM_P1 : C::TM_P0);
+        if (type == ITEM_P) {
+#pragma unroll
+          for (int kk = 0; kk < BKH / 16; ++kk) {        // UMMA_K = 16 for fp16: 32 bytes along the swizzled row
+            const uint64_t ad = make_smem_desc(a_addr + kk * 32, 16, 1024, 2);
+            const uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, 1024, 2);
+            tcgen05_mma_f16(pbuf, ad, bd, idesc1, (j > 0 || kk > 0) ? 1u : 0u);
+          }
+          tcgen05_commit(smem_u32(&empty_bar[s]));
+          if (j == kb1 - 1) tcgen05_commit(smem_u32(&p_full_bar[k & 1]));
+        } else if (type == ITEM_SS) {
+#pragma unroll
+          for (int kk = 0; kk < BKH / 16; ++kk) {
+            const uint64_t ad = make_smem_desc(a_addr + kk * 32, 16, 1024, 2);
+            const uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, 1024, 2);
+            tcgen05_mma_f16(tmem_base + C::TM_ACC, ad, bd, idesc2, (acc_on || kk > 0) ? 1u : 0u);
+          }
+          acc_on = true;
+          tcgen05_commit(smem_u32(&empty_bar[s]));
+        } else {
+          if (j == 0 && part == 0) {                     // P_k has been packed to fp16 in place by the rounding warps
+            mbar_wait_b(smem_u32(&p_ready_bar[k & 1]), ((uint32_t)(k >> 1)) & 1u);
+            tcgen05_fence_after();
+          }
+#pragma unroll
+          for (int kk = 0; kk < BKH / 16; ++kk) {        // 16 halves of K = 8 packed TMEM columns
+            const uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, 1024, 2);
+            tcgen05_mma_f16_ts(tmem_base + C::TM_ACC, pbuf + (uint32_t)(j * (BKH / 2) + kk * 8), bd, idesc2, (acc_on || kk > 0) ? 1u : 0u);
+          }
+          acc_on = true;
+          tcgen05_commit(smem_u32(&empty_bar[s]));
+        }
+        ++it;
+      });
+      tcgen05_commit(smem_u32(&acc_full_bar));
+      MCRN_TLH(233);
+    }
+  } else {                                               // ===== rounding + epilogue warps =====
+    const int quarter = warp & 3;                        // TMEM lane quarter this warp may access
+    const int ew = warp - 2, half_id = ew >> 2;          // ew 0..7; warps 2..5 (half_id 0) also do the P rounding
+    const int cq = (lane & 7) * 4, r0 = lane >> 3;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const int node0 = m0 + quarter * 32;
+    if (half_id == 0) {
+      // ---- P_k: fp32 accumulator -> fp16 pairs packed in place; training: store the rounded block for the backward ----
+      float* scr = reinterpret_cast<float*>(smem_al + (size_t)NST * C::STAGE) + ew * (32 * 36);
+      for (int k = 0; k < p.KS; ++k) {
+        mbar_wait_b(smem_u32(&p_full_bar[k & 1]), ((uint32_t)(k >> 1)) & 1u);
+        tcgen05_fence_after();
+        if (warp == 2 && lane == 0 && k < 5) MCRN_TLH(210 + 4 * k);
+        const uint32_t pbuf = tmem_base + ((k & 1) ? C::TM_P1 : C::TM_P0) + lane_off;
+#pragma unroll 1
+        for (int c = 0; c < HS / 32; ++c) {
+          float v[32];
+          tmem_ld_32x32b_x32(pbuf + (uint32_t)(c * 32), v);
+          uint32_t u[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) u[i] = pack_h2(v[2 * i], v[2 * i + 1]);
+          tmem_st_32x32b_x16(pbuf + (uint32_t)(c * 16), u);      // columns [16c, 16c+16) <= columns already read
+          if (p.xp_save != nullptr && node0 < p.N) {
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              *reinterpret_cast<float4*>(&scr[lane * 36 + i]) = make_float4(round_h(v[i]), round_h(v[i + 1]), round_h(v[i + 2]), round_h(v[i + 3]));
+            __syncwarp();
+            float* dst = p.xp_save + (int64_t)(1 + k) * p.blk_stride + c * 32 + cq;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = r0 + 4 * i, node = node0 + rr;
+              if (node < p.N)
+                *reinterpret_cast<float4*>(dst + ((int64_t)node * p.B + b) * HS) = *reinterpret_cast<const float4*>(&scr[rr * 36 + cq]);
+            }
+          }
+        }
+        tmem_wait_st();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&p_ready_bar[k & 1]));
+        if (warp == 2 && lane == 0 && k < 5) MCRN_TLH(211 + 4 * k);
+      }
+    }
+    // ---- epilogue: accumulator -> gate / update math; rows = (node, b); this warp takes chunks c = half_id (mod 2) ----
+    mbar_wait_b(smem_u32(&acc_full_bar), 0);
+    tcgen05_fence_after();
+    if (warp == 2 && lane == 0) MCRN_TLH(230);
+    if (node0 < p.N) {
+      float* scr = reinterpret_cast<float*>(smem_al) + ew * (32 * 36);      // the ring is idle now
+#pragma unroll 1
+      for (int c = half_id; c < O / 32; c += 2) {
+        float v[32];
+        tmem_ld_32x32b_x32(tmem_base + C::TM_ACC + lane_off + (uint32_t)(c * 32), v);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(&scr[lane * 36 + i]) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        __syncwarp();
+        const int col = c * 32 + cq;
+        constexpr int RB = Epi::NP <= 1 ? 8 : 4;
+#pragma unroll
+        for (int b0 = 0; b0 < 8; b0 += RB) {
+          float4 pre[RB][Epi::NP];
+#pragma unroll
+          for (int i = 0; i < RB; ++i) {
+            const int node = node0 + r0 + 4 * (b0 + i);
+            if (node < p.N) epi.load4(node * p.B + b, col, pre[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < RB; ++i) {
+            const int rr = r0 + 4 * (b0 + i), node = node0 + rr;
+            if (node < p.N) {
+              const float4 t = *reinterpret_cast<const float4*>(&scr[rr * 36 + cq]);
+              const float a4[4] = {t.x, t.y, t.z, t.w};
+              float st[4] = {0.f, 0.f, 0.f, 0.f};
+              epi.fin4(node * p.B + b, col, pre[i], a4, st);
+              *reinterpret_cast<float4*>(&scr[rr * 36 + cq]) = make_float4(st[0], st[1], st[2], st[3]);
+            }
+          }
+        }
+        // node-transposed fp16 copy of the new operand: X^T[b][c*32 + j][node0 + lane]
+        if (epi.has_state(c * 32) && epi.x16T != nullptr) {
+          __syncwarp();
+          const int node = node0 + lane;
+          if (node < p.N) {
+            __half* dst = epi.x16T + ((int64_t)b * HS + c * 32) * epi.ldT + node;
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) dst[(int64_t)j * epi.ldT] = __float2half_rn(scr[lane * 36 + j]);
+          }
+        }
+      }
+    }
+  }
+  if (warp == 2 && lane == 0) MCRN_TLH(231);
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+  }
+}
+
+// ---- operand conversion kernels ---------------------------------------------------------------
+// supports fp32 [KS][N][ld] -> fp16 [KS][N][ld16]
+__global__ void k_supports_to_half(const float* __restrict__ S, __half* __restrict__ S16, int rows, int n, int ld, int ld16) {
+  const int64_t total = (int64_t)rows * ld16;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / ld16;
+    const int c = (int)(i - r * ld16);
+    S16[i] = __float2half_rn(c < n ? S[r * ld + c] : 0.f);
+  }
+}
+// state fp32 [N][B][HS] -> fp16 row-major [N][B][HS] and node-transposed [B][HS][ldT]
+__global__ void k_state_to_half(const float* __restrict__ x, __half* __restrict__ x16, __half* __restrict__ x16T, int N, int B,
+                                int HS, int ldT) {
+  const int64_t total = (int64_t)N * B * HS;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % HS);
+    const int64_t row = i / HS;
+    const int n = (int)(row / B), b = (int)(row - (int64_t)n * B);
+    const __half v = __float2half_rn(x[i]);
+    x16[i] = v;
+    x16T[((int64_t)b * HS + c) * ldT + n] = v;
+  }
+}
+// folded weights fp32 [2 (TF32 hi, lo)][KS+2][HS][O] -> fp16 hi / lo, transposed: [2][KS+2][O][HS]
+__global__ void k_weights_to_half(const float* __restrict__ wall, __half* __restrict__ w16, int nseg, int HS, int O) {
+  const int64_t total = (int64_t)nseg * HS * O;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % HS);
+    const int o = (int)((i / HS) % O);
+    const int seg = (int)(i / ((int64_t)HS * O));
+    const int64_t src = ((int64_t)seg * HS + c) * O + o;
+    const float w = wall[src] + wall[total + src];            // hi + lo of the TF32 split = the weight to ~21 bits
+    const __half hi = __float2half_rn(w);
+    w16[i] = hi;
+    w16[total + i] = __float2half_rn(w - __half2float(hi));
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+int encode_tensor_map_h(CUtensorMap* out, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                        const uint32_t box[4]);
+
+static inline int ld_half(int n) { return (n + 7) / 8 * 8; }     // 16-byte row stride for fp16 rows
+
+struct HOperands {
+  const __half* S16;      // [KS][N][ld_half(N)]
+  const __half* X16T;     // [B][HS][ld_half(N)]
+  const __half* X16;      // [R][HS]
+  const __half* IB16;     // [R][HS]
+  const __half* W16;      // [nparts][KS+2][O][HS]
+  float* xp_save;         // fp32 XP buffer (training) or null
+};
+
+template <int HS, int O, class Epi>
+int launch_agcn_fused_h(int N, int B, int KS, const HOperands& op, int nparts, const Epi& epi, cudaStream_t st) {
+  using C = CfgH<HS, O>;
+  const int64_t R = (int64_t)N * B;
+  const int ldn = ld_half(N);
+  CUtensorMap tS, tXT, tXA, tIB, tW;
+  {
+    uint64_t dims[4] = {(uint64_t)N, (uint64_t)N, (uint64_t)KS, 1};
+    uint64_t str[3] = {(uint64_t)ldn * 2, (uint64_t)N * ldn * 2, (uint64_t)KS * N * ldn * 2};
+    uint32_t box[4] = {BKH, BM, 1, 1};
+    MCRN_TRY(encode_tensor_map_h(&tS, op.S16, dims, str, box));
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)N, (uint64_t)HS, (uint64_t)B, 1};
+    uint64_t str[3] = {(uint64_t)ldn * 2, (uint64_t)HS * ldn * 2, (uint64_t)B * HS * ldn * 2};
+    uint32_t box[4] = {BKH, (uint32_t)HS, 1, 1};
+    MCRN_TRY(encode_tensor_map_h(&tXT, op.X16T, dims, str, box));
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)HS, (uint64_t)B, (uint64_t)N, 1};
+    uint64_t str[3] = {(uint64_t)HS * 2, (uint64_t)B * HS * 2, (uint64_t)R * HS * 2};
+    uint32_t box[4] = {BKH, 1, BM, 1};
+    MCRN_TRY(encode_tensor_map_h(&tXA, op.X16, dims, str, box));
+    MCRN_TRY(encode_tensor_map_h(&tIB, op.IB16, dims, str, box));
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)HS, (uint64_t)O, (uint64_t)(nparts * (KS + 2)), 1};
+    uint64_t str[3] = {(uint64_t)HS * 2, (uint64_t)O * HS * 2, (uint64_t)nparts * (KS + 2) * O * HS * 2};
+    uint32_t box[4] = {BKH, (uint32_t)O, 1, 1};
+    MCRN_TRY(encode_tensor_map_h(&tW, op.W16, dims, str, box));
+  }
+  HParams p;
+  p.N = N; p.B = B; p.KS = KS; p.nparts = nparts;
+  p.xp_save = op.xp_save;
+  p.blk_stride = R * HS;
+  p.dbg = nullptr;
+  if (fused::g_dbg_timeline != nullptr) {
+    if (fused::g_dbg_which < 0 || fused::g_dbg_count == fused::g_dbg_which) p.dbg = fused::g_dbg_timeline;
+    ++fused::g_dbg_count;
+  }
+  auto kern = agcn_fused_h_kernel<HS, O, Epi>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MCRN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(N, BM), B, 1);
+  MCRN_LAUNCH(kern, grid, FTHREADS, C::SMEM, st, tS, tXT, tXA, tIB, tW, p, epi);
+  return MCRN_OK;
+}
+
+}  // namespace fusedh
+}  // namespace mcrn

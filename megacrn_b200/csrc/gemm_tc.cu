@@ -49,6 +49,32 @@ int encode_tensor_map(CUtensorMap* out, const float* base, const uint64_t dims[4
   return MCRN_OK;
 }
 
+}  // namespace tc
+namespace fusedh {
+// fp16 operands of the fused AGCN kernel: K-major, 128-byte swizzle.
+int encode_tensor_map_h(CUtensorMap* out, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                        const uint32_t box[4]) {
+  std::call_once(tc::g_once, tc::resolve_encode);
+  if (!tc::g_encode) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return MCRN_ERR_CUDA; }
+  cuuint64_t gdim[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t gstr[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = tc::g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), gdim, gstr, bx, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(fp16) failed (%d): dims=[%llu,%llu,%llu,%llu] strides=[%llu,%llu,%llu] box=[%u,%u,%u,%u] base=%p",
+              (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+              (unsigned long long)dims[3], (unsigned long long)strides_bytes[0], (unsigned long long)strides_bytes[1],
+              (unsigned long long)strides_bytes[2], box[0], box[1], box[2], box[3], base);
+    return MCRN_ERR_CUDA;
+  }
+  return MCRN_OK;
+}
+}  // namespace fusedh
+namespace tc {
+
 static bool ok_stride(int64_t elems) { return elems > 0 && (elems % 4) == 0 && elems * 4 < ((int64_t)1 << 40); }
 
 bool eligible(const GemmDesc& g) {

@@ -10,6 +10,7 @@
 
 #include "engine.cuh"
 #include "agcn_fused.cuh"
+#include "agcn_fused_h.cuh"
 #include "plan.cuh"
 #include "loss.cuh"
 #include "small_kernels.cuh"
@@ -64,11 +65,15 @@ static inline int ew_grid(int64_t n) { int64_t b = (n + 255) / 256; return (int)
 struct CellW {           // folded weights of one cell (plan buffers): [hi | lo][NB+1][Hs][O]
   const float *wg, *wu;
   int Hs, Cin;
+  const __half *wg16 = nullptr, *wu16 = nullptr;   // fp16 hi/lo, transposed [2][NB+1][O][Hs] (fused fp16 forward)
+  const __half* S16 = nullptr;                     // fp16 supports [KS][N][ld_half(N)]
 };
 struct CellBufs {        // per-step activations
   const float* xpin; int64_t xp_k, xp_n;
   float *xpg, *xpu, *z, *r, *hc;
   float* hx;             // exact fp32 input state of the step (xpg block 0 is its tensor-core copy)
+  // fp16 operand copies (fused fp16 forward): state h (row-major, node-transposed), z*h, input block
+  __half *x16 = nullptr, *x16T = nullptr, *zh16 = nullptr, *zh16T = nullptr, *ib16 = nullptr;
 };
 
 // Numerics mode of the run: with the tcgen05 engine every tensor-core operand is stored TF32-rounded
@@ -98,8 +103,10 @@ static inline void hilo(GemmDesc& q, int NBX) {
 }
 
 // Fused AGCN kernel (agcn_fused.cuh): propagation + weight contraction + gate/update tail in one launch per AGCN.
-// g_fused: 0 = off (per-stage GEMMs), 1 = on where the shape is instantiated.  g_fused_parts: 2 = hi + lo weights, 1 = hi only.
-int g_fused = getenv("MCRN_FUSED") ? atoi(getenv("MCRN_FUSED")) : 1;
+// g_fused_parts: 2 = hi + lo weights, 1 = hi only.
+namespace fused { long long* g_dbg_timeline = nullptr; int g_dbg_which = -1, g_dbg_count = 0; }
+// g_fused: 0 = per-stage GEMMs, 1 = fused kernel with TF32 operands, 2 = fused kernel with fp16 operands (default).
+int g_fused = getenv("MCRN_FUSED") ? atoi(getenv("MCRN_FUSED")) : 2;
 int g_fused_parts = getenv("MCRN_FUSED_PARTS") ? atoi(getenv("MCRN_FUSED_PARTS")) : 2;
 
 template <int HS>
@@ -113,15 +120,42 @@ static int cell_forward_fused(const Geo& g, const float* S, const CellW& w, cons
   return MCRN_OK;
 }
 
+static bool fused_h_shape(const Geo& g, int Hs) {
+  return tf32_mode() && g_fused == 2 && !(g_simt_mask & 3) && (Hs == 64 || Hs == 128) && g.B <= 65535;
+}
+
+// fp16-operand fused cell (agcn_fused_h.cuh).  last: no next step consumes the new state as a tensor-core operand.
+template <int HS>
+static int cell_forward_fused_h(const Geo& g, const CellW& w, const CellBufs& b, float* h_out, float* h_mma, bool last,
+                                cudaStream_t st) {
+  const bool save = b.z != nullptr;
+  const int ldT = fusedh::ld_half(g.N);
+  fusedh::HOperands og{w.S16, b.x16T, b.x16, b.ib16, w.wg16, save ? b.xpg : nullptr};
+  fusedh::EpiGateH eg{HS, b.hx, b.z, b.r, save ? b.xpu : nullptr, b.zh16, b.zh16T, ldT};
+  MCRN_TRY((fusedh::launch_agcn_fused_h<HS, 2 * HS>(g.N, g.B, g.KS, og, g_fused_parts, eg, st)));
+  fusedh::HOperands ou{w.S16, b.zh16T, b.zh16, b.ib16, w.wu16, save ? b.xpu : nullptr};
+  fusedh::EpiUpdateH eu{HS, b.hx, b.r, b.hc, h_out, save ? h_mma : nullptr, last ? nullptr : b.x16, last ? nullptr : b.x16T, ldT};
+  MCRN_TRY((fusedh::launch_agcn_fused_h<HS, HS>(g.N, g.B, g.KS, ou, g_fused_parts, eu, st)));
+  return MCRN_OK;
+}
+
 static int cell_forward(const Geo& g, const float* S, const CellW& w, const CellBufs& b, float* h_out, float* h_mma,
                         cudaStream_t st) {
   const int Hs = w.Hs, NBX = g.NB + 1;
   const int rnd = tf32_mode();
   const int64_t nH = g.R * Hs;
+  if (fused_h_shape(g, Hs)) {
+    const bool save = b.z != nullptr;
+    MCRN_LAUNCH(k_build_input_block, ew_grid(nH), 256, 0, st, b.xpin, b.xp_k, b.xp_n, g.NB, w.Cin, g.B, g.R, Hs, rnd,
+                save ? b.xpg + (int64_t)g.NB * nH : nullptr, save ? b.xpu + (int64_t)g.NB * nH : nullptr, b.ib16);
+    const bool last = (h_mma == nullptr);
+    return Hs == 64 ? cell_forward_fused_h<64>(g, w, b, h_out, h_mma, last, st)
+                    : cell_forward_fused_h<128>(g, w, b, h_out, h_mma, last, st);
+  }
   // input block (input channels + bias) of both AGCNs of this step
   MCRN_LAUNCH(k_build_input_block, ew_grid(nH), 256, 0, st, b.xpin, b.xp_k, b.xp_n, g.NB, w.Cin, g.B, g.R, Hs, rnd,
-              b.xpg + (int64_t)g.NB * nH, b.xpu + (int64_t)g.NB * nH);
-  if (rnd && g_fused && !(g_simt_mask & 3) && fused::fused_eligible(g.N, g.B, Hs, 2 * Hs, S, b.xpg, w.wg) &&
+              b.xpg + (int64_t)g.NB * nH, b.xpu + (int64_t)g.NB * nH, (__half*)nullptr);
+  if (rnd && g_fused == 1 && !(g_simt_mask & 3) && fused::fused_eligible(g.N, g.B, Hs, 2 * Hs, S, b.xpg, w.wg) &&
       fused::fused_eligible(g.N, g.B, Hs, Hs, S, b.xpu, w.wu)) {
     return Hs == 64 ? cell_forward_fused<64>(g, S, w, b, h_out, h_mma, st) : cell_forward_fused<128>(g, S, w, b, h_out, h_mma, st);
   }
@@ -217,6 +251,9 @@ static CellBufs enc_bufs(const Geo& g, const Plan& p, float* ws, int t) {
   b.r = ws + p.enc_r + p.enc_v_sz * s;
   b.hc = p.save ? ws + p.enc_hc + p.enc_v_sz * s : nullptr;
   b.hx = ws + p.enc_hx + p.enc_v_sz * s;
+  b.x16 = reinterpret_cast<__half*>(ws + p.enc_x16); b.x16T = reinterpret_cast<__half*>(ws + p.enc_x16T);
+  b.zh16 = reinterpret_cast<__half*>(ws + p.enc_zh16); b.zh16T = reinterpret_cast<__half*>(ws + p.enc_zh16T);
+  b.ib16 = reinterpret_cast<__half*>(ws + p.enc_ib16);
   return b;
 }
 static CellBufs dec_bufs(const Geo& g, const Plan& p, float* ws, int t) {
@@ -231,10 +268,19 @@ static CellBufs dec_bufs(const Geo& g, const Plan& p, float* ws, int t) {
   b.r = ws + p.dec_r + p.dec_v_sz * s;
   b.hc = p.save ? ws + p.dec_hc + p.dec_v_sz * s : nullptr;
   b.hx = ws + p.dec_hx + p.dec_v_sz * s;
+  b.x16 = reinterpret_cast<__half*>(ws + p.dec_x16); b.x16T = reinterpret_cast<__half*>(ws + p.dec_x16T);
+  b.zh16 = reinterpret_cast<__half*>(ws + p.dec_zh16); b.zh16T = reinterpret_cast<__half*>(ws + p.dec_zh16T);
+  b.ib16 = reinterpret_cast<__half*>(ws + p.dec_ib16);
   return b;
 }
-static CellW enc_w(const Geo& g, const Plan& p, float* ws) { return CellW{ws + p.e_wg, ws + p.e_wu, g.H, g.Cin}; }
-static CellW dec_w(const Geo& g, const Plan& p, float* ws) { return CellW{ws + p.d_wg, ws + p.d_wu, g.D, g.Cdec}; }
+static CellW enc_w(const Geo& g, const Plan& p, float* ws) {
+  return CellW{ws + p.e_wg, ws + p.e_wu, g.H, g.Cin, reinterpret_cast<const __half*>(ws + p.e_wg16),
+               reinterpret_cast<const __half*>(ws + p.e_wu16), reinterpret_cast<const __half*>(ws + p.s16)};
+}
+static CellW dec_w(const Geo& g, const Plan& p, float* ws) {
+  return CellW{ws + p.d_wg, ws + p.d_wu, g.D, g.Cdec, reinterpret_cast<const __half*>(ws + p.d_wg16),
+               reinterpret_cast<const __half*>(ws + p.d_wu16), reinterpret_cast<const __half*>(ws + p.s16)};
+}
 
 // ======================================================================================
 // forward                                                        model/MegaCRN.py:168-194
@@ -245,6 +291,20 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
   float* S = ws + p.Sr;     // the recurrent GEMMs read the tensor-core copy of the supports
   MCRN_TRY(supports_forward(g, p, ws, prm->memory, prm->we1, prm->we2, ws + p.S, ws + p.Sr, st));
   MCRN_TRY(fold_all_weights(g, p, ws, prm, st));
+  const bool enc_h = fused_h_shape(g, g.H), dec_h = fused_h_shape(g, g.D);
+  if (enc_h || dec_h) {  // fp16 operand copies for the fused forward: supports (exact fp32 -> half) and weights (hi/lo, transposed)
+    const int ld16 = fusedh::ld_half(g.N);
+    MCRN_LAUNCH(fusedh::k_supports_to_half, ew_grid((int64_t)g.KS * g.N * ld16), 256, 0, st, ws + p.S,
+                reinterpret_cast<__half*>(ws + p.s16), g.KS * g.N, g.N, g.ldS, ld16);
+    if (enc_h) {
+      MCRN_LAUNCH(fusedh::k_weights_to_half, 128, 256, 0, st, ws + p.e_wg, reinterpret_cast<__half*>(ws + p.e_wg16), g.NB + 1, g.H, 2 * g.H);
+      MCRN_LAUNCH(fusedh::k_weights_to_half, 128, 256, 0, st, ws + p.e_wu, reinterpret_cast<__half*>(ws + p.e_wu16), g.NB + 1, g.H, g.H);
+    }
+    if (dec_h) {
+      MCRN_LAUNCH(fusedh::k_weights_to_half, 128, 256, 0, st, ws + p.d_wg, reinterpret_cast<__half*>(ws + p.d_wg16), g.NB + 1, g.D, 2 * g.D);
+      MCRN_LAUNCH(fusedh::k_weights_to_half, 128, 256, 0, st, ws + p.d_wu, reinterpret_cast<__half*>(ws + p.d_wu16), g.NB + 1, g.D, g.D);
+    }
+  }
   // ---- encoder (ADCRNN_Encoder.forward :65-83; zero initial state :50-51, :174) ----
   {
     int64_t n_in = (int64_t)g.N * g.T_in * g.B * g.Cin;
@@ -253,6 +313,10 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
                           g.T_in * g.B * g.Cin, st));
     MCRN_CUDA_OK(cudaMemsetAsync(ws + p.enc_xpg, 0, (size_t)g.R * g.H * sizeof(float), st));
     MCRN_CUDA_OK(cudaMemsetAsync(ws + p.enc_hx, 0, (size_t)g.R * g.H * sizeof(float), st));
+    if (enc_h) {
+      MCRN_CUDA_OK(cudaMemsetAsync(ws + p.enc_x16, 0, (size_t)g.R * g.H * sizeof(__half), st));
+      MCRN_CUDA_OK(cudaMemsetAsync(ws + p.enc_x16T, 0, (size_t)g.B * g.H * fusedh::ld_half(g.N) * sizeof(__half), st));
+    }
     CellW w = enc_w(g, p, ws);
     for (int t = 0; t < g.T_in; ++t) {
       CellBufs b = enc_bufs(g, p, ws, t);
@@ -269,6 +333,9 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
     MCRN_LAUNCH(k_memory_query, (int)ceil_div64(g.R, 8), 256, shm, st, ws + p.h_enc, prm->wq, prm->memory,
                 ws + p.mq_q, ws + p.mq_att, reinterpret_cast<int*>(ws + p.mq_ind), h_att, query, pos, neg, b0.hx,
                 b0.xpg, tf32_mode(), g.B, g.N, g.H, g.M, g.d);
+    if (dec_h)
+      MCRN_LAUNCH(fusedh::k_state_to_half, ew_grid(g.R * g.D), 256, 0, st, b0.xpg, b0.x16, b0.x16T, g.N, g.B, g.D,
+                  fusedh::ld_half(g.N));
   }
   // ---- decoder loop (:181-192) ----
   {

@@ -21,6 +21,10 @@ struct Plan {
   size_t mq_q, mq_att, mq_ind;           // [R][d], [R][M], int[R][2]
   size_t dec_xpin, dec_xpg, dec_xpu, dec_z, dec_r, dec_hc, dec_hx;
   size_t h_dec_last;                     // [R][D]
+  // fp16 operand copies of the fused forward (agcn_fused_h.cuh); offsets in floats, contents are halves
+  size_t s16, e_wg16, e_wu16, d_wg16, d_wu16;
+  size_t enc_x16, enc_x16T, enc_zh16, enc_zh16T, enc_ib16;
+  size_t dec_x16, dec_x16T, dec_zh16, dec_zh16T, dec_ib16;
   // per-slot sizes (floats)
   size_t enc_xp_sz, enc_v_sz, dec_xpin_sz, dec_xp_sz, dec_v_sz;
   // ---- backward temporaries -------------------------------------------------
@@ -81,6 +85,21 @@ static inline int make_plan(const Geo& g, bool save, Plan* p) {
   p->dec_hc = take(p->dec_v_sz * p->dec_slots);
   p->dec_hx = take(p->dec_v_sz * p->dec_slots);
   p->h_dec_last = take(R * g.D);
+  {
+    const size_t ld16 = (N + 7) / 8 * 8;
+    auto halves = [&](size_t n) { return take((n + 1) / 2); };
+    p->s16 = halves(KS * N * ld16);
+    p->e_wg16 = halves(2 * (NB + 1) * g.H * 2 * g.H);
+    p->e_wu16 = halves(2 * (NB + 1) * g.H * g.H);
+    p->d_wg16 = halves(2 * (NB + 1) * g.D * 2 * g.D);
+    p->d_wu16 = halves(2 * (NB + 1) * g.D * g.D);
+    p->enc_x16 = halves(R * g.H);  p->enc_x16T = halves((size_t)g.B * g.H * ld16);
+    p->enc_zh16 = halves(R * g.H); p->enc_zh16T = halves((size_t)g.B * g.H * ld16);
+    p->enc_ib16 = halves(R * g.H);
+    p->dec_x16 = halves(R * g.D);  p->dec_x16T = halves((size_t)g.B * g.D * ld16);
+    p->dec_zh16 = halves(R * g.D); p->dec_zh16T = halves((size_t)g.B * g.D * ld16);
+    p->dec_ib16 = halves(R * g.D);
+  }
   p->loss_scratch = take(64);
   if (save) {
     const size_t Cm = (size_t)(g.Cin > g.Cdec ? g.Cin : g.Cdec);

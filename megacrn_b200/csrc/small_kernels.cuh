@@ -3,6 +3,8 @@
 // pieces of the BPTT backward.  All HBM-bound; coalesced on the channel axis.
 #pragma once
 
+#include <cuda_fp16.h>
+
 #include "gemm.cuh"
 
 namespace mcrn {
@@ -154,7 +156,7 @@ __global__ void k_unfold_grads(const float* __restrict__ dwall, float* __restric
 // (TF32-rounded when rnd), column NB*cin = 1 (multiplies the bias row), remaining columns 0.
 __global__ void k_build_input_block(const float* __restrict__ xpin, int64_t xp_k, int64_t xp_n, int NB, int cin,
                                     int B, int64_t R, int hs, int rnd, float* __restrict__ ib_g,
-                                    float* __restrict__ ib_u) {
+                                    float* __restrict__ ib_u, __half* __restrict__ ib16) {
   const int64_t total = R * hs;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / hs;
@@ -167,6 +169,11 @@ __global__ void k_build_input_block(const float* __restrict__ xpin, int64_t xp_k
       if (rnd) v = tf32_rn(v);
     } else if (j == NB * cin) {
       v = 1.0f;
+    }
+    if (ib16 != nullptr) {                 // fp16 fused path: the tensor-core operand is the half copy
+      ib16[i] = __float2half_rn(v);
+      v = __half2float(__float2half_rn(v));
+      if (ib_g == nullptr) continue;       // eval: the fp32 copies are only read by the backward
     }
     ib_g[i] = v;
     ib_u[i] = v;

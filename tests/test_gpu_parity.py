@@ -281,7 +281,7 @@ def test_fused_agcn_kernel_matches_per_stage_path(N, H, dm, B, T):
     gen = torch.Generator().manual_seed(3)
     res = {}
     try:
-        for fused, parts in ((0, 2), (1, 2), (1, 1)):
+        for fused, parts in ((0, 2), (1, 2), (1, 1), (2, 2), (2, 1)):
             assert lib.mcrn_set_fused(fused, parts) == 0
             m = _model(d, p).train()
             outs = m(x.to(dv), y_cov.to(dv), labels.to(dv), teacher_forcing=flags)
@@ -290,9 +290,10 @@ def test_fused_agcn_kernel_matches_per_stage_path(N, H, dm, B, T):
             torch.autograd.backward([outs[0], outs[2]], ups)
             res[(fused, parts)] = ([o.detach().cpu() for o in outs[:3]], {k: v.grad.cpu() for k, v in m.named_parameters()})
     finally:
-        lib.mcrn_set_fused(1, 2)
+        lib.mcrn_set_fused(2, 2)
     ref_o, ref_g = res[(0, 2)]
-    for (fused, parts), tol_o, tol_g in (((1, 2), 1e-4, 1e-3), ((1, 1), 1e-3, 4e-3)):
+    # fused = 2: fp16 operands (same 11-bit significand as TF32, different rounding points) -> TF32-noise-level agreement
+    for (fused, parts), tol_o, tol_g in (((1, 2), 1e-4, 1e-3), ((1, 1), 1e-3, 4e-3), ((2, 2), 5e-4, 4e-3), ((2, 1), 1e-3, 4e-3)):
         got_o, got_g = res[(fused, parts)]
         for k, a, b in zip(OUT_NAMES[:3], got_o, ref_o):
             assert rel_l2(a, b) < tol_o, (parts, k, rel_l2(a, b))

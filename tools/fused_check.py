@@ -47,14 +47,14 @@ for title, d, B, t_in in cases:
     for train in (False, True):
         try:
             ref, gref = run(d, B, t_in, 0, 2, train)
-            for parts in (2, 1):
-                got, gg = run(d, B, t_in, 1, parts, train)
+            for fmode, parts in ((1, 2), (2, 2), (2, 1)):
+                got, gg = run(d, B, t_in, fmode, parts, train)
                 line = " ".join(f"{n}={rel(a, b):.2e}" for n, a, b in zip(names[:3], got, ref))
                 if train:
                     worst = max((rel(gg[k], gref[k]), k) for k in gg)
                     line += f"  worst-grad={worst[0]:.2e} ({worst[1]})"
-                print(f"[{title}] train={int(train)} parts={parts}: fused vs unfused {line}", flush=True)
+                print(f"[{title}] train={int(train)} fused={fmode} parts={parts}: vs unfused {line}", flush=True)
         except Exception as e:
             print(f"[{title}] train={int(train)} FAILED: {e}", flush=True)
             raise
-lib.mcrn_set_fused(1, 2)
+lib.mcrn_set_fused(2, 2)
