@@ -184,6 +184,9 @@ int mcrn_set_debug_mask(int mask);
  * operands (csrc/agcn_fused.cuh), 0 = per-stage GEMM kernels.
  * weight_parts: 2 = hi + lo residual of the weights (default), 1 = hi only. */
 int mcrn_set_fused(int fused, int weight_parts);
+/* Backward data path of every AGCN as one fused kernel (csrc/agcn_bwd_fused.cuh): 1 = on (default) where the hidden
+ * width is 64 or 128, 0 = per-stage GEMM kernels.  Set it before the forward whose backward it governs. */
+int mcrn_set_bwd_fused(int fused);
 /* Debug aid (tools/fused_timeline.py): while device_slots != NULL the `which`-th fused AGCN launch after this call
  * (-1 = every launch) records clock64 timestamps of CTA (0,0) into it (512 x int64; slot map in csrc/agcn_fused.cuh).
  * NULL switches the recording off. */

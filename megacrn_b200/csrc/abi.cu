@@ -8,7 +8,7 @@
 namespace mcrn {
 int g_engine = 0;
 extern int g_simt_mask;
-extern int g_fused, g_fused_parts;
+extern int g_fused, g_fused_parts, g_bwd_fused;
 namespace fused { extern long long* g_dbg_timeline; extern int g_dbg_which, g_dbg_count; }
 const char* last_error();
 int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const float* x, const float* y_cov,
@@ -79,6 +79,7 @@ int mcrn_debug_fused_timeline(long long* device_slots, int which) {
   fused::g_dbg_timeline = device_slots; fused::g_dbg_which = which; fused::g_dbg_count = 0;
   return MCRN_OK;
 }
+int mcrn_set_bwd_fused(int fused) { g_bwd_fused = fused ? 1 : 0; return MCRN_OK; }
 int mcrn_set_fused(int fused, int weight_parts) {
   if (fused < 0 || fused > 2 || weight_parts < 1 || weight_parts > 2) { set_error("mcrn_set_fused: fused in {0,1,2}, weight_parts in {1,2}"); return MCRN_ERR_BAD_DIMS; }
   g_fused = fused; g_fused_parts = weight_parts;

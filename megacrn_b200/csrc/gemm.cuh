@@ -165,11 +165,12 @@ struct EpiBlocks {
   int rnd = 0;                               // 1: blocks 1..last-1 (tensor-core operands downstream) are TF32-rounded
   int last = -1;
   float* last_out = nullptr;
+  int blk0 = 0;                              // index of the first stored block (output column 0 belongs to block blk0)
   template <int V>
   __device__ __forceinline__ void apply(int, int m, int n0, int nv, const float (&acc)[V]) const {
     if constexpr (V == 4) {
       if (nv == 4 && (W & 3) == 0) {
-        const int blk = n0 / W, c = n0 - blk * W;
+        const int blk = n0 / W + blk0, c = n0 - (blk - blk0) * W;
         float* dst = (blk == last && last_out) ? last_out + (int64_t)m * W + c
                                                : C + (int64_t)blk * blk_stride + (int64_t)m * W + c;
         if (is16(dst)) {
@@ -183,7 +184,7 @@ struct EpiBlocks {
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       if (j < nv) {
-        int n = n0 + j, blk = n / W, c = n - blk * W;
+        int n = n0 + j, blk = n / W + blk0, c = n - (blk - blk0) * W;
         if (blk == last && last_out) {
           last_out[(int64_t)m * W + c] = acc[j];
         } else {

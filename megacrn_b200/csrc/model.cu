@@ -11,6 +11,7 @@
 #include "engine.cuh"
 #include "agcn_fused.cuh"
 #include "agcn_fused_h.cuh"
+#include "agcn_bwd_fused.cuh"
 #include "plan.cuh"
 #include "loss.cuh"
 #include "small_kernels.cuh"
@@ -120,6 +121,12 @@ static int cell_forward_fused(const Geo& g, const float* S, const CellW& w, cons
   return MCRN_OK;
 }
 
+// Fused backward (agcn_bwd_fused.cuh): 1 = on where the shape is instantiated (default), 0 = per-stage GEMM backward.
+int g_bwd_fused = getenv("MCRN_BWD_FUSED") ? atoi(getenv("MCRN_BWD_FUSED")) : 1;
+static bool bwd_fused_shape(const Geo& g, int Hs, int Cin) {
+  return tf32_mode() && g_bwd_fused && !g_simt_mask && (Hs == 64 || Hs == 128) && g.NB * Cin + 1 <= fusedb::IBW && g.B <= 65535;
+}
+
 static bool fused_h_shape(const Geo& g, int Hs) {
   return tf32_mode() && g_fused == 2 && !(g_simt_mask & 3) && (Hs == 64 || Hs == 128) && g.B <= 65535;
 }
@@ -129,11 +136,12 @@ template <int HS>
 static int cell_forward_fused_h(const Geo& g, const CellW& w, const CellBufs& b, float* h_out, float* h_mma, bool last,
                                 cudaStream_t st) {
   const bool save = b.z != nullptr;
+  const bool save_p = save && !bwd_fused_shape(g, HS, w.Cin);     // the fused backward recomputes nothing from P_k: dW_k = X^T Q_k
   const int ldT = fusedh::ld_half(g.N);
-  fusedh::HOperands og{w.S16, b.x16T, b.x16, b.ib16, w.wg16, save ? b.xpg : nullptr};
+  fusedh::HOperands og{w.S16, b.x16T, b.x16, b.ib16, w.wg16, save_p ? b.xpg : nullptr};
   fusedh::EpiGateH eg{HS, b.hx, b.z, b.r, save ? b.xpu : nullptr, b.zh16, b.zh16T, ldT};
   MCRN_TRY((fusedh::launch_agcn_fused_h<HS, 2 * HS>(g.N, g.B, g.KS, og, g_fused_parts, eg, st)));
-  fusedh::HOperands ou{w.S16, b.zh16T, b.zh16, b.ib16, w.wu16, save ? b.xpu : nullptr};
+  fusedh::HOperands ou{w.S16, b.zh16T, b.zh16, b.ib16, w.wu16, save_p ? b.xpu : nullptr};
   fusedh::EpiUpdateH eu{HS, b.hx, b.r, b.hc, h_out, save ? h_mma : nullptr, last ? nullptr : b.x16, last ? nullptr : b.x16T, ldT};
   MCRN_TRY((fusedh::launch_agcn_fused_h<HS, HS>(g.N, g.B, g.KS, ou, g_fused_parts, eu, st)));
   return MCRN_OK;
@@ -431,6 +439,7 @@ struct Side {
   cudaEvent_t ready[3] = {nullptr, nullptr, nullptr};   // main -> side: buffer i has been written
   cudaEvent_t freed[3] = {nullptr, nullptr, nullptr};   // side -> main: buffer i has been consumed
   bool pending[3] = {false, false, false};
+  bool fused_pending = false;                           // fused backward: side work enqueued since the last join
   cudaEvent_t join = nullptr;
 };
 static Side g_side;
@@ -509,6 +518,92 @@ static int cell_backward(const Geo& g, const Plan& p, float* ws, const float* S,
   MCRN_TRY(acc_ds(g, dXPin + g.R * w.Cin, (int64_t)g.B * w.Cin, b.xpin, b.xp_n, g.B * w.Cin, dS, sd));
   MCRN_TRY(side_end(2));
   if (dxin) MCRN_TRY(propagate_T(g, S, dXPin, w.Cin, nullptr, dxin, st));
+  return MCRN_OK;
+}
+
+// ---- fused backward of one cell (agcn_bwd_fused.cuh) ------------------------------------------------------------
+// In: dH = grad of h_t (already through k_bwd_glue, which also produced dU = dU_all[t]).  Out: dH = grad of h_{t-1};
+// dxin (optional) = grad of the cell's input channels [N][B][Cin].
+struct BwdStep {
+  float *dU, *dG;          // this step's slices of dU_all / dG_all
+  float *Qu, *Qg;          // this step's Q blocks [KS][R][Hs] / [2 KS][R][Hs]
+  float* dXPin;            // this step's [NB][R][Cin]
+};
+// dXP[1..KS] = dV * Wall[1..KS]^T for the dS accumulation (side stream)
+static int make_dxp_s(const Geo& g, const float* dv, int O, const float* wall, int Hs, float* dxp, cudaStream_t st) {
+  GemmDesc q;
+  q.A = dv; q.a_row = O; q.a_k = 1; q.M = (int)g.R; q.Kseg = O;
+  q.B = wall + (int64_t)Hs * O; q.b_k = 1; q.b_n = O; q.N = g.KS * Hs;
+  EpiBlocks e{dxp, Hs, g.R * Hs, 1, -1, nullptr, 1};
+  return gemm(q, e, st);
+}
+template <int HS>
+static int cell_backward_fused(const Geo& g, const Plan& p, float* ws, const float* S, const CellW& w, const CellBufs& b,
+                               const BwdStep& bs, float* dH, float* dxin, cudaStream_t st) {
+  const int64_t nH = g.R * HS;
+  const float* St = ws + p.St;
+  float *dXP = ws + p.dXP, *dXP2 = ws + p.dXP2, *dHp = ws + p.dHp, *dS = ws + p.dS;
+  cudaStream_t sd = g_side.s;
+  // update AGCN: dZH (+ gate backward in the epilogue) ; its dS contribution on the side stream
+  MCRN_TRY(side_begin(0, st));
+  MCRN_TRY(make_dxp_s(g, bs.dU, HS, w.wu, HS, dXP, sd));
+  MCRN_TRY(acc_ds(g, dXP + nH, (int64_t)g.B * HS, b.xpu, (int64_t)g.B * HS, g.B * HS, dS, sd));
+  fusedb::EpiBU eu{HS, b.z, b.r, b.hx, b.hc, dH, bs.dG, dHp};
+  MCRN_TRY((fusedb::launch_agcn_bwd<HS>(g.N, g.B, g.KS, g.ldS, 1, St, bs.dU, w.wu, bs.Qu, ws + p.dIBu16, eu, st)));
+  // gate AGCN
+  MCRN_TRY(side_begin(1, st));
+  MCRN_TRY(make_dxp_s(g, bs.dG, 2 * HS, w.wg, HS, dXP2, sd));
+  MCRN_TRY(acc_ds(g, dXP2 + nH, (int64_t)g.B * HS, b.xpg, (int64_t)g.B * HS, g.B * HS, dS, sd));
+  fusedb::EpiBG eg{HS, dHp, dH};
+  MCRN_TRY((fusedb::launch_agcn_bwd<HS>(g.N, g.B, g.KS, g.ldS, 2, St, bs.dG, w.wg, bs.Qg, ws + p.dIBg16, eg, st)));
+  // input channels: d(input block) of both AGCNs -> dXPin [NB][R][Cin]
+  const int64_t nIn = (int64_t)g.NB * g.R * w.Cin;
+  MCRN_LAUNCH(k_repack_dib, ew_grid(nIn), 256, 0, st, ws + p.dIBu16, ws + p.dIBg16, g.NB, w.Cin, g.R, fusedb::IBW, bs.dXPin, 1);
+  MCRN_TRY(side_begin(2, st));
+  MCRN_TRY(acc_ds(g, bs.dXPin + g.R * w.Cin, (int64_t)g.B * w.Cin, b.xpin, b.xp_n, g.B * w.Cin, dS, sd));
+  g_side.fused_pending = true;   // side work outstanding: joined by side_join_fused
+  if (dxin) MCRN_TRY(propagate_T(g, S, bs.dXPin, w.Cin, nullptr, dxin, st));
+  return MCRN_OK;
+}
+static int side_join_fused(cudaStream_t mainst) {
+  if (g_side.fused_pending) {
+    MCRN_CUDA_OK(cudaEventRecord(g_side.join, g_side.s));
+    MCRN_CUDA_OK(cudaStreamWaitEvent(mainst, g_side.join, 0));
+    g_side.fused_pending = false;
+  }
+  return MCRN_OK;
+}
+// Weight gradients of one AGCN over all steps, fused-backward form:
+//   blocks 0 and NB : dW = sum_t XP_t[blk]^T dV_t            (as acc_dw_all, two blocks)
+//   blocks 1..KS    : dW_k[:, half] = sum_t X_t^T Q_t[k, half]     (X_t = XP_t[0])
+static int acc_dw_fused(const Geo& g, const float* xp0, int64_t xp_step, int T, int Hs, const float* dv_all, const float* q_all,
+                        int nhalf, float* dw, cudaStream_t st) {
+  const int O = nhalf * Hs;
+  for (int t0 = 0; t0 < T; t0 += 16) {
+    const int nt = T - t0 < 16 ? T - t0 : 16;
+    {
+      GemmDesc q;
+      q.A = xp0 + (int64_t)t0 * xp_step; q.a_row = 1; q.a_k = Hs; q.a_batch = (int64_t)g.NB * g.R * Hs; q.a_seg = xp_step;
+      q.M = Hs; q.Kseg = (int)g.R; q.nseg = nt;
+      q.B = dv_all + (int64_t)t0 * g.R * O; q.b_k = O; q.b_n = 1; q.b_batch = 0; q.b_seg = g.R * O; q.N = O;
+      q.nbatch = 2;
+      q.splits = split_for((int64_t)ceil_div(Hs, 128) * ceil_div(O, 128) * 2, (int64_t)nt * g.R / 32);
+      EpiAtomicAdd e{dw, O, (int64_t)g.NB * Hs * O};
+      MCRN_TRY(gemm(q, e, st));
+    }
+    const int64_t q_step = (int64_t)g.KS * nhalf * g.R * Hs;
+    for (int h = 0; h < nhalf; ++h) {
+      GemmDesc q;
+      q.A = xp0 + (int64_t)t0 * xp_step; q.a_row = 1; q.a_k = Hs; q.a_batch = 0; q.a_seg = xp_step;
+      q.M = Hs; q.Kseg = (int)g.R; q.nseg = nt;
+      q.B = q_all + (int64_t)t0 * q_step + (int64_t)h * g.R * Hs; q.b_k = Hs; q.b_n = 1; q.b_batch = (int64_t)nhalf * g.R * Hs;
+      q.b_seg = q_step; q.N = Hs;
+      q.nbatch = g.KS;
+      q.splits = split_for((int64_t)ceil_div(Hs, 128) * ceil_div(Hs, 128) * g.KS, (int64_t)nt * g.R / 32);
+      EpiAtomicAdd e{dw + (int64_t)Hs * O + (int64_t)h * Hs, O, (int64_t)Hs * O};
+      MCRN_TRY(gemm(q, e, st));
+    }
+  }
   return MCRN_OK;
 }
 
@@ -593,16 +688,33 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
   MCRN_CUDA_OK(cudaMemsetAsync(grads->proj_w, 0, (size_t)g.Cout * g.D * sizeof(float), st));
   MCRN_CUDA_OK(cudaMemsetAsync(grads->proj_b, 0, (size_t)g.Cout * sizeof(float), st));
   float *dH = ws + p.dH, *dXin = ws + p.dXin;
+  if (bwd_fused_shape(g, g.D, g.Cdec) || bwd_fused_shape(g, g.H, g.Cin))
+    MCRN_LAUNCH(fusedb::k_transpose_supports, dim3(ceil_div(g.N, 32), ceil_div(g.N, 32), g.KS), dim3(32, 8), 0, st, S, ws + p.St,
+                g.N, g.ldS);
   // ---- decoder, reverse time ----
   {
     CellW w = dec_w(g, p, ws);
     float *dU_all = ws + p.d_dU, *dG_all = ws + p.d_dG;
     bool have_dgo = false;
+    const bool fb = bwd_fused_shape(g, g.D, g.Cdec);
     for (int t = g.T_out - 1; t >= 0; --t) {
       CellBufs b = dec_bufs(g, p, ws, t);
       const float* h_t = (t + 1 < g.T_out) ? dec_bufs(g, p, ws, t + 1).hx : ws + p.h_dec_last;
       bool use_dgo = have_dgo && !(tf && tf[t]);
       size_t shm = (size_t)32 * g.Cout * sizeof(float);
+      if (fb) {
+        bool need_dxin = (t > 0) && !(tf && tf[t - 1]);
+        float* dU_t = dU_all + (int64_t)t * g.R * g.D;
+        MCRN_LAUNCH(fusedb::k_bwd_glue, (int)ceil_div64(g.R, 32), 256, shm, st, d_output, use_dgo ? dXin : nullptr, g.Cdec, h_t,
+                    prm->proj_w, dH, (t == g.T_out - 1) ? 1 : 0, b.r, b.hc, dU_t, grads->proj_w, grads->proj_b, g.B, g.T_out,
+                    g.N, g.D, g.Cout, t);
+        BwdStep bs{dU_t, dG_all + (int64_t)t * g.R * 2 * g.D, ws + p.d_Qu + (int64_t)t * g.KS * g.R * g.D,
+                   ws + p.d_Qg + (int64_t)t * 2 * g.KS * g.R * g.D, ws + p.dXPin_all + p.dXPin_sz * t};
+        if (g.D == 64) MCRN_TRY(cell_backward_fused<64>(g, p, ws, S, w, b, bs, dH, need_dxin ? dXin : nullptr, st));
+        else MCRN_TRY(cell_backward_fused<128>(g, p, ws, S, w, b, bs, dH, need_dxin ? dXin : nullptr, st));
+        have_dgo = need_dxin;
+        continue;
+      }
       MCRN_LAUNCH(k_proj_bwd, (int)ceil_div64(g.R, 32), 256, shm, st, d_output, use_dgo ? dXin : nullptr, g.Cdec, h_t,
                   prm->proj_w, dH, (t == g.T_out - 1) ? 1 : 0, grads->proj_w, grads->proj_b, g.B, g.T_out, g.N, g.D,
                   g.Cout, t);
@@ -612,8 +724,13 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
                              need_dxin ? dXin : nullptr, st));
       have_dgo = need_dxin;
     }
+    if (fb) {
+      MCRN_TRY(acc_dw_fused(g, ws + p.dec_xpu, (int64_t)p.dec_xp_sz, g.T_out, g.D, dU_all, ws + p.d_Qu, 1, ws + p.a_d_wu, st));
+      MCRN_TRY(acc_dw_fused(g, ws + p.dec_xpg, (int64_t)p.dec_xp_sz, g.T_out, g.D, dG_all, ws + p.d_Qg, 2, ws + p.a_d_wg, st));
+    } else {
     MCRN_TRY(acc_dw_all(g, ws + p.dec_xpu, (int64_t)p.dec_xp_sz, g.T_out, g.D, dU_all, g.D, ws + p.a_d_wu, st));
     MCRN_TRY(acc_dw_all(g, ws + p.dec_xpg, (int64_t)p.dec_xp_sz, g.T_out, g.D, dG_all, 2 * g.D, ws + p.a_d_wg, st));
+    }
   }
   // ---- memory query ----
   {
@@ -653,15 +770,33 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
     CellW w = enc_w(g, p, ws);
     float *dU_all = ws + p.e_dU, *dG_all = ws + p.e_dG;
     float* dHe = ws + p.dHenc;
+    const bool fb = bwd_fused_shape(g, g.H, g.Cin);
     for (int t = g.T_in - 1; t >= 0; --t) {
       CellBufs b = enc_bufs(g, p, ws, t);
+      if (fb) {
+        float* dU_t = dU_all + (int64_t)t * g.R * g.H;
+        MCRN_LAUNCH(fusedb::k_bwd_glue, (int)ceil_div64(g.R, 32), 256, 0, st, (const float*)nullptr, (const float*)nullptr, 0,
+                    (const float*)nullptr, (const float*)nullptr, dHe, 0, b.r, b.hc, dU_t, (float*)nullptr, (float*)nullptr, g.B,
+                    g.T_in, g.N, g.H, 0, t);
+        BwdStep bs{dU_t, dG_all + (int64_t)t * g.R * 2 * g.H, ws + p.e_Qu + (int64_t)t * g.KS * g.R * g.H,
+                   ws + p.e_Qg + (int64_t)t * 2 * g.KS * g.R * g.H, ws + p.dXPin_all + p.dXPin_sz * t};
+        if (g.H == 64) MCRN_TRY(cell_backward_fused<64>(g, p, ws, S, w, b, bs, dHe, nullptr, st));
+        else MCRN_TRY(cell_backward_fused<128>(g, p, ws, S, w, b, bs, dHe, nullptr, st));
+        continue;
+      }
       MCRN_TRY(cell_backward(g, p, ws, S, w, b, dU_all + (int64_t)t * g.R * g.H, dG_all + (int64_t)t * g.R * 2 * g.H, dHe, dHe,
                              nullptr, st));
     }
+    if (fb) {
+      MCRN_TRY(acc_dw_fused(g, ws + p.enc_xpu, (int64_t)p.enc_xp_sz, g.T_in, g.H, dU_all, ws + p.e_Qu, 1, ws + p.a_e_wu, st));
+      MCRN_TRY(acc_dw_fused(g, ws + p.enc_xpg, (int64_t)p.enc_xp_sz, g.T_in, g.H, dG_all, ws + p.e_Qg, 2, ws + p.a_e_wg, st));
+    } else {
     MCRN_TRY(acc_dw_all(g, ws + p.enc_xpu, (int64_t)p.enc_xp_sz, g.T_in, g.H, dU_all, g.H, ws + p.a_e_wu, st));
     MCRN_TRY(acc_dw_all(g, ws + p.enc_xpg, (int64_t)p.enc_xp_sz, g.T_in, g.H, dG_all, 2 * g.H, ws + p.a_e_wg, st));
+    }
   }
   MCRN_TRY(side_join(st));        // all dS contributions have landed
+  MCRN_TRY(side_join_fused(st));
   MCRN_TRY(supports_backward(g, p, ws, prm, grads, st));
   // ---- un-fold weight gradients into the reference layout ----
   MCRN_LAUNCH(k_unfold_grads, 128, 256, 0, st, ws + p.a_e_wg, grads->enc_gate_w, grads->enc_gate_b, g.Cin, g.H, 2 * g.H, g.cheb_k);

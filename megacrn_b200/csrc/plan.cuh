@@ -34,6 +34,10 @@ struct Plan {
   size_t dS, a_e_wg, a_e_wu, a_d_wg, a_d_wu;
   size_t dg1, dg2;
   size_t dLa, dLb, dL1, dE1, dE2;
+  // fused backward (agcn_bwd_fused.cuh): transposed supports, Q blocks of every step, input-block gradients,
+  // per-step dXPin
+  size_t St, e_Qu, e_Qg, d_Qu, d_Qg, dIBu16, dIBg16, dXPin_all;
+  size_t dXPin_sz;
   // loss scratch
   size_t loss_scratch;                   // 8 floats
 };
@@ -118,6 +122,15 @@ static inline int make_plan(const Geo& g, bool save, Plan* p) {
     p->mq_dsc = take(R * g.M);
     p->mq_dq = take(R * g.d);
     p->dHenc = take(R * g.H);
+    p->St = take(KS * N * ldS);
+    p->e_Qu = take((size_t)g.T_in * KS * R * g.H);
+    p->e_Qg = take((size_t)g.T_in * 2 * KS * R * g.H);
+    p->d_Qu = take((size_t)g.T_out * KS * R * g.D);
+    p->d_Qg = take((size_t)g.T_out * 2 * KS * R * g.D);
+    p->dIBu16 = take(R * 16);
+    p->dIBg16 = take(R * 16);
+    p->dXPin_sz = (NB * R * Cm + 63) / 64 * 64;
+    p->dXPin_all = take(p->dXPin_sz * (size_t)(g.T_in > g.T_out ? g.T_in : g.T_out));
     p->acc_begin = off;
     p->dS = take(KS * N * ldS);
     p->a_e_wg = take((NB + 1) * g.H * 2 * g.H);
