@@ -85,27 +85,23 @@ __device__ __forceinline__ void for_each_item_b(int nks, int nhalf, int kb1, F&&
 
 // ---- epilogue functors (4 consecutive columns of one (node, b) row) -----------------------------
 // Update-AGCN backward tail = the gate backward of the cell (tests/kernel_spec.py:cell_bwd):
-//   dZH = acc ; dG[:, :H] = dZH*h*z(1-z) ; dG[:, H:] = dH'*(h-hc)*r(1-r) ; dh_part = dH'*r + dZH*z
+//   dZH = acc ; dG[:, :H] = dZH*h*z(1-z) ; dh_part = dH'*r + dZH*z
+// (dG[:, H:] = dH'*(h-hc)*r(1-r) and dHr = dH'*r do not depend on dZH: k_bwd_glue has already written them)
 struct EpiBU {
-  static constexpr int NP = 5;
+  static constexpr int NP = 3;
   int H;
-  const float *z, *r, *h, *hc, *dH;
+  const float *z, *h, *dHr;
   float *dG, *dh_part;
   __device__ __forceinline__ void load4(int row, int n0, float4 (&p)[NP]) const {
     const int64_t f = (int64_t)row * H + n0;
-    p[0] = ldg4(z + f); p[1] = ldg4(r + f); p[2] = ldg4(h + f); p[3] = ldg4(dH + f); p[4] = ldg4(hc + f);
+    p[0] = ldg4(z + f); p[1] = ldg4(h + f); p[2] = ldg4(dHr + f);
   }
   __device__ __forceinline__ void fin4(int row, int n0, const float4 (&p)[NP], const float (&acc)[4]) const {
-    const float4 zz = p[0], rr = p[1], hh = p[2], dh = p[3], cc = p[4];
+    const float4 zz = p[0], hh = p[1], dr = p[2];
     const float d0 = acc[0], d1 = acc[1], d2 = acc[2], d3 = acc[3];
-    const float g0 = tf32_rn(d0 * hh.x * zz.x * (1.0f - zz.x)), g1 = tf32_rn(d1 * hh.y * zz.y * (1.0f - zz.y));
-    const float g2 = tf32_rn(d2 * hh.z * zz.z * (1.0f - zz.z)), g3 = tf32_rn(d3 * hh.w * zz.w * (1.0f - zz.w));
-    const float q0 = tf32_rn(dh.x * (hh.x - cc.x) * rr.x * (1.0f - rr.x)), q1 = tf32_rn(dh.y * (hh.y - cc.y) * rr.y * (1.0f - rr.y));
-    const float q2 = tf32_rn(dh.z * (hh.z - cc.z) * rr.z * (1.0f - rr.z)), q3 = tf32_rn(dh.w * (hh.w - cc.w) * rr.w * (1.0f - rr.w));
-    float* g = dG + (int64_t)row * 2 * H + n0;
-    st4(g, g0, g1, g2, g3);
-    st4(g + H, q0, q1, q2, q3);
-    st4(dh_part + (int64_t)row * H + n0, dh.x * rr.x + d0 * zz.x, dh.y * rr.y + d1 * zz.y, dh.z * rr.z + d2 * zz.z, dh.w * rr.w + d3 * zz.w);
+    st4(dG + (int64_t)row * 2 * H + n0, tf32_rn(d0 * hh.x * zz.x * (1.0f - zz.x)), tf32_rn(d1 * hh.y * zz.y * (1.0f - zz.y)),
+        tf32_rn(d2 * hh.z * zz.z * (1.0f - zz.z)), tf32_rn(d3 * hh.w * zz.w * (1.0f - zz.w)));
+    st4(dh_part + (int64_t)row * H + n0, dr.x + d0 * zz.x, dr.y + d1 * zz.y, dr.z + d2 * zz.z, dr.w + d3 * zz.w);
   }
 };
 // Gate-AGCN backward tail: dH_prev = acc + dh_part
@@ -301,7 +297,7 @@ agcn_bwd_kernel(const __grid_constant__ CUtensorMap tmST, const __grid_constant_
         for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(&scr[lane * 36 + i]) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         __syncwarp();
         const int col = c * 32 + cq;
-        constexpr int RB = Epi::NP <= 2 ? 8 : (Epi::NP <= 4 ? 4 : 2);
+        constexpr int RB = Epi::NP <= 2 ? 8 : 4;
 #pragma unroll
         for (int b0 = 0; b0 < 8; b0 += RB) {
           float4 pre[RB][Epi::NP];
@@ -358,15 +354,22 @@ __global__ void k_transpose_supports(const float* __restrict__ S, float* __restr
   }
 }
 
-// Step glue of the fused backward: dH = [dH_in] + d_out_t . wp (projection backward, model/MegaCRN.py:186), then
-// dU = dH * (1-r) * (1-hc^2) (TF32-rounded).  Also accumulates dwp, dbp.  One block = 32 rows, thread j = column j.
+// Step glue of the fused backward (everything elementwise between two cells, one pass):
+//   dH   = [dH_in] + d_out_t . wp                       projection backward (model/MegaCRN.py:186); dwp, dbp accumulate
+//   dU   = dH * (1-r) * (1-hc^2)                        -> dV of the update AGCN (TF32-rounded)
+//   dG_r = dH * (h-hc) * r(1-r)                         -> columns [D, 2D) of dG (TF32-rounded)
+//   dHr  = dH * r                                       -> the part of dh_part that does not depend on dZH
+// One block = 32 rows; a thread owns 4 consecutive columns.  D % 4 == 0, D <= 1024.
 __global__ void __launch_bounds__(256) k_bwd_glue(const float* __restrict__ dOut, const float* __restrict__ dxin, int dxin_stride,
                                                   const float* __restrict__ h_t, const float* __restrict__ wp,
-                                                  float* __restrict__ dH, int dh_init, const float* __restrict__ r,
-                                                  const float* __restrict__ hc, float* __restrict__ dU,
+                                                  const float* __restrict__ dH, int dh_init, const float* __restrict__ r,
+                                                  const float* __restrict__ hc, const float* __restrict__ hx,
+                                                  float* __restrict__ dU, float* __restrict__ dG, float* __restrict__ dHr,
                                                   float* __restrict__ dwp, float* __restrict__ dbp, int B, int T, int N,
                                                   int D, int Cout, int t) {
-  extern __shared__ float sh_do[];                 // [32][Cout]
+  extern __shared__ float sh[];                    // [32][Cout] d_out rows, then [Cout][D] dwp partials
+  float* sh_do = sh;
+  float* sh_w = sh + 32 * Cout;
   const int64_t R = (int64_t)N * B, r0 = (int64_t)blockIdx.x * 32;
   const bool proj = (dOut != nullptr) || (dxin != nullptr);
   if (proj) {
@@ -381,36 +384,41 @@ __global__ void __launch_bounds__(256) k_bwd_glue(const float* __restrict__ dOut
       }
       sh_do[i] = v;
     }
+    for (int i = threadIdx.x; i < Cout * D; i += blockDim.x) sh_w[i] = 0.f;
     __syncthreads();
   }
-  for (int j = threadIdx.x; j < D; j += blockDim.x) {
-    float accw[4] = {0.f, 0.f, 0.f, 0.f};          // Cout <= 4 accumulated in registers, more via the slow path below
-#pragma unroll 4
-    for (int i = 0; i < 32; ++i) {
-      const int64_t row = r0 + i;
-      if (row >= R) break;
-      const int64_t o = row * D + j;
-      float v = dh_init ? 0.f : dH[o];
-      if (proj) {
-        const float hv = __ldg(h_t + o);
-        for (int co = 0; co < Cout; ++co) {
-          const float d = sh_do[i * Cout + co];
-          v = fmaf(d, __ldg(wp + (int64_t)co * D + j), v);
-          if (co < 4) accw[co] = fmaf(d, hv, accw[co]);
-          else atomicAdd(dwp + (int64_t)co * D + j, d * hv);
-        }
+  const int Q = D >> 2;
+  for (int e = threadIdx.x; e < 32 * Q; e += blockDim.x) {
+    const int i = e / Q, q4 = (e - i * Q) * 4;
+    const int64_t row = r0 + i;
+    if (row >= R) continue;
+    const int64_t o = row * D + q4;
+    float4 v = dh_init ? make_float4(0.f, 0.f, 0.f, 0.f) : ldg4(dH + o);
+    if (proj) {
+      const float4 hv = ldg4(h_t + o);
+      for (int co = 0; co < Cout; ++co) {
+        const float d = sh_do[i * Cout + co];
+        const float4 w4 = ldg4(wp + (int64_t)co * D + q4);
+        v.x = fmaf(d, w4.x, v.x); v.y = fmaf(d, w4.y, v.y); v.z = fmaf(d, w4.z, v.z); v.w = fmaf(d, w4.w, v.w);
+        float* sw = sh_w + co * D + q4;
+        atomicAdd(sw, d * hv.x); atomicAdd(sw + 1, d * hv.y); atomicAdd(sw + 2, d * hv.z); atomicAdd(sw + 3, d * hv.w);
       }
-      dH[o] = v;
-      const float c = __ldg(hc + o);
-      dU[o] = tf32_rn(v * (1.0f - __ldg(r + o)) * (1.0f - c * c));
     }
-    if (proj)
-      for (int co = 0; co < Cout && co < 4; ++co) atomicAdd(dwp + (int64_t)co * D + j, accw[co]);
+    const float4 rr = ldg4(r + o), cc = ldg4(hc + o), hh = ldg4(hx + o);
+    st4(dU + o, tf32_rn(v.x * (1.0f - rr.x) * (1.0f - cc.x * cc.x)), tf32_rn(v.y * (1.0f - rr.y) * (1.0f - cc.y * cc.y)),
+        tf32_rn(v.z * (1.0f - rr.z) * (1.0f - cc.z * cc.z)), tf32_rn(v.w * (1.0f - rr.w) * (1.0f - cc.w * cc.w)));
+    st4(dG + row * 2 * D + D + q4, tf32_rn(v.x * (hh.x - cc.x) * rr.x * (1.0f - rr.x)), tf32_rn(v.y * (hh.y - cc.y) * rr.y * (1.0f - rr.y)),
+        tf32_rn(v.z * (hh.z - cc.z) * rr.z * (1.0f - rr.z)), tf32_rn(v.w * (hh.w - cc.w) * rr.w * (1.0f - rr.w)));
+    st4(dHr + o, v.x * rr.x, v.y * rr.y, v.z * rr.z, v.w * rr.w);
   }
-  if (proj && threadIdx.x < Cout) {
-    float s = 0.f;
-    for (int i = 0; i < 32; ++i) s += sh_do[i * Cout + threadIdx.x];
-    atomicAdd(dbp + threadIdx.x, s);
+  if (proj) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < Cout * D; i += blockDim.x) atomicAdd(dwp + i, sh_w[i]);
+    if (threadIdx.x < Cout) {
+      float s = 0.f;
+      for (int i = 0; i < 32; ++i) s += sh_do[i * Cout + threadIdx.x];
+      atomicAdd(dbp + threadIdx.x, s);
+    }
   }
 }
 

@@ -548,7 +548,7 @@ static int cell_backward_fused(const Geo& g, const Plan& p, float* ws, const flo
   MCRN_TRY(side_begin(0, st));
   MCRN_TRY(make_dxp_s(g, bs.dU, HS, w.wu, HS, dXP, sd));
   MCRN_TRY(acc_ds(g, dXP + nH, (int64_t)g.B * HS, b.xpu, (int64_t)g.B * HS, g.B * HS, dS, sd));
-  fusedb::EpiBU eu{HS, b.z, b.r, b.hx, b.hc, dH, bs.dG, dHp};
+  fusedb::EpiBU eu{HS, b.z, b.hx, ws + p.dHr, bs.dG, dHp};
   MCRN_TRY((fusedb::launch_agcn_bwd<HS>(g.N, g.B, g.KS, g.ldS, 1, St, bs.dU, w.wu, bs.Qu, ws + p.dIBu16, eu, st)));
   // gate AGCN
   MCRN_TRY(side_begin(1, st));
@@ -705,9 +705,10 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
       if (fb) {
         bool need_dxin = (t > 0) && !(tf && tf[t - 1]);
         float* dU_t = dU_all + (int64_t)t * g.R * g.D;
-        MCRN_LAUNCH(fusedb::k_bwd_glue, (int)ceil_div64(g.R, 32), 256, shm, st, d_output, use_dgo ? dXin : nullptr, g.Cdec, h_t,
-                    prm->proj_w, dH, (t == g.T_out - 1) ? 1 : 0, b.r, b.hc, dU_t, grads->proj_w, grads->proj_b, g.B, g.T_out,
-                    g.N, g.D, g.Cout, t);
+        MCRN_LAUNCH(fusedb::k_bwd_glue, (int)ceil_div64(g.R, 32), 256, (size_t)(32 + g.D) * g.Cout * sizeof(float), st, d_output,
+                    use_dgo ? dXin : nullptr, g.Cdec, h_t, prm->proj_w, dH, (t == g.T_out - 1) ? 1 : 0, b.r, b.hc, b.hx, dU_t,
+                    dG_all + (int64_t)t * g.R * 2 * g.D, ws + p.dHr, grads->proj_w, grads->proj_b, g.B, g.T_out, g.N, g.D,
+                    g.Cout, t);
         BwdStep bs{dU_t, dG_all + (int64_t)t * g.R * 2 * g.D, ws + p.d_Qu + (int64_t)t * g.KS * g.R * g.D,
                    ws + p.d_Qg + (int64_t)t * 2 * g.KS * g.R * g.D, ws + p.dXPin_all + p.dXPin_sz * t};
         if (g.D == 64) MCRN_TRY(cell_backward_fused<64>(g, p, ws, S, w, b, bs, dH, need_dxin ? dXin : nullptr, st));
@@ -776,8 +777,8 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
       if (fb) {
         float* dU_t = dU_all + (int64_t)t * g.R * g.H;
         MCRN_LAUNCH(fusedb::k_bwd_glue, (int)ceil_div64(g.R, 32), 256, 0, st, (const float*)nullptr, (const float*)nullptr, 0,
-                    (const float*)nullptr, (const float*)nullptr, dHe, 0, b.r, b.hc, dU_t, (float*)nullptr, (float*)nullptr, g.B,
-                    g.T_in, g.N, g.H, 0, t);
+                    (const float*)nullptr, (const float*)nullptr, dHe, 0, b.r, b.hc, b.hx, dU_t,
+                    dG_all + (int64_t)t * g.R * 2 * g.H, ws + p.dHr, (float*)nullptr, (float*)nullptr, g.B, g.T_in, g.N, g.H, 0, t);
         BwdStep bs{dU_t, dG_all + (int64_t)t * g.R * 2 * g.H, ws + p.e_Qu + (int64_t)t * g.KS * g.R * g.H,
                    ws + p.e_Qg + (int64_t)t * 2 * g.KS * g.R * g.H, ws + p.dXPin_all + p.dXPin_sz * t};
         if (g.H == 64) MCRN_TRY(cell_backward_fused<64>(g, p, ws, S, w, b, bs, dHe, nullptr, st));

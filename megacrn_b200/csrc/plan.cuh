@@ -36,7 +36,7 @@ struct Plan {
   size_t dLa, dLb, dL1, dE1, dE2;
   // fused backward (agcn_bwd_fused.cuh): transposed supports, Q blocks of every step, input-block gradients,
   // per-step dXPin
-  size_t St, e_Qu, e_Qg, d_Qu, d_Qg, dIBu16, dIBg16, dXPin_all;
+  size_t St, e_Qu, e_Qg, d_Qu, d_Qg, dIBu16, dIBg16, dXPin_all, dHr;
   size_t dXPin_sz;
   // loss scratch
   size_t loss_scratch;                   // 8 floats
@@ -127,6 +127,7 @@ static inline int make_plan(const Geo& g, bool save, Plan* p) {
     p->e_Qg = take((size_t)g.T_in * 2 * KS * R * g.H);
     p->d_Qu = take((size_t)g.T_out * KS * R * g.D);
     p->d_Qg = take((size_t)g.T_out * 2 * KS * R * g.D);
+    p->dHr = take(R * g.D);
     p->dIBu16 = take(R * 16);
     p->dIBg16 = take(R * 16);
     p->dXPin_sz = (NB * R * Cm + 63) / 64 * 64;
