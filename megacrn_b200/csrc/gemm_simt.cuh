@@ -1,15 +1,17 @@
 // SIMT fp32 GEMM: exact-fp32 engine used (a) for shapes the tcgen05 path does not take
 // (stride alignment below 16 B, tiny problems), (b) as the on-device cross-check of the
 // tensor-core kernels in tests, and (c) when mcrn_set_engine(1) forces it.
-// 64x64x16 tiles, 256 threads, 4x4 register micro-tiles, operands through generic strides.
+// 64x64x32 tiles, 256 threads, 4x4 register micro-tiles, register-prefetched k-tiles, operands through generic strides.
 #pragma once
 
 #include "gemm.cuh"
 
 namespace mcrn {
 
-constexpr int SIMT_BM = 64, SIMT_BN = 64, SIMT_BK = 16, SIMT_THREADS = 256;
+constexpr int SIMT_BM = 64, SIMT_BN = 64, SIMT_BK = 32, SIMT_THREADS = 256;
 
+// 64x64x32 tiles; the global loads of k-tile i+1 are issued into registers before the FMAs of k-tile i, so the load
+// latency of the (short, latency-bound) problems this engine serves overlaps the arithmetic.
 template <class Epi>
 __global__ void __launch_bounds__(SIMT_THREADS) gemm_simt_kernel(GemmDesc g, Epi epi) {
   __shared__ float As[SIMT_BK][SIMT_BM + 4];
@@ -25,29 +27,44 @@ __global__ void __launch_bounds__(SIMT_THREADS) gemm_simt_kernel(GemmDesc g, Epi
   const int it0 = split * per, it1 = min(total, it0 + per);
   const bool a_kc = (g.a_k == 1), b_nc = (g.b_n == 1);
   const int tx = tid & 15, ty = tid >> 4;
+  constexpr int EPT = SIMT_BM * SIMT_BK / SIMT_THREADS;      // 8 elements of each operand per thread and k-tile
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-
-  for (int it = it0; it < it1; ++it) {
+  float ra[EPT], rb[EPT];
+  auto fetch = [&](int it) {
     const int seg = it / ktiles, k0 = (it - seg * ktiles) * SIMT_BK;
     const float* As_g = A + (int64_t)g.seg_a(seg) * g.a_seg;
     const float* Bs_g = B + (int64_t)g.seg_b(seg) * g.b_seg;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      int idx = tid + e * SIMT_THREADS;     // 0..1023
+    for (int e = 0; e < EPT; ++e) {
+      const int idx = tid + e * SIMT_THREADS;     // 0..2047
       int mm, kk;
-      if (a_kc) { mm = idx >> 4; kk = idx & 15; } else { kk = idx >> 6; mm = idx & 63; }
-      int gm = m0 + mm, gk = k0 + kk;
-      As[kk][mm] = (gm < g.M && gk < g.Kseg) ? As_g[(int64_t)gm * g.a_row + (int64_t)gk * g.a_k] : 0.f;
+      if (a_kc) { mm = idx >> 5; kk = idx & 31; } else { kk = idx >> 6; mm = idx & 63; }
+      const int gm = m0 + mm, gk = k0 + kk;
+      ra[e] = (gm < g.M && gk < g.Kseg) ? __ldg(As_g + (int64_t)gm * g.a_row + (int64_t)gk * g.a_k) : 0.f;
       int nn, kb;
-      if (b_nc) { kb = idx >> 6; nn = idx & 63; } else { nn = idx >> 4; kb = idx & 15; }
-      int gn = n0 + nn, gkb = k0 + kb;
-      Bs[kb][nn] = (gn < g.N && gkb < g.Kseg) ? Bs_g[(int64_t)gkb * g.b_k + (int64_t)gn * g.b_n] : 0.f;
+      if (b_nc) { kb = idx >> 6; nn = idx & 63; } else { nn = idx >> 5; kb = idx & 31; }
+      const int gn = n0 + nn, gkb = k0 + kb;
+      rb[e] = (gn < g.N && gkb < g.Kseg) ? __ldg(Bs_g + (int64_t)gkb * g.b_k + (int64_t)gn * g.b_n) : 0.f;
+    }
+  };
+  if (it0 < it1) fetch(it0);
+  for (int it = it0; it < it1; ++it) {
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      const int idx = tid + e * SIMT_THREADS;
+      int mm, kk;
+      if (a_kc) { mm = idx >> 5; kk = idx & 31; } else { kk = idx >> 6; mm = idx & 63; }
+      As[kk][mm] = ra[e];
+      int nn, kb;
+      if (b_nc) { kb = idx >> 6; nn = idx & 63; } else { nn = idx >> 5; kb = idx & 31; }
+      Bs[kb][nn] = rb[e];
     }
     __syncthreads();
+    if (it + 1 < it1) fetch(it + 1);                // in flight while this tile is multiplied
 #pragma unroll
     for (int kk = 0; kk < SIMT_BK; ++kk) {
       float a[4], b[4];

@@ -441,6 +441,9 @@ struct Side {
   bool pending[3] = {false, false, false};
   bool fused_pending = false;                           // fused backward: side work enqueued since the last join
   cudaEvent_t join = nullptr;
+  cudaStream_t s2 = nullptr;                            // second side stream: the weight-gradient GEMMs of the fused backward
+  cudaEvent_t fork2 = nullptr, join2 = nullptr;
+  bool s2_pending = false;
 };
 static Side g_side;
 static int side_init() {
@@ -451,6 +454,9 @@ static int side_init() {
     MCRN_CUDA_OK(cudaEventCreateWithFlags(&g_side.freed[i], cudaEventDisableTiming));
   }
   MCRN_CUDA_OK(cudaEventCreateWithFlags(&g_side.join, cudaEventDisableTiming));
+  MCRN_CUDA_OK(cudaStreamCreateWithFlags(&g_side.s2, cudaStreamNonBlocking));
+  MCRN_CUDA_OK(cudaEventCreateWithFlags(&g_side.fork2, cudaEventDisableTiming));
+  MCRN_CUDA_OK(cudaEventCreateWithFlags(&g_side.join2, cudaEventDisableTiming));
   return MCRN_OK;
 }
 // main stream has just produced buffer i: let the side stream start on it
@@ -563,6 +569,21 @@ static int cell_backward_fused(const Geo& g, const Plan& p, float* ws, const flo
   MCRN_TRY(acc_ds(g, bs.dXPin + g.R * w.Cin, (int64_t)g.B * w.Cin, b.xpin, b.xp_n, g.B * w.Cin, dS, sd));
   g_side.fused_pending = true;   // side work outstanding: joined by side_join_fused
   if (dxin) MCRN_TRY(propagate_T(g, S, bs.dXPin, w.Cin, nullptr, dxin, st));
+  return MCRN_OK;
+}
+// second side stream: everything enqueued on main so far is a dependency of what follows on s2
+static int side2_fork(cudaStream_t mainst) {
+  MCRN_CUDA_OK(cudaEventRecord(g_side.fork2, mainst));
+  MCRN_CUDA_OK(cudaStreamWaitEvent(g_side.s2, g_side.fork2, 0));
+  g_side.s2_pending = true;
+  return MCRN_OK;
+}
+static int side2_join(cudaStream_t mainst) {
+  if (g_side.s2_pending) {
+    MCRN_CUDA_OK(cudaEventRecord(g_side.join2, g_side.s2));
+    MCRN_CUDA_OK(cudaStreamWaitEvent(mainst, g_side.join2, 0));
+    g_side.s2_pending = false;
+  }
   return MCRN_OK;
 }
 static int side_join_fused(cudaStream_t mainst) {
@@ -725,9 +746,10 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
                              need_dxin ? dXin : nullptr, st));
       have_dgo = need_dxin;
     }
-    if (fb) {
-      MCRN_TRY(acc_dw_fused(g, ws + p.dec_xpu, (int64_t)p.dec_xp_sz, g.T_out, g.D, dU_all, ws + p.d_Qu, 1, ws + p.a_d_wu, st));
-      MCRN_TRY(acc_dw_fused(g, ws + p.dec_xpg, (int64_t)p.dec_xp_sz, g.T_out, g.D, dG_all, ws + p.d_Qg, 2, ws + p.a_d_wg, st));
+    if (fb) {   // weight gradients of the decoder: off the critical path, concurrent with the memory / encoder backward
+      MCRN_TRY(side2_fork(st));
+      MCRN_TRY(acc_dw_fused(g, ws + p.dec_xpu, (int64_t)p.dec_xp_sz, g.T_out, g.D, dU_all, ws + p.d_Qu, 1, ws + p.a_d_wu, g_side.s2));
+      MCRN_TRY(acc_dw_fused(g, ws + p.dec_xpg, (int64_t)p.dec_xp_sz, g.T_out, g.D, dG_all, ws + p.d_Qg, 2, ws + p.a_d_wg, g_side.s2));
     } else {
     MCRN_TRY(acc_dw_all(g, ws + p.dec_xpu, (int64_t)p.dec_xp_sz, g.T_out, g.D, dU_all, g.D, ws + p.a_d_wu, st));
     MCRN_TRY(acc_dw_all(g, ws + p.dec_xpg, (int64_t)p.dec_xp_sz, g.T_out, g.D, dG_all, 2 * g.D, ws + p.a_d_wg, st));
@@ -788,9 +810,10 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
       MCRN_TRY(cell_backward(g, p, ws, S, w, b, dU_all + (int64_t)t * g.R * g.H, dG_all + (int64_t)t * g.R * 2 * g.H, dHe, dHe,
                              nullptr, st));
     }
-    if (fb) {
-      MCRN_TRY(acc_dw_fused(g, ws + p.enc_xpu, (int64_t)p.enc_xp_sz, g.T_in, g.H, dU_all, ws + p.e_Qu, 1, ws + p.a_e_wu, st));
-      MCRN_TRY(acc_dw_fused(g, ws + p.enc_xpg, (int64_t)p.enc_xp_sz, g.T_in, g.H, dG_all, ws + p.e_Qg, 2, ws + p.a_e_wg, st));
+    if (fb) {   // concurrent with the supports backward
+      MCRN_TRY(side2_fork(st));
+      MCRN_TRY(acc_dw_fused(g, ws + p.enc_xpu, (int64_t)p.enc_xp_sz, g.T_in, g.H, dU_all, ws + p.e_Qu, 1, ws + p.a_e_wu, g_side.s2));
+      MCRN_TRY(acc_dw_fused(g, ws + p.enc_xpg, (int64_t)p.enc_xp_sz, g.T_in, g.H, dG_all, ws + p.e_Qg, 2, ws + p.a_e_wg, g_side.s2));
     } else {
     MCRN_TRY(acc_dw_all(g, ws + p.enc_xpu, (int64_t)p.enc_xp_sz, g.T_in, g.H, dU_all, g.H, ws + p.a_e_wu, st));
     MCRN_TRY(acc_dw_all(g, ws + p.enc_xpg, (int64_t)p.enc_xp_sz, g.T_in, g.H, dG_all, 2 * g.H, ws + p.a_e_wg, st));
@@ -799,6 +822,7 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
   MCRN_TRY(side_join(st));        // all dS contributions have landed
   MCRN_TRY(side_join_fused(st));
   MCRN_TRY(supports_backward(g, p, ws, prm, grads, st));
+  MCRN_TRY(side2_join(st));
   // ---- un-fold weight gradients into the reference layout ----
   MCRN_LAUNCH(k_unfold_grads, 128, 256, 0, st, ws + p.a_e_wg, grads->enc_gate_w, grads->enc_gate_b, g.Cin, g.H, 2 * g.H, g.cheb_k);
   MCRN_LAUNCH(k_unfold_grads, 128, 256, 0, st, ws + p.a_e_wu, grads->enc_update_w, grads->enc_update_b, g.Cin, g.H, g.H, g.cheb_k);
