@@ -184,6 +184,12 @@ int mcrn_set_debug_mask(int mask);
  * operands (csrc/agcn_fused.cuh), 0 = per-stage GEMM kernels.
  * weight_parts: 2 = hi + lo residual of the weights (default), 1 = hi only. */
 int mcrn_set_fused(int fused, int weight_parts);
+/* Per-kernel timing for bench.py's roofline: while enabled, every EAGER launch of a fused AGCN kernel is bracketed by CUDA
+ * events on its launching stream (launches under stream capture are not).  kernel_class = direction*8 + (HS==128 ? 4 : 0) +
+ * variant; direction 0 = forward (variant 0 gate, 1 update), 1 = backward (variant 0 update-AGCN, 1 gate-AGCN).
+ * mcrn_kernel_timing(1) also resets the record; _read synchronises the recorded events and returns their summed duration. */
+int mcrn_kernel_timing(int enable);
+int mcrn_kernel_timing_read(int kernel_class, float* ms_total, int* launches);
 /* Backward data path of every AGCN as one fused kernel (csrc/agcn_bwd_fused.cuh): 1 = on (default) where the hidden
  * width is 64 or 128, 0 = per-stage GEMM kernels.  Set it before the forward whose backward it governs. */
 int mcrn_set_bwd_fused(int fused);

@@ -68,6 +68,10 @@ def load() -> C.CDLL:
     lib.mcrn_get_engine.restype = C.c_int
     lib.mcrn_debug_fused_timeline.restype = C.c_int
     lib.mcrn_debug_fused_timeline.argtypes = [C.c_void_p, C.c_int]
+    lib.mcrn_kernel_timing.restype = C.c_int
+    lib.mcrn_kernel_timing.argtypes = [C.c_int]
+    lib.mcrn_kernel_timing_read.restype = C.c_int
+    lib.mcrn_kernel_timing_read.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     lib.mcrn_set_bwd_fused.restype = C.c_int
     lib.mcrn_set_bwd_fused.argtypes = [C.c_int]
     lib.mcrn_set_fused.restype = C.c_int

@@ -3,13 +3,13 @@
 #include <unordered_map>
 
 #include "engine.cuh"
+#include "agcn_fused.cuh"
 #include "plan.cuh"
 
 namespace mcrn {
 int g_engine = 0;
 extern int g_simt_mask;
 extern int g_fused, g_fused_parts, g_bwd_fused;
-namespace fused { extern long long* g_dbg_timeline; extern int g_dbg_which, g_dbg_count; }
 const char* last_error();
 int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const float* x, const float* y_cov,
                  const float* labels, const uint8_t* tf, float* output, float* h_att, float* query, float* pos,
@@ -77,6 +77,25 @@ int mcrn_get_engine(void) { return g_engine; }
 int mcrn_set_debug_mask(int mask) { g_simt_mask = mask; return MCRN_OK; }
 int mcrn_debug_fused_timeline(long long* device_slots, int which) {
   fused::g_dbg_timeline = device_slots; fused::g_dbg_which = which; fused::g_dbg_count = 0;
+  return MCRN_OK;
+}
+int mcrn_kernel_timing(int enable) {
+  fused::g_prof.enabled = enable ? 1 : 0;
+  if (enable) fused::g_prof.count = 0;
+  return MCRN_OK;
+}
+int mcrn_kernel_timing_read(int kernel_class, float* ms_total, int* launches) {
+  if (!ms_total || !launches) { set_error("mcrn_kernel_timing_read: null output"); return MCRN_ERR_BAD_POINTER; }
+  *ms_total = 0.f; *launches = 0;
+  for (int i = 0; i < fused::g_prof.count; ++i) {
+    if (fused::g_prof.cls[i] != kernel_class) continue;
+    float ms = 0.f;
+    if (cudaEventSynchronize(fused::g_prof.ev[i][1]) != cudaSuccess || cudaEventElapsedTime(&ms, fused::g_prof.ev[i][0], fused::g_prof.ev[i][1]) != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    *ms_total += ms; *launches += 1;
+  }
   return MCRN_OK;
 }
 int mcrn_set_bwd_fused(int fused) { g_bwd_fused = fused ? 1 : 0; return MCRN_OK; }

@@ -464,7 +464,9 @@ int launch_agcn_bwd(int N, int B, int KS, int ldS, int nhalf, const float* St, c
     attr_set = true;
   }
   dim3 grid(ceil_div(N, BM), B, 1);
+  const int pi = fused::prof_begin(fused::prof_class(1, HS, nhalf == 2 ? 1 : 0), st);
   MCRN_LAUNCH(kern, grid, BTHREADS, C::SMEM, st, tST, tVB, tVA, tW, tWib, p, epi);
+  fused::prof_end(pi, st);
   return MCRN_OK;
 }
 

@@ -91,6 +91,34 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 
 enum : int { ITEM_P = 0, ITEM_SS = 1, ITEM_TS = 2 };
 
+// ---- per-kernel-class timing (bench.py roofline): CUDA events recorded on the launching stream around every fused
+// launch while enabled (eager launches only; a capturing stream is left alone).  Classes: HS/O/direction, see prof_class.
+struct KernelProf {
+  static constexpr int NCLS = 16, NEV = 1024;
+  int enabled = 0;
+  int count = 0;
+  cudaEvent_t ev[NEV][2];
+  int cls[NEV];
+  bool created = false;
+};
+extern KernelProf g_prof;
+// class id: direction (0 fwd, 1 bwd) * 8 + (HS == 128 ? 4 : 0) + variant (fwd: 0 gate / 1 update; bwd: 0 BU / 1 BG)
+static inline int prof_class(int bwd, int HS, int variant) { return bwd * 8 + (HS == 128 ? 4 : 0) + variant; }
+static inline int prof_begin(int cls, cudaStream_t st) {
+  if (!g_prof.enabled || g_prof.count >= KernelProf::NEV) return -1;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return -1;
+  if (!g_prof.created) {
+    for (int i = 0; i < KernelProf::NEV; ++i) { cudaEventCreate(&g_prof.ev[i][0]); cudaEventCreate(&g_prof.ev[i][1]); }
+    g_prof.created = true;
+  }
+  const int i = g_prof.count++;
+  g_prof.cls[i] = cls;
+  cudaEventRecord(g_prof.ev[i][0], st);
+  return i;
+}
+static inline void prof_end(int i, cudaStream_t st) { if (i >= 0) cudaEventRecord(g_prof.ev[i][1], st); }
+
 constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
 template <int HS, int O>
@@ -410,7 +438,9 @@ int launch_agcn_fused(int N, int B, int KS, int ldS, const float* S, float* xp, 
     attr_set = true;
   }
   dim3 grid(ceil_div(N, BM), B, 1);
+  const int pi = prof_begin(prof_class(0, HS, O == HS ? 1 : 0), st);
   MCRN_LAUNCH(kern, grid, THREADS, C::SMEM, st, tS, tXA, tXB, tW, p, epi);
+  prof_end(pi, st);
   return MCRN_OK;
 }
 

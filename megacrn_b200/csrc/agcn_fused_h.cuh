@@ -498,7 +498,9 @@ int launch_agcn_fused_h(int N, int B, int KS, const HOperands& op, int nparts, c
     attr_set = true;
   }
   dim3 grid(ceil_div(N, BM), B, 1);
+  const int pi = fused::prof_begin(fused::prof_class(0, HS, O == HS ? 1 : 0), st);
   MCRN_LAUNCH(kern, grid, FTHREADS, C::SMEM, st, tS, tXT, tXA, tIB, tW, p, epi);
+  fused::prof_end(pi, st);
   return MCRN_OK;
 }
 

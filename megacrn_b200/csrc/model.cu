@@ -105,7 +105,7 @@ static inline void hilo(GemmDesc& q, int NBX) {
 
 // Fused AGCN kernel (agcn_fused.cuh): propagation + weight contraction + gate/update tail in one launch per AGCN.
 // g_fused_parts: 2 = hi + lo weights, 1 = hi only.
-namespace fused { long long* g_dbg_timeline = nullptr; int g_dbg_which = -1, g_dbg_count = 0; }
+namespace fused { long long* g_dbg_timeline = nullptr; int g_dbg_which = -1, g_dbg_count = 0; KernelProf g_prof; }
 // g_fused: 0 = per-stage GEMMs, 1 = fused kernel with TF32 operands, 2 = fused kernel with fp16 operands (default).
 int g_fused = getenv("MCRN_FUSED") ? atoi(getenv("MCRN_FUSED")) : 2;
 int g_fused_parts = getenv("MCRN_FUSED_PARTS") ? atoi(getenv("MCRN_FUSED_PARTS")) : 2;

@@ -62,6 +62,17 @@ def engine(request):
     lib.mcrn_set_engine(0)
 
 
+@pytest.fixture
+def default_engine():
+    """Tests of the fused kernels run on the default (tensor-core) engine whatever engine-parametrised test ran last."""
+    from megacrn_b200 import _abi
+    lib = _abi.load()
+    prev = lib.mcrn_get_engine()
+    lib.mcrn_set_engine(0)
+    yield lib
+    lib.mcrn_set_engine(prev)
+
+
 def test_library_loaded_and_device_ok():
     from megacrn_b200 import _abi
     lib = _abi.load()
@@ -267,7 +278,7 @@ def test_batch_split_invariance(engine):
 
 
 @pytest.mark.parametrize("N,H,dm,B,T", [(207, 64, 64, 4, 3), (300, 64, 64, 3, 2), (130, 32, 32, 2, 2), (100, 128, 64, 2, 2)])
-def test_fused_agcn_kernel_matches_per_stage_path(N, H, dm, B, T):
+def test_fused_agcn_kernel_matches_per_stage_path(N, H, dm, B, T, default_engine):
     """csrc/agcn_fused.cuh (graph conv + weight contraction + gate tail in one kernel, P_k kept in TMEM) against the
     per-stage tcgen05 GEMM path of the same library: same TF32 rounding points, different accumulation order only.
     (130, 32, 32): encoder per-stage (H=32), decoder fused (D=64); (100, 128, 64): encoder fused, decoder per-stage."""
@@ -299,6 +310,58 @@ def test_fused_agcn_kernel_matches_per_stage_path(N, H, dm, B, T):
             assert rel_l2(a, b) < tol_o, (parts, k, rel_l2(a, b))
         for k in ref_g:
             assert rel_l2(got_g[k], ref_g[k]) < tol_g, (parts, k, rel_l2(got_g[k], ref_g[k]))
+
+
+@pytest.mark.parametrize("N,H,dm,B,T", [(207, 64, 64, 4, 3), (300, 64, 64, 3, 2), (130, 32, 32, 2, 2), (100, 128, 64, 2, 2)])
+def test_fused_backward_kernel_matches_per_stage_backward(N, H, dm, B, T, default_engine):
+    """csrc/agcn_bwd_fused.cuh (S^T dV chained into the weight contraction, gate backward in the epilogue, dW from the
+    stored Q blocks) against the per-stage GEMM backward of the same library on the identical forward; both teacher-forced
+    and free-running decoder steps (the latter exercise d(go) through the input-channel block)."""
+    from megacrn_b200 import _abi
+    lib = _abi.load()
+    d = O.Dims(num_nodes=N, horizon=T, rnn_units=H, mem_dim=dm)
+    p = O.init_params(d, seed=1)
+    x, y_cov, labels = O.synthetic_batch(d, B, T, seed=8)
+    dv = _dev()
+    gen = torch.Generator().manual_seed(3)
+    for flags in ([True] * T, [t % 2 == 1 for t in range(T)]):
+        res, ups = {}, None
+        try:
+            for bf in (0, 1):
+                assert lib.mcrn_set_bwd_fused(bf) == 0
+                m = _model(d, p).train()
+                outs = m(x.to(dv), y_cov.to(dv), labels.to(dv), teacher_forcing=flags)
+                if ups is None:
+                    ups = [torch.randn(outs[0].shape, generator=gen).to(dv), torch.randn(outs[2].shape, generator=gen).to(dv)]
+                torch.autograd.backward([outs[0], outs[2]], ups)
+                res[bf] = ([o.detach().cpu() for o in outs[:3]], {k: v.grad.cpu() for k, v in m.named_parameters()})
+        finally:
+            lib.mcrn_set_bwd_fused(1)
+        for a, b in zip(res[1][0], res[0][0]):
+            assert torch.equal(a, b)                      # the forward results do not depend on the backward mode
+        for k in res[0][1]:
+            assert rel_l2(res[1][1][k], res[0][1][k]) < 1.5e-3, (flags, k, rel_l2(res[1][1][k], res[0][1][k]))
+
+
+def test_kernel_timing_api_counts_fused_launches(default_engine):
+    import ctypes
+    from megacrn_b200 import _abi
+    lib = _abi.load()
+    d = O.Dims(num_nodes=64, horizon=2, rnn_units=64)
+    p = O.init_params(d, seed=0)
+    x, y_cov, labels = O.synthetic_batch(d, 2, 3, seed=1)
+    m = _model(d, p).eval()
+    dv = _dev()
+    lib.mcrn_kernel_timing(1)
+    with torch.no_grad():
+        m(x.to(dv), y_cov.to(dv))
+    torch.cuda.synchronize()
+    lib.mcrn_kernel_timing(0)
+    ms, n = ctypes.c_float(0), ctypes.c_int(0)
+    assert lib.mcrn_kernel_timing_read(0, ctypes.byref(ms), ctypes.byref(n)) == 0     # forward, HS=64, gate
+    assert n.value == 3 and ms.value > 0
+    assert lib.mcrn_kernel_timing_read(4, ctypes.byref(ms), ctypes.byref(n)) == 0     # forward, HS=128, gate (decoder)
+    assert n.value == 2 and ms.value > 0
 
 
 def test_fused_trainer_loss_matches_torch():
