@@ -16,7 +16,7 @@
 //     X16  [R][HS], IB16 [R][HS] state / input block rows      A of MMA2 (identity + input segments)  box [64 k][1][128 m]
 //     W16  [parts][KS+2][O][HS] folded weights, transposed     B of MMA2   box [64 k][O n]
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = P rounding + epilogue,
-// warps 6..9 = epilogue only (each TMEM lane quarter is served by two warps that split the column chunks).
+// warps 6..17 = epilogue only (each TMEM lane quarter is served by four warps that split the column chunks).
 #pragma once
 
 #include <cuda_fp16.h>
@@ -35,7 +35,8 @@ using fused::ITEM_P;
 using fused::ITEM_SS;
 using fused::ITEM_TS;
 
-constexpr int FTHREADS = 320;
+constexpr int EPI_WARPS = 16;                   // epilogue warps: 4 per TMEM lane quarter (latency-bound tail: more warps in flight)
+constexpr int FTHREADS = 64 + 32 * EPI_WARPS;
 constexpr int BKH = 64;                         // halves per k-block = one 128-byte swizzle row
 
 struct HParams {
@@ -95,7 +96,7 @@ struct CfgH {
   static constexpr int NST = O >= 256 ? 4 : (O >= 128 ? 6 : 8);
   static constexpr uint32_t SCRATCH = 4 * 32 * 36 * 4;            // rounding warps: 32 x 36 floats each
   static constexpr size_t SMEM = (size_t)NST * STAGE + SCRATCH + 1024;
-  static_assert((size_t)NST * STAGE >= 8 * 32 * 36 * 4, "the epilogue stages through the (idle) ring");
+  static_assert((size_t)NST * STAGE >= EPI_WARPS * 32 * 36 * 4, "the epilogue stages through the (idle) ring");
   static constexpr uint32_t TM_ACC = 0, TM_P0 = O, TM_P1 = O + HS;
   static constexpr uint32_t TMEM_COLS = pow2_cols(O + 2 * HS);
   static constexpr int KB2 = HS / BKH;                            // k-blocks of the weight contraction per segment
@@ -299,7 +300,7 @@ agcn_fused_h_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_consta
     }
   } else {                                               // ===== rounding + epilogue warps =====
     const int quarter = warp & 3;                        // TMEM lane quarter this warp may access
-    const int ew = warp - 2, half_id = ew >> 2;          // ew 0..7; warps 2..5 (half_id 0) also do the P rounding
+    const int ew = warp - 2, half_id = ew >> 2;          // ew 0..15; warps 2..5 (half_id 0) also do the P rounding
     const int cq = (lane & 7) * 4, r0 = lane >> 3;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const int node0 = m0 + quarter * 32;
@@ -341,14 +342,14 @@ agcn_fused_h_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_consta
         if (warp == 2 && lane == 0 && k < 5) MCRN_TLH(211 + 4 * k);
       }
     }
-    // ---- epilogue: accumulator -> gate / update math; rows = (node, b); this warp takes chunks c = half_id (mod 2) ----
+    // ---- epilogue: accumulator -> gate / update math; rows = (node, b); this warp takes chunks c = half_id (mod 4) ----
     mbar_wait_b(smem_u32(&acc_full_bar), 0);
     tcgen05_fence_after();
     if (warp == 2 && lane == 0) MCRN_TLH(230);
     if (node0 < p.N) {
       float* scr = reinterpret_cast<float*>(smem_al) + ew * (32 * 36);      // the ring is idle now
 #pragma unroll 1
-      for (int c = half_id; c < O / 32; c += 2) {
+      for (int c = half_id; c < O / 32; c += EPI_WARPS / 4) {
         float v[32];
         tmem_ld_32x32b_x32(tmem_base + C::TM_ACC + lane_off + (uint32_t)(c * 32), v);
         __syncwarp();
