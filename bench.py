@@ -265,6 +265,27 @@ def main():
         dev_ms, launches = timed(step_device, args.steps)
         e2e_ms, _ = timed(step_e2e, args.steps)
     final_loss = float(step_e2e().item())
+    # secondary number: the same step followed by clip_grad_norm_(5.0) + Adam(lr 0.01, eps 1e-3), fused
+    # (mcrn_adam_step); single GPU: inside the captured graph, data parallel: after the gradient all-reduce
+    from megacrn_b200.optim import FusedClipAdam
+    opt_ms = None
+    try:
+        opt = FusedClipAdam(model, lr=0.01, eps=1e-3, max_grad_norm=5.0)
+        g2 = None if (args.no_graph or world > 1) else GraphedTrainStep(model, B, t_in, optimizer=opt)
+        if g2 is not None:
+            g2.load(dx, dy, dl)
+
+        def step_opt():
+            if g2 is not None:
+                return g2(batches_seen=0)
+            loss = step_device()
+            opt.step()
+            return loss
+        for _ in range(3):
+            step_opt()
+        opt_ms, _ = timed(step_opt, args.steps)
+    except Exception as e:      # the secondary number must never cost the headline
+        print(f"[bench] optimizer-step measurement skipped: {e}", file=sys.stderr)
     # host-side cost of enqueueing one step (no device wait inside): tells CPU-bound from GPU-bound
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
@@ -356,6 +377,9 @@ def main():
                        "final_loss": final_loss},
             "e2e": {"value": e2e_value, "unit": "sequences/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": int(4 * (hx.numel() + hy.numel() + hl.numel())), "d2h_bytes_per_step": 4},
+            "with_optimizer": None if opt_ms is None else {
+                "value": gB * args.steps / (opt_ms / 1e3), "unit": "sequences/s", "ms_per_step": opt_ms / args.steps,
+                "what": "step + fused clip_grad_norm_(5.0) + Adam(lr 0.01, eps 1e-3) (mcrn_adam_step)"},
             "gpu_launches": int(launches), "host_enqueue_ms_per_step": enqueue_ms,
             "clocks": clocks.summary(),
             "roofline": {"bound": "tensor", "kernel": k_name,

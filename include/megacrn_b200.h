@@ -132,6 +132,16 @@ int mcrn_trainer_loss(const mcrn_dims* dims, const float* output, const float* l
                       float* loss_out, float* d_output, float* d_query,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* The optimiser half of the training step, fused over the 14 parameter tensors:
+ * torch.nn.utils.clip_grad_norm_(parameters, max_grad_norm)   (model/traintest_MegaCRN.py:129; max_grad_norm <= 0: no clipping)
+ * followed by torch.optim.Adam(lr, betas=(beta1, beta2), eps).step()   (:104, :130; no weight decay, no amsgrad).
+ * params / grads / exp_avg / exp_avg_sq: device tensors in mcrn_params layout (shapes from dims).
+ * dev_state: 4 device floats = { step count (incremented by the call), learning rate (read), total gradient norm (written),
+ * clip coefficient (written) } -- device-resident so the call is CUDA-graph capturable and needs no host sync. */
+int mcrn_adam_step(const mcrn_dims* dims, const mcrn_params* params, const mcrn_params* grads,
+                   const mcrn_params* exp_avg, const mcrn_params* exp_avg_sq, float* dev_state,
+                   float beta1, float beta2, float eps, float max_grad_norm, void* stream);
+
 /* HOST-buffer convenience entries (what a non-PyTorch caller would bind): every
  * pointer in params/grads/x/... is a HOST pointer; the library stages through the
  * caller-provided DEVICE workspace, which must be at least

@@ -68,6 +68,9 @@ def load() -> C.CDLL:
     lib.mcrn_get_engine.restype = C.c_int
     lib.mcrn_debug_fused_timeline.restype = C.c_int
     lib.mcrn_debug_fused_timeline.argtypes = [C.c_void_p, C.c_int]
+    lib.mcrn_adam_step.restype = C.c_int
+    lib.mcrn_adam_step.argtypes = [C.POINTER(Dims), C.POINTER(Params), C.POINTER(Params), C.POINTER(Params), C.POINTER(Params),
+                                   fp, C.c_float, C.c_float, C.c_float, C.c_float, vp]
     lib.mcrn_kernel_timing.restype = C.c_int
     lib.mcrn_kernel_timing.argtypes = [C.c_int]
     lib.mcrn_kernel_timing_read.restype = C.c_int

@@ -23,6 +23,9 @@ int trainer_loss_impl(const Geo& g, const float* output, const float* labels, co
                       const float* neg, float mean, float std, float lamb, float lamb1, float* loss_out,
                       float* d_output, float* d_query, float* scratch, cudaStream_t st);
 
+int adam_step_impl(const Geo& g, const mcrn_params* prm, const mcrn_params* grads, const mcrn_params* m, const mcrn_params* v,
+                   float* state, float beta1, float beta2, float eps, float max_norm, cudaStream_t st);
+
 static std::mutex g_mu;
 static std::unordered_map<const void*, uint64_t> g_saved;   // workspace -> dims hash of the last saving forward
 
@@ -78,6 +81,20 @@ int mcrn_set_debug_mask(int mask) { g_simt_mask = mask; return MCRN_OK; }
 int mcrn_debug_fused_timeline(long long* device_slots, int which) {
   fused::g_dbg_timeline = device_slots; fused::g_dbg_which = which; fused::g_dbg_count = 0;
   return MCRN_OK;
+}
+int mcrn_adam_step(const mcrn_dims* dims, const mcrn_params* params, const mcrn_params* grads, const mcrn_params* exp_avg,
+                   const mcrn_params* exp_avg_sq, float* dev_state, float beta1, float beta2, float eps, float max_grad_norm,
+                   void* stream) {
+  Geo g;
+  MCRN_TRY(make_geo(dims, &g));
+  MCRN_TRY(check_params(params, "params"));
+  MCRN_TRY(check_params(grads, "grads"));
+  MCRN_TRY(check_params(exp_avg, "exp_avg"));
+  MCRN_TRY(check_params(exp_avg_sq, "exp_avg_sq"));
+  if (!dev_state) { set_error("mcrn_adam_step: dev_state is null"); return MCRN_ERR_BAD_POINTER; }
+  MCRN_TRY(check_device());
+  return adam_step_impl(g, params, grads, exp_avg, exp_avg_sq, dev_state, beta1, beta2, eps, max_grad_norm,
+                        static_cast<cudaStream_t>(stream));
 }
 int mcrn_kernel_timing(int enable) {
   fused::g_prof.enabled = enable ? 1 : 0;

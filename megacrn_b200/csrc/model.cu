@@ -853,6 +853,30 @@ int trainer_loss_impl(const Geo& g, const float* output, const float* labels, co
   return MCRN_OK;
 }
 
+int adam_step_impl(const Geo& g, const mcrn_params* prm, const mcrn_params* grads, const mcrn_params* m, const mcrn_params* v,
+                   float* state, float beta1, float beta2, float eps, float max_norm, cudaStream_t st) {
+  const int64_t ck2 = 2 * g.cheb_k;
+  const int64_t n[14] = {(int64_t)g.M * g.d, (int64_t)g.H * g.d, (int64_t)g.N * g.M, (int64_t)g.N * g.M,
+                         ck2 * (g.Cin + g.H) * 2 * g.H, 2 * g.H, ck2 * (g.Cin + g.H) * g.H, g.H,
+                         ck2 * (g.Cdec + g.D) * 2 * g.D, 2 * g.D, ck2 * (g.Cdec + g.D) * g.D, g.D,
+                         (int64_t)g.Cout * g.D, g.Cout};
+  ParamTable t;
+  float* const* pp = reinterpret_cast<float* const*>(prm);
+  float* const* gg = reinterpret_cast<float* const*>(grads);
+  float* const* mm = reinterpret_cast<float* const*>(m);
+  float* const* vv = reinterpret_cast<float* const*>(v);
+  t.off[0] = 0;
+  for (int i = 0; i < 14; ++i) {
+    t.p[i] = pp[i]; t.g[i] = gg[i]; t.m[i] = mm[i]; t.v[i] = vv[i];
+    t.off[i + 1] = t.off[i] + n[i];
+  }
+  MCRN_CUDA_OK(cudaMemsetAsync(state + 2, 0, sizeof(float), st));
+  const int grid = ew_grid(t.off[14]) > 592 ? 592 : ew_grid(t.off[14]);
+  MCRN_LAUNCH(k_grad_sqnorm, grid, 256, 0, st, t, state);
+  MCRN_LAUNCH(k_clip_adam, grid, 256, 0, st, t, state, beta1, beta2, eps, max_norm);
+  return MCRN_OK;
+}
+
 const char* last_error() { return t_err; }
 
 }  // namespace mcrn

@@ -58,8 +58,10 @@ class GraphedTrainStep:
     alias one flat buffer (``flat_grad``), the loss in ``loss`` (a 1-element device tensor).
     """
 
-    def __init__(self, model, batch, seq_len, max_graphs=16, **loss_kw):
-        self.model, self.loss_kw, self.max_graphs = model, loss_kw, max_graphs
+    def __init__(self, model, batch, seq_len, max_graphs=16, optimizer=None, **loss_kw):
+        """optimizer: a ``megacrn_b200.optim.FusedClipAdam``; if given, clip + Adam are part of the captured step
+        (single-GPU; with data parallelism call ``optimizer.step()`` after the gradient all-reduce instead)."""
+        self.model, self.loss_kw, self.max_graphs, self.optimizer = model, loss_kw, max_graphs, optimizer
         dev = next(model.parameters()).device
         self.x = torch.zeros(batch, seq_len, model.num_nodes, model.input_dim, device=dev)
         self.y_cov = torch.zeros(batch, model.horizon, model.num_nodes, model.ycov_dim, device=dev)
@@ -78,14 +80,25 @@ class GraphedTrainStep:
     def _eager(self, flags):
         for p in self.params:
             p.grad = None
-        return train_step(self.model, self.x, self.y_cov, self.labels, teacher_forcing=flags, **self.loss_kw)
+        loss = train_step(self.model, self.x, self.y_cov, self.labels, teacher_forcing=flags, **self.loss_kw)
+        if self.optimizer is not None:
+            self.optimizer.step()
+        return loss
 
     def _capture(self, flags):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
+        saved = None
+        if self.optimizer is not None:                 # the warm-up steps must not advance the optimiser / the weights
+            saved = (self.optimizer.state_dict(), [p.detach().clone() for p in self.params])
         with torch.cuda.stream(side):                  # warm-up outside capture (lazy inits, allocator)
             for _ in range(2):
                 self._eager(flags)
+        if saved is not None:
+            with torch.no_grad():
+                self.optimizer.load_state_dict(saved[0])
+                for p, q in zip(self.params, saved[1]):
+                    p.copy_(q)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
@@ -95,6 +108,8 @@ class GraphedTrainStep:
         n0 = lib.mcrn_launch_count()
         with torch.cuda.graph(g, pool=self.pool):
             loss = train_step(self.model, self.x, self.y_cov, self.labels, teacher_forcing=flags, **self.loss_kw)
+            if self.optimizer is not None:
+                self.optimizer.step()
         kernels = int(lib.mcrn_launch_count() - n0)       # library kernels recorded in this graph
         if self.pool is None:
             self.pool = g.pool()

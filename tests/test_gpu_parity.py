@@ -364,6 +364,36 @@ def test_kernel_timing_api_counts_fused_launches(default_engine):
     assert n.value == 2 and ms.value > 0
 
 
+def test_fused_clip_adam_matches_torch():
+    """mcrn_adam_step vs torch.nn.utils.clip_grad_norm_ + torch.optim.Adam(lr=0.01, eps=1e-3) (traintest:104, :129-130)."""
+    from megacrn_b200.optim import FusedClipAdam
+    d = O.Dims(num_nodes=30, horizon=2, rnn_units=8, mem_num=5, mem_dim=8)
+    p = O.init_params(d, seed=4)
+    dv = _dev()
+    m = _model(d, p)
+    ref = {k: v.clone().to(dv).requires_grad_(True) for k, v in p.items()}
+    topt = torch.optim.Adam(list(ref.values()), lr=0.01, eps=1e-3)
+    fopt = FusedClipAdam(m, lr=0.01, eps=1e-3, max_grad_norm=5.0)
+    gen = torch.Generator().manual_seed(0)
+    named = dict(m.named_parameters())
+    for it in range(5):
+        scale = 30.0 if it % 2 == 0 else 0.01          # one clipped and one unclipped regime
+        for k in ref:
+            g = (torch.randn(ref[k].shape, generator=gen) * scale).to(dv)
+            ref[k].grad = g.clone()
+            named[k].grad = g.clone()
+        if it == 3:
+            for grp in topt.param_groups:
+                grp["lr"] = 0.001
+            fopt.lr = 0.001
+        tn = torch.nn.utils.clip_grad_norm_(list(ref.values()), 5.0)
+        topt.step()
+        fopt.step()
+        assert abs(fopt.last_grad_norm - float(tn)) < 1e-4 * float(tn)
+        for k in ref:
+            assert rel_l2(named[k].detach().cpu(), ref[k].detach().cpu()) < 2e-6, (it, k)
+
+
 def test_fused_trainer_loss_matches_torch():
     from megacrn_b200 import _abi
     from megacrn_b200.train_step import fused_trainer_loss
