@@ -12,6 +12,7 @@
 #include "agcn_fused.cuh"
 #include "agcn_fused_h.cuh"
 #include "agcn_bwd_fused.cuh"
+#include "agcn_ds_fused.cuh"
 #include "plan.cuh"
 #include "loss.cuh"
 #include "small_kernels.cuh"
@@ -543,6 +544,10 @@ static int make_dxp_s(const Geo& g, const float* dv, int O, const float* wall, i
   EpiBlocks e{dxp, Hs, g.R * Hs, 1, -1, nullptr, 1};
   return gemm(q, e, st);
 }
+int g_ds_fused = getenv("MCRN_DS_FUSED") ? atoi(getenv("MCRN_DS_FUSED")) : 1;
+static bool ds_fused_shape(const Geo& g, int Hs) { return g_ds_fused && fusedd::ds_fused_eligible(g.N, Hs); }
+// experiment knobs (timing only -- gradients are wrong when set): bit 0 = skip the dS side-stream work, bit 1 = skip dW GEMMs
+static int g_dbg_skip = getenv("MCRN_DEBUG_SKIP") ? atoi(getenv("MCRN_DEBUG_SKIP")) : 0;
 template <int HS>
 static int cell_backward_fused(const Geo& g, const Plan& p, float* ws, const float* S, const CellW& w, const CellBufs& b,
                                const BwdStep& bs, float* dH, float* dxin, cudaStream_t st) {
@@ -551,23 +556,32 @@ static int cell_backward_fused(const Geo& g, const Plan& p, float* ws, const flo
   float *dXP = ws + p.dXP, *dXP2 = ws + p.dXP2, *dHp = ws + p.dHp, *dS = ws + p.dS;
   cudaStream_t sd = g_side.s;
   // update AGCN: dZH (+ gate backward in the epilogue) ; its dS contribution on the side stream
+  // N <= 256: the support gradients of the state terms are ONE fused launch per AGCN type after the time loop
+  // (agcn_ds_fused.cuh), the input-channel term one batched GEMM; otherwise per step on the side stream
+  const bool do_ds = !(g_dbg_skip & 1) && !ds_fused_shape(g, HS);
+  if (do_ds) {
   MCRN_TRY(side_begin(0, st));
   MCRN_TRY(make_dxp_s(g, bs.dU, HS, w.wu, HS, dXP, sd));
   MCRN_TRY(acc_ds(g, dXP + nH, (int64_t)g.B * HS, b.xpu, (int64_t)g.B * HS, g.B * HS, dS, sd));
+  }
   fusedb::EpiBU eu{HS, b.z, b.hx, ws + p.dHr, bs.dG, dHp};
   MCRN_TRY((fusedb::launch_agcn_bwd<HS>(g.N, g.B, g.KS, g.ldS, 1, St, bs.dU, w.wu, bs.Qu, ws + p.dIBu16, eu, st)));
   // gate AGCN
+  if (do_ds) {
   MCRN_TRY(side_begin(1, st));
   MCRN_TRY(make_dxp_s(g, bs.dG, 2 * HS, w.wg, HS, dXP2, sd));
   MCRN_TRY(acc_ds(g, dXP2 + nH, (int64_t)g.B * HS, b.xpg, (int64_t)g.B * HS, g.B * HS, dS, sd));
+  }
   fusedb::EpiBG eg{HS, dHp, dH};
   MCRN_TRY((fusedb::launch_agcn_bwd<HS>(g.N, g.B, g.KS, g.ldS, 2, St, bs.dG, w.wg, bs.Qg, ws + p.dIBg16, eg, st)));
   // input channels: d(input block) of both AGCNs -> dXPin [NB][R][Cin]
   const int64_t nIn = (int64_t)g.NB * g.R * w.Cin;
   MCRN_LAUNCH(k_repack_dib, ew_grid(nIn), 256, 0, st, ws + p.dIBu16, ws + p.dIBg16, g.NB, w.Cin, g.R, fusedb::IBW, bs.dXPin, 1);
+  if (do_ds) {
   MCRN_TRY(side_begin(2, st));
   MCRN_TRY(acc_ds(g, bs.dXPin + g.R * w.Cin, (int64_t)g.B * w.Cin, b.xpin, b.xp_n, g.B * w.Cin, dS, sd));
-  g_side.fused_pending = true;   // side work outstanding: joined by side_join_fused
+  }
+  if (do_ds) g_side.fused_pending = true;   // side work outstanding: joined by side_join_fused
   if (dxin) MCRN_TRY(propagate_T(g, S, bs.dXPin, w.Cin, nullptr, dxin, st));
   return MCRN_OK;
 }
@@ -594,11 +608,40 @@ static int side_join_fused(cudaStream_t mainst) {
   }
   return MCRN_OK;
 }
+// Support gradients of one cell type over all steps (fused backward, N <= 256), on the side stream:
+//   state terms: agcn_ds_kernel per AGCN (update: dV = dU, X = XPu block 0; gate: dV = dG, X = XPg block 0)
+//   input-channel term: dS_k += sum_t dXPin_t[1+k] * xin_t^T as one GEMM with T K-segments
+template <int HS>
+static int acc_ds_fused_all(const Geo& g, const Plan& p, float* ws, const CellW& w, int T, const float* dU_all,
+                            const float* dG_all, const float* xpu0, const float* xpg0, int64_t xp_step, const float* xpin0,
+                            int64_t xpin_n, int64_t xpin_seg, cudaStream_t mainst) {
+  if (g_dbg_skip & 1) return MCRN_OK;
+  float* dS = ws + p.dS;
+  cudaStream_t sd = g_side.s;
+  MCRN_TRY(side_begin(0, mainst));
+  MCRN_TRY((fusedd::launch_agcn_ds<HS>(g.N, g.B, T, g.KS, g.ldS, HS, dU_all, w.wu, xpu0, xp_step, dS, sd)));
+  MCRN_TRY((fusedd::launch_agcn_ds<HS>(g.N, g.B, T, g.KS, g.ldS, 2 * HS, dG_all, w.wg, xpg0, xp_step, dS, sd)));
+  for (int t0 = 0; t0 < T; t0 += 16) {
+    const int nt = T - t0 < 16 ? T - t0 : 16;
+    const int cols = g.B * w.Cin;
+    GemmDesc q;
+    q.A = ws + p.dXPin_all + p.dXPin_sz * t0 + g.R * w.Cin; q.a_row = cols; q.a_k = 1; q.a_seg = (int64_t)p.dXPin_sz;
+    q.M = g.KS * g.N; q.Kseg = cols; q.nseg = nt;
+    q.B = xpin0 + (int64_t)t0 * xpin_seg; q.b_k = 1; q.b_n = xpin_n; q.b_seg = xpin_seg; q.N = g.N;
+    q.splits = split_for((int64_t)ceil_div(q.M, 64) * ceil_div(q.N, 64), (int64_t)nt * cols / 16);
+    EpiAtomicAdd e{dS, g.ldS, 0};
+    MCRN_TRY(gemm(q, e, sd));
+  }
+  g_side.fused_pending = true;
+  return MCRN_OK;
+}
+
 // Weight gradients of one AGCN over all steps, fused-backward form:
 //   blocks 0 and NB : dW = sum_t XP_t[blk]^T dV_t            (as acc_dw_all, two blocks)
 //   blocks 1..KS    : dW_k[:, half] = sum_t X_t^T Q_t[k, half]     (X_t = XP_t[0])
 static int acc_dw_fused(const Geo& g, const float* xp0, int64_t xp_step, int T, int Hs, const float* dv_all, const float* q_all,
                         int nhalf, float* dw, cudaStream_t st) {
+  if (g_dbg_skip & 2) return MCRN_OK;
   const int O = nhalf * Hs;
   for (int t0 = 0; t0 < T; t0 += 16) {
     const int nt = T - t0 < 16 ? T - t0 : 16;
@@ -746,6 +789,11 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
                              need_dxin ? dXin : nullptr, st));
       have_dgo = need_dxin;
     }
+    if (fb && ds_fused_shape(g, g.D)) {
+      CellBufs b0 = dec_bufs(g, p, ws, 0);
+      if (g.D == 64) MCRN_TRY(acc_ds_fused_all<64>(g, p, ws, w, g.T_out, dU_all, dG_all, b0.xpu, b0.xpg, (int64_t)p.dec_xp_sz, b0.xpin, b0.xp_n, (int64_t)p.dec_xpin_sz, st));
+      else MCRN_TRY(acc_ds_fused_all<128>(g, p, ws, w, g.T_out, dU_all, dG_all, b0.xpu, b0.xpg, (int64_t)p.dec_xp_sz, b0.xpin, b0.xp_n, (int64_t)p.dec_xpin_sz, st));
+    }
     if (fb) {   // weight gradients of the decoder: off the critical path, concurrent with the memory / encoder backward
       MCRN_TRY(side2_fork(st));
       MCRN_TRY(acc_dw_fused(g, ws + p.dec_xpu, (int64_t)p.dec_xp_sz, g.T_out, g.D, dU_all, ws + p.d_Qu, 1, ws + p.a_d_wu, g_side.s2));
@@ -809,6 +857,11 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
       }
       MCRN_TRY(cell_backward(g, p, ws, S, w, b, dU_all + (int64_t)t * g.R * g.H, dG_all + (int64_t)t * g.R * 2 * g.H, dHe, dHe,
                              nullptr, st));
+    }
+    if (fb && ds_fused_shape(g, g.H)) {
+      CellBufs b0 = enc_bufs(g, p, ws, 0);
+      if (g.H == 64) MCRN_TRY(acc_ds_fused_all<64>(g, p, ws, w, g.T_in, dU_all, dG_all, b0.xpu, b0.xpg, (int64_t)p.enc_xp_sz, b0.xpin, b0.xp_n, (int64_t)g.B * g.Cin, st));
+      else MCRN_TRY(acc_ds_fused_all<128>(g, p, ws, w, g.T_in, dU_all, dG_all, b0.xpu, b0.xpg, (int64_t)p.enc_xp_sz, b0.xpin, b0.xp_n, (int64_t)g.B * g.Cin, st));
     }
     if (fb) {   // concurrent with the supports backward
       MCRN_TRY(side2_fork(st));
