@@ -41,6 +41,7 @@ constexpr int BKH = 64;                         // halves per k-block = one 128-
 
 struct HParams {
   int N, B, KS, nparts;
+  int ib_blocks;        // k-blocks (64 halves) of the input-block segment: HS/64, or 1 for the compact [R][64] input block
   float* xp_save;       // training: fp32 XP buffer [KS+2][R][HS]; the (fp16-rounded) P_k goes to block 1+k.  null = eval
   int64_t blk_stride;   // R * HS
   long long* dbg;       // debug timeline (see agcn_fused.cuh)
@@ -84,6 +85,24 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f,
 __device__ __forceinline__ float tanh_fast(float x) {
   const float t = __expf(-2.0f * fabsf(x));
   return copysignf(__fdividef(1.0f - t, 1.0f + t), x);
+}
+
+// ring items of one CTA, in issue order (as fused::for_each_item, but the input-block segment has `ibk` k-blocks)
+template <int KB2, class F>
+__device__ __forceinline__ void for_each_item_h(int KS, int kb1, int nparts, int ibk, F&& f) {
+  for (int j = 0; j < kb1; ++j) f(ITEM_P, 0, j, 0);
+  if (KS > 1)
+    for (int j = 0; j < kb1; ++j) f(ITEM_P, 1, j, 0);
+  for (int part = 0; part < nparts; ++part)
+    for (int j = 0; j < KB2; ++j) f(ITEM_SS, 0, j, part);
+  for (int part = 0; part < nparts; ++part)
+    for (int j = 0; j < ibk; ++j) f(ITEM_SS, KS + 1, j, part);
+  for (int k = 0; k < KS; ++k) {
+    for (int part = 0; part < nparts; ++part)
+      for (int j = 0; j < KB2; ++j) f(ITEM_TS, k, j, part);
+    if (k + 2 < KS)
+      for (int j = 0; j < kb1; ++j) f(ITEM_P, k + 2, j, 0);
+  }
 }
 
 template <int HS, int O>
@@ -225,7 +244,7 @@ agcn_fused_h_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_consta
   if (warp == 0) {
     if (lane == 0) {                                     // ===== TMA producer =====
       int it = 0;
-      fused::for_each_item<C::KB2>(p.KS, kb1, p.nparts, [&](int type, int k, int j, int part) {
+      for_each_item_h<C::KB2>(p.KS, kb1, p.nparts, p.ib_blocks, [&](int type, int k, int j, int part) {
         const int s = it % NST;
         if (it >= NST) mbar_wait_b(smem_u32(&empty_bar[s]), (((uint32_t)(it / NST)) & 1u) ^ 1u);
         if (it < 200) MCRN_TLH(240 + it);
@@ -255,7 +274,7 @@ agcn_fused_h_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_consta
       constexpr uint32_t idesc2 = make_idesc_f16<O>();
       int it = 0;
       bool acc_on = false;
-      fused::for_each_item<C::KB2>(p.KS, kb1, p.nparts, [&](int type, int k, int j, int part) {
+      for_each_item_h<C::KB2>(p.KS, kb1, p.nparts, p.ib_blocks, [&](int type, int k, int j, int part) {
         const int s = it % NST;
         mbar_wait_b(smem_u32(&full_bar[s]), ((uint32_t)(it / NST)) & 1u);
         tcgen05_fence_after();
@@ -437,6 +456,138 @@ __global__ void k_weights_to_half(const float* __restrict__ wall, __half* __rest
   }
 }
 
+// ---- compact input block ----------------------------------------------------------------------
+// The "input block" of an AGCN contraction (input channels of every support + the bias one) has only NB*Cin + 1 <= 16
+// non-zero columns.  Compact form: ib16c [R][64] halves (one 128-byte swizzle row per (node, b): exactly one k-block of
+// the fused kernel) and, for the weight gradient of that block, ib32c [R][16] floats.
+constexpr int IBC = 64, IBF = 16;
+
+// Encoder, all steps at once.  xpin: [NB][N][T][B][Cin] (block 0 = staged input, 1.. = propagated).
+__global__ void k_encoder_input_blocks(const float* __restrict__ xpin, int NB, int N, int T, int B, int Cin,
+                                       __half* __restrict__ ib16c, float* __restrict__ ib32c) {
+  const int64_t R = (int64_t)N * B, total = (int64_t)T * R * IBC;
+  const int nin = NB * Cin;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % IBC);
+    const int64_t row = (i / IBC) % R;
+    const int t = (int)(i / ((int64_t)IBC * R));
+    float v = 0.f;
+    if (j < nin) {
+      const int k = j / Cin, ci = j - k * Cin;
+      const int n = (int)(row / B), b = (int)(row - (int64_t)n * B);
+      v = round_h(xpin[((((int64_t)k * N + n) * T + t) * B + b) * Cin + ci]);
+    } else if (j == nin) {
+      v = 1.0f;
+    }
+    ib16c[i] = __float2half_rn(v);
+    if (ib32c != nullptr && j < IBF) ib32c[((int64_t)t * R + row) * IBF + j] = v;
+  }
+}
+
+// Decoder step t: staging of [go | y_cov[:, t]] (model/MegaCRN.py:185), its propagation through the KS supports and the
+// compact input block, in one kernel.  go_src: nullptr (zeros) or a [B][T][N][Cout] tensor read at step t-1.
+// S: exact fp32 supports [KS][N][ldS].  A block owns DI_NODES nodes x (DI_COLS / Cd) batch elements: it stages the
+// DI_COLS input columns (all N source nodes) and the KS * DI_NODES support rows in shared memory with coalesced loads,
+// accumulates, assembles the complete 128-byte rows of the input block in shared memory and writes them with 16-byte
+// stores.  Needs KS * DI_NODES <= 8 * DI_RPT rows (KS <= 4 with the constants below) and (KS + 1) * Cd + 1 <= 16.
+constexpr int DI_COLS = 32, DI_NODES = 6, DI_RPT = 3, DI_ROWS = 8 * DI_RPT;
+__global__ void __launch_bounds__(256) k_decoder_input_block(const float* __restrict__ go_src, const float* __restrict__ ycov,
+                                                             const float* __restrict__ S, int ldS, int KS, int N, int B, int T,
+                                                             int Cout, int Ycov, int t, float* __restrict__ xin_out,
+                                                             __half* __restrict__ ib16c, float* __restrict__ ib32c) {
+  extern __shared__ float sh[];                        // xs [N][DI_COLS], ss [DI_ROWS][N + 1], os [DI_NODES * DI_COLS][IBF + 1]
+  const int Cd = Cout + Ycov, cols = B * Cd, nin = (KS + 1) * Cd;
+  const int c0 = blockIdx.x * DI_COLS, n0 = blockIdx.y * DI_NODES;
+  float* xs = sh;
+  float* ss = xs + N * DI_COLS;
+  float* os = ss + DI_ROWS * (N + 1);
+  auto xin = [&](int m, int col) -> float {
+    const int b = col / Cd, c = col - b * Cd;
+    if (c < Cout) return go_src ? __ldg(go_src + (((int64_t)b * T + (t - 1)) * N + m) * Cout + c) : 0.f;
+    return __ldg(ycov + (((int64_t)b * T + t) * N + m) * Ycov + (c - Cout));
+  };
+  // staging loops: 8 independent global loads in flight per thread (the block is alone on its SM: latency, not bandwidth)
+  constexpr int U = 8;
+  for (int base = threadIdx.x; base < N * DI_COLS; base += blockDim.x * U) {
+    float v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * blockDim.x;
+      const int cl = i / N, m = i - cl * N, col = c0 + cl;          // m fastest: coalesced reads of labels / output / y_cov
+      v[u] = (i < N * DI_COLS && col < cols) ? xin(m, col) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * blockDim.x;
+      if (i < N * DI_COLS) { const int cl = i / N, m = i - cl * N; xs[m * DI_COLS + cl] = v[u]; }
+    }
+  }
+  for (int base = threadIdx.x; base < DI_ROWS * N; base += blockDim.x * U) {
+    float v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * blockDim.x;
+      const int rl = i / N, m = i - rl * N;                         // local row rl = k * DI_NODES + nl
+      const int k = rl / DI_NODES, n = n0 + (rl - k * DI_NODES);
+      v[u] = (i < DI_ROWS * N && k < KS && n < N) ? __ldg(S + ((int64_t)k * N + n) * ldS + m) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * blockDim.x;
+      if (i < DI_ROWS * N) { const int rl = i / N, m = i - rl * N; ss[rl * (N + 1) + m] = v[u]; }
+    }
+  }
+  for (int i = threadIdx.x; i < DI_NODES * DI_COLS * (IBF + 1); i += blockDim.x) os[i] = 0.f;
+  __syncthreads();
+  const int cl = threadIdx.x & (DI_COLS - 1), rg = threadIdx.x / DI_COLS;     // 8 row lanes x 32 columns
+  float acc[DI_RPT];
+#pragma unroll
+  for (int i = 0; i < DI_RPT; ++i) acc[i] = 0.f;
+  for (int m = 0; m < N; ++m) {
+    const float xv = xs[m * DI_COLS + cl];
+#pragma unroll
+    for (int i = 0; i < DI_RPT; ++i) acc[i] = fmaf(ss[(rg * DI_RPT + i) * (N + 1) + m], xv, acc[i]);
+  }
+  // stage the block's values: local output row = nl * (DI_COLS / Cd) + b_local, column j of the input block
+  const int bl = cl / Cd, c = cl - bl * Cd, bpb = DI_COLS / Cd;
+#pragma unroll
+  for (int i = 0; i < DI_RPT; ++i) {
+    const int rl = rg * DI_RPT + i, k = rl / DI_NODES, nl = rl - k * DI_NODES;
+    if (k < KS) os[(nl * bpb + bl) * (IBF + 1) + (1 + k) * Cd + c] = round_h(acc[i]);
+  }
+  for (int i = threadIdx.x; i < DI_NODES * DI_COLS; i += blockDim.x) {        // block 0 = the input itself, bias one
+    const int nl = i / DI_COLS, cc = i - nl * DI_COLS, b2 = cc / Cd, c2 = cc - b2 * Cd;
+    if (n0 + nl < N) {
+      os[(nl * bpb + b2) * (IBF + 1) + c2] = xs[(n0 + nl) * DI_COLS + cc];     // raw; rounded at the store below
+      if (c2 == 0) os[(nl * bpb + b2) * (IBF + 1) + nin] = 1.0f;
+    }
+  }
+  __syncthreads();
+  // write complete rows: ib16c row = 8 x 16 bytes (chunks 0,1 from the staged values, the rest zero), ib32c row = 4 x float4
+  const int b0 = c0 / Cd;
+  for (int i = threadIdx.x; i < DI_NODES * bpb * 8; i += blockDim.x) {
+    const int q = i & 7, lr = i >> 3, nl = lr / bpb, b2 = lr - nl * bpb;
+    const int n = n0 + nl, b = b0 + b2;
+    if (n >= N || b >= B) continue;
+    const int64_t row = (int64_t)n * B + b;
+    uint4 u = make_uint4(0u, 0u, 0u, 0u);
+    if (q < 2) {
+      const float* o = os + lr * (IBF + 1) + q * 8;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = (q * 8 + e < Cd) ? round_h(o[e]) : o[e];
+      u = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+      if (ib32c != nullptr) {
+        st4(ib32c + row * IBF + q * 8, v[0], v[1], v[2], v[3]);
+        st4(ib32c + row * IBF + q * 8 + 4, v[4], v[5], v[6], v[7]);
+      }
+      if (xin_out != nullptr && q == 0)
+        for (int e = 0; e < Cd; ++e) xin_out[row * Cd + e] = tf32_rn(o[e]);   // operand of the TF32 dS / dxin GEMMs of the backward
+    }
+    *reinterpret_cast<uint4*>(ib16c + row * IBC + q * 8) = u;
+  }
+}
+
 // ---- host side ----------------------------------------------------------------------------------
 int encode_tensor_map_h(CUtensorMap* out, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
                         const uint32_t box[4]);
@@ -447,9 +598,10 @@ struct HOperands {
   const __half* S16;      // [KS][N][ld_half(N)]
   const __half* X16T;     // [B][HS][ld_half(N)]
   const __half* X16;      // [R][HS]
-  const __half* IB16;     // [R][HS]
+  const __half* IB16;     // [R][ib_ld]: ib_ld = HS (full input block) or 64 (compact: only the first k-block is non-zero)
   const __half* W16;      // [nparts][KS+2][O][HS]
   float* xp_save;         // fp32 XP buffer (training) or null
+  int ib_ld = 0;          // 0 = HS
 };
 
 template <int HS, int O, class Epi>
@@ -475,7 +627,10 @@ int launch_agcn_fused_h(int N, int B, int KS, const HOperands& op, int nparts, c
     uint64_t str[3] = {(uint64_t)HS * 2, (uint64_t)B * HS * 2, (uint64_t)R * HS * 2};
     uint32_t box[4] = {BKH, 1, BM, 1};
     MCRN_TRY(encode_tensor_map_h(&tXA, op.X16, dims, str, box));
-    MCRN_TRY(encode_tensor_map_h(&tIB, op.IB16, dims, str, box));
+    const uint64_t il = op.ib_ld ? (uint64_t)op.ib_ld : (uint64_t)HS;
+    uint64_t dimi[4] = {il, (uint64_t)B, (uint64_t)N, 1};
+    uint64_t stri[3] = {il * 2, (uint64_t)B * il * 2, (uint64_t)R * il * 2};
+    MCRN_TRY(encode_tensor_map_h(&tIB, op.IB16, dimi, stri, box));
   }
   {
     uint64_t dims[4] = {(uint64_t)HS, (uint64_t)O, (uint64_t)(nparts * (KS + 2)), 1};
@@ -485,6 +640,7 @@ int launch_agcn_fused_h(int N, int B, int KS, const HOperands& op, int nparts, c
   }
   HParams p;
   p.N = N; p.B = B; p.KS = KS; p.nparts = nparts;
+  p.ib_blocks = (op.ib_ld ? op.ib_ld : HS) / BKH;
   p.xp_save = op.xp_save;
   p.blk_stride = R * HS;
   p.dbg = nullptr;

@@ -76,6 +76,8 @@ struct CellBufs {        // per-step activations
   float* hx;             // exact fp32 input state of the step (xpg block 0 is its tensor-core copy)
   // fp16 operand copies (fused fp16 forward): state h (row-major, node-transposed), z*h, input block
   __half *x16 = nullptr, *x16T = nullptr, *zh16 = nullptr, *zh16T = nullptr, *ib16 = nullptr;
+  __half* ib16c = nullptr;   // compact input block of this step [R][64] (fused fp16 forward + fused backward / eval)
+  float* ib32c = nullptr;    // [R][16] fp32 copy (training)
 };
 
 // Numerics mode of the run: with the tcgen05 engine every tensor-core operand is stored TF32-rounded
@@ -132,6 +134,16 @@ static bool fused_h_shape(const Geo& g, int Hs) {
   return tf32_mode() && g_fused == 2 && !(g_simt_mask & 3) && (Hs == 64 || Hs == 128) && g.B <= 65535;
 }
 
+// Compact input block (agcn_fused_h.cuh): fused fp16 forward, and either no backward (eval) or the fused backward (which
+// reads the [R][16] fp32 copy instead of the full-width block NB of the XP buffers).
+static int g_ib_compact = getenv("MCRN_IB_COMPACT") ? atoi(getenv("MCRN_IB_COMPACT")) : 1;
+static bool ib_compact_shape(const Geo& g, int Hs, int Cin, bool save) {
+  // (the fused decoder input kernel stages N x 32 inputs + 24 support rows in shared memory)
+  return g_ib_compact && ((size_t)g.N * fusedh::DI_COLS + (size_t)fusedh::DI_ROWS * (g.N + 1)) * sizeof(float) <= 180 * 1024 &&
+         g.KS * fusedh::DI_NODES <= fusedh::DI_ROWS && fusedh::DI_COLS % (Cin) == 0 &&
+         fused_h_shape(g, Hs) && g.NB * Cin + 1 <= fusedh::IBF && (!save || bwd_fused_shape(g, Hs, Cin));
+}
+
 // fp16-operand fused cell (agcn_fused_h.cuh).  last: no next step consumes the new state as a tensor-core operand.
 template <int HS>
 static int cell_forward_fused_h(const Geo& g, const CellW& w, const CellBufs& b, float* h_out, float* h_mma, bool last,
@@ -139,10 +151,13 @@ static int cell_forward_fused_h(const Geo& g, const CellW& w, const CellBufs& b,
   const bool save = b.z != nullptr;
   const bool save_p = save && !bwd_fused_shape(g, HS, w.Cin);     // the fused backward recomputes nothing from P_k: dW_k = X^T Q_k
   const int ldT = fusedh::ld_half(g.N);
-  fusedh::HOperands og{w.S16, b.x16T, b.x16, b.ib16, w.wg16, save_p ? b.xpg : nullptr};
+  const bool ibc = ib_compact_shape(g, HS, w.Cin, save);
+  const __half* ib = ibc ? b.ib16c : b.ib16;
+  const int ib_ld = ibc ? fusedh::IBC : 0;
+  fusedh::HOperands og{w.S16, b.x16T, b.x16, ib, w.wg16, save_p ? b.xpg : nullptr, ib_ld};
   fusedh::EpiGateH eg{HS, b.hx, b.z, b.r, save ? b.xpu : nullptr, b.zh16, b.zh16T, ldT};
   MCRN_TRY((fusedh::launch_agcn_fused_h<HS, 2 * HS>(g.N, g.B, g.KS, og, g_fused_parts, eg, st)));
-  fusedh::HOperands ou{w.S16, b.zh16T, b.zh16, b.ib16, w.wu16, save_p ? b.xpu : nullptr};
+  fusedh::HOperands ou{w.S16, b.zh16T, b.zh16, ib, w.wu16, save_p ? b.xpu : nullptr, ib_ld};
   fusedh::EpiUpdateH eu{HS, b.hx, b.r, b.hc, h_out, save ? h_mma : nullptr, last ? nullptr : b.x16, last ? nullptr : b.x16T, ldT};
   MCRN_TRY((fusedh::launch_agcn_fused_h<HS, HS>(g.N, g.B, g.KS, ou, g_fused_parts, eu, st)));
   return MCRN_OK;
@@ -155,6 +170,7 @@ static int cell_forward(const Geo& g, const float* S, const CellW& w, const Cell
   const int64_t nH = g.R * Hs;
   if (fused_h_shape(g, Hs)) {
     const bool save = b.z != nullptr;
+    if (!ib_compact_shape(g, Hs, w.Cin, save))      // compact input blocks are built by the caller (all encoder steps at once / fused decoder input kernel)
     MCRN_LAUNCH(k_build_input_block, ew_grid(nH), 256, 0, st, b.xpin, b.xp_k, b.xp_n, g.NB, w.Cin, g.B, g.R, Hs, rnd,
                 save ? b.xpg + (int64_t)g.NB * nH : nullptr, save ? b.xpu + (int64_t)g.NB * nH : nullptr, b.ib16);
     const bool last = (h_mma == nullptr);
@@ -263,6 +279,8 @@ static CellBufs enc_bufs(const Geo& g, const Plan& p, float* ws, int t) {
   b.x16 = reinterpret_cast<__half*>(ws + p.enc_x16); b.x16T = reinterpret_cast<__half*>(ws + p.enc_x16T);
   b.zh16 = reinterpret_cast<__half*>(ws + p.enc_zh16); b.zh16T = reinterpret_cast<__half*>(ws + p.enc_zh16T);
   b.ib16 = reinterpret_cast<__half*>(ws + p.enc_ib16);
+  b.ib16c = reinterpret_cast<__half*>(ws + p.enc_ib16c) + (int64_t)t * g.R * 64;
+  b.ib32c = p.save ? ws + p.enc_ib32c + (int64_t)t * g.R * 16 : nullptr;
   return b;
 }
 static CellBufs dec_bufs(const Geo& g, const Plan& p, float* ws, int t) {
@@ -280,6 +298,8 @@ static CellBufs dec_bufs(const Geo& g, const Plan& p, float* ws, int t) {
   b.x16 = reinterpret_cast<__half*>(ws + p.dec_x16); b.x16T = reinterpret_cast<__half*>(ws + p.dec_x16T);
   b.zh16 = reinterpret_cast<__half*>(ws + p.dec_zh16); b.zh16T = reinterpret_cast<__half*>(ws + p.dec_zh16T);
   b.ib16 = reinterpret_cast<__half*>(ws + p.dec_ib16);
+  b.ib16c = reinterpret_cast<__half*>(ws + p.dec_ib16c);
+  b.ib32c = p.save ? ws + p.dec_ib32c + (int64_t)t * g.R * 16 : nullptr;
   return b;
 }
 static CellW enc_w(const Geo& g, const Plan& p, float* ws) {
@@ -320,6 +340,9 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
     MCRN_LAUNCH(k_stage_encoder_input, ew_grid(n_in), 256, 0, st, x, ws + p.enc_xpin, g.B, g.T_in, g.N, g.Cin, tf32_mode());
     MCRN_TRY(propagate_in(g, S, ws + p.enc_xpin, (int64_t)g.N * g.T_in * g.B * g.Cin, (int64_t)g.T_in * g.B * g.Cin,
                           g.T_in * g.B * g.Cin, st));
+    if (ib_compact_shape(g, g.H, g.Cin, p.save))
+      MCRN_LAUNCH(fusedh::k_encoder_input_blocks, ew_grid((int64_t)g.T_in * g.R * 64), 256, 0, st, ws + p.enc_xpin, g.NB, g.N, g.T_in,
+                  g.B, g.Cin, reinterpret_cast<__half*>(ws + p.enc_ib16c), p.save ? ws + p.enc_ib32c : nullptr);
     MCRN_CUDA_OK(cudaMemsetAsync(ws + p.enc_xpg, 0, (size_t)g.R * g.H * sizeof(float), st));
     MCRN_CUDA_OK(cudaMemsetAsync(ws + p.enc_hx, 0, (size_t)g.R * g.H * sizeof(float), st));
     if (enc_h) {
@@ -354,9 +377,23 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
       const float* go_src = nullptr;
       if (t > 0) go_src = (tf && tf[t - 1]) ? labels : output;
       int64_t n_in = (int64_t)g.R * g.Cdec;
+      if (ib_compact_shape(g, g.D, g.Cdec, p.save)) {
+        const size_t shm = ((size_t)g.N * fusedh::DI_COLS + (size_t)fusedh::DI_ROWS * (g.N + 1) +
+                            (size_t)fusedh::DI_NODES * fusedh::DI_COLS * (fusedh::IBF + 1)) * sizeof(float);
+        static bool di_attr = false;
+        if (!di_attr) {
+          MCRN_CUDA_OK(cudaFuncSetAttribute(fusedh::k_decoder_input_block, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+          di_attr = true;
+        }
+        if (shm > 200 * 1024) { set_error("k_decoder_input_block: N=%d needs %zu bytes of shared memory", g.N, shm); return MCRN_ERR_BAD_DIMS; }
+        MCRN_LAUNCH(fusedh::k_decoder_input_block,
+                    dim3(ceil_div(g.B * g.Cdec, fusedh::DI_COLS), ceil_div(g.N, fusedh::DI_NODES)), 256, shm, st, go_src, y_cov, ws + p.S, g.ldS, g.KS, g.N,
+                    g.B, g.T_out, g.Cout, g.Ycov, t, p.save ? const_cast<float*>(b.xpin) : nullptr, b.ib16c, b.ib32c);
+      } else {
       MCRN_LAUNCH(k_stage_decoder_input, ew_grid(n_in), 256, 0, st, go_src, y_cov, const_cast<float*>(b.xpin), g.B,
                   g.T_out, g.N, g.Cout, g.Ycov, t, tf32_mode());
       MCRN_TRY(propagate_in(g, S, const_cast<float*>(b.xpin), b.xp_k, b.xp_n, g.B * g.Cdec, st));
+      }
       const bool last = (t + 1 == g.T_out);
       float* h_out = last ? ws + p.h_dec_last : dec_bufs(g, p, ws, t + 1).hx;
       float* h_mma = last ? nullptr : dec_bufs(g, p, ws, t + 1).xpg;
@@ -640,18 +677,27 @@ static int acc_ds_fused_all(const Geo& g, const Plan& p, float* ws, const CellW&
 //   blocks 0 and NB : dW = sum_t XP_t[blk]^T dV_t            (as acc_dw_all, two blocks)
 //   blocks 1..KS    : dW_k[:, half] = sum_t X_t^T Q_t[k, half]     (X_t = XP_t[0])
 static int acc_dw_fused(const Geo& g, const float* xp0, int64_t xp_step, int T, int Hs, const float* dv_all, const float* q_all,
-                        int nhalf, float* dw, cudaStream_t st) {
+                        int nhalf, float* dw, const float* ib32c, cudaStream_t st) {
   if (g_dbg_skip & 2) return MCRN_OK;
   const int O = nhalf * Hs;
   for (int t0 = 0; t0 < T; t0 += 16) {
     const int nt = T - t0 < 16 ? T - t0 : 16;
+    if (ib32c != nullptr) {        // compact input block: dW[NB][0..16) = sum_t IB_t^T dV_t ; block 0 on its own below
+      GemmDesc q;
+      q.A = ib32c + (int64_t)t0 * g.R * fusedh::IBF; q.a_row = 1; q.a_k = fusedh::IBF; q.a_seg = g.R * fusedh::IBF;
+      q.M = fusedh::IBF; q.Kseg = (int)g.R; q.nseg = nt;
+      q.B = dv_all + (int64_t)t0 * g.R * O; q.b_k = O; q.b_n = 1; q.b_seg = g.R * O; q.N = O;
+      q.splits = split_for((int64_t)ceil_div(O, 128), (int64_t)nt * g.R / 32);
+      EpiAtomicAdd e{dw + (int64_t)g.NB * Hs * O, O, 0};
+      MCRN_TRY(gemm(q, e, st));
+    }
     {
       GemmDesc q;
       q.A = xp0 + (int64_t)t0 * xp_step; q.a_row = 1; q.a_k = Hs; q.a_batch = (int64_t)g.NB * g.R * Hs; q.a_seg = xp_step;
       q.M = Hs; q.Kseg = (int)g.R; q.nseg = nt;
       q.B = dv_all + (int64_t)t0 * g.R * O; q.b_k = O; q.b_n = 1; q.b_batch = 0; q.b_seg = g.R * O; q.N = O;
-      q.nbatch = 2;
-      q.splits = split_for((int64_t)ceil_div(Hs, 128) * ceil_div(O, 128) * 2, (int64_t)nt * g.R / 32);
+      q.nbatch = ib32c != nullptr ? 1 : 2;
+      q.splits = split_for((int64_t)ceil_div(Hs, 128) * ceil_div(O, 128) * q.nbatch, (int64_t)nt * g.R / 32);
       EpiAtomicAdd e{dw, O, (int64_t)g.NB * Hs * O};
       MCRN_TRY(gemm(q, e, st));
     }
@@ -796,8 +842,9 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
     }
     if (fb) {   // weight gradients of the decoder: off the critical path, concurrent with the memory / encoder backward
       MCRN_TRY(side2_fork(st));
-      MCRN_TRY(acc_dw_fused(g, ws + p.dec_xpu, (int64_t)p.dec_xp_sz, g.T_out, g.D, dU_all, ws + p.d_Qu, 1, ws + p.a_d_wu, g_side.s2));
-      MCRN_TRY(acc_dw_fused(g, ws + p.dec_xpg, (int64_t)p.dec_xp_sz, g.T_out, g.D, dG_all, ws + p.d_Qg, 2, ws + p.a_d_wg, g_side.s2));
+      const float* ibc = ib_compact_shape(g, g.D, g.Cdec, true) ? ws + p.dec_ib32c : nullptr;
+      MCRN_TRY(acc_dw_fused(g, ws + p.dec_xpu, (int64_t)p.dec_xp_sz, g.T_out, g.D, dU_all, ws + p.d_Qu, 1, ws + p.a_d_wu, ibc, g_side.s2));
+      MCRN_TRY(acc_dw_fused(g, ws + p.dec_xpg, (int64_t)p.dec_xp_sz, g.T_out, g.D, dG_all, ws + p.d_Qg, 2, ws + p.a_d_wg, ibc, g_side.s2));
     } else {
     MCRN_TRY(acc_dw_all(g, ws + p.dec_xpu, (int64_t)p.dec_xp_sz, g.T_out, g.D, dU_all, g.D, ws + p.a_d_wu, st));
     MCRN_TRY(acc_dw_all(g, ws + p.dec_xpg, (int64_t)p.dec_xp_sz, g.T_out, g.D, dG_all, 2 * g.D, ws + p.a_d_wg, st));
@@ -865,8 +912,9 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
     }
     if (fb) {   // concurrent with the supports backward
       MCRN_TRY(side2_fork(st));
-      MCRN_TRY(acc_dw_fused(g, ws + p.enc_xpu, (int64_t)p.enc_xp_sz, g.T_in, g.H, dU_all, ws + p.e_Qu, 1, ws + p.a_e_wu, g_side.s2));
-      MCRN_TRY(acc_dw_fused(g, ws + p.enc_xpg, (int64_t)p.enc_xp_sz, g.T_in, g.H, dG_all, ws + p.e_Qg, 2, ws + p.a_e_wg, g_side.s2));
+      const float* ibc = ib_compact_shape(g, g.H, g.Cin, true) ? ws + p.enc_ib32c : nullptr;
+      MCRN_TRY(acc_dw_fused(g, ws + p.enc_xpu, (int64_t)p.enc_xp_sz, g.T_in, g.H, dU_all, ws + p.e_Qu, 1, ws + p.a_e_wu, ibc, g_side.s2));
+      MCRN_TRY(acc_dw_fused(g, ws + p.enc_xpg, (int64_t)p.enc_xp_sz, g.T_in, g.H, dG_all, ws + p.e_Qg, 2, ws + p.a_e_wg, ibc, g_side.s2));
     } else {
     MCRN_TRY(acc_dw_all(g, ws + p.enc_xpu, (int64_t)p.enc_xp_sz, g.T_in, g.H, dU_all, g.H, ws + p.a_e_wu, st));
     MCRN_TRY(acc_dw_all(g, ws + p.enc_xpg, (int64_t)p.enc_xp_sz, g.T_in, g.H, dG_all, 2 * g.H, ws + p.a_e_wg, st));
