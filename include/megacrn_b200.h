@@ -200,8 +200,9 @@ int mcrn_set_fused(int fused, int weight_parts);
  * mcrn_kernel_timing(1) also resets the record; _read synchronises the recorded events and returns their summed duration. */
 int mcrn_kernel_timing(int enable);
 int mcrn_kernel_timing_read(int kernel_class, float* ms_total, int* launches);
-/* Backward data path of every AGCN as one fused kernel (csrc/agcn_bwd_fused.cuh): 1 = on (default) where the hidden
- * width is 64 or 128, 0 = per-stage GEMM kernels.  Set it before the forward whose backward it governs. */
+/* Backward data path of every AGCN as one fused kernel where the hidden width is 64 or 128: 2 (default) = fp16 operands
+ * with a per-backward power-of-two loss scale (csrc/agcn_bwd_fused_h.cuh), 1 = TF32 operands (csrc/agcn_bwd_fused.cuh),
+ * 0 = per-stage GEMM kernels.  Set it before the forward whose backward it governs. */
 int mcrn_set_bwd_fused(int fused);
 /* Debug aid (tools/fused_timeline.py): while device_slots != NULL the `which`-th fused AGCN launch after this call
  * (-1 = every launch) records clock64 timestamps of CTA (0,0) into it (512 x int64; slot map in csrc/agcn_fused.cuh).

@@ -115,7 +115,11 @@ int mcrn_kernel_timing_read(int kernel_class, float* ms_total, int* launches) {
   }
   return MCRN_OK;
 }
-int mcrn_set_bwd_fused(int fused) { g_bwd_fused = fused ? 1 : 0; return MCRN_OK; }
+int mcrn_set_bwd_fused(int fused) {
+  if (fused < 0 || fused > 2) { set_error("mcrn_set_bwd_fused: 0, 1 or 2"); return MCRN_ERR_BAD_DIMS; }
+  g_bwd_fused = fused;
+  return MCRN_OK;
+}
 int mcrn_set_fused(int fused, int weight_parts) {
   if (fused < 0 || fused > 2 || weight_parts < 1 || weight_parts > 2) { set_error("mcrn_set_fused: fused in {0,1,2}, weight_parts in {1,2}"); return MCRN_ERR_BAD_DIMS; }
   g_fused = fused; g_fused_parts = weight_parts;

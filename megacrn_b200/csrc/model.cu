@@ -13,6 +13,7 @@
 #include "agcn_fused_h.cuh"
 #include "agcn_bwd_fused.cuh"
 #include "agcn_ds_fused.cuh"
+#include "agcn_bwd_fused_h.cuh"
 #include "plan.cuh"
 #include "loss.cuh"
 #include "small_kernels.cuh"
@@ -69,6 +70,7 @@ struct CellW {           // folded weights of one cell (plan buffers): [hi | lo]
   int Hs, Cin;
   const __half *wg16 = nullptr, *wu16 = nullptr;   // fp16 hi/lo, transposed [2][NB+1][O][Hs] (fused fp16 forward)
   const __half* S16 = nullptr;                     // fp16 supports [KS][N][ld_half(N)]
+  const __half *wg16n = nullptr, *wu16n = nullptr; // fp16 weights [NB+1][Hs][O] (fp16 fused backward)
 };
 struct CellBufs {        // per-step activations
   const float* xpin; int64_t xp_k, xp_n;
@@ -124,8 +126,9 @@ static int cell_forward_fused(const Geo& g, const float* S, const CellW& w, cons
   return MCRN_OK;
 }
 
-// Fused backward (agcn_bwd_fused.cuh): 1 = on where the shape is instantiated (default), 0 = per-stage GEMM backward.
-int g_bwd_fused = getenv("MCRN_BWD_FUSED") ? atoi(getenv("MCRN_BWD_FUSED")) : 1;
+// Fused backward: 2 = fp16 operands with a loss scale (agcn_bwd_fused_h.cuh, default), 1 = TF32 operands
+// (agcn_bwd_fused.cuh), 0 = per-stage GEMM backward.
+int g_bwd_fused = getenv("MCRN_BWD_FUSED") ? atoi(getenv("MCRN_BWD_FUSED")) : 2;
 static bool bwd_fused_shape(const Geo& g, int Hs, int Cin) {
   return tf32_mode() && g_bwd_fused && !g_simt_mask && (Hs == 64 || Hs == 128) && g.NB * Cin + 1 <= fusedb::IBW && g.B <= 65535;
 }
@@ -304,11 +307,13 @@ static CellBufs dec_bufs(const Geo& g, const Plan& p, float* ws, int t) {
 }
 static CellW enc_w(const Geo& g, const Plan& p, float* ws) {
   return CellW{ws + p.e_wg, ws + p.e_wu, g.H, g.Cin, reinterpret_cast<const __half*>(ws + p.e_wg16),
-               reinterpret_cast<const __half*>(ws + p.e_wu16), reinterpret_cast<const __half*>(ws + p.s16)};
+               reinterpret_cast<const __half*>(ws + p.e_wu16), reinterpret_cast<const __half*>(ws + p.s16),
+               p.save ? reinterpret_cast<const __half*>(ws + p.e_wg16n) : nullptr, p.save ? reinterpret_cast<const __half*>(ws + p.e_wu16n) : nullptr};
 }
 static CellW dec_w(const Geo& g, const Plan& p, float* ws) {
   return CellW{ws + p.d_wg, ws + p.d_wu, g.D, g.Cdec, reinterpret_cast<const __half*>(ws + p.d_wg16),
-               reinterpret_cast<const __half*>(ws + p.d_wu16), reinterpret_cast<const __half*>(ws + p.s16)};
+               reinterpret_cast<const __half*>(ws + p.d_wu16), reinterpret_cast<const __half*>(ws + p.s16),
+               p.save ? reinterpret_cast<const __half*>(ws + p.d_wg16n) : nullptr, p.save ? reinterpret_cast<const __half*>(ws + p.d_wu16n) : nullptr};
 }
 
 // ======================================================================================
@@ -601,16 +606,34 @@ static int cell_backward_fused(const Geo& g, const Plan& p, float* ws, const flo
   MCRN_TRY(make_dxp_s(g, bs.dU, HS, w.wu, HS, dXP, sd));
   MCRN_TRY(acc_ds(g, dXP + nH, (int64_t)g.B * HS, b.xpu, (int64_t)g.B * HS, g.B * HS, dS, sd));
   }
+  const bool h16 = (g_bwd_fused == 2);
+  __half* dU16 = reinterpret_cast<__half*>(ws + p.dU16);
+  __half* dU16T = reinterpret_cast<__half*>(ws + p.dU16T);
+  __half* dG16 = reinterpret_cast<__half*>(ws + p.dG16);
+  __half* dG16T = reinterpret_cast<__half*>(ws + p.dG16T);
+  const __half* S16T = reinterpret_cast<const __half*>(ws + p.s16T);
+  if (h16) {
+    fusedbh::BHOperands ou{S16T, dU16T, dU16, w.wu16n, ws + p.gs};
+    fusedbh::EpiBUH eu{HS, b.z, b.hx, ws + p.dHr, bs.dG, dHp, dG16, dG16T, fusedh::ld_half(g.N)};
+    MCRN_TRY((fusedbh::launch_agcn_bwd_h<HS>(g.N, g.B, g.KS, 1, ou, bs.Qu, ws + p.dIBu16, eu, st)));
+  } else {
   fusedb::EpiBU eu{HS, b.z, b.hx, ws + p.dHr, bs.dG, dHp};
   MCRN_TRY((fusedb::launch_agcn_bwd<HS>(g.N, g.B, g.KS, g.ldS, 1, St, bs.dU, w.wu, bs.Qu, ws + p.dIBu16, eu, st)));
+  }
   // gate AGCN
   if (do_ds) {
   MCRN_TRY(side_begin(1, st));
   MCRN_TRY(make_dxp_s(g, bs.dG, 2 * HS, w.wg, HS, dXP2, sd));
   MCRN_TRY(acc_ds(g, dXP2 + nH, (int64_t)g.B * HS, b.xpg, (int64_t)g.B * HS, g.B * HS, dS, sd));
   }
+  if (h16) {
+    fusedbh::BHOperands og{S16T, dG16T, dG16, w.wg16n, ws + p.gs};
+    fusedbh::EpiBGH eg{HS, dHp, dH};
+    MCRN_TRY((fusedbh::launch_agcn_bwd_h<HS>(g.N, g.B, g.KS, 2, og, bs.Qg, ws + p.dIBg16, eg, st)));
+  } else {
   fusedb::EpiBG eg{HS, dHp, dH};
   MCRN_TRY((fusedb::launch_agcn_bwd<HS>(g.N, g.B, g.KS, g.ldS, 2, St, bs.dG, w.wg, bs.Qg, ws + p.dIBg16, eg, st)));
+  }
   // input channels: d(input block) of both AGCNs -> dXPin [NB][R][Cin]
   const int64_t nIn = (int64_t)g.NB * g.R * w.Cin;
   MCRN_LAUNCH(k_repack_dib, ew_grid(nIn), 256, 0, st, ws + p.dIBu16, ws + p.dIBg16, g.NB, w.Cin, g.R, fusedb::IBW, bs.dXPin, 1);
@@ -798,6 +821,27 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
   MCRN_CUDA_OK(cudaMemsetAsync(grads->proj_w, 0, (size_t)g.Cout * g.D * sizeof(float), st));
   MCRN_CUDA_OK(cudaMemsetAsync(grads->proj_b, 0, (size_t)g.Cout * sizeof(float), st));
   float *dH = ws + p.dH, *dXin = ws + p.dXin;
+  if (g_bwd_fused == 2 && (bwd_fused_shape(g, g.D, g.Cdec) || bwd_fused_shape(g, g.H, g.Cin))) {
+    // loss scale from the upstream gradients, fp16 operand copies of the transposed supports and of the weights
+    unsigned* amax = reinterpret_cast<unsigned*>(ws + p.gs + 2);
+    MCRN_CUDA_OK(cudaMemsetAsync(amax, 0, sizeof(unsigned), st));
+    const int64_t n_out = d_output ? (int64_t)g.B * g.T_out * g.N * g.Cout : 0, n_q = d_query ? (int64_t)g.B * g.N * g.d : 0;
+    if (n_out + n_q > 0) MCRN_LAUNCH(fusedbh::k_grad_amax, ew_grid(n_out + n_q), 256, 0, st, d_output, n_out, d_query, n_q, amax);
+    MCRN_LAUNCH(fusedbh::k_grad_scale, 1, 1, 0, st, amax, ws + p.gs);
+    const int ld16 = fusedh::ld_half(g.N);
+    MCRN_LAUNCH(fusedbh::k_supports_to_half_T, dim3(ceil_div(g.N, 32), ceil_div(ld16, 32), g.KS), dim3(32, 8), 0, st, ws + p.S,
+                reinterpret_cast<__half*>(ws + p.s16T), g.N, g.ldS, ld16);
+    if (bwd_fused_shape(g, g.H, g.Cin)) {
+      const int64_t ng = (int64_t)(g.NB + 1) * g.H * 2 * g.H, nu = (int64_t)(g.NB + 1) * g.H * g.H;
+      MCRN_LAUNCH(fusedbh::k_weights_to_half_n, ew_grid(ng), 256, 0, st, ws + p.e_wg, reinterpret_cast<__half*>(ws + p.e_wg16n), ng);
+      MCRN_LAUNCH(fusedbh::k_weights_to_half_n, ew_grid(nu), 256, 0, st, ws + p.e_wu, reinterpret_cast<__half*>(ws + p.e_wu16n), nu);
+    }
+    if (bwd_fused_shape(g, g.D, g.Cdec)) {
+      const int64_t ng = (int64_t)(g.NB + 1) * g.D * 2 * g.D, nu = (int64_t)(g.NB + 1) * g.D * g.D;
+      MCRN_LAUNCH(fusedbh::k_weights_to_half_n, ew_grid(ng), 256, 0, st, ws + p.d_wg, reinterpret_cast<__half*>(ws + p.d_wg16n), ng);
+      MCRN_LAUNCH(fusedbh::k_weights_to_half_n, ew_grid(nu), 256, 0, st, ws + p.d_wu, reinterpret_cast<__half*>(ws + p.d_wu16n), nu);
+    }
+  }
   if (bwd_fused_shape(g, g.D, g.Cdec) || bwd_fused_shape(g, g.H, g.Cin))
     MCRN_LAUNCH(fusedb::k_transpose_supports, dim3(ceil_div(g.N, 32), ceil_div(g.N, 32), g.KS), dim3(32, 8), 0, st, S, ws + p.St,
                 g.N, g.ldS);
@@ -815,6 +859,14 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
       if (fb) {
         bool need_dxin = (t > 0) && !(tf && tf[t - 1]);
         float* dU_t = dU_all + (int64_t)t * g.R * g.D;
+        if (g_bwd_fused == 2) {
+          const size_t gsm = ((size_t)(32 + g.D) * g.Cout + 2 * 32 * (g.D + 1)) * sizeof(float);
+          MCRN_LAUNCH(fusedbh::k_bwd_glue_h, dim3(ceil_div(g.N, 32), g.B), 256, gsm, st, d_output, use_dgo ? dXin : nullptr, g.Cdec, h_t,
+                      prm->proj_w, dH, (t == g.T_out - 1) ? 1 : 0, b.r, b.hc, b.hx, dU_t, dG_all + (int64_t)t * g.R * 2 * g.D,
+                      ws + p.dHr, reinterpret_cast<__half*>(ws + p.dU16), reinterpret_cast<__half*>(ws + p.dU16T),
+                      reinterpret_cast<__half*>(ws + p.dG16), reinterpret_cast<__half*>(ws + p.dG16T), fusedh::ld_half(g.N),
+                      ws + p.gs, grads->proj_w, grads->proj_b, g.B, g.T_out, g.N, g.D, g.Cout, t);
+        } else
         MCRN_LAUNCH(fusedb::k_bwd_glue, (int)ceil_div64(g.R, 32), 256, (size_t)(32 + g.D) * g.Cout * sizeof(float), st, d_output,
                     use_dgo ? dXin : nullptr, g.Cdec, h_t, prm->proj_w, dH, (t == g.T_out - 1) ? 1 : 0, b.r, b.hc, b.hx, dU_t,
                     dG_all + (int64_t)t * g.R * 2 * g.D, ws + p.dHr, grads->proj_w, grads->proj_b, g.B, g.T_out, g.N, g.D,
@@ -893,6 +945,14 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
       CellBufs b = enc_bufs(g, p, ws, t);
       if (fb) {
         float* dU_t = dU_all + (int64_t)t * g.R * g.H;
+        if (g_bwd_fused == 2) {
+          const size_t gsm = (size_t)2 * 32 * (g.H + 1) * sizeof(float);
+          MCRN_LAUNCH(fusedbh::k_bwd_glue_h, dim3(ceil_div(g.N, 32), g.B), 256, gsm, st, (const float*)nullptr, (const float*)nullptr, 0,
+                      (const float*)nullptr, (const float*)nullptr, dHe, 0, b.r, b.hc, b.hx, dU_t, dG_all + (int64_t)t * g.R * 2 * g.H,
+                      ws + p.dHr, reinterpret_cast<__half*>(ws + p.dU16), reinterpret_cast<__half*>(ws + p.dU16T),
+                      reinterpret_cast<__half*>(ws + p.dG16), reinterpret_cast<__half*>(ws + p.dG16T), fusedh::ld_half(g.N),
+                      ws + p.gs, (float*)nullptr, (float*)nullptr, g.B, g.T_in, g.N, g.H, 0, t);
+        } else
         MCRN_LAUNCH(fusedb::k_bwd_glue, (int)ceil_div64(g.R, 32), 256, 0, st, (const float*)nullptr, (const float*)nullptr, 0,
                     (const float*)nullptr, (const float*)nullptr, dHe, 0, b.r, b.hc, b.hx, dU_t,
                     dG_all + (int64_t)t * g.R * 2 * g.H, ws + p.dHr, (float*)nullptr, (float*)nullptr, g.B, g.T_in, g.N, g.H, 0, t);

@@ -39,6 +39,9 @@ struct Plan {
   // fused backward (agcn_bwd_fused.cuh): transposed supports, Q blocks of every step, input-block gradients,
   // per-step dXPin
   size_t St, e_Qu, e_Qg, d_Qu, d_Qg, dIBu16, dIBg16, dXPin_all, dHr;
+  // fp16 fused backward (agcn_bwd_fused_h.cuh): loss scale {s, 1/s, amax bits}, transposed fp16 supports, fp16 weights,
+  // scaled fp16 operand copies of dU / dG (row-major and node-transposed)
+  size_t gs, s16T, e_wg16n, e_wu16n, d_wg16n, d_wu16n, dU16, dU16T, dG16, dG16T;
   size_t dXPin_sz;
   // loss scratch
   size_t loss_scratch;                   // 8 floats
@@ -134,6 +137,20 @@ static inline int make_plan(const Geo& g, bool save, Plan* p) {
     p->d_Qu = take((size_t)g.T_out * KS * R * g.D);
     p->d_Qg = take((size_t)g.T_out * 2 * KS * R * g.D);
     p->dHr = take(R * g.D);
+    {
+      const size_t ld16 = (N + 7) / 8 * 8;
+      auto halves = [&](size_t n) { return take((n + 1) / 2); };
+      p->gs = take(64);
+      p->s16T = halves(KS * N * ld16);
+      p->e_wg16n = halves((NB + 1) * g.H * 2 * g.H);
+      p->e_wu16n = halves((NB + 1) * g.H * g.H);
+      p->d_wg16n = halves((NB + 1) * g.D * 2 * g.D);
+      p->d_wu16n = halves((NB + 1) * g.D * g.D);
+      p->dU16 = halves(R * g.D);
+      p->dU16T = halves((size_t)g.B * g.D * ld16);
+      p->dG16 = halves(R * 2 * g.D);
+      p->dG16T = halves((size_t)g.B * 2 * g.D * ld16);
+    }
     p->dIBu16 = take(R * 16);
     p->dIBg16 = take(R * 16);
     p->dXPin_sz = (NB * R * Cm + 63) / 64 * 64;

@@ -327,7 +327,7 @@ def test_fused_backward_kernel_matches_per_stage_backward(N, H, dm, B, T, defaul
     for flags in ([True] * T, [t % 2 == 1 for t in range(T)]):
         res, ups = {}, None
         try:
-            for bf in (0, 1):
+            for bf in (0, 1, 2):
                 assert lib.mcrn_set_bwd_fused(bf) == 0
                 m = _model(d, p).train()
                 outs = m(x.to(dv), y_cov.to(dv), labels.to(dv), teacher_forcing=flags)
@@ -336,11 +336,12 @@ def test_fused_backward_kernel_matches_per_stage_backward(N, H, dm, B, T, defaul
                 torch.autograd.backward([outs[0], outs[2]], ups)
                 res[bf] = ([o.detach().cpu() for o in outs[:3]], {k: v.grad.cpu() for k, v in m.named_parameters()})
         finally:
-            lib.mcrn_set_bwd_fused(1)
-        for a, b in zip(res[1][0], res[0][0]):            # same forward kernels; only the input-block path differs (compact,
-            assert rel_l2(a, b) < 6e-4                    # exact-fp32 input propagation with the fused backward)
-        for k in res[0][1]:
-            assert rel_l2(res[1][1][k], res[0][1][k]) < 1.5e-3, (flags, k, rel_l2(res[1][1][k], res[0][1][k]))
+            lib.mcrn_set_bwd_fused(2)
+        for bf in (1, 2):                                 # 1 = TF32 operands, 2 = fp16 operands + loss scale
+            for a, b in zip(res[bf][0], res[0][0]):       # same forward kernels; only the input-block path differs (compact,
+                assert rel_l2(a, b) < 6e-4                # exact-fp32 input propagation with the fused backward)
+            for k in res[0][1]:
+                assert rel_l2(res[bf][1][k], res[0][1][k]) < 1.5e-3, (bf, flags, k, rel_l2(res[bf][1][k], res[0][1][k]))
 
 
 def test_kernel_timing_api_counts_fused_launches(default_engine):

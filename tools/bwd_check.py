@@ -37,8 +37,9 @@ cases = [("N=100 H=64 T=1 B=2", O.Dims(num_nodes=100, horizon=1, rnn_units=64), 
 for title, d, B, t_in in cases:
     for flags in ([True] * d.horizon, [t % 2 == 1 for t in range(d.horizon)]):
         o0, g0 = run(d, B, t_in, 0, flags)
-        o1, g1 = run(d, B, t_in, 1, flags)
-        errs = sorted(((rel(g1[k], g0[k]), k) for k in g0), reverse=True)
-        print(f"[{title}] tf={''.join('1' if f else '0' for f in flags)} out={rel(o1[0], o0[0]):.1e}  " +
-              "  ".join(f"{k.split('.')[-3][:3] if k.count('.') > 1 else ''}.{k.split('.')[-2]}.{k.split('.')[-1]}={e:.1e}" for e, k in errs[:5]), flush=True)
-lib.mcrn_set_bwd_fused(1)
+        for mode in (1, 2):
+          o1, g1 = run(d, B, t_in, mode, flags)
+          errs = sorted(((rel(g1[k], g0[k]), k) for k in g0), reverse=True)
+          print(f"[{title}] mode={mode} tf={''.join('1' if f else '0' for f in flags)} out={rel(o1[0], o0[0]):.1e}  " +
+                "  ".join(f"{k.split('.')[-3][:3] if k.count('.') > 1 else ''}.{k.split('.')[-2]}.{k.split('.')[-1]}={e:.1e}" for e, k in errs[:5]), flush=True)
+lib.mcrn_set_bwd_fused(2)
