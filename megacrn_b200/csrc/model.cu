@@ -586,6 +586,9 @@ static int make_dxp_s(const Geo& g, const float* dv, int O, const float* wall, i
   EpiBlocks e{dxp, Hs, g.R * Hs, 1, -1, nullptr, 1};
   return gemm(q, e, st);
 }
+// dS / dW launches per cell type: 1 = one launch after the time loop (measured best at C2: 4.41 ms/step vs 4.47-4.54 with 3
+// chunks -- the extra launches and their interference with the recurrent chain cost more than the shorter tail saves)
+static int g_side_chunks = getenv("MCRN_SIDE_CHUNKS") ? (atoi(getenv("MCRN_SIDE_CHUNKS")) > 0 ? atoi(getenv("MCRN_SIDE_CHUNKS")) : 1) : 1;
 int g_ds_fused = getenv("MCRN_DS_FUSED") ? atoi(getenv("MCRN_DS_FUSED")) : 1;
 static bool ds_fused_shape(const Geo& g, int Hs) { return g_ds_fused && fusedd::ds_fused_eligible(g.N, Hs); }
 // experiment knobs (timing only -- gradients are wrong when set): bit 0 = skip the dS side-stream work, bit 1 = skip dW GEMMs
@@ -671,16 +674,22 @@ static int side_join_fused(cudaStream_t mainst) {
 // Support gradients of one cell type over all steps (fused backward, N <= 256), on the side stream:
 //   state terms: agcn_ds_kernel per AGCN (update: dV = dU, X = XPu block 0; gate: dV = dG, X = XPg block 0)
 //   input-channel term: dS_k += sum_t dXPin_t[1+k] * xin_t^T as one GEMM with T K-segments
+// steps [ta, tb) of the state terms (launched as soon as those steps' dU / dG exist, so that only the last chunk is
+// exposed after the time loop); the input-channel term for all T steps with the chunk that starts at step 0
 template <int HS>
-static int acc_ds_fused_all(const Geo& g, const Plan& p, float* ws, const CellW& w, int T, const float* dU_all,
+static int acc_ds_fused_all(const Geo& g, const Plan& p, float* ws, const CellW& w, int T, int ta, int tb, const float* dU_all,
                             const float* dG_all, const float* xpu0, const float* xpg0, int64_t xp_step, const float* xpin0,
                             int64_t xpin_n, int64_t xpin_seg, cudaStream_t mainst) {
   if (g_dbg_skip & 1) return MCRN_OK;
   float* dS = ws + p.dS;
   cudaStream_t sd = g_side.s;
   MCRN_TRY(side_begin(0, mainst));
-  MCRN_TRY((fusedd::launch_agcn_ds<HS>(g.N, g.B, T, g.KS, g.ldS, HS, dU_all, w.wu, xpu0, xp_step, dS, sd)));
-  MCRN_TRY((fusedd::launch_agcn_ds<HS>(g.N, g.B, T, g.KS, g.ldS, 2 * HS, dG_all, w.wg, xpg0, xp_step, dS, sd)));
+  MCRN_TRY((fusedd::launch_agcn_ds<HS>(g.N, g.B, tb - ta, g.KS, g.ldS, HS, dU_all + (int64_t)ta * g.R * HS, w.wu,
+                                       xpu0 + (int64_t)ta * xp_step, xp_step, dS, sd)));
+  MCRN_TRY((fusedd::launch_agcn_ds<HS>(g.N, g.B, tb - ta, g.KS, g.ldS, 2 * HS, dG_all + (int64_t)ta * g.R * 2 * HS, w.wg,
+                                       xpg0 + (int64_t)ta * xp_step, xp_step, dS, sd)));
+  g_side.fused_pending = true;
+  if (ta != 0) return MCRN_OK;
   for (int t0 = 0; t0 < T; t0 += 16) {
     const int nt = T - t0 < 16 ? T - t0 : 16;
     const int cols = g.B * w.Cin;
@@ -699,12 +708,12 @@ static int acc_ds_fused_all(const Geo& g, const Plan& p, float* ws, const CellW&
 // Weight gradients of one AGCN over all steps, fused-backward form:
 //   blocks 0 and NB : dW = sum_t XP_t[blk]^T dV_t            (as acc_dw_all, two blocks)
 //   blocks 1..KS    : dW_k[:, half] = sum_t X_t^T Q_t[k, half]     (X_t = XP_t[0])
-static int acc_dw_fused(const Geo& g, const float* xp0, int64_t xp_step, int T, int Hs, const float* dv_all, const float* q_all,
+static int acc_dw_fused(const Geo& g, const float* xp0, int64_t xp_step, int ta, int tb, int Hs, const float* dv_all, const float* q_all,
                         int nhalf, float* dw, const float* ib32c, cudaStream_t st) {
   if (g_dbg_skip & 2) return MCRN_OK;
   const int O = nhalf * Hs;
-  for (int t0 = 0; t0 < T; t0 += 16) {
-    const int nt = T - t0 < 16 ? T - t0 : 16;
+  for (int t0 = ta; t0 < tb; t0 += 16) {
+    const int nt = tb - t0 < 16 ? tb - t0 : 16;
     if (ib32c != nullptr) {        // compact input block: dW[NB][0..16) = sum_t IB_t^T dV_t ; block 0 on its own below
       GemmDesc q;
       q.A = ib32c + (int64_t)t0 * g.R * fusedh::IBF; q.a_row = 1; q.a_k = fusedh::IBF; q.a_seg = g.R * fusedh::IBF;
@@ -851,6 +860,22 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
     float *dU_all = ws + p.d_dU, *dG_all = ws + p.d_dG;
     bool have_dgo = false;
     const bool fb = bwd_fused_shape(g, g.D, g.Cdec);
+    // dS / dW of the steps [ta, tb) on the side streams, launched as soon as those steps are done
+    const int dchunk = (g.T_out + g_side_chunks - 1) / g_side_chunks;
+    int dec_done = g.T_out;
+    auto dec_side_chunk = [&](int ta, int tb) -> int {
+      if (tb <= ta) return MCRN_OK;
+      CellBufs b0 = dec_bufs(g, p, ws, 0);
+      if (ds_fused_shape(g, g.D)) {
+        if (g.D == 64) MCRN_TRY(acc_ds_fused_all<64>(g, p, ws, w, g.T_out, ta, tb, dU_all, dG_all, b0.xpu, b0.xpg, (int64_t)p.dec_xp_sz, b0.xpin, b0.xp_n, (int64_t)p.dec_xpin_sz, st));
+        else MCRN_TRY(acc_ds_fused_all<128>(g, p, ws, w, g.T_out, ta, tb, dU_all, dG_all, b0.xpu, b0.xpg, (int64_t)p.dec_xp_sz, b0.xpin, b0.xp_n, (int64_t)p.dec_xpin_sz, st));
+      }
+      MCRN_TRY(side2_fork(st));
+      const float* ibc = ib_compact_shape(g, g.D, g.Cdec, true) ? ws + p.dec_ib32c : nullptr;
+      MCRN_TRY(acc_dw_fused(g, ws + p.dec_xpu, (int64_t)p.dec_xp_sz, ta, tb, g.D, dU_all, ws + p.d_Qu, 1, ws + p.a_d_wu, ibc, g_side.s2));
+      MCRN_TRY(acc_dw_fused(g, ws + p.dec_xpg, (int64_t)p.dec_xp_sz, ta, tb, g.D, dG_all, ws + p.d_Qg, 2, ws + p.a_d_wg, ibc, g_side.s2));
+      return MCRN_OK;
+    };
     for (int t = g.T_out - 1; t >= 0; --t) {
       CellBufs b = dec_bufs(g, p, ws, t);
       const float* h_t = (t + 1 < g.T_out) ? dec_bufs(g, p, ws, t + 1).hx : ws + p.h_dec_last;
@@ -876,6 +901,7 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
         if (g.D == 64) MCRN_TRY(cell_backward_fused<64>(g, p, ws, S, w, b, bs, dH, need_dxin ? dXin : nullptr, st));
         else MCRN_TRY(cell_backward_fused<128>(g, p, ws, S, w, b, bs, dH, need_dxin ? dXin : nullptr, st));
         have_dgo = need_dxin;
+        if (t > 0 && dec_done - t >= dchunk) { MCRN_TRY(dec_side_chunk(t, dec_done)); dec_done = t; }
         continue;
       }
       MCRN_LAUNCH(k_proj_bwd, (int)ceil_div64(g.R, 32), 256, shm, st, d_output, use_dgo ? dXin : nullptr, g.Cdec, h_t,
@@ -887,16 +913,8 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
                              need_dxin ? dXin : nullptr, st));
       have_dgo = need_dxin;
     }
-    if (fb && ds_fused_shape(g, g.D)) {
-      CellBufs b0 = dec_bufs(g, p, ws, 0);
-      if (g.D == 64) MCRN_TRY(acc_ds_fused_all<64>(g, p, ws, w, g.T_out, dU_all, dG_all, b0.xpu, b0.xpg, (int64_t)p.dec_xp_sz, b0.xpin, b0.xp_n, (int64_t)p.dec_xpin_sz, st));
-      else MCRN_TRY(acc_ds_fused_all<128>(g, p, ws, w, g.T_out, dU_all, dG_all, b0.xpu, b0.xpg, (int64_t)p.dec_xp_sz, b0.xpin, b0.xp_n, (int64_t)p.dec_xpin_sz, st));
-    }
-    if (fb) {   // weight gradients of the decoder: off the critical path, concurrent with the memory / encoder backward
-      MCRN_TRY(side2_fork(st));
-      const float* ibc = ib_compact_shape(g, g.D, g.Cdec, true) ? ws + p.dec_ib32c : nullptr;
-      MCRN_TRY(acc_dw_fused(g, ws + p.dec_xpu, (int64_t)p.dec_xp_sz, g.T_out, g.D, dU_all, ws + p.d_Qu, 1, ws + p.a_d_wu, ibc, g_side.s2));
-      MCRN_TRY(acc_dw_fused(g, ws + p.dec_xpg, (int64_t)p.dec_xp_sz, g.T_out, g.D, dG_all, ws + p.d_Qg, 2, ws + p.a_d_wg, ibc, g_side.s2));
+    if (fb) {
+      MCRN_TRY(dec_side_chunk(0, dec_done));
     } else {
     MCRN_TRY(acc_dw_all(g, ws + p.dec_xpu, (int64_t)p.dec_xp_sz, g.T_out, g.D, dU_all, g.D, ws + p.a_d_wu, st));
     MCRN_TRY(acc_dw_all(g, ws + p.dec_xpg, (int64_t)p.dec_xp_sz, g.T_out, g.D, dG_all, 2 * g.D, ws + p.a_d_wg, st));
@@ -941,6 +959,21 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
     float *dU_all = ws + p.e_dU, *dG_all = ws + p.e_dG;
     float* dHe = ws + p.dHenc;
     const bool fb = bwd_fused_shape(g, g.H, g.Cin);
+    const int echunk = (g.T_in + g_side_chunks - 1) / g_side_chunks;
+    int enc_done = g.T_in;
+    auto enc_side_chunk = [&](int ta, int tb) -> int {
+      if (tb <= ta) return MCRN_OK;
+      CellBufs b0 = enc_bufs(g, p, ws, 0);
+      if (ds_fused_shape(g, g.H)) {
+        if (g.H == 64) MCRN_TRY(acc_ds_fused_all<64>(g, p, ws, w, g.T_in, ta, tb, dU_all, dG_all, b0.xpu, b0.xpg, (int64_t)p.enc_xp_sz, b0.xpin, b0.xp_n, (int64_t)g.B * g.Cin, st));
+        else MCRN_TRY(acc_ds_fused_all<128>(g, p, ws, w, g.T_in, ta, tb, dU_all, dG_all, b0.xpu, b0.xpg, (int64_t)p.enc_xp_sz, b0.xpin, b0.xp_n, (int64_t)g.B * g.Cin, st));
+      }
+      MCRN_TRY(side2_fork(st));
+      const float* ibc = ib_compact_shape(g, g.H, g.Cin, true) ? ws + p.enc_ib32c : nullptr;
+      MCRN_TRY(acc_dw_fused(g, ws + p.enc_xpu, (int64_t)p.enc_xp_sz, ta, tb, g.H, dU_all, ws + p.e_Qu, 1, ws + p.a_e_wu, ibc, g_side.s2));
+      MCRN_TRY(acc_dw_fused(g, ws + p.enc_xpg, (int64_t)p.enc_xp_sz, ta, tb, g.H, dG_all, ws + p.e_Qg, 2, ws + p.a_e_wg, ibc, g_side.s2));
+      return MCRN_OK;
+    };
     for (int t = g.T_in - 1; t >= 0; --t) {
       CellBufs b = enc_bufs(g, p, ws, t);
       if (fb) {
@@ -960,21 +993,14 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
                    ws + p.e_Qg + (int64_t)t * 2 * g.KS * g.R * g.H, ws + p.dXPin_all + p.dXPin_sz * t};
         if (g.H == 64) MCRN_TRY(cell_backward_fused<64>(g, p, ws, S, w, b, bs, dHe, nullptr, st));
         else MCRN_TRY(cell_backward_fused<128>(g, p, ws, S, w, b, bs, dHe, nullptr, st));
+        if (t > 0 && enc_done - t >= echunk) { MCRN_TRY(enc_side_chunk(t, enc_done)); enc_done = t; }
         continue;
       }
       MCRN_TRY(cell_backward(g, p, ws, S, w, b, dU_all + (int64_t)t * g.R * g.H, dG_all + (int64_t)t * g.R * 2 * g.H, dHe, dHe,
                              nullptr, st));
     }
-    if (fb && ds_fused_shape(g, g.H)) {
-      CellBufs b0 = enc_bufs(g, p, ws, 0);
-      if (g.H == 64) MCRN_TRY(acc_ds_fused_all<64>(g, p, ws, w, g.T_in, dU_all, dG_all, b0.xpu, b0.xpg, (int64_t)p.enc_xp_sz, b0.xpin, b0.xp_n, (int64_t)g.B * g.Cin, st));
-      else MCRN_TRY(acc_ds_fused_all<128>(g, p, ws, w, g.T_in, dU_all, dG_all, b0.xpu, b0.xpg, (int64_t)p.enc_xp_sz, b0.xpin, b0.xp_n, (int64_t)g.B * g.Cin, st));
-    }
-    if (fb) {   // concurrent with the supports backward
-      MCRN_TRY(side2_fork(st));
-      const float* ibc = ib_compact_shape(g, g.H, g.Cin, true) ? ws + p.enc_ib32c : nullptr;
-      MCRN_TRY(acc_dw_fused(g, ws + p.enc_xpu, (int64_t)p.enc_xp_sz, g.T_in, g.H, dU_all, ws + p.e_Qu, 1, ws + p.a_e_wu, ibc, g_side.s2));
-      MCRN_TRY(acc_dw_fused(g, ws + p.enc_xpg, (int64_t)p.enc_xp_sz, g.T_in, g.H, dG_all, ws + p.e_Qg, 2, ws + p.a_e_wg, ibc, g_side.s2));
+    if (fb) {
+      MCRN_TRY(enc_side_chunk(0, enc_done));
     } else {
     MCRN_TRY(acc_dw_all(g, ws + p.enc_xpu, (int64_t)p.enc_xp_sz, g.T_in, g.H, dU_all, g.H, ws + p.a_e_wu, st));
     MCRN_TRY(acc_dw_all(g, ws + p.enc_xpg, (int64_t)p.enc_xp_sz, g.T_in, g.H, dG_all, 2 * g.H, ws + p.a_e_wg, st));
