@@ -495,46 +495,51 @@ __global__ void __launch_bounds__(256) k_decoder_input_block(const float* __rest
                                                              const float* __restrict__ S, int ldS, int KS, int N, int B, int T,
                                                              int Cout, int Ycov, int t, float* __restrict__ xin_out,
                                                              __half* __restrict__ ib16c, float* __restrict__ ib32c) {
-  extern __shared__ float sh[];                        // xs [N][DI_COLS], ss [DI_ROWS][N + 1], os [DI_NODES * DI_COLS][IBF + 1]
+  extern __shared__ float sh[];                        // xs [DI_COLS][N|1], ss [DI_ROWS][N + 1], os [DI_NODES * DI_COLS][IBF + 1]
   const int Cd = Cout + Ycov, cols = B * Cd, nin = (KS + 1) * Cd;
   const int c0 = blockIdx.x * DI_COLS, n0 = blockIdx.y * DI_NODES;
-  float* xs = sh;
-  float* ss = xs + N * DI_COLS;
+  const int xld = N | 1;                               // odd leading dimension: column-major input tile without bank conflicts
+  float* xs = sh;                                      // xs[cl * xld + m]
+  float* ss = xs + xld * DI_COLS;
   float* os = ss + DI_ROWS * (N + 1);
   auto xin = [&](int m, int col) -> float {
     const int b = col / Cd, c = col - b * Cd;
     if (c < Cout) return go_src ? __ldg(go_src + (((int64_t)b * T + (t - 1)) * N + m) * Cout + c) : 0.f;
     return __ldg(ycov + (((int64_t)b * T + t) * N + m) * Ycov + (c - Cout));
   };
-  // staging loops: 8 independent global loads in flight per thread (the block is alone on its SM: latency, not bandwidth)
-  constexpr int U = 8;
-  for (int base = threadIdx.x; base < N * DI_COLS; base += blockDim.x * U) {
-    float v[U];
+  // staging: threads along the source node m (coalesced); per input column / support row the base address is
+  // block-uniform (no per-element index arithmetic); 8 independent loads are issued before their shared-memory stores --
+  // the block is alone on its SM and bound by load latency, not bandwidth
+  for (int mb = 0; mb < N; mb += blockDim.x) {
+    const int m = mb + threadIdx.x;
+    for (int cb = 0; cb < DI_COLS; cb += 8) {
+      float v[8];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = base + u * blockDim.x;
-      const int cl = i / N, m = i - cl * N, col = c0 + cl;          // m fastest: coalesced reads of labels / output / y_cov
-      v[u] = (i < N * DI_COLS && col < cols) ? xin(m, col) : 0.f;
+      for (int u = 0; u < 8; ++u) {
+        const int col = c0 + cb + u;
+        const int b = col / Cd, c = col - b * Cd;
+        v[u] = 0.f;
+        if (m < N && col < cols) {
+          if (c < Cout) { if (go_src) v[u] = __ldg(go_src + (((int64_t)b * T + (t - 1)) * N + m) * Cout + c); }
+          else v[u] = __ldg(ycov + (((int64_t)b * T + t) * N + m) * Ycov + (c - Cout));
+        }
+      }
+      if (m < N) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) xs[(cb + u) * xld + m] = v[u];
+      }
     }
+    for (int rb = 0; rb < DI_ROWS; rb += 8) {                       // local row rl = k * DI_NODES + nl
+      float v[8];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = base + u * blockDim.x;
-      if (i < N * DI_COLS) { const int cl = i / N, m = i - cl * N; xs[m * DI_COLS + cl] = v[u]; }
-    }
-  }
-  for (int base = threadIdx.x; base < DI_ROWS * N; base += blockDim.x * U) {
-    float v[U];
+      for (int u = 0; u < 8; ++u) {
+        const int rl = rb + u, k = rl / DI_NODES, n = n0 + (rl - k * DI_NODES);
+        v[u] = (m < N && k < KS && n < N) ? __ldg(S + ((int64_t)k * N + n) * ldS + m) : 0.f;
+      }
+      if (m < N) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = base + u * blockDim.x;
-      const int rl = i / N, m = i - rl * N;                         // local row rl = k * DI_NODES + nl
-      const int k = rl / DI_NODES, n = n0 + (rl - k * DI_NODES);
-      v[u] = (i < DI_ROWS * N && k < KS && n < N) ? __ldg(S + ((int64_t)k * N + n) * ldS + m) : 0.f;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = base + u * blockDim.x;
-      if (i < DI_ROWS * N) { const int rl = i / N, m = i - rl * N; ss[rl * (N + 1) + m] = v[u]; }
+        for (int u = 0; u < 8; ++u) ss[(rb + u) * (N + 1) + m] = v[u];
+      }
     }
   }
   for (int i = threadIdx.x; i < DI_NODES * DI_COLS * (IBF + 1); i += blockDim.x) os[i] = 0.f;
@@ -544,7 +549,7 @@ __global__ void __launch_bounds__(256) k_decoder_input_block(const float* __rest
 #pragma unroll
   for (int i = 0; i < DI_RPT; ++i) acc[i] = 0.f;
   for (int m = 0; m < N; ++m) {
-    const float xv = xs[m * DI_COLS + cl];
+    const float xv = xs[cl * xld + m];
 #pragma unroll
     for (int i = 0; i < DI_RPT; ++i) acc[i] = fmaf(ss[(rg * DI_RPT + i) * (N + 1) + m], xv, acc[i]);
   }
@@ -558,7 +563,7 @@ __global__ void __launch_bounds__(256) k_decoder_input_block(const float* __rest
   for (int i = threadIdx.x; i < DI_NODES * DI_COLS; i += blockDim.x) {        // block 0 = the input itself, bias one
     const int nl = i / DI_COLS, cc = i - nl * DI_COLS, b2 = cc / Cd, c2 = cc - b2 * Cd;
     if (n0 + nl < N) {
-      os[(nl * bpb + b2) * (IBF + 1) + c2] = xs[(n0 + nl) * DI_COLS + cc];     // raw; rounded at the store below
+      os[(nl * bpb + b2) * (IBF + 1) + c2] = xs[cc * xld + n0 + nl];           // raw; rounded at the store below
       if (c2 == 0) os[(nl * bpb + b2) * (IBF + 1) + nin] = 1.0f;
     }
   }

@@ -142,7 +142,7 @@ static bool fused_h_shape(const Geo& g, int Hs) {
 static int g_ib_compact = getenv("MCRN_IB_COMPACT") ? atoi(getenv("MCRN_IB_COMPACT")) : 1;
 static bool ib_compact_shape(const Geo& g, int Hs, int Cin, bool save) {
   // (the fused decoder input kernel stages N x 32 inputs + 24 support rows in shared memory)
-  return g_ib_compact && ((size_t)g.N * fusedh::DI_COLS + (size_t)fusedh::DI_ROWS * (g.N + 1)) * sizeof(float) <= 180 * 1024 &&
+  return g_ib_compact && ((size_t)(g.N | 1) * fusedh::DI_COLS + (size_t)fusedh::DI_ROWS * (g.N + 1)) * sizeof(float) <= 180 * 1024 &&
          g.KS * fusedh::DI_NODES <= fusedh::DI_ROWS && fusedh::DI_COLS % (Cin) == 0 &&
          fused_h_shape(g, Hs) && g.NB * Cin + 1 <= fusedh::IBF && (!save || bwd_fused_shape(g, Hs, Cin));
 }
@@ -366,7 +366,7 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
   // ---- memory query (:159-166) + decoder initial state (:179) ----
   {
     CellBufs b0 = dec_bufs(g, p, ws, 0);
-    size_t shm = 8 * (g.d + g.M) * sizeof(float);
+    size_t shm = (8 * (g.d + g.M) + (size_t)g.M * (g.d + 1)) * sizeof(float);
     MCRN_LAUNCH(k_memory_query, (int)ceil_div64(g.R, 8), 256, shm, st, ws + p.h_enc, prm->wq, prm->memory,
                 ws + p.mq_q, ws + p.mq_att, reinterpret_cast<int*>(ws + p.mq_ind), h_att, query, pos, neg, b0.hx,
                 b0.xpg, tf32_mode(), g.B, g.N, g.H, g.M, g.d);
@@ -383,7 +383,7 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
       if (t > 0) go_src = (tf && tf[t - 1]) ? labels : output;
       int64_t n_in = (int64_t)g.R * g.Cdec;
       if (ib_compact_shape(g, g.D, g.Cdec, p.save)) {
-        const size_t shm = ((size_t)g.N * fusedh::DI_COLS + (size_t)fusedh::DI_ROWS * (g.N + 1) +
+        const size_t shm = ((size_t)(g.N | 1) * fusedh::DI_COLS + (size_t)fusedh::DI_ROWS * (g.N + 1) +
                             (size_t)fusedh::DI_NODES * fusedh::DI_COLS * (fusedh::IBF + 1)) * sizeof(float);
         static bool di_attr = false;
         if (!di_attr) {
@@ -922,7 +922,7 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
   }
   // ---- memory query ----
   {
-    size_t shm = 8 * (g.d + g.M) * sizeof(float);
+    size_t shm = (8 * (g.d + g.M) + (size_t)g.M * (g.d + 1)) * sizeof(float);
     float *dv = ws + p.mq_dv, *dsc = ws + p.mq_dsc, *dq = ws + p.mq_dq;
     MCRN_LAUNCH(k_memory_query_bwd_rows, (int)ceil_div64(g.R, 8), 256, shm, st, dH, d_hatt, d_query, d_pos, d_neg,
                 prm->memory, ws + p.mq_att, reinterpret_cast<const int*>(ws + p.mq_ind), dv, dsc, dq, grads->memory,

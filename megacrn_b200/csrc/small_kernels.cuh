@@ -300,8 +300,12 @@ __global__ void __launch_bounds__(256) k_memory_query(const float* __restrict__ 
                                                       float* __restrict__ o_pos, float* __restrict__ o_neg,
                                                       float* __restrict__ dec_h0, float* __restrict__ dec_h0_mma,
                                                       int rnd, int B, int N, int H, int M, int d) {
-  extern __shared__ float shm[];                   // per warp: q[d] + sc[M]
-  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  extern __shared__ float shm[];                   // per warp: q[d] + sc[M]; then the memory bank [M][d + 1] (padded:
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;   // lanes that walk different memory rows hit different banks)
+  float* memS = shm + 8 * (d + M);
+  const int dp = d + 1;
+  for (int i = threadIdx.x; i < M * d; i += blockDim.x) memS[(i / d) * dp + (i % d)] = mem[i];
+  __syncthreads();
   int64_t row = (int64_t)blockIdx.x * 8 + warp;
   if (row >= (int64_t)N * B) return;
   float* q = shm + warp * (d + M);
@@ -316,7 +320,7 @@ __global__ void __launch_bounds__(256) k_memory_query(const float* __restrict__ 
   __syncwarp();
   for (int m = lane; m < M; m += 32) {             // logits = q Mem^T        :161
     float s = 0.f;
-    for (int k = 0; k < d; ++k) s = fmaf(q[k], mem[(int64_t)m * d + k], s);
+    for (int k = 0; k < d; ++k) s = fmaf(q[k], memS[m * dp + k], s);
     sc[m] = s;
   }
   __syncwarp();
@@ -346,11 +350,11 @@ __global__ void __launch_bounds__(256) k_memory_query(const float* __restrict__ 
   int64_t ob = ((int64_t)b * N + n) * d;
   for (int j = lane; j < d; j += 32) {             // value = att Mem          :162
     float s = 0.f;
-    for (int m = 0; m < M; ++m) s = fmaf(sc[m], mem[(int64_t)m * d + j], s);
+    for (int m = 0; m < M; ++m) s = fmaf(sc[m], memS[m * dp + j], s);
     o_hatt[ob + j] = s;
     o_query[ob + j] = q[j];
-    o_pos[ob + j] = mem[(int64_t)i0 * d + j];      // :164
-    o_neg[ob + j] = mem[(int64_t)i1 * d + j];      // :165
+    o_pos[ob + j] = memS[i0 * dp + j];             // :164
+    o_neg[ob + j] = memS[i1 * dp + j];             // :165
     dec_h0[row * (H + d) + H + j] = s;             // :179
     dec_h0_mma[row * (H + d) + H + j] = rnd ? tf32_rn(s) : s;
     if (q_nm) q_nm[row * d + j] = q[j];
@@ -372,8 +376,12 @@ __global__ void __launch_bounds__(256) k_memory_query_bwd_rows(
     const float* __restrict__ d_pos, const float* __restrict__ d_neg, const float* __restrict__ mem,
     const float* __restrict__ att, const int* __restrict__ ind, float* __restrict__ dv, float* __restrict__ dsc,
     float* __restrict__ dq, float* __restrict__ dMem, int B, int N, int H, int M, int d) {
-  extern __shared__ float shm[];                   // per warp: dv[d] + ds[M]
+  extern __shared__ float shm[];                   // per warp: dv[d] + ds[M]; then the memory bank [M][d + 1]
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* memS = shm + 8 * (d + M);
+  const int dp = d + 1;
+  for (int i = threadIdx.x; i < M * d; i += blockDim.x) memS[(i / d) * dp + (i % d)] = mem[i];
+  __syncthreads();
   int64_t row = (int64_t)blockIdx.x * 8 + warp;
   if (row >= (int64_t)N * B) return;
   float* v = shm + warp * (d + M);
@@ -390,7 +398,7 @@ __global__ void __launch_bounds__(256) k_memory_query_bwd_rows(
   float part = 0.f;
   for (int m = lane; m < M; m += 32) {
     float s = 0.f;
-    for (int k = 0; k < d; ++k) s = fmaf(v[k], mem[(int64_t)m * d + k], s);
+    for (int k = 0; k < d; ++k) s = fmaf(v[k], memS[m * dp + k], s);
     ds[m] = s;                                     // d_att
     part = fmaf(att[row * M + m], s, part);
   }
@@ -405,7 +413,7 @@ __global__ void __launch_bounds__(256) k_memory_query_bwd_rows(
   int i0 = ind[row * 2], i1 = ind[row * 2 + 1];
   for (int j = lane; j < d; j += 32) {
     float s = d_query ? d_query[ob + j] : 0.f;
-    for (int m = 0; m < M; ++m) s = fmaf(ds[m], mem[(int64_t)m * d + j], s);
+    for (int m = 0; m < M; ++m) s = fmaf(ds[m], memS[m * dp + j], s);
     dq[row * d + j] = s;
     if (d_pos) atomicAdd(dMem + (int64_t)i0 * d + j, d_pos[ob + j]);
     if (d_neg) atomicAdd(dMem + (int64_t)i1 * d + j, d_neg[ob + j]);
