@@ -78,6 +78,10 @@ typedef struct mcrn_params {
 
 /* Flags for mcrn_forward. */
 #define MCRN_FWD_SAVE_FOR_BACKWARD 1u   /* keep per-step activations in the workspace */
+#define MCRN_FWD_REUSE_PROLOGUE    2u   /* eval fast path: the supports (model/MegaCRN.py:169-173, :19-23), the folded
+                                         * weights and their operand copies depend on the parameters only; the caller asserts that the
+                                         * workspace still holds them from a previous mcrn_forward with the SAME dims, flags, parameter
+                                         * values and library mode (mcrn_mode_epoch unchanged), and the prologue kernels are skipped */
 
 int mcrn_abi_version(void);
 const char* mcrn_last_error(void);
@@ -187,6 +191,8 @@ uint64_t mcrn_launch_count(void);
 /* 0 = default (tcgen05 TF32 where the shape allows, SIMT otherwise), 1 = force SIMT fp32. */
 int mcrn_set_engine(int engine);
 int mcrn_get_engine(void);
+/* Counter incremented by every mcrn_set_* call: part of the validity key of MCRN_FWD_REUSE_PROLOGUE. */
+uint64_t mcrn_mode_epoch(void);
 /* Debug: bit i forces GEMM call-site class i onto the SIMT engine (see model.cu). */
 int mcrn_set_debug_mask(int mask);
 /* Forward AGCN as ONE fused kernel per AGCN call (graph convolution + weight contraction + gate/update tail) where the

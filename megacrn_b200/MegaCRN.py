@@ -85,6 +85,7 @@ class _Workspace:
         self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
         self.nbytes = nbytes
         self.busy = False
+        self.prologue_key = None      # validity key of the parameter-only prologue held by this workspace (eval fast path)
 
 
 def _release(ws):
@@ -100,6 +101,13 @@ class _MegaCRNFunction(torch.autograd.Function):
         dims = module._dims(x)
         flags = _abi.MCRN_FWD_SAVE_FOR_BACKWARD if need_grad else 0
         ws = module._workspace(dims, flags, x.device)
+        # eval fast path: supports, folded weights and their operand copies depend on the parameters only; they
+        # are reused while no parameter has been modified in place or re-allocated and the library mode is unchanged
+        key = (tuple(getattr(dims, f) for f, _ in dims._fields_), flags, lib.mcrn_mode_epoch(),
+               tuple((p.data_ptr(), p._version) for p in params))
+        if not need_grad and not module.training and ws.prologue_key == key:
+            flags |= _abi.MCRN_FWD_REUSE_PROLOGUE
+        ws.prologue_key = None
         B, N, d = x.shape[0], module.num_nodes, module.mem_dim
         output = torch.empty(B, module.horizon, N, module.output_dim, device=x.device, dtype=torch.float32)
         h_att, query, pos, neg = (torch.empty(B, N, d, device=x.device, dtype=torch.float32) for _ in range(4))
@@ -110,6 +118,7 @@ class _MegaCRNFunction(torch.autograd.Function):
                                   output.data_ptr(), h_att.data_ptr(), query.data_ptr(), pos.data_ptr(),
                                   neg.data_ptr(), ws.buf.data_ptr(), ws.nbytes, flags, stream)
         _abi.check(st, "mcrn_forward")
+        ws.prologue_key = key
         if need_grad:
             ws.busy = True
             weakref.finalize(ctx, _release, ws)

@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmegacrn_b200.so")
 
 MCRN_FWD_SAVE_FOR_BACKWARD = 1
+MCRN_FWD_REUSE_PROLOGUE = 2
 ABI_VERSION = 1
 
 PARAM_FIELDS = (
@@ -66,6 +67,7 @@ def load() -> C.CDLL:
     lib.mcrn_launch_count.restype = C.c_uint64
     lib.mcrn_set_engine.argtypes = [C.c_int]
     lib.mcrn_get_engine.restype = C.c_int
+    lib.mcrn_mode_epoch.restype = C.c_uint64
     lib.mcrn_debug_fused_timeline.restype = C.c_int
     lib.mcrn_debug_fused_timeline.argtypes = [C.c_void_p, C.c_int]
     lib.mcrn_adam_step.restype = C.c_int

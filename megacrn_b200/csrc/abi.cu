@@ -13,7 +13,7 @@ extern int g_fused, g_fused_parts, g_bwd_fused;
 const char* last_error();
 int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const float* x, const float* y_cov,
                  const float* labels, const uint8_t* tf, float* output, float* h_att, float* query, float* pos,
-                 float* neg, float* ws, cudaStream_t st);
+                 float* neg, float* ws, cudaStream_t st, bool reuse_prologue);
 int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uint8_t* tf, const float* d_output,
                   const float* d_hatt, const float* d_query, const float* d_pos, const float* d_neg,
                   const mcrn_params* grads, float* ws, cudaStream_t st);
@@ -26,6 +26,7 @@ int trainer_loss_impl(const Geo& g, const float* output, const float* labels, co
 int adam_step_impl(const Geo& g, const mcrn_params* prm, const mcrn_params* grads, const mcrn_params* m, const mcrn_params* v,
                    float* state, float beta1, float beta2, float eps, float max_norm, cudaStream_t st);
 
+static std::atomic<uint64_t> g_mode_epoch{0};
 static std::mutex g_mu;
 static std::unordered_map<const void*, uint64_t> g_saved;   // workspace -> dims hash of the last saving forward
 
@@ -74,10 +75,12 @@ uint64_t mcrn_launch_count(void) { return g_launches.load(); }
 int mcrn_set_engine(int engine) {
   if (engine < 0 || engine > 2) { set_error("engine must be 0, 1 or 2"); return MCRN_ERR_BAD_DIMS; }
   g_engine = engine;
+  g_mode_epoch.fetch_add(1);
   return MCRN_OK;
 }
 int mcrn_get_engine(void) { return g_engine; }
-int mcrn_set_debug_mask(int mask) { g_simt_mask = mask; return MCRN_OK; }
+int mcrn_set_debug_mask(int mask) { g_simt_mask = mask; g_mode_epoch.fetch_add(1); return MCRN_OK; }
+uint64_t mcrn_mode_epoch(void) { return g_mode_epoch.load(); }
 int mcrn_debug_fused_timeline(long long* device_slots, int which) {
   fused::g_dbg_timeline = device_slots; fused::g_dbg_which = which; fused::g_dbg_count = 0;
   return MCRN_OK;
@@ -118,11 +121,13 @@ int mcrn_kernel_timing_read(int kernel_class, float* ms_total, int* launches) {
 int mcrn_set_bwd_fused(int fused) {
   if (fused < 0 || fused > 2) { set_error("mcrn_set_bwd_fused: 0, 1 or 2"); return MCRN_ERR_BAD_DIMS; }
   g_bwd_fused = fused;
+  g_mode_epoch.fetch_add(1);
   return MCRN_OK;
 }
 int mcrn_set_fused(int fused, int weight_parts) {
   if (fused < 0 || fused > 2 || weight_parts < 1 || weight_parts > 2) { set_error("mcrn_set_fused: fused in {0,1,2}, weight_parts in {1,2}"); return MCRN_ERR_BAD_DIMS; }
   g_fused = fused; g_fused_parts = weight_parts;
+  g_mode_epoch.fetch_add(1);
   return MCRN_OK;
 }
 int mcrn_support_ld(int n) { return support_ld(n); }
@@ -159,7 +164,8 @@ int mcrn_forward(const mcrn_dims* dims, const mcrn_params* params, const float* 
     return MCRN_ERR_WORKSPACE;
   }
   int s = forward_impl(g, p, params, x, y_cov, labels, teacher_forcing, output, h_att, query, pos, neg,
-                       static_cast<float*>(workspace), static_cast<cudaStream_t>(stream));
+                       static_cast<float*>(workspace), static_cast<cudaStream_t>(stream),
+                       (flags & MCRN_FWD_REUSE_PROLOGUE) != 0);
   {
     std::lock_guard<std::mutex> lk(g_mu);
     if (s == MCRN_OK && save) g_saved[workspace] = dims_hash(dims);

@@ -321,12 +321,15 @@ static CellW dec_w(const Geo& g, const Plan& p, float* ws) {
 // ======================================================================================
 int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const float* x, const float* y_cov,
                  const float* labels, const uint8_t* tf, float* output, float* h_att, float* query, float* pos,
-                 float* neg, float* ws, cudaStream_t st) {
+                 float* neg, float* ws, cudaStream_t st, bool reuse_prologue) {
   float* S = ws + p.Sr;     // the recurrent GEMMs read the tensor-core copy of the supports
+  // eval fast path (MCRN_FWD_REUSE_PROLOGUE): everything below that depends on the parameters only is still in the workspace
+  if (!reuse_prologue) {
   MCRN_TRY(supports_forward(g, p, ws, prm->memory, prm->we1, prm->we2, ws + p.S, ws + p.Sr, st));
   MCRN_TRY(fold_all_weights(g, p, ws, prm, st));
+  }
   const bool enc_h = fused_h_shape(g, g.H), dec_h = fused_h_shape(g, g.D);
-  if (enc_h || dec_h) {  // fp16 operand copies for the fused forward: supports (exact fp32 -> half) and weights (hi/lo, transposed)
+  if ((enc_h || dec_h) && !reuse_prologue) {  // fp16 operand copies for the fused forward: supports (exact fp32 -> half) and weights (hi/lo, transposed)
     const int ld16 = fusedh::ld_half(g.N);
     MCRN_LAUNCH(fusedh::k_supports_to_half, ew_grid((int64_t)g.KS * g.N * ld16), 256, 0, st, ws + p.S,
                 reinterpret_cast<__half*>(ws + p.s16), g.KS * g.N, g.N, g.ldS, ld16);

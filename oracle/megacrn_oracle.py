@@ -268,3 +268,32 @@ def synthetic_batch(d: Dims, batch: int, t_in: int, seed: int = 1234, dtype=torc
     y_cov = torch.rand(batch, d.horizon, d.num_nodes, d.ycov_dim, generator=g)
     labels = torch.randn(batch, d.horizon, d.num_nodes, d.output_dim, generator=g)
     return x.to(dtype), y_cov.to(dtype), labels.to(dtype)
+
+
+# ---- host input pipeline of the reference (model/utils.py:6-43, model/traintest_MegaCRN.py:33-48), restated ----
+class DataLoaderOracle:
+    """numpy restatement of the reference ``DataLoader``: pad with the last sample (:17-22), one ``np.random.permutation``
+    when shuffling (:25-27), ``num_batch = size // batch_size`` full batches (:24, :33-40)."""
+
+    def __init__(self, xs, ys, batch_size, pad_with_last_sample=True, shuffle=False):
+        import numpy as np
+        self.batch_size = batch_size
+        if pad_with_last_sample:
+            num_padding = (batch_size - (len(xs) % batch_size)) % batch_size
+            xs = np.concatenate([xs, np.repeat(xs[-1:], num_padding, axis=0)], axis=0)
+            ys = np.concatenate([ys, np.repeat(ys[-1:], num_padding, axis=0)], axis=0)
+        self.size = len(xs)
+        self.num_batch = int(self.size // self.batch_size)
+        if shuffle:
+            permutation = np.random.permutation(self.size)
+            xs, ys = xs[permutation], ys[permutation]
+        self.xs, self.ys = xs, ys
+
+    def batches(self, input_dim=1, output_dim=1):
+        """(x, y, y_cov) float32 arrays per batch, as prepare_x_y slices them (traintest:41-47)."""
+        import numpy as np
+        for i in range(self.num_batch):
+            s, e = self.batch_size * i, min(self.size, self.batch_size * (i + 1))
+            x, y = self.xs[s:e], self.ys[s:e]
+            yield (x[..., :input_dim].astype(np.float32), y[..., :output_dim].astype(np.float32),
+                   y[..., output_dim:].astype(np.float32))

@@ -395,6 +395,35 @@ def test_fused_clip_adam_matches_torch():
             assert rel_l2(named[k].detach().cpu(), ref[k].detach().cpu()) < 2e-6, (it, k)
 
 
+def test_eval_fast_path_reuses_and_invalidates_the_prologue(default_engine):
+    """MCRN_FWD_REUSE_PROLOGUE: the second eval forward skips the parameter-only prologue (fewer launches, same
+    results); an in-place parameter update invalidates the cache."""
+    lib = default_engine
+    d = O.Dims(num_nodes=50, horizon=3, rnn_units=64)
+    p = O.init_params(d, seed=5)
+    x, y_cov, _ = O.synthetic_batch(d, 3, 4, seed=2)
+    dv = _dev()
+    m = _model(d, p).eval()
+    with torch.no_grad():
+        n0 = lib.mcrn_launch_count()
+        a = m(x.to(dv), y_cov.to(dv))
+        n1 = lib.mcrn_launch_count()
+        b = m(x.to(dv), y_cov.to(dv))
+        n2 = lib.mcrn_launch_count()
+        assert n2 - n1 < n1 - n0                                  # prologue kernels skipped
+        for u, v in zip(a, b):
+            assert torch.equal(u, v)
+        for prm in m.parameters():
+            prm.mul_(1.01)                                         # in-place update bumps the version counters
+        c = m(x.to(dv), y_cov.to(dv))
+        n3 = lib.mcrn_launch_count()
+        assert n3 - n2 == n1 - n0                                  # recomputed
+        fresh = _model(d, {k: v * 1.01 for k, v in p.items()}).eval()
+        ref = fresh(x.to(dv), y_cov.to(dv))
+    assert rel_l2(c[0].cpu(), ref[0].cpu()) < 1e-5
+    assert rel_l2(c[0].cpu(), a[0].cpu()) > 1e-4
+
+
 def test_fused_trainer_loss_matches_torch():
     from megacrn_b200 import _abi
     from megacrn_b200.train_step import fused_trainer_loss
