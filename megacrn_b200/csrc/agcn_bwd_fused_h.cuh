@@ -46,8 +46,13 @@ struct BHParams {
   int N, B, KS, nhalf;
   float* qsave;          // [KS * nhalf][R][HS] fp32, unscaled
   int64_t blk_stride;    // R * HS
-  float* dib;            // [R][IBW], unscaled
+  float* dib;            // [R][IBW], unscaled (written when dxpin == null)
   const float* gs;       // device: {scale, 1 / scale}
+  // gate-AGCN launch: the input-block gradient of the update AGCN (dib_in, written by the previous launch) is added and the
+  // sum is scattered straight into dXPin [NB][R][Cin] (TF32-rounded), replacing a separate repack kernel
+  const float* dib_in;
+  float* dxpin;
+  int nb, cin;
 };
 
 template <int HS>
@@ -66,44 +71,89 @@ struct CfgBH {
 };
 
 // ---- epilogue functors: load4 / fin4 on 4 consecutive columns of one (node, b) row; acc is already unscaled ----------
+// NT = number of node-transposed fp16 operand copies the functor produces; fin4 returns their (scaled, fp16-rounded)
+// values in st[0..NT); tdst(i, b, col) = address of element (b, column col, node 0) of copy i (null: not wanted).
+
 // Update-AGCN tail (the cell's gate backward): dZH = acc; dG[:, :H] = dZH*h*z(1-z); dh_part = dHr + dZH*z.
-// st[] returns the SCALED fp16-rounded dG values for the operand copies (row-major here, node-transposed by the kernel).
 struct EpiBUH {
-  static constexpr int NP = 3;
+  static constexpr int NP = 3, NT = 1;
   int H;
   const float *z, *h, *dHr;
   float *dG, *dh_part;     // dG: fp32 [R][2H] (columns [0, H) written here)
   __half* g16;             // [R][2H] scaled fp16 copy (columns [0, H))
   __half* g16T;            // [B][2H][ldT]
   int ldT;
-  __device__ __forceinline__ bool has_state() const { return true; }
-  __device__ __forceinline__ void load4(int row, int n0, float4 (&p)[NP]) const {
+  __device__ __forceinline__ __half* tdst(int, int b, int col) const { return g16T + ((int64_t)b * 2 * H + col) * ldT; }
+  __device__ __forceinline__ void load4(int row, int, int, int n0, float4 (&p)[NP]) const {
     const int64_t f = (int64_t)row * H + n0;
     p[0] = ldg4(z + f); p[1] = ldg4(h + f); p[2] = ldg4(dHr + f);
   }
-  __device__ __forceinline__ void fin4(int row, int n0, const float4 (&p)[NP], const float (&acc)[4], float s, float inv_s,
-                                       float (&st)[4]) const {
+  __device__ __forceinline__ void fin4(int row, int, int, int n0, const float4 (&p)[NP], const float (&acc)[4], float s, float inv_s,
+                                       float (&st)[1][4]) const {
     const float4 zz = p[0], hh = p[1], dr = p[2];
     const float d0 = acc[0], d1 = acc[1], d2 = acc[2], d3 = acc[3];
-    st[0] = round_h(d0 * hh.x * zz.x * (1.0f - zz.x) * s); st[1] = round_h(d1 * hh.y * zz.y * (1.0f - zz.y) * s);
-    st[2] = round_h(d2 * hh.z * zz.z * (1.0f - zz.z) * s); st[3] = round_h(d3 * hh.w * zz.w * (1.0f - zz.w) * s);
-    st4(dG + (int64_t)row * 2 * H + n0, st[0] * inv_s, st[1] * inv_s, st[2] * inv_s, st[3] * inv_s);
-    *reinterpret_cast<uint2*>(g16 + (int64_t)row * 2 * H + n0) = make_uint2(pack_h2(st[0], st[1]), pack_h2(st[2], st[3]));
+    st[0][0] = round_h(d0 * hh.x * zz.x * (1.0f - zz.x) * s); st[0][1] = round_h(d1 * hh.y * zz.y * (1.0f - zz.y) * s);
+    st[0][2] = round_h(d2 * hh.z * zz.z * (1.0f - zz.z) * s); st[0][3] = round_h(d3 * hh.w * zz.w * (1.0f - zz.w) * s);
+    st4(dG + (int64_t)row * 2 * H + n0, st[0][0] * inv_s, st[0][1] * inv_s, st[0][2] * inv_s, st[0][3] * inv_s);
+    *reinterpret_cast<uint2*>(g16 + (int64_t)row * 2 * H + n0) = make_uint2(pack_h2(st[0][0], st[0][1]), pack_h2(st[0][2], st[0][3]));
     st4(dh_part + (int64_t)row * H + n0, dr.x + d0 * zz.x, dr.y + d1 * zz.y, dr.z + d2 * zz.z, dr.w + d3 * zz.w);
   }
 };
 // Gate-AGCN tail: dH_prev = acc + dh_part
 struct EpiBGH {
-  static constexpr int NP = 1;
+  static constexpr int NP = 1, NT = 0;
   int H;
   const float* dh_part;
   float* dH_out;
-  __half* g16T = nullptr;
-  int ldT = 0;
-  __device__ __forceinline__ bool has_state() const { return false; }
-  __device__ __forceinline__ void load4(int row, int n0, float4 (&p)[NP]) const { p[0] = ldg4(dh_part + (int64_t)row * H + n0); }
-  __device__ __forceinline__ void fin4(int row, int n0, const float4 (&p)[NP], const float (&acc)[4], float, float, float (&)[4]) const {
+  __device__ __forceinline__ __half* tdst(int, int, int) const { return nullptr; }
+  __device__ __forceinline__ void load4(int row, int, int, int n0, float4 (&p)[NP]) const { p[0] = ldg4(dh_part + (int64_t)row * H + n0); }
+  __device__ __forceinline__ void fin4(int row, int, int, int n0, const float4 (&p)[NP], const float (&acc)[4], float, float,
+                                       float (&)[1][4]) const {
     st4(dH_out + (int64_t)row * H + n0, acc[0] + p[0].x, acc[1] + p[0].y, acc[2] + p[0].z, acc[3] + p[0].w);
+  }
+};
+// Gate-AGCN tail + the step glue of the NEXT cell to be processed (time step t-1), when that step's decoder input was
+// teacher-forced (no gradient arrives through go) or in the encoder:
+//   dH' = acc + dh_part + d_out_{t-1} . wp ;  dU' = dH'(1-r')(1-hc'^2) ;  dG'[:, H:] = dH'(h'-hc')r'(1-r') ;  dHr' = dH' r'
+// with r', hc', h' the saved activations of step t-1.  Replaces k_bwd_glue_h for that step (dwp / dbp: k_proj_wgrad).
+struct EpiBGHG {
+  static constexpr int NP = 4, NT = 2;
+  int H;
+  const float *dh_part, *r, *hc, *hx;      // r, hc, hx: step t-1
+  const float* dOut;                       // [B][T][N][Cout] upstream gradient or null
+  const float* wp;                         // [Cout][H]
+  int B, T, N, Cout, tprev;
+  float *dU, *dG, *dHr;                    // step t-1: dU [R][H], dG [R][2H] (columns [H, 2H)), dHr [R][H]
+  __half *u16, *u16T, *g16, *g16T;         // scaled fp16 operand copies of step t-1
+  int ldT;
+  __device__ __forceinline__ __half* tdst(int i, int b, int col) const {
+    return i == 0 ? u16T + ((int64_t)b * H + col) * ldT : g16T + ((int64_t)b * 2 * H + H + col) * ldT;
+  }
+  __device__ __forceinline__ void load4(int row, int, int, int n0, float4 (&p)[NP]) const {
+    const int64_t f = (int64_t)row * H + n0;
+    p[0] = ldg4(dh_part + f); p[1] = ldg4(r + f); p[2] = ldg4(hc + f); p[3] = ldg4(hx + f);
+  }
+  __device__ __forceinline__ void fin4(int row, int node, int b, int n0, const float4 (&p)[NP], const float (&acc)[4], float s,
+                                       float inv_s, float (&st)[2][4]) const {
+    const float4 rr = p[1], cc = p[2], hh = p[3];
+    float4 v = make_float4(acc[0] + p[0].x, acc[1] + p[0].y, acc[2] + p[0].z, acc[3] + p[0].w);
+    if (dOut != nullptr) {
+      for (int co = 0; co < Cout; ++co) {
+        const float d = __ldg(dOut + (((int64_t)b * T + tprev) * N + node) * Cout + co);
+        const float4 w4 = ldg4(wp + (int64_t)co * H + n0);
+        v.x = fmaf(d, w4.x, v.x); v.y = fmaf(d, w4.y, v.y); v.z = fmaf(d, w4.z, v.z); v.w = fmaf(d, w4.w, v.w);
+      }
+    }
+    st[0][0] = round_h(v.x * (1.0f - rr.x) * (1.0f - cc.x * cc.x) * s); st[0][1] = round_h(v.y * (1.0f - rr.y) * (1.0f - cc.y * cc.y) * s);
+    st[0][2] = round_h(v.z * (1.0f - rr.z) * (1.0f - cc.z * cc.z) * s); st[0][3] = round_h(v.w * (1.0f - rr.w) * (1.0f - cc.w * cc.w) * s);
+    st[1][0] = round_h(v.x * (hh.x - cc.x) * rr.x * (1.0f - rr.x) * s); st[1][1] = round_h(v.y * (hh.y - cc.y) * rr.y * (1.0f - rr.y) * s);
+    st[1][2] = round_h(v.z * (hh.z - cc.z) * rr.z * (1.0f - rr.z) * s); st[1][3] = round_h(v.w * (hh.w - cc.w) * rr.w * (1.0f - rr.w) * s);
+    const int64_t o = (int64_t)row * H + n0, og = (int64_t)row * 2 * H + H + n0;
+    st4(dU + o, st[0][0] * inv_s, st[0][1] * inv_s, st[0][2] * inv_s, st[0][3] * inv_s);
+    st4(dG + og, st[1][0] * inv_s, st[1][1] * inv_s, st[1][2] * inv_s, st[1][3] * inv_s);
+    st4(dHr + o, v.x * rr.x, v.y * rr.y, v.z * rr.z, v.w * rr.w);
+    *reinterpret_cast<uint2*>(u16 + o) = make_uint2(pack_h2(st[0][0], st[0][1]), pack_h2(st[0][2], st[0][3]));
+    *reinterpret_cast<uint2*>(g16 + og) = make_uint2(pack_h2(st[1][0], st[1][1]), pack_h2(st[1][2], st[1][3]));
   }
 };
 
@@ -304,13 +354,15 @@ agcn_bwd_h_kernel(const __grid_constant__ CUtensorMap tmST, const __grid_constan
         __syncwarp();
         const int col = c * 32 + cq;
         constexpr int RB = Epi::NP <= 2 ? 8 : 4;
+        constexpr int NTS = Epi::NT > 0 ? Epi::NT : 1;
+        float* scr2 = scr + 8 * (32 * 36);               // second staging area (second transposed copy)
 #pragma unroll
         for (int b0 = 0; b0 < 8; b0 += RB) {
           float4 pre[RB][Epi::NP];
 #pragma unroll
           for (int i = 0; i < RB; ++i) {
             const int node = node0 + r0 + 4 * (b0 + i);
-            if (node < p.N) epi.load4(node * p.B + b, col, pre[i]);
+            if (node < p.N) epi.load4(node * p.B + b, node, b, col, pre[i]);
           }
 #pragma unroll
           for (int i = 0; i < RB; ++i) {
@@ -318,19 +370,25 @@ agcn_bwd_h_kernel(const __grid_constant__ CUtensorMap tmST, const __grid_constan
             if (node < p.N) {
               const float4 t = *reinterpret_cast<const float4*>(&scr[rr * 36 + cq]);
               const float a4[4] = {t.x, t.y, t.z, t.w};
-              float st[4] = {0.f, 0.f, 0.f, 0.f};
-              epi.fin4(node * p.B + b, col, pre[i], a4, gs, inv_gs, st);
-              *reinterpret_cast<float4*>(&scr[rr * 36 + cq]) = make_float4(st[0], st[1], st[2], st[3]);
+              float st[NTS][4];
+              epi.fin4(node * p.B + b, node, b, col, pre[i], a4, gs, inv_gs, st);
+              if constexpr (Epi::NT >= 1) *reinterpret_cast<float4*>(&scr[rr * 36 + cq]) = make_float4(st[0][0], st[0][1], st[0][2], st[0][3]);
+              if constexpr (Epi::NT >= 2) *reinterpret_cast<float4*>(&scr2[rr * 36 + cq]) = make_float4(st[1][0], st[1][1], st[1][2], st[1][3]);
             }
           }
         }
-        if (epi.has_state() && epi.g16T != nullptr) {     // node-transposed scaled fp16 copy: dG^T[b][c*32 + j][node0 + lane]
+        if constexpr (Epi::NT >= 1) {                     // node-transposed scaled fp16 copies: X^T[b][c*32 + j][node0 + lane]
           __syncwarp();
           const int node = node0 + lane;
-          if (node < p.N) {
-            __half* dst = epi.g16T + ((int64_t)b * 2 * HS + c * 32) * epi.ldT + node;
+#pragma unroll
+          for (int ti = 0; ti < Epi::NT; ++ti) {
+            __half* base = epi.tdst(ti, b, c * 32);
+            const float* src = ti == 0 ? scr : scr2;
+            if (base != nullptr && node < p.N) {
+              __half* dst = base + node;
 #pragma unroll 8
-            for (int j = 0; j < 32; ++j) dst[(int64_t)j * epi.ldT] = __float2half_rn(scr[lane * 36 + j]);
+              for (int j = 0; j < 32; ++j) dst[(int64_t)j * epi.ldT] = __float2half_rn(src[lane * 36 + j]);
+            }
           }
         }
       }
@@ -339,9 +397,27 @@ agcn_bwd_h_kernel(const __grid_constant__ CUtensorMap tmST, const __grid_constan
         tmem_ld_32x32b_x16(tmem_base + C::TM_IB + lane_off, v);
         const int node = node0 + lane;
         if (node < p.N) {
-          float* dst = p.dib + ((int64_t)node * p.B + b) * IBW;
+          const int64_t row = (int64_t)node * p.B + b;
+          if (p.dxpin == nullptr) {
+            float* dst = p.dib + row * IBW;
 #pragma unroll
-          for (int i = 0; i < 16; i += 4) st4(dst + i, v[i] * inv_gs, v[i + 1] * inv_gs, v[i + 2] * inv_gs, v[i + 3] * inv_gs);
+            for (int i = 0; i < 16; i += 4) st4(dst + i, v[i] * inv_gs, v[i + 1] * inv_gs, v[i + 2] * inv_gs, v[i + 3] * inv_gs);
+          } else {
+            const float* src = p.dib_in + row * IBW;
+            const int64_t R = (int64_t)p.N * p.B;
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 u4 = ldg4(src + i);
+              v[i] = v[i] * inv_gs + u4.x; v[i + 1] = v[i + 1] * inv_gs + u4.y; v[i + 2] = v[i + 2] * inv_gs + u4.z; v[i + 3] = v[i + 3] * inv_gs + u4.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (j < p.nb * p.cin) {
+                const int k = j / p.cin, ci = j - k * p.cin;
+                p.dxpin[((int64_t)k * R + row) * p.cin + ci] = tf32_rn(v[j]);
+              }
+            }
+          }
         }
       }
     }
@@ -486,6 +562,52 @@ __global__ void __launch_bounds__(256) k_bwd_glue_h(const float* __restrict__ dO
   }
 }
 
+// Projection weight gradient of the steps whose glue ran inside the gate-AGCN epilogue (bit t of `mask`):
+//   dwp[co][:] += sum_rows d_out_t[row][co] * h_t[row][:],  dbp[co] += sum_rows d_out_t[row][co]
+// h_t = hx_base + (t + 1) * hx_step for t + 1 < T, else h_last.  Grid (row blocks of 32, T); thread = 4 columns.
+__global__ void __launch_bounds__(256) k_proj_wgrad(const float* __restrict__ dOut, const float* __restrict__ hx_base, int64_t hx_step,
+                                                    const float* __restrict__ h_last, unsigned mask, float* __restrict__ dwp,
+                                                    float* __restrict__ dbp, int B, int T, int N, int D, int Cout) {
+  const int t = blockIdx.y;
+  if (!((mask >> t) & 1u)) return;
+  extern __shared__ float sh[];                    // [32][Cout] d_out rows, [Cout][D] partials
+  float* sh_do = sh;
+  float* sh_w = sh + 32 * Cout;
+  const int64_t R = (int64_t)N * B, r0 = (int64_t)blockIdx.x * 32;
+  const float* h_t = (t + 1 < T) ? hx_base + (int64_t)(t + 1) * hx_step : h_last;
+  for (int i = threadIdx.x; i < 32 * Cout; i += blockDim.x) {
+    const int64_t row = r0 + i / Cout;
+    const int co = i % Cout;
+    float v = 0.f;
+    if (row < R) {
+      const int n = (int)(row / B), b = (int)(row % B);
+      v = dOut[(((int64_t)b * T + t) * N + n) * Cout + co];
+    }
+    sh_do[i] = v;
+  }
+  for (int i = threadIdx.x; i < Cout * D; i += blockDim.x) sh_w[i] = 0.f;
+  __syncthreads();
+  const int Q = D >> 2;
+  for (int e = threadIdx.x; e < 32 * Q; e += blockDim.x) {
+    const int i = e / Q, q4 = (e - i * Q) * 4;
+    const int64_t row = r0 + i;
+    if (row >= R) continue;
+    const float4 hv = ldg4(h_t + row * D + q4);
+    for (int co = 0; co < Cout; ++co) {
+      const float d = sh_do[i * Cout + co];
+      float* sw = sh_w + co * D + q4;
+      atomicAdd(sw, d * hv.x); atomicAdd(sw + 1, d * hv.y); atomicAdd(sw + 2, d * hv.z); atomicAdd(sw + 3, d * hv.w);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Cout * D; i += blockDim.x) atomicAdd(dwp + i, sh_w[i]);
+  if (threadIdx.x < Cout) {
+    float sm = 0.f;
+    for (int i = 0; i < 32; ++i) sm += sh_do[i * Cout + threadIdx.x];
+    atomicAdd(dbp + threadIdx.x, sm);
+  }
+}
+
 // ---- host side ----------------------------------------------------------------------------------
 struct BHOperands {
   const __half* S16T;    // [KS][N][ld_half(N)]
@@ -497,7 +619,7 @@ struct BHOperands {
 
 template <int HS, class Epi>
 int launch_agcn_bwd_h(int N, int B, int KS, int nhalf, const BHOperands& op, float* qsave, float* dib, const Epi& epi,
-                      cudaStream_t st) {
+                      cudaStream_t st, const float* dib_in = nullptr, float* dxpin = nullptr, int cin = 0) {
   using C = CfgBH<HS>;
   const int64_t R = (int64_t)N * B;
   const int O = nhalf * HS, ldn = fusedh::ld_half(N);
@@ -531,6 +653,7 @@ int launch_agcn_bwd_h(int N, int B, int KS, int nhalf, const BHOperands& op, flo
   BHParams p;
   p.N = N; p.B = B; p.KS = KS; p.nhalf = nhalf;
   p.qsave = qsave; p.blk_stride = R * HS; p.dib = dib; p.gs = op.gs;
+  p.dib_in = dib_in; p.dxpin = dxpin; p.nb = KS + 1; p.cin = cin;
   auto kern = agcn_bwd_h_kernel<HS, Epi>;
   static bool attr_set = false;
   if (!attr_set) {

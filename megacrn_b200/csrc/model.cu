@@ -580,7 +580,18 @@ struct BwdStep {
   float *dU, *dG;          // this step's slices of dU_all / dG_all
   float *Qu, *Qg;          // this step's Q blocks [KS][R][Hs] / [2 KS][R][Hs]
   float* dXPin;            // this step's [NB][R][Cin]
+  int t = 0;               // time step (parity selects the dG16 / dG16T operand buffers of the fp16 backward)
+  // fp16 backward: glue of the next cell to process (step t-1) folded into this step's gate-AGCN epilogue (null = no)
+  const float *ng_r = nullptr, *ng_hc = nullptr, *ng_hx = nullptr, *ng_dOut = nullptr, *ng_wp = nullptr;
+  float *ng_dU = nullptr, *ng_dG = nullptr;
+  int ng_T = 0, ng_Cout = 0;
 };
+static inline __half* dg16_buf(const Geo& g, const Plan& p, float* ws, int Hs, int t) {
+  return reinterpret_cast<__half*>(ws + p.dG16) + (size_t)(t & 1) * g.R * 2 * Hs;
+}
+static inline __half* dg16T_buf(const Geo& g, const Plan& p, float* ws, int Hs, int t) {
+  return reinterpret_cast<__half*>(ws + p.dG16T) + (size_t)(t & 1) * g.B * 2 * Hs * fusedh::ld_half(g.N);
+}
 // dXP[1..KS] = dV * Wall[1..KS]^T for the dS accumulation (side stream)
 static int make_dxp_s(const Geo& g, const float* dv, int O, const float* wall, int Hs, float* dxp, cudaStream_t st) {
   GemmDesc q;
@@ -594,6 +605,9 @@ static int make_dxp_s(const Geo& g, const float* dv, int O, const float* wall, i
 static int g_side_chunks = getenv("MCRN_SIDE_CHUNKS") ? (atoi(getenv("MCRN_SIDE_CHUNKS")) > 0 ? atoi(getenv("MCRN_SIDE_CHUNKS")) : 1) : 1;
 int g_ds_fused = getenv("MCRN_DS_FUSED") ? atoi(getenv("MCRN_DS_FUSED")) : 1;
 static bool ds_fused_shape(const Geo& g, int Hs) { return g_ds_fused && fusedd::ds_fused_eligible(g.N, Hs); }
+// Step glue of the next cell inside the gate-AGCN epilogue (EpiBGHG): correct and tested, but measured slower at C2 (4.38 vs
+// 4.25 ms/step): the exposed, latency-bound epilogue grows by more than the 15 us HBM-rate glue kernel it replaces.  Off by default.
+static int g_glue_fuse = getenv("MCRN_GLUE_FUSE") ? atoi(getenv("MCRN_GLUE_FUSE")) : 0;
 // experiment knobs (timing only -- gradients are wrong when set): bit 0 = skip the dS side-stream work, bit 1 = skip dW GEMMs
 static int g_dbg_skip = getenv("MCRN_DEBUG_SKIP") ? atoi(getenv("MCRN_DEBUG_SKIP")) : 0;
 template <int HS>
@@ -615,8 +629,8 @@ static int cell_backward_fused(const Geo& g, const Plan& p, float* ws, const flo
   const bool h16 = (g_bwd_fused == 2);
   __half* dU16 = reinterpret_cast<__half*>(ws + p.dU16);
   __half* dU16T = reinterpret_cast<__half*>(ws + p.dU16T);
-  __half* dG16 = reinterpret_cast<__half*>(ws + p.dG16);
-  __half* dG16T = reinterpret_cast<__half*>(ws + p.dG16T);
+  __half* dG16 = dg16_buf(g, p, ws, HS, bs.t);
+  __half* dG16T = dg16T_buf(g, p, ws, HS, bs.t);
   const __half* S16T = reinterpret_cast<const __half*>(ws + p.s16T);
   if (h16) {
     fusedbh::BHOperands ou{S16T, dU16T, dU16, w.wu16n, ws + p.gs};
@@ -634,15 +648,23 @@ static int cell_backward_fused(const Geo& g, const Plan& p, float* ws, const flo
   }
   if (h16) {
     fusedbh::BHOperands og{S16T, dG16T, dG16, w.wg16n, ws + p.gs};
-    fusedbh::EpiBGH eg{HS, dHp, dH};
-    MCRN_TRY((fusedbh::launch_agcn_bwd_h<HS>(g.N, g.B, g.KS, 2, og, bs.Qg, ws + p.dIBg16, eg, st)));
+    // the gate-AGCN launch also sums both input-block gradients into dXPin (no repack kernel)
+    if (bs.ng_r != nullptr) {     // ... and runs the glue of step t-1 in its epilogue
+      fusedbh::EpiBGHG eg{HS, dHp, bs.ng_r, bs.ng_hc, bs.ng_hx, bs.ng_dOut, bs.ng_wp, g.B, bs.ng_T, g.N, bs.ng_Cout, bs.t - 1,
+                          bs.ng_dU, bs.ng_dG, ws + p.dHr, dU16, dU16T, dg16_buf(g, p, ws, HS, bs.t - 1), dg16T_buf(g, p, ws, HS, bs.t - 1),
+                          fusedh::ld_half(g.N)};
+      MCRN_TRY((fusedbh::launch_agcn_bwd_h<HS>(g.N, g.B, g.KS, 2, og, bs.Qg, ws + p.dIBg16, eg, st, ws + p.dIBu16, bs.dXPin, w.Cin)));
+    } else {
+      fusedbh::EpiBGH eg{HS, dHp, dH};
+      MCRN_TRY((fusedbh::launch_agcn_bwd_h<HS>(g.N, g.B, g.KS, 2, og, bs.Qg, ws + p.dIBg16, eg, st, ws + p.dIBu16, bs.dXPin, w.Cin)));
+    }
   } else {
   fusedb::EpiBG eg{HS, dHp, dH};
   MCRN_TRY((fusedb::launch_agcn_bwd<HS>(g.N, g.B, g.KS, g.ldS, 2, St, bs.dG, w.wg, bs.Qg, ws + p.dIBg16, eg, st)));
   }
   // input channels: d(input block) of both AGCNs -> dXPin [NB][R][Cin]
   const int64_t nIn = (int64_t)g.NB * g.R * w.Cin;
-  MCRN_LAUNCH(k_repack_dib, ew_grid(nIn), 256, 0, st, ws + p.dIBu16, ws + p.dIBg16, g.NB, w.Cin, g.R, fusedb::IBW, bs.dXPin, 1);
+  if (!h16) MCRN_LAUNCH(k_repack_dib, ew_grid(nIn), 256, 0, st, ws + p.dIBu16, ws + p.dIBg16, g.NB, w.Cin, g.R, fusedb::IBW, bs.dXPin, 1);
   if (do_ds) {
   MCRN_TRY(side_begin(2, st));
   MCRN_TRY(acc_ds(g, bs.dXPin + g.R * w.Cin, (int64_t)g.B * w.Cin, b.xpin, b.xp_n, g.B * w.Cin, dS, sd));
@@ -862,6 +884,8 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
     CellW w = dec_w(g, p, ws);
     float *dU_all = ws + p.d_dU, *dG_all = ws + p.d_dG;
     bool have_dgo = false;
+    bool dec_glue_fused = false;       // the glue of the step about to be processed already ran (previous launch's epilogue)
+    unsigned dec_wgrad_mask = 0;       // steps whose projection weight gradient is still owed (k_proj_wgrad)
     const bool fb = bwd_fused_shape(g, g.D, g.Cdec);
     // dS / dW of the steps [ta, tb) on the side streams, launched as soon as those steps are done
     const int dchunk = (g.T_out + g_side_chunks - 1) / g_side_chunks;
@@ -887,20 +911,32 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
       if (fb) {
         bool need_dxin = (t > 0) && !(tf && tf[t - 1]);
         float* dU_t = dU_all + (int64_t)t * g.R * g.D;
-        if (g_bwd_fused == 2) {
+        // fp16 backward: the glue of a teacher-forced step (no gradient through go) runs in the previous launch's epilogue
+        const bool glue_fused_here = (g_bwd_fused == 2) && dec_glue_fused;
+        dec_glue_fused = false;
+        if (g_bwd_fused == 2 && !glue_fused_here) {
           const size_t gsm = ((size_t)(32 + g.D) * g.Cout + 2 * 32 * (g.D + 1)) * sizeof(float);
           MCRN_LAUNCH(fusedbh::k_bwd_glue_h, dim3(ceil_div(g.N, 32), g.B), 256, gsm, st, d_output, use_dgo ? dXin : nullptr, g.Cdec, h_t,
                       prm->proj_w, dH, (t == g.T_out - 1) ? 1 : 0, b.r, b.hc, b.hx, dU_t, dG_all + (int64_t)t * g.R * 2 * g.D,
                       ws + p.dHr, reinterpret_cast<__half*>(ws + p.dU16), reinterpret_cast<__half*>(ws + p.dU16T),
-                      reinterpret_cast<__half*>(ws + p.dG16), reinterpret_cast<__half*>(ws + p.dG16T), fusedh::ld_half(g.N),
+                      dg16_buf(g, p, ws, g.D, t), dg16T_buf(g, p, ws, g.D, t), fusedh::ld_half(g.N),
                       ws + p.gs, grads->proj_w, grads->proj_b, g.B, g.T_out, g.N, g.D, g.Cout, t);
-        } else
-        MCRN_LAUNCH(fusedb::k_bwd_glue, (int)ceil_div64(g.R, 32), 256, (size_t)(32 + g.D) * g.Cout * sizeof(float), st, d_output,
-                    use_dgo ? dXin : nullptr, g.Cdec, h_t, prm->proj_w, dH, (t == g.T_out - 1) ? 1 : 0, b.r, b.hc, b.hx, dU_t,
-                    dG_all + (int64_t)t * g.R * 2 * g.D, ws + p.dHr, grads->proj_w, grads->proj_b, g.B, g.T_out, g.N, g.D,
-                    g.Cout, t);
+        } else if (g_bwd_fused != 2)
+          MCRN_LAUNCH(fusedb::k_bwd_glue, (int)ceil_div64(g.R, 32), 256, (size_t)(32 + g.D) * g.Cout * sizeof(float), st, d_output,
+                      use_dgo ? dXin : nullptr, g.Cdec, h_t, prm->proj_w, dH, (t == g.T_out - 1) ? 1 : 0, b.r, b.hc, b.hx, dU_t,
+                      dG_all + (int64_t)t * g.R * 2 * g.D, ws + p.dHr, grads->proj_w, grads->proj_b, g.B, g.T_out, g.N, g.D,
+                      g.Cout, t);
         BwdStep bs{dU_t, dG_all + (int64_t)t * g.R * 2 * g.D, ws + p.d_Qu + (int64_t)t * g.KS * g.R * g.D,
                    ws + p.d_Qg + (int64_t)t * 2 * g.KS * g.R * g.D, ws + p.dXPin_all + p.dXPin_sz * t};
+        bs.t = t;
+        if (g_bwd_fused == 2 && g_glue_fuse && t > 0 && tf && tf[t - 1]) {     // step t-1 is teacher-forced: fold its glue in
+          CellBufs bp = dec_bufs(g, p, ws, t - 1);
+          bs.ng_r = bp.r; bs.ng_hc = bp.hc; bs.ng_hx = bp.hx; bs.ng_dOut = d_output; bs.ng_wp = prm->proj_w;
+          bs.ng_dU = dU_all + (int64_t)(t - 1) * g.R * g.D; bs.ng_dG = dG_all + (int64_t)(t - 1) * g.R * 2 * g.D;
+          bs.ng_T = g.T_out; bs.ng_Cout = g.Cout;
+          dec_glue_fused = true;
+          if (d_output) dec_wgrad_mask |= 1u << (t - 1);
+        }
         if (g.D == 64) MCRN_TRY(cell_backward_fused<64>(g, p, ws, S, w, b, bs, dH, need_dxin ? dXin : nullptr, st));
         else MCRN_TRY(cell_backward_fused<128>(g, p, ws, S, w, b, bs, dH, need_dxin ? dXin : nullptr, st));
         have_dgo = need_dxin;
@@ -918,6 +954,11 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
     }
     if (fb) {
       MCRN_TRY(dec_side_chunk(0, dec_done));
+      if (dec_wgrad_mask) {      // off the critical path, with the weight-gradient GEMMs
+        MCRN_LAUNCH(fusedbh::k_proj_wgrad, dim3((int)ceil_div64(g.R, 32), g.T_out), 256, (size_t)(32 + g.D) * g.Cout * sizeof(float), g_side.s2,
+                    d_output, ws + p.dec_hx, (int64_t)p.dec_v_sz, ws + p.h_dec_last, dec_wgrad_mask, grads->proj_w, grads->proj_b, g.B,
+                    g.T_out, g.N, g.D, g.Cout);
+      }
     } else {
     MCRN_TRY(acc_dw_all(g, ws + p.dec_xpu, (int64_t)p.dec_xp_sz, g.T_out, g.D, dU_all, g.D, ws + p.a_d_wu, st));
     MCRN_TRY(acc_dw_all(g, ws + p.dec_xpg, (int64_t)p.dec_xp_sz, g.T_out, g.D, dG_all, 2 * g.D, ws + p.a_d_wg, st));
@@ -962,6 +1003,7 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
     float *dU_all = ws + p.e_dU, *dG_all = ws + p.e_dG;
     float* dHe = ws + p.dHenc;
     const bool fb = bwd_fused_shape(g, g.H, g.Cin);
+    bool enc_glue_fused = false;
     const int echunk = (g.T_in + g_side_chunks - 1) / g_side_chunks;
     int enc_done = g.T_in;
     auto enc_side_chunk = [&](int ta, int tb) -> int {
@@ -981,19 +1023,29 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
       CellBufs b = enc_bufs(g, p, ws, t);
       if (fb) {
         float* dU_t = dU_all + (int64_t)t * g.R * g.H;
-        if (g_bwd_fused == 2) {
+        const bool glue_fused_here = (g_bwd_fused == 2) && enc_glue_fused;
+        enc_glue_fused = false;
+        if (g_bwd_fused == 2 && !glue_fused_here) {
           const size_t gsm = (size_t)2 * 32 * (g.H + 1) * sizeof(float);
           MCRN_LAUNCH(fusedbh::k_bwd_glue_h, dim3(ceil_div(g.N, 32), g.B), 256, gsm, st, (const float*)nullptr, (const float*)nullptr, 0,
                       (const float*)nullptr, (const float*)nullptr, dHe, 0, b.r, b.hc, b.hx, dU_t, dG_all + (int64_t)t * g.R * 2 * g.H,
                       ws + p.dHr, reinterpret_cast<__half*>(ws + p.dU16), reinterpret_cast<__half*>(ws + p.dU16T),
-                      reinterpret_cast<__half*>(ws + p.dG16), reinterpret_cast<__half*>(ws + p.dG16T), fusedh::ld_half(g.N),
+                      dg16_buf(g, p, ws, g.H, t), dg16T_buf(g, p, ws, g.H, t), fusedh::ld_half(g.N),
                       ws + p.gs, (float*)nullptr, (float*)nullptr, g.B, g.T_in, g.N, g.H, 0, t);
-        } else
-        MCRN_LAUNCH(fusedb::k_bwd_glue, (int)ceil_div64(g.R, 32), 256, 0, st, (const float*)nullptr, (const float*)nullptr, 0,
-                    (const float*)nullptr, (const float*)nullptr, dHe, 0, b.r, b.hc, b.hx, dU_t,
-                    dG_all + (int64_t)t * g.R * 2 * g.H, ws + p.dHr, (float*)nullptr, (float*)nullptr, g.B, g.T_in, g.N, g.H, 0, t);
+        } else if (g_bwd_fused != 2)
+          MCRN_LAUNCH(fusedb::k_bwd_glue, (int)ceil_div64(g.R, 32), 256, 0, st, (const float*)nullptr, (const float*)nullptr, 0,
+                      (const float*)nullptr, (const float*)nullptr, dHe, 0, b.r, b.hc, b.hx, dU_t,
+                      dG_all + (int64_t)t * g.R * 2 * g.H, ws + p.dHr, (float*)nullptr, (float*)nullptr, g.B, g.T_in, g.N, g.H, 0, t);
         BwdStep bs{dU_t, dG_all + (int64_t)t * g.R * 2 * g.H, ws + p.e_Qu + (int64_t)t * g.KS * g.R * g.H,
                    ws + p.e_Qg + (int64_t)t * 2 * g.KS * g.R * g.H, ws + p.dXPin_all + p.dXPin_sz * t};
+        bs.t = t;
+        if (g_bwd_fused == 2 && g_glue_fuse && t > 0) {       // encoder: the glue of step t-1 always folds into this step's epilogue
+          CellBufs bp = enc_bufs(g, p, ws, t - 1);
+          bs.ng_r = bp.r; bs.ng_hc = bp.hc; bs.ng_hx = bp.hx;
+          bs.ng_dU = dU_all + (int64_t)(t - 1) * g.R * g.H; bs.ng_dG = dG_all + (int64_t)(t - 1) * g.R * 2 * g.H;
+          bs.ng_T = g.T_in; bs.ng_Cout = 0;
+          enc_glue_fused = true;
+        }
         if (g.H == 64) MCRN_TRY(cell_backward_fused<64>(g, p, ws, S, w, b, bs, dHe, nullptr, st));
         else MCRN_TRY(cell_backward_fused<128>(g, p, ws, S, w, b, bs, dHe, nullptr, st));
         if (t > 0 && enc_done - t >= echunk) { MCRN_TRY(enc_side_chunk(t, enc_done)); enc_done = t; }

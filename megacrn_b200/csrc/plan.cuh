@@ -148,8 +148,8 @@ static inline int make_plan(const Geo& g, bool save, Plan* p) {
       p->d_wu16n = halves((NB + 1) * g.D * g.D);
       p->dU16 = halves(R * g.D);
       p->dU16T = halves((size_t)g.B * g.D * ld16);
-      p->dG16 = halves(R * 2 * g.D);
-      p->dG16T = halves((size_t)g.B * 2 * g.D * ld16);
+      p->dG16 = halves(2 * R * 2 * g.D);                       // two buffers, ping-pong over the time step
+      p->dG16T = halves(2 * (size_t)g.B * 2 * g.D * ld16);
     }
     p->dIBu16 = take(R * 16);
     p->dIBg16 = take(R * 16);
