@@ -26,6 +26,7 @@ int trainer_loss_impl(const Geo& g, const float* output, const float* labels, co
 int adam_step_impl(const Geo& g, const mcrn_params* prm, const mcrn_params* grads, const mcrn_params* m, const mcrn_params* v,
                    float* state, float beta1, float beta2, float eps, float max_norm, cudaStream_t st);
 
+bool set_option(const char* name, int value);
 static std::atomic<uint64_t> g_mode_epoch{0};
 static std::mutex g_mu;
 static std::unordered_map<const void*, uint64_t> g_saved;   // workspace -> dims hash of the last saving forward
@@ -81,6 +82,11 @@ int mcrn_set_engine(int engine) {
 int mcrn_get_engine(void) { return g_engine; }
 int mcrn_set_debug_mask(int mask) { g_simt_mask = mask; g_mode_epoch.fetch_add(1); return MCRN_OK; }
 uint64_t mcrn_mode_epoch(void) { return g_mode_epoch.load(); }
+int mcrn_set_option(const char* name, int value) {
+  if (!set_option(name, value)) { set_error("mcrn_set_option: unknown option '%s'", name ? name : "(null)"); return MCRN_ERR_BAD_DIMS; }
+  g_mode_epoch.fetch_add(1);
+  return MCRN_OK;
+}
 int mcrn_debug_fused_timeline(long long* device_slots, int which) {
   fused::g_dbg_timeline = device_slots; fused::g_dbg_which = which; fused::g_dbg_count = 0;
   return MCRN_OK;

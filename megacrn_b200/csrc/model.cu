@@ -1119,6 +1119,17 @@ int adam_step_impl(const Geo& g, const mcrn_params* prm, const mcrn_params* grad
   return MCRN_OK;
 }
 
+// internal tuning knobs by name (tests / experiments); returns false for an unknown name
+bool set_option(const char* name, int value) {
+  const std::string n(name ? name : "");
+  if (n == "glue_fuse") g_glue_fuse = value;
+  else if (n == "side_chunks") g_side_chunks = value > 0 ? value : 1;
+  else if (n == "ds_fused") g_ds_fused = value;
+  else if (n == "ib_compact") g_ib_compact = value;
+  else return false;
+  return true;
+}
+
 const char* last_error() { return t_err; }
 
 }  // namespace mcrn

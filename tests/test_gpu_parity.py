@@ -344,6 +344,36 @@ def test_fused_backward_kernel_matches_per_stage_backward(N, H, dm, B, T, defaul
                 assert rel_l2(res[bf][1][k], res[0][1][k]) < 1.5e-3, (bf, flags, k, rel_l2(res[bf][1][k], res[0][1][k]))
 
 
+@pytest.mark.parametrize("opt,val", [("glue_fuse", 1), ("side_chunks", 3), ("ds_fused", 0), ("ib_compact", 0)])
+def test_backward_variants_agree(opt, val, default_engine):
+    """Non-default variants of the fused backward (glue inside the gate-AGCN epilogue, chunked dS / dW launches, per-step dS
+    GEMMs, full-width input block) give the same gradients as the default."""
+    lib = default_engine
+    d = O.Dims(num_nodes=207, horizon=4, rnn_units=64)
+    p = O.init_params(d, seed=1)
+    x, y_cov, labels = O.synthetic_batch(d, 3, 4, seed=8)
+    flags = [True, True, False, True]
+    dv = _dev()
+    gen = torch.Generator().manual_seed(3)
+    res, ups = {}, None
+    try:
+        for v in (None, val):
+            if v is not None:
+                assert lib.mcrn_set_option(opt.encode(), v) == 0
+            m = _model(d, p).train()
+            outs = m(x.to(dv), y_cov.to(dv), labels.to(dv), teacher_forcing=flags)
+            if ups is None:
+                ups = [torch.randn(outs[0].shape, generator=gen).to(dv), torch.randn(outs[2].shape, generator=gen).to(dv)]
+            torch.autograd.backward([outs[0], outs[2]], ups)
+            res[v] = {k: t.grad.cpu() for k, t in m.named_parameters()}
+    finally:
+        lib.mcrn_set_option(opt.encode(), {"glue_fuse": 0, "side_chunks": 1, "ds_fused": 1, "ib_compact": 1}[opt])
+    tol = 1e-3 if opt in ("ds_fused", "ib_compact") else 2e-5      # different rounding points vs same arithmetic, atomics order
+    for k in res[None]:
+        assert rel_l2(res[val][k], res[None][k]) < tol, (opt, k, rel_l2(res[val][k], res[None][k]))
+    assert lib.mcrn_set_option(b"no_such_option", 1) != 0
+
+
 def test_kernel_timing_api_counts_fused_launches(default_engine):
     import ctypes
     from megacrn_b200 import _abi
