@@ -132,10 +132,12 @@ static inline int make_plan(const Geo& g, bool save, Plan* p) {
     p->mq_dq = take(R * g.d);
     p->dHenc = take(R * g.H);
     p->St = take(KS * N * ldS);
-    p->e_Qu = take((size_t)g.T_in * KS * R * g.H);
-    p->e_Qg = take((size_t)g.T_in * 2 * KS * R * g.H);
-    p->d_Qu = take((size_t)g.T_out * KS * R * g.D);
-    p->d_Qg = take((size_t)g.T_out * 2 * KS * R * g.D);
+    // Q blocks of every step: only where the fused backward is instantiated (hidden width 64 / 128)
+    const bool eq = (g.H == 64 || g.H == 128), dq = (g.D == 64 || g.D == 128);
+    p->e_Qu = take(eq ? (size_t)g.T_in * KS * R * g.H : 0);
+    p->e_Qg = take(eq ? (size_t)g.T_in * 2 * KS * R * g.H : 0);
+    p->d_Qu = take(dq ? (size_t)g.T_out * KS * R * g.D : 0);
+    p->d_Qg = take(dq ? (size_t)g.T_out * 2 * KS * R * g.D : 0);
     p->dHr = take(R * g.D);
     {
       const size_t ld16 = (N + 7) / 8 * 8;

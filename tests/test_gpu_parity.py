@@ -374,6 +374,31 @@ def test_backward_variants_agree(opt, val, default_engine):
     assert lib.mcrn_set_option(b"no_such_option", 1) != 0
 
 
+@pytest.mark.parametrize("scale", [2.0 ** -30, 2.0 ** 17])
+def test_fp16_backward_loss_scale_is_magnitude_invariant(scale, default_engine):
+    """The fp16 fused backward stores gradient operands times a power-of-two loss scale chosen from max|upstream|: the
+    parameter gradients must be linear in the upstream gradient over many orders of magnitude (no underflow / overflow).
+    Power-of-two factors keep every rounding decision identical, so only the atomic accumulation order differs."""
+    d = O.Dims(num_nodes=150, horizon=3, rnn_units=64)
+    p = O.init_params(d, seed=2)
+    x, y_cov, labels = O.synthetic_batch(d, 2, 3, seed=4)
+    flags = [True, False, True]
+    dv = _dev()
+    gen = torch.Generator().manual_seed(9)
+    res = {}
+    ups = None
+    for a in (1.0, scale):
+        m = _model(d, p).train()
+        outs = m(x.to(dv), y_cov.to(dv), labels.to(dv), teacher_forcing=flags)
+        if ups is None:
+            ups = [torch.randn(outs[0].shape, generator=gen).to(dv), torch.randn(outs[2].shape, generator=gen).to(dv)]
+        torch.autograd.backward([outs[0], outs[2]], [u * a for u in ups])
+        res[a] = {k: t.grad.double().cpu() / a for k, t in m.named_parameters()}
+    for k in res[1.0]:
+        assert torch.isfinite(res[scale][k]).all(), k
+        assert rel_l2(res[scale][k], res[1.0][k]) < 5e-5, (k, rel_l2(res[scale][k], res[1.0][k]))
+
+
 def test_kernel_timing_api_counts_fused_launches(default_engine):
     import ctypes
     from megacrn_b200 import _abi
