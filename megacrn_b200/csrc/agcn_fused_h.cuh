@@ -493,8 +493,22 @@ __global__ void k_encoder_input_blocks(const float* __restrict__ xpin, int NB, i
 constexpr int DI_COLS = 32, DI_NODES = 6, DI_RPT = 3, DI_ROWS = 8 * DI_RPT;
 __global__ void __launch_bounds__(256) k_decoder_input_block(const float* __restrict__ go_src, const float* __restrict__ ycov,
                                                              const float* __restrict__ S, int ldS, int KS, int N, int B, int T,
-                                                             int Cout, int Ycov, int t, float* __restrict__ xin_out,
-                                                             __half* __restrict__ ib16c, float* __restrict__ ib32c) {
+                                                             int Cout, int Ycov, unsigned tmask, float* __restrict__ xin_base,
+                                                             int64_t xin_step, __half* __restrict__ ib16_base,
+                                                             float* __restrict__ ib32_base) {
+  // blockIdx.z selects the z-th set bit of tmask = the decoder step this block builds (all teacher-forced steps of a
+  // forward are built by ONE launch; a free-running step by a launch of its own once the previous output exists)
+  int t = 0;
+  {
+    unsigned m = tmask;
+    for (int z = blockIdx.z; z > 0; --z) m &= m - 1;
+    t = __ffs(m) - 1;
+  }
+  const int64_t Rr = (int64_t)N * B;
+  float* xin_out = xin_base ? xin_base + (int64_t)t * xin_step : nullptr;
+  __half* ib16c = ib16_base + (int64_t)t * Rr * IBC;
+  float* ib32c = ib32_base ? ib32_base + (int64_t)t * Rr * IBF : nullptr;
+  if (t == 0) go_src = nullptr;                        // go_0 = 0 (model/MegaCRN.py:182)
   extern __shared__ float sh[];                        // xs [DI_COLS][N|1], ss [DI_ROWS][N + 1], os [DI_NODES * DI_COLS][IBF + 1]
   const int Cd = Cout + Ycov, cols = B * Cd, nin = (KS + 1) * Cd;
   const int c0 = blockIdx.x * DI_COLS, n0 = blockIdx.y * DI_NODES;

@@ -143,7 +143,7 @@ static int g_ib_compact = getenv("MCRN_IB_COMPACT") ? atoi(getenv("MCRN_IB_COMPA
 static bool ib_compact_shape(const Geo& g, int Hs, int Cin, bool save) {
   // (the fused decoder input kernel stages N x 32 inputs + 24 support rows in shared memory)
   return g_ib_compact && ((size_t)(g.N | 1) * fusedh::DI_COLS + (size_t)fusedh::DI_ROWS * (g.N + 1)) * sizeof(float) <= 180 * 1024 &&
-         g.KS * fusedh::DI_NODES <= fusedh::DI_ROWS && fusedh::DI_COLS % (Cin) == 0 &&
+         g.KS * fusedh::DI_NODES <= fusedh::DI_ROWS && fusedh::DI_COLS % (Cin) == 0 && g.T_out <= 32 &&
          fused_h_shape(g, Hs) && g.NB * Cin + 1 <= fusedh::IBF && (!save || bwd_fused_shape(g, Hs, Cin));
 }
 
@@ -301,7 +301,7 @@ static CellBufs dec_bufs(const Geo& g, const Plan& p, float* ws, int t) {
   b.x16 = reinterpret_cast<__half*>(ws + p.dec_x16); b.x16T = reinterpret_cast<__half*>(ws + p.dec_x16T);
   b.zh16 = reinterpret_cast<__half*>(ws + p.dec_zh16); b.zh16T = reinterpret_cast<__half*>(ws + p.dec_zh16T);
   b.ib16 = reinterpret_cast<__half*>(ws + p.dec_ib16);
-  b.ib16c = reinterpret_cast<__half*>(ws + p.dec_ib16c);
+  b.ib16c = reinterpret_cast<__half*>(ws + p.dec_ib16c) + (int64_t)t * g.R * 64;
   b.ib32c = p.save ? ws + p.dec_ib32c + (int64_t)t * g.R * 16 : nullptr;
   return b;
 }
@@ -380,23 +380,38 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
   // ---- decoder loop (:181-192) ----
   {
     CellW w = dec_w(g, p, ws);
+    // compact input blocks: every step whose decoder input is known up front (step 0: zeros; step t after a teacher-forced
+    // coin flip: labels[:, t-1]) is built by ONE launch before the loop; free-running steps by a launch of their own
+    const bool dec_compact = ib_compact_shape(g, g.D, g.Cdec, p.save);
+    unsigned dec_tf_mask = 0;
+    auto launch_dec_input = [&](const float* go_src, unsigned mask) -> int {
+      const size_t shm = ((size_t)(g.N | 1) * fusedh::DI_COLS + (size_t)fusedh::DI_ROWS * (g.N + 1) +
+                          (size_t)fusedh::DI_NODES * fusedh::DI_COLS * (fusedh::IBF + 1)) * sizeof(float);
+      static bool di_attr = false;
+      if (!di_attr) {
+        MCRN_CUDA_OK(cudaFuncSetAttribute(fusedh::k_decoder_input_block, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        di_attr = true;
+      }
+      MCRN_LAUNCH(fusedh::k_decoder_input_block,
+                  dim3(ceil_div(g.B * g.Cdec, fusedh::DI_COLS), ceil_div(g.N, fusedh::DI_NODES), __builtin_popcount(mask)), 256, shm, st,
+                  go_src, y_cov, ws + p.S, g.ldS, g.KS, g.N, g.B, g.T_out, g.Cout, g.Ycov, mask,
+                  p.save ? ws + p.dec_xpin : nullptr, (int64_t)p.dec_xpin_sz, reinterpret_cast<__half*>(ws + p.dec_ib16c),
+                  p.save ? ws + p.dec_ib32c : nullptr);
+      return MCRN_OK;
+    };
+    if (dec_compact && g.T_out <= 32) {
+      for (int t = 0; t < g.T_out; ++t)
+        if (t == 0 || (tf && tf[t - 1])) dec_tf_mask |= 1u << t;
+      MCRN_TRY(launch_dec_input(labels, dec_tf_mask));
+    }
     for (int t = 0; t < g.T_out; ++t) {
       CellBufs b = dec_bufs(g, p, ws, t);
       const float* go_src = nullptr;
       if (t > 0) go_src = (tf && tf[t - 1]) ? labels : output;
       int64_t n_in = (int64_t)g.R * g.Cdec;
-      if (ib_compact_shape(g, g.D, g.Cdec, p.save)) {
-        const size_t shm = ((size_t)(g.N | 1) * fusedh::DI_COLS + (size_t)fusedh::DI_ROWS * (g.N + 1) +
-                            (size_t)fusedh::DI_NODES * fusedh::DI_COLS * (fusedh::IBF + 1)) * sizeof(float);
-        static bool di_attr = false;
-        if (!di_attr) {
-          MCRN_CUDA_OK(cudaFuncSetAttribute(fusedh::k_decoder_input_block, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-          di_attr = true;
-        }
-        if (shm > 200 * 1024) { set_error("k_decoder_input_block: N=%d needs %zu bytes of shared memory", g.N, shm); return MCRN_ERR_BAD_DIMS; }
-        MCRN_LAUNCH(fusedh::k_decoder_input_block,
-                    dim3(ceil_div(g.B * g.Cdec, fusedh::DI_COLS), ceil_div(g.N, fusedh::DI_NODES)), 256, shm, st, go_src, y_cov, ws + p.S, g.ldS, g.KS, g.N,
-                    g.B, g.T_out, g.Cout, g.Ycov, t, p.save ? const_cast<float*>(b.xpin) : nullptr, b.ib16c, b.ib32c);
+      if (dec_compact) {
+        if (!((dec_tf_mask >> t) & 1u))      // free-running step: its input is the previous prediction
+          MCRN_TRY(launch_dec_input(output, 1u << t));
       } else {
       MCRN_LAUNCH(k_stage_decoder_input, ew_grid(n_in), 256, 0, st, go_src, y_cov, const_cast<float*>(b.xpin), g.B,
                   g.T_out, g.N, g.Cout, g.Ycov, t, tf32_mode());

@@ -25,7 +25,7 @@ struct Plan {
   size_t s16, e_wg16, e_wu16, d_wg16, d_wu16;
   size_t enc_x16, enc_x16T, enc_zh16, enc_zh16T, enc_ib16;
   size_t dec_x16, dec_x16T, dec_zh16, dec_zh16T, dec_ib16;
-  size_t enc_ib16c, dec_ib16c;           // compact input blocks: [T_in][R][64] / [R][64] halves
+  size_t enc_ib16c, dec_ib16c;           // compact input blocks: [T_in][R][64] / [T_out][R][64] halves
   size_t enc_ib32c, dec_ib32c;           // [T][R][16] floats (training: operand of the input-block weight gradient)
   // per-slot sizes (floats)
   size_t enc_xp_sz, enc_v_sz, dec_xpin_sz, dec_xp_sz, dec_v_sz;
@@ -109,7 +109,7 @@ static inline int make_plan(const Geo& g, bool save, Plan* p) {
     p->dec_zh16 = halves(R * g.D); p->dec_zh16T = halves((size_t)g.B * g.D * ld16);
     p->dec_ib16 = halves(R * g.D);
     p->enc_ib16c = halves((size_t)g.T_in * R * 64);
-    p->dec_ib16c = halves(R * 64);
+    p->dec_ib16c = halves((size_t)g.T_out * R * 64);
     p->enc_ib32c = take(save ? (size_t)g.T_in * R * 16 : 0);
     p->dec_ib32c = take(save ? (size_t)g.T_out * R * 16 : 0);
   }
