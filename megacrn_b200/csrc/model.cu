@@ -383,7 +383,7 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
     // compact input blocks: every step whose decoder input is known up front (step 0: zeros; step t after a teacher-forced
     // coin flip: labels[:, t-1]) is built by ONE launch before the loop; free-running steps by a launch of their own
     const bool dec_compact = ib_compact_shape(g, g.D, g.Cdec, p.save);
-    unsigned dec_tf_mask = 0;
+    unsigned dec_tf_mask = 0, proj_mask = 0;
     auto launch_dec_input = [&](const float* go_src, unsigned mask) -> int {
       const size_t shm = ((size_t)(g.N | 1) * fusedh::DI_COLS + (size_t)fusedh::DI_ROWS * (g.N + 1) +
                           (size_t)fusedh::DI_NODES * fusedh::DI_COLS * (fusedh::IBF + 1)) * sizeof(float);
@@ -421,9 +421,19 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
       float* h_out = last ? ws + p.h_dec_last : dec_bufs(g, p, ws, t + 1).hx;
       float* h_mma = last ? nullptr : dec_bufs(g, p, ws, t + 1).xpg;
       MCRN_TRY(cell_forward(g, S, w, b, h_out, h_mma, st));
-      MCRN_LAUNCH(k_proj_fwd, (int)ceil_div64(g.R, 8), 256, 0, st, h_out, prm->proj_w, prm->proj_b, output, g.B,
-                  g.T_out, g.N, g.D, g.Cout, t);
+      // projection (:186): needed now only if the next step feeds on it; otherwise (training: every state is kept) all such
+      // steps are projected by one launch after the loop
+      const bool next_needs_it = !last && !((dec_tf_mask >> (t + 1)) & 1u);
+      if (p.save && dec_compact && !next_needs_it) {
+        proj_mask |= 1u << t;
+      } else {
+        MCRN_LAUNCH(k_proj_fwd, (int)ceil_div64(g.R, 8), 256, 0, st, h_out, prm->proj_w, prm->proj_b, output, g.B,
+                    g.T_out, g.N, g.D, g.Cout, t);
+      }
     }
+    if (proj_mask)
+      MCRN_LAUNCH(k_proj_fwd_steps, dim3((int)ceil_div64(g.R, 8), __builtin_popcount(proj_mask)), 256, 0, st, ws + p.dec_hx,
+                  (int64_t)p.dec_v_sz, ws + p.h_dec_last, prm->proj_w, prm->proj_b, output, proj_mask, g.B, g.T_out, g.N, g.D, g.Cout);
   }
   return MCRN_OK;
 }

@@ -243,6 +243,32 @@ __global__ void __launch_bounds__(256) k_proj_fwd(const float* __restrict__ h, c
   }
 }
 
+// Projection of several decoder steps in one launch (steps = set bits of tmask; blockIdx.y selects the y-th one):
+// h_t = hx_base + (t + 1) * hx_step for t + 1 < T, else h_last (the per-step states kept for the backward).
+__global__ void __launch_bounds__(256) k_proj_fwd_steps(const float* __restrict__ hx_base, int64_t hx_step,
+                                                        const float* __restrict__ h_last, const float* __restrict__ wp,
+                                                        const float* __restrict__ bp, float* __restrict__ out, unsigned tmask,
+                                                        int B, int T, int N, int D, int Cout) {
+  int t = 0;
+  {
+    unsigned m = tmask;
+    for (int y = blockIdx.y; y > 0; --y) m &= m - 1;
+    t = __ffs(m) - 1;
+  }
+  const float* h = (t + 1 < T) ? hx_base + (int64_t)(t + 1) * hx_step : h_last;
+  int64_t row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= (int64_t)N * B) return;
+  int n = (int)(row / B), b = (int)(row % B);
+  const float* hr = h + row * D;
+  for (int co = 0; co < Cout; ++co) {
+    float s = 0.f;
+    for (int j = lane; j < D; j += 32) s = fmaf(hr[j], wp[(int64_t)co * D + j], s);
+    s = warp_sum(s);
+    if (lane == 0) out[(((int64_t)b * T + t) * N + n) * Cout + co] = s + bp[co];
+  }
+}
+
 // Projection backward for step t.  d_out_t[n][b][co] = dOut[b][t][n][co] (+ dgo[n][b][co] when the next
 // decoder input was this step's own prediction); dH[r][:] (+)= d_out_t[r] . wp; dwp, dbp accumulate.
 // One block = 32 rows; thread j owns column(s) j of D.
