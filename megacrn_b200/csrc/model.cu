@@ -14,6 +14,7 @@
 #include "agcn_bwd_fused.cuh"
 #include "agcn_ds_fused.cuh"
 #include "agcn_bwd_fused_h.cuh"
+#include "agcn_ds_fused_h.cuh"
 #include "plan.cuh"
 #include "loss.cuh"
 #include "small_kernels.cuh"
@@ -150,7 +151,7 @@ static bool ib_compact_shape(const Geo& g, int Hs, int Cin, bool save) {
 // fp16-operand fused cell (agcn_fused_h.cuh).  last: no next step consumes the new state as a tensor-core operand.
 template <int HS>
 static int cell_forward_fused_h(const Geo& g, const CellW& w, const CellBufs& b, float* h_out, float* h_mma, bool last,
-                                cudaStream_t st) {
+                                __half* x16_next, cudaStream_t st) {
   const bool save = b.z != nullptr;
   const bool save_p = save && !bwd_fused_shape(g, HS, w.Cin);     // the fused backward recomputes nothing from P_k: dW_k = X^T Q_k
   const int ldT = fusedh::ld_half(g.N);
@@ -161,13 +162,13 @@ static int cell_forward_fused_h(const Geo& g, const CellW& w, const CellBufs& b,
   fusedh::EpiGateH eg{HS, b.hx, b.z, b.r, save ? b.xpu : nullptr, b.zh16, b.zh16T, ldT};
   MCRN_TRY((fusedh::launch_agcn_fused_h<HS, 2 * HS>(g.N, g.B, g.KS, og, g_fused_parts, eg, st)));
   fusedh::HOperands ou{w.S16, b.zh16T, b.zh16, ib, w.wu16, save_p ? b.xpu : nullptr, ib_ld};
-  fusedh::EpiUpdateH eu{HS, b.hx, b.r, b.hc, h_out, save ? h_mma : nullptr, last ? nullptr : b.x16, last ? nullptr : b.x16T, ldT};
+  fusedh::EpiUpdateH eu{HS, b.hx, b.r, b.hc, h_out, save ? h_mma : nullptr, last ? nullptr : x16_next, last ? nullptr : b.x16T, ldT};
   MCRN_TRY((fusedh::launch_agcn_fused_h<HS, HS>(g.N, g.B, g.KS, ou, g_fused_parts, eu, st)));
   return MCRN_OK;
 }
 
 static int cell_forward(const Geo& g, const float* S, const CellW& w, const CellBufs& b, float* h_out, float* h_mma,
-                        cudaStream_t st) {
+                        cudaStream_t st, __half* x16_next = nullptr) {
   const int Hs = w.Hs, NBX = g.NB + 1;
   const int rnd = tf32_mode();
   const int64_t nH = g.R * Hs;
@@ -177,8 +178,8 @@ static int cell_forward(const Geo& g, const float* S, const CellW& w, const Cell
     MCRN_LAUNCH(k_build_input_block, ew_grid(nH), 256, 0, st, b.xpin, b.xp_k, b.xp_n, g.NB, w.Cin, g.B, g.R, Hs, rnd,
                 save ? b.xpg + (int64_t)g.NB * nH : nullptr, save ? b.xpu + (int64_t)g.NB * nH : nullptr, b.ib16);
     const bool last = (h_mma == nullptr);
-    return Hs == 64 ? cell_forward_fused_h<64>(g, w, b, h_out, h_mma, last, st)
-                    : cell_forward_fused_h<128>(g, w, b, h_out, h_mma, last, st);
+    return Hs == 64 ? cell_forward_fused_h<64>(g, w, b, h_out, h_mma, last, x16_next, st)
+                    : cell_forward_fused_h<128>(g, w, b, h_out, h_mma, last, x16_next, st);
   }
   // input block (input channels + bias) of both AGCNs of this step
   MCRN_LAUNCH(k_build_input_block, ew_grid(nH), 256, 0, st, b.xpin, b.xp_k, b.xp_n, g.NB, w.Cin, g.B, g.R, Hs, rnd,
@@ -279,8 +280,9 @@ static CellBufs enc_bufs(const Geo& g, const Plan& p, float* ws, int t) {
   b.r = ws + p.enc_r + p.enc_v_sz * s;
   b.hc = p.save ? ws + p.enc_hc + p.enc_v_sz * s : nullptr;
   b.hx = ws + p.enc_hx + p.enc_v_sz * s;
-  b.x16 = reinterpret_cast<__half*>(ws + p.enc_x16); b.x16T = reinterpret_cast<__half*>(ws + p.enc_x16T);
-  b.zh16 = reinterpret_cast<__half*>(ws + p.enc_zh16); b.zh16T = reinterpret_cast<__half*>(ws + p.enc_zh16T);
+  const int64_t hs = p.save ? (int64_t)t * g.R * g.H : 0;        // training: per-step row-major fp16 copies
+  b.x16 = reinterpret_cast<__half*>(ws + p.enc_x16) + hs; b.x16T = reinterpret_cast<__half*>(ws + p.enc_x16T);
+  b.zh16 = reinterpret_cast<__half*>(ws + p.enc_zh16) + hs; b.zh16T = reinterpret_cast<__half*>(ws + p.enc_zh16T);
   b.ib16 = reinterpret_cast<__half*>(ws + p.enc_ib16);
   b.ib16c = reinterpret_cast<__half*>(ws + p.enc_ib16c) + (int64_t)t * g.R * 64;
   b.ib32c = p.save ? ws + p.enc_ib32c + (int64_t)t * g.R * 16 : nullptr;
@@ -298,8 +300,9 @@ static CellBufs dec_bufs(const Geo& g, const Plan& p, float* ws, int t) {
   b.r = ws + p.dec_r + p.dec_v_sz * s;
   b.hc = p.save ? ws + p.dec_hc + p.dec_v_sz * s : nullptr;
   b.hx = ws + p.dec_hx + p.dec_v_sz * s;
-  b.x16 = reinterpret_cast<__half*>(ws + p.dec_x16); b.x16T = reinterpret_cast<__half*>(ws + p.dec_x16T);
-  b.zh16 = reinterpret_cast<__half*>(ws + p.dec_zh16); b.zh16T = reinterpret_cast<__half*>(ws + p.dec_zh16T);
+  const int64_t hs = p.save ? (int64_t)t * g.R * g.D : 0;
+  b.x16 = reinterpret_cast<__half*>(ws + p.dec_x16) + hs; b.x16T = reinterpret_cast<__half*>(ws + p.dec_x16T);
+  b.zh16 = reinterpret_cast<__half*>(ws + p.dec_zh16) + hs; b.zh16T = reinterpret_cast<__half*>(ws + p.dec_zh16T);
   b.ib16 = reinterpret_cast<__half*>(ws + p.dec_ib16);
   b.ib16c = reinterpret_cast<__half*>(ws + p.dec_ib16c) + (int64_t)t * g.R * 64;
   b.ib32c = p.save ? ws + p.dec_ib32c + (int64_t)t * g.R * 16 : nullptr;
@@ -363,7 +366,7 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
       const bool last = (t + 1 == g.T_in);
       float* h_out = last ? ws + p.h_enc : enc_bufs(g, p, ws, t + 1).hx;
       float* h_mma = last ? nullptr : enc_bufs(g, p, ws, t + 1).xpg;
-      MCRN_TRY(cell_forward(g, S, w, b, h_out, h_mma, st));
+      MCRN_TRY(cell_forward(g, S, w, b, h_out, h_mma, st, last ? nullptr : enc_bufs(g, p, ws, t + 1).x16));
     }
   }
   // ---- memory query (:159-166) + decoder initial state (:179) ----
@@ -420,7 +423,7 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
       const bool last = (t + 1 == g.T_out);
       float* h_out = last ? ws + p.h_dec_last : dec_bufs(g, p, ws, t + 1).hx;
       float* h_mma = last ? nullptr : dec_bufs(g, p, ws, t + 1).xpg;
-      MCRN_TRY(cell_forward(g, S, w, b, h_out, h_mma, st));
+      MCRN_TRY(cell_forward(g, S, w, b, h_out, h_mma, st, last ? nullptr : dec_bufs(g, p, ws, t + 1).x16));
       // projection (:186): needed now only if the next step feeds on it; otherwise (training: every state is kept) all such
       // steps are projected by one launch after the loop
       const bool next_needs_it = !last && !((dec_tf_mask >> (t + 1)) & 1u);
@@ -611,8 +614,11 @@ struct BwdStep {
   float *ng_dU = nullptr, *ng_dG = nullptr;
   int ng_T = 0, ng_Cout = 0;
 };
-static inline __half* dg16_buf(const Geo& g, const Plan& p, float* ws, int Hs, int t) {
-  return reinterpret_cast<__half*>(ws + p.dG16) + (size_t)(t & 1) * g.R * 2 * Hs;
+static inline __half* dg16_buf(const Geo& g, const Plan& p, float* ws, int Hs, int t) {      // row-major, one per step
+  return reinterpret_cast<__half*>(ws + (Hs == g.D ? p.dG16 : p.e_dG16)) + (size_t)t * g.R * 2 * Hs;
+}
+static inline __half* du16_buf(const Geo& g, const Plan& p, float* ws, int Hs, int t) {      // row-major, one per step
+  return reinterpret_cast<__half*>(ws + (Hs == g.D ? p.dU16 : p.e_dU16)) + (size_t)t * g.R * Hs;
 }
 static inline __half* dg16T_buf(const Geo& g, const Plan& p, float* ws, int Hs, int t) {
   return reinterpret_cast<__half*>(ws + p.dG16T) + (size_t)(t & 1) * g.B * 2 * Hs * fusedh::ld_half(g.N);
@@ -628,7 +634,8 @@ static int make_dxp_s(const Geo& g, const float* dv, int O, const float* wall, i
 // dS / dW launches per cell type: 1 = one launch after the time loop (measured best at C2: 4.41 ms/step vs 4.47-4.54 with 3
 // chunks -- the extra launches and their interference with the recurrent chain cost more than the shorter tail saves)
 static int g_side_chunks = getenv("MCRN_SIDE_CHUNKS") ? (atoi(getenv("MCRN_SIDE_CHUNKS")) > 0 ? atoi(getenv("MCRN_SIDE_CHUNKS")) : 1) : 1;
-int g_ds_fused = getenv("MCRN_DS_FUSED") ? atoi(getenv("MCRN_DS_FUSED")) : 1;
+// fused support-gradient kernel: 2 = fp16 operands where the fp16 forward + backward provide them (default), 1 = TF32, 0 = per step
+int g_ds_fused = getenv("MCRN_DS_FUSED") ? atoi(getenv("MCRN_DS_FUSED")) : 2;
 static bool ds_fused_shape(const Geo& g, int Hs) { return g_ds_fused && fusedd::ds_fused_eligible(g.N, Hs); }
 // Step glue of the next cell inside the gate-AGCN epilogue (EpiBGHG): correct and tested, but measured slower at C2 (4.38 vs
 // 4.25 ms/step): the exposed, latency-bound epilogue grows by more than the 15 us HBM-rate glue kernel it replaces.  Off by default.
@@ -652,7 +659,7 @@ static int cell_backward_fused(const Geo& g, const Plan& p, float* ws, const flo
   MCRN_TRY(acc_ds(g, dXP + nH, (int64_t)g.B * HS, b.xpu, (int64_t)g.B * HS, g.B * HS, dS, sd));
   }
   const bool h16 = (g_bwd_fused == 2);
-  __half* dU16 = reinterpret_cast<__half*>(ws + p.dU16);
+  __half* dU16 = du16_buf(g, p, ws, HS, bs.t);
   __half* dU16T = reinterpret_cast<__half*>(ws + p.dU16T);
   __half* dG16 = dg16_buf(g, p, ws, HS, bs.t);
   __half* dG16T = dg16T_buf(g, p, ws, HS, bs.t);
@@ -676,7 +683,8 @@ static int cell_backward_fused(const Geo& g, const Plan& p, float* ws, const flo
     // the gate-AGCN launch also sums both input-block gradients into dXPin (no repack kernel)
     if (bs.ng_r != nullptr) {     // ... and runs the glue of step t-1 in its epilogue
       fusedbh::EpiBGHG eg{HS, dHp, bs.ng_r, bs.ng_hc, bs.ng_hx, bs.ng_dOut, bs.ng_wp, g.B, bs.ng_T, g.N, bs.ng_Cout, bs.t - 1,
-                          bs.ng_dU, bs.ng_dG, ws + p.dHr, dU16, dU16T, dg16_buf(g, p, ws, HS, bs.t - 1), dg16T_buf(g, p, ws, HS, bs.t - 1),
+                          bs.ng_dU, bs.ng_dG, ws + p.dHr, du16_buf(g, p, ws, HS, bs.t - 1), dU16T, dg16_buf(g, p, ws, HS, bs.t - 1),
+                          dg16T_buf(g, p, ws, HS, bs.t - 1),
                           fusedh::ld_half(g.N)};
       MCRN_TRY((fusedbh::launch_agcn_bwd_h<HS>(g.N, g.B, g.KS, 2, og, bs.Qg, ws + p.dIBg16, eg, st, ws + p.dIBu16, bs.dXPin, w.Cin)));
     } else {
@@ -729,15 +737,23 @@ static int side_join_fused(cudaStream_t mainst) {
 template <int HS>
 static int acc_ds_fused_all(const Geo& g, const Plan& p, float* ws, const CellW& w, int T, int ta, int tb, const float* dU_all,
                             const float* dG_all, const float* xpu0, const float* xpg0, int64_t xp_step, const float* xpin0,
-                            int64_t xpin_n, int64_t xpin_seg, cudaStream_t mainst) {
+                            int64_t xpin_n, int64_t xpin_seg, const __half* x16_0, const __half* zh16_0, cudaStream_t mainst) {
   if (g_dbg_skip & 1) return MCRN_OK;
   float* dS = ws + p.dS;
   cudaStream_t sd = g_side.s;
   MCRN_TRY(side_begin(0, mainst));
+  if (g_bwd_fused == 2 && g_ds_fused == 2 && fused_h_shape(g, HS)) {
+    // fp16 operands: the per-step scaled dV16 copies of the fp16 backward and the per-step state copies of the fp16 forward
+    MCRN_TRY((fuseddh::launch_agcn_ds_h<HS>(g.N, g.B, tb - ta, g.KS, g.ldS, HS, du16_buf(g, p, ws, HS, ta), w.wu16n,
+                                            zh16_0 + (int64_t)ta * g.R * HS, ws + p.gs, dS, sd)));
+    MCRN_TRY((fuseddh::launch_agcn_ds_h<HS>(g.N, g.B, tb - ta, g.KS, g.ldS, 2 * HS, dg16_buf(g, p, ws, HS, ta), w.wg16n,
+                                            x16_0 + (int64_t)ta * g.R * HS, ws + p.gs, dS, sd)));
+  } else {
   MCRN_TRY((fusedd::launch_agcn_ds<HS>(g.N, g.B, tb - ta, g.KS, g.ldS, HS, dU_all + (int64_t)ta * g.R * HS, w.wu,
                                        xpu0 + (int64_t)ta * xp_step, xp_step, dS, sd)));
   MCRN_TRY((fusedd::launch_agcn_ds<HS>(g.N, g.B, tb - ta, g.KS, g.ldS, 2 * HS, dG_all + (int64_t)ta * g.R * 2 * HS, w.wg,
                                        xpg0 + (int64_t)ta * xp_step, xp_step, dS, sd)));
+  }
   g_side.fused_pending = true;
   if (ta != 0) return MCRN_OK;
   for (int t0 = 0; t0 < T; t0 += 16) {
@@ -919,8 +935,8 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
       if (tb <= ta) return MCRN_OK;
       CellBufs b0 = dec_bufs(g, p, ws, 0);
       if (ds_fused_shape(g, g.D)) {
-        if (g.D == 64) MCRN_TRY(acc_ds_fused_all<64>(g, p, ws, w, g.T_out, ta, tb, dU_all, dG_all, b0.xpu, b0.xpg, (int64_t)p.dec_xp_sz, b0.xpin, b0.xp_n, (int64_t)p.dec_xpin_sz, st));
-        else MCRN_TRY(acc_ds_fused_all<128>(g, p, ws, w, g.T_out, ta, tb, dU_all, dG_all, b0.xpu, b0.xpg, (int64_t)p.dec_xp_sz, b0.xpin, b0.xp_n, (int64_t)p.dec_xpin_sz, st));
+        if (g.D == 64) MCRN_TRY(acc_ds_fused_all<64>(g, p, ws, w, g.T_out, ta, tb, dU_all, dG_all, b0.xpu, b0.xpg, (int64_t)p.dec_xp_sz, b0.xpin, b0.xp_n, (int64_t)p.dec_xpin_sz, b0.x16, b0.zh16, st));
+        else MCRN_TRY(acc_ds_fused_all<128>(g, p, ws, w, g.T_out, ta, tb, dU_all, dG_all, b0.xpu, b0.xpg, (int64_t)p.dec_xp_sz, b0.xpin, b0.xp_n, (int64_t)p.dec_xpin_sz, b0.x16, b0.zh16, st));
       }
       MCRN_TRY(side2_fork(st));
       const float* ibc = ib_compact_shape(g, g.D, g.Cdec, true) ? ws + p.dec_ib32c : nullptr;
@@ -943,7 +959,7 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
           const size_t gsm = ((size_t)(32 + g.D) * g.Cout + 2 * 32 * (g.D + 1)) * sizeof(float);
           MCRN_LAUNCH(fusedbh::k_bwd_glue_h, dim3(ceil_div(g.N, 32), g.B), 256, gsm, st, d_output, use_dgo ? dXin : nullptr, g.Cdec, h_t,
                       prm->proj_w, dH, (t == g.T_out - 1) ? 1 : 0, b.r, b.hc, b.hx, dU_t, dG_all + (int64_t)t * g.R * 2 * g.D,
-                      ws + p.dHr, reinterpret_cast<__half*>(ws + p.dU16), reinterpret_cast<__half*>(ws + p.dU16T),
+                      ws + p.dHr, du16_buf(g, p, ws, g.D, t), reinterpret_cast<__half*>(ws + p.dU16T),
                       dg16_buf(g, p, ws, g.D, t), dg16T_buf(g, p, ws, g.D, t), fusedh::ld_half(g.N),
                       ws + p.gs, grads->proj_w, grads->proj_b, g.B, g.T_out, g.N, g.D, g.Cout, t);
         } else if (g_bwd_fused != 2)
@@ -1035,8 +1051,8 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
       if (tb <= ta) return MCRN_OK;
       CellBufs b0 = enc_bufs(g, p, ws, 0);
       if (ds_fused_shape(g, g.H)) {
-        if (g.H == 64) MCRN_TRY(acc_ds_fused_all<64>(g, p, ws, w, g.T_in, ta, tb, dU_all, dG_all, b0.xpu, b0.xpg, (int64_t)p.enc_xp_sz, b0.xpin, b0.xp_n, (int64_t)g.B * g.Cin, st));
-        else MCRN_TRY(acc_ds_fused_all<128>(g, p, ws, w, g.T_in, ta, tb, dU_all, dG_all, b0.xpu, b0.xpg, (int64_t)p.enc_xp_sz, b0.xpin, b0.xp_n, (int64_t)g.B * g.Cin, st));
+        if (g.H == 64) MCRN_TRY(acc_ds_fused_all<64>(g, p, ws, w, g.T_in, ta, tb, dU_all, dG_all, b0.xpu, b0.xpg, (int64_t)p.enc_xp_sz, b0.xpin, b0.xp_n, (int64_t)g.B * g.Cin, b0.x16, b0.zh16, st));
+        else MCRN_TRY(acc_ds_fused_all<128>(g, p, ws, w, g.T_in, ta, tb, dU_all, dG_all, b0.xpu, b0.xpg, (int64_t)p.enc_xp_sz, b0.xpin, b0.xp_n, (int64_t)g.B * g.Cin, b0.x16, b0.zh16, st));
       }
       MCRN_TRY(side2_fork(st));
       const float* ibc = ib_compact_shape(g, g.H, g.Cin, true) ? ws + p.enc_ib32c : nullptr;
@@ -1054,7 +1070,7 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
           const size_t gsm = (size_t)2 * 32 * (g.H + 1) * sizeof(float);
           MCRN_LAUNCH(fusedbh::k_bwd_glue_h, dim3(ceil_div(g.N, 32), g.B), 256, gsm, st, (const float*)nullptr, (const float*)nullptr, 0,
                       (const float*)nullptr, (const float*)nullptr, dHe, 0, b.r, b.hc, b.hx, dU_t, dG_all + (int64_t)t * g.R * 2 * g.H,
-                      ws + p.dHr, reinterpret_cast<__half*>(ws + p.dU16), reinterpret_cast<__half*>(ws + p.dU16T),
+                      ws + p.dHr, du16_buf(g, p, ws, g.H, t), reinterpret_cast<__half*>(ws + p.dU16T),
                       dg16_buf(g, p, ws, g.H, t), dg16T_buf(g, p, ws, g.H, t), fusedh::ld_half(g.N),
                       ws + p.gs, (float*)nullptr, (float*)nullptr, g.B, g.T_in, g.N, g.H, 0, t);
         } else if (g_bwd_fused != 2)
