@@ -193,7 +193,7 @@ int mcrn_set_engine(int engine);
 int mcrn_get_engine(void);
 /* Internal tuning knobs by name (tests / experiments): "glue_fuse" (step glue inside the gate-AGCN backward epilogue, default 0),
  * "side_chunks" (dS / dW launches per cell type, default 1), "ds_fused" (fused support-gradient kernel: 2 = fp16 operands (default), 1 = TF32, 0 = per-step GEMMs),
- * "ib_compact" (compact input block, default 1). */
+ * "ib_compact" (compact input block, default 1), "dw_fused" (fp16 weight-gradient kernel agcn_dw_fused_h.cuh, default 1). */
 int mcrn_set_option(const char* name, int value);
 /* Counter incremented by every mcrn_set_* call: part of the validity key of MCRN_FWD_REUSE_PROLOGUE. */
 uint64_t mcrn_mode_epoch(void);

@@ -44,8 +44,10 @@ constexpr int BHTHREADS = 320;
 
 struct BHParams {
   int N, B, KS, nhalf;
-  float* qsave;          // [KS * nhalf][R][HS] fp32, unscaled
+  float* qsave;          // [KS * nhalf][R][HS] fp32, unscaled (TF32 weight-gradient GEMMs); null when q16T is used
   int64_t blk_stride;    // R * HS
+  __half* q16T;          // [KS * nhalf][B][HS][ldT] scaled fp16, node index contiguous (fp16 weight-gradient kernel); or null
+  int ldT;
   float* dib;            // [R][IBW], unscaled (written when dxpin == null)
   const float* gs;       // device: {scale, 1 / scale}
   // gate-AGCN launch: the input-block gradient of the update AGCN (dib_in, written by the previous launch) is added and the
@@ -309,7 +311,14 @@ agcn_bwd_h_kernel(const __grid_constant__ CUtensorMap tmST, const __grid_constan
             tmem_ld_32x32b_x32(qbuf + (uint32_t)(c * 32), v);
 #pragma unroll
             for (int i = 0; i < 16; ++i) u[ci][i] = pack_h2(v[2 * i], v[2 * i + 1]);
-            if (node0 < p.N) {
+            if (p.q16T != nullptr) {                     // node-transposed fp16 copy straight from the accumulator layout
+              const int node = node0 + lane;             // (lane = node row): 64 contiguous bytes per warp store
+              if (node < p.N) {
+                __half* dst = p.q16T + (((int64_t)ks * p.B + b) * HS + c * 32) * p.ldT + node;
+#pragma unroll 8
+                for (int j = 0; j < 32; ++j) dst[(int64_t)j * p.ldT] = __float2half_rn(v[j]);
+              }
+            } else if (node0 < p.N) {
               __syncwarp();
 #pragma unroll
               for (int i = 0; i < 32; i += 4)
@@ -619,7 +628,7 @@ struct BHOperands {
 
 template <int HS, class Epi>
 int launch_agcn_bwd_h(int N, int B, int KS, int nhalf, const BHOperands& op, float* qsave, float* dib, const Epi& epi,
-                      cudaStream_t st, const float* dib_in = nullptr, float* dxpin = nullptr, int cin = 0) {
+                      cudaStream_t st, const float* dib_in = nullptr, float* dxpin = nullptr, int cin = 0, __half* q16T = nullptr) {
   using C = CfgBH<HS>;
   const int64_t R = (int64_t)N * B;
   const int O = nhalf * HS, ldn = fusedh::ld_half(N);
@@ -653,6 +662,7 @@ int launch_agcn_bwd_h(int N, int B, int KS, int nhalf, const BHOperands& op, flo
   BHParams p;
   p.N = N; p.B = B; p.KS = KS; p.nhalf = nhalf;
   p.qsave = qsave; p.blk_stride = R * HS; p.dib = dib; p.gs = op.gs;
+  p.q16T = q16T; p.ldT = ldn;
   p.dib_in = dib_in; p.dxpin = dxpin; p.nb = KS + 1; p.cin = cin;
   auto kern = agcn_bwd_h_kernel<HS, Epi>;
   static bool attr_set = false;

@@ -1,0 +1,197 @@
+// Weight gradients of ONE AGCN over all time steps and batch elements, fp16 operands (tcgen05 kind::f16, fp32 accumulate):
+//     dW[blk][c][h*HS + o] = sum_{t,b,n} X_t[n,b,c] * Y_t[n,b,o]
+// with Y = dV (blk = 0, the folded identity block) or Y = Q_{k,h} = S_k^T dV (blk = 1 + k; agcn_bwd_fused_h.cuh).  Both
+// operands are the node-transposed fp16 copies the fused forward / backward write anyway:
+//     X16T [T][B][HS][ldT]          A: rows c, K = node (box [64 k][128 m]; rows >= HS are out of bounds = 0)
+//     dV16T [T][B][O][ldT]          B for blk 0: rows o
+//     Q16T [T * nks][B][HS][ldT]    B for blk >= 1: rows o, block ks = k * nhalf + h
+// A plain split-K GEMM: CTA = (output tile (blk, h), group g) loops over its (t, b) units, ceil(N / 64) ring items each,
+// accumulator [128 x HS] in TMEM, one red.global.add.v4.f32 pass at the end (times 1 / loss scale: dV16T and Q16T carry it).
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+#pragma once
+
+#include "agcn_bwd_fused_h.cuh"
+
+namespace mcrn {
+namespace fusedwh {
+
+using namespace tc;
+using fused::mbar_wait_b;
+using fusedh::BKH;
+using fusedh::make_idesc_f16;
+using fusedh::tcgen05_mma_f16;
+
+constexpr int WTHREADS = 192;
+
+struct WParams {
+  int N, B, T, KS, nhalf, O;
+  float* dw;             // [KS+2][HS][O] accumulators
+  const float* gs;       // device {scale, 1 / scale}
+};
+
+template <int HS>
+struct CfgW {
+  static constexpr uint32_t A_SLOT = BM * 128, B_SLOT = (uint32_t)HS * 128, STAGE = A_SLOT + B_SLOT;
+  static constexpr int NST = 6;
+  static constexpr size_t SMEM = (size_t)NST * STAGE + 1024;
+  static constexpr uint32_t TMEM_COLS = HS >= 128 ? 128 : 64;
+};
+
+template <int HS>
+__global__ void __launch_bounds__(WTHREADS, 1)
+agcn_dw_h_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmV,
+                 const __grid_constant__ CUtensorMap tmQ, WParams p) {
+  using C = CfgW<HS>;
+  constexpr int NST = C::NST;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[NST];
+  __shared__ __align__(8) uint64_t empty_bar[NST];
+  __shared__ __align__(8) uint64_t acc_full_bar;
+  __shared__ uint32_t tmem_slot;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, grp = blockIdx.y, G = gridDim.y;
+  const int blk = tile / p.nhalf, half = tile - blk * p.nhalf;      // blk 0 = identity block, 1 + k = support k
+  const int U = p.T * p.B;
+  const int nu = (U - grp + G - 1) / G;
+  const int kb = (p.N + BKH - 1) / BKH;
+  const int nks = p.KS * p.nhalf;
+  if (nu <= 0) return;
+  const int nit = nu * kb;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
+#pragma unroll
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&acc_full_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {                                     // ===== TMA producer =====
+      for (int it = 0; it < nit; ++it) {
+        const int s = it % NST;
+        if (it >= NST) mbar_wait_b(smem_u32(&empty_bar[s]), (((uint32_t)(it / NST)) & 1u) ^ 1u);
+        const uint32_t fb = smem_u32(&full_bar[s]);
+        const uint32_t a_dst = smem_base + (uint32_t)s * C::STAGE, b_dst = a_dst + C::A_SLOT;
+        const int i = it / kb, j = it - i * kb;
+        const int u = grp + i * G, t = u / p.B, b = u - t * p.B;
+        mbar_expect_tx(fb, C::A_SLOT + C::B_SLOT);
+        tma_load_4d(a_dst, &tmX, fb, j * BKH, 0, b, t);                                   // X^T_t[b][0..128 (HS valid)][64 j..]
+        if (blk == 0) tma_load_4d(b_dst, &tmV, fb, j * BKH, half * HS, b, t);             // dV^T_t[b][half*HS..][64 j..]
+        else tma_load_4d(b_dst, &tmQ, fb, j * BKH, 0, b, t * nks + (blk - 1) * p.nhalf + half);   // Q^T_t[ks][b][0..HS][64 j..]
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {                                     // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc_f16<HS>();
+      for (int it = 0; it < nit; ++it) {
+        const int s = it % NST;
+        mbar_wait_b(smem_u32(&full_bar[s]), ((uint32_t)(it / NST)) & 1u);
+        tcgen05_fence_after();
+        const uint32_t a_addr = smem_base + (uint32_t)s * C::STAGE, b_addr = a_addr + C::A_SLOT;
+#pragma unroll
+        for (int kk = 0; kk < BKH / 16; ++kk) {
+          const uint64_t ad = make_smem_desc(a_addr + kk * 32, 16, 1024, 2);
+          const uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, 1024, 2);
+          tcgen05_mma_f16(tmem_base, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+        }
+        tcgen05_commit(smem_u32(&empty_bar[s]));
+      }
+      tcgen05_commit(smem_u32(&acc_full_bar));
+    }
+  } else {                                               // ===== epilogue warps =====
+    const int quarter = warp & 3;
+    mbar_wait_b(smem_u32(&acc_full_bar), 0);
+    tcgen05_fence_after();
+    const int c0 = quarter * 32;                         // accumulator rows = weight rows c
+    if (c0 < HS) {
+      const float inv_gs = __ldg(p.gs + 1);
+      float* scr = reinterpret_cast<float*>(smem_al) + (warp - 2) * (32 * 36);     // the ring is idle now
+      const int cq = (lane & 7) * 4, r0 = lane >> 3;
+      float* dst = p.dw + (int64_t)blk * HS * p.O + half * HS;
+#pragma unroll 1
+      for (int ch = 0; ch < HS / 32; ++ch) {
+        float v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ch * 32), v);
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < 32; e += 4)
+          *reinterpret_cast<float4*>(&scr[lane * 36 + e]) = make_float4(v[e] * inv_gs, v[e + 1] * inv_gs, v[e + 2] * inv_gs, v[e + 3] * inv_gs);
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int rr = r0 + 4 * e, c = c0 + rr;
+          if (c < HS) {
+            const float4 t4 = *reinterpret_cast<const float4*>(&scr[rr * 36 + cq]);
+            atomicAdd(reinterpret_cast<float4*>(dst + (int64_t)c * p.O + ch * 32 + cq), t4);
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+  }
+}
+
+// x16T_all [T][B][HS][ldT], v16T_all [T][B][O][ldT], q16T_all [T * KS * nhalf][B][HS][ldT] (steps [0, T) of the launch)
+template <int HS>
+int launch_agcn_dw_h(int N, int B, int T, int KS, int nhalf, const __half* x16T_all, const __half* v16T_all, const __half* q16T_all,
+                     const float* gs, float* dw, cudaStream_t st) {
+  using C = CfgW<HS>;
+  const int O = nhalf * HS, ldn = fusedh::ld_half(N), nks = KS * nhalf;
+  CUtensorMap tX, tV, tQ;
+  {
+    uint64_t dims[4] = {(uint64_t)N, (uint64_t)HS, (uint64_t)B, (uint64_t)T};
+    uint64_t str[3] = {(uint64_t)ldn * 2, (uint64_t)HS * ldn * 2, (uint64_t)B * HS * ldn * 2};
+    uint32_t box[4] = {BKH, BM, 1, 1};                   // 128 rows: rows >= HS are out of bounds (zero) when HS = 64
+    MCRN_TRY(fusedh::encode_tensor_map_h(&tX, x16T_all, dims, str, box));
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)N, (uint64_t)O, (uint64_t)B, (uint64_t)T};
+    uint64_t str[3] = {(uint64_t)ldn * 2, (uint64_t)O * ldn * 2, (uint64_t)B * O * ldn * 2};
+    uint32_t box[4] = {BKH, (uint32_t)HS, 1, 1};
+    MCRN_TRY(fusedh::encode_tensor_map_h(&tV, v16T_all, dims, str, box));
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)N, (uint64_t)HS, (uint64_t)B, (uint64_t)T * nks};
+    uint64_t str[3] = {(uint64_t)ldn * 2, (uint64_t)HS * ldn * 2, (uint64_t)B * HS * ldn * 2};
+    uint32_t box[4] = {BKH, (uint32_t)HS, 1, 1};
+    MCRN_TRY(fusedh::encode_tensor_map_h(&tQ, q16T_all, dims, str, box));
+  }
+  WParams p;
+  p.N = N; p.B = B; p.T = T; p.KS = KS; p.nhalf = nhalf; p.O = O; p.dw = dw; p.gs = gs;
+  auto kern = agcn_dw_h_kernel<HS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MCRN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    attr_set = true;
+  }
+  const int tiles = (1 + KS) * nhalf;
+  int G = 148 / tiles;
+  if (G < 1) G = 1;
+  if (G > T * B) G = T * B;
+  MCRN_LAUNCH(kern, dim3(tiles, G), WTHREADS, C::SMEM, st, tX, tV, tQ, p);
+  return MCRN_OK;
+}
+
+}  // namespace fusedwh
+}  // namespace mcrn

@@ -15,6 +15,7 @@
 #include "agcn_ds_fused.cuh"
 #include "agcn_bwd_fused_h.cuh"
 #include "agcn_ds_fused_h.cuh"
+#include "agcn_dw_fused_h.cuh"
 #include "plan.cuh"
 #include "loss.cuh"
 #include "small_kernels.cuh"
@@ -151,7 +152,7 @@ static bool ib_compact_shape(const Geo& g, int Hs, int Cin, bool save) {
 // fp16-operand fused cell (agcn_fused_h.cuh).  last: no next step consumes the new state as a tensor-core operand.
 template <int HS>
 static int cell_forward_fused_h(const Geo& g, const CellW& w, const CellBufs& b, float* h_out, float* h_mma, bool last,
-                                __half* x16_next, cudaStream_t st) {
+                                __half* x16_next, __half* x16T_next, cudaStream_t st) {
   const bool save = b.z != nullptr;
   const bool save_p = save && !bwd_fused_shape(g, HS, w.Cin);     // the fused backward recomputes nothing from P_k: dW_k = X^T Q_k
   const int ldT = fusedh::ld_half(g.N);
@@ -162,13 +163,13 @@ static int cell_forward_fused_h(const Geo& g, const CellW& w, const CellBufs& b,
   fusedh::EpiGateH eg{HS, b.hx, b.z, b.r, save ? b.xpu : nullptr, b.zh16, b.zh16T, ldT};
   MCRN_TRY((fusedh::launch_agcn_fused_h<HS, 2 * HS>(g.N, g.B, g.KS, og, g_fused_parts, eg, st)));
   fusedh::HOperands ou{w.S16, b.zh16T, b.zh16, ib, w.wu16, save_p ? b.xpu : nullptr, ib_ld};
-  fusedh::EpiUpdateH eu{HS, b.hx, b.r, b.hc, h_out, save ? h_mma : nullptr, last ? nullptr : x16_next, last ? nullptr : b.x16T, ldT};
+  fusedh::EpiUpdateH eu{HS, b.hx, b.r, b.hc, h_out, save ? h_mma : nullptr, last ? nullptr : x16_next, last ? nullptr : x16T_next, ldT};
   MCRN_TRY((fusedh::launch_agcn_fused_h<HS, HS>(g.N, g.B, g.KS, ou, g_fused_parts, eu, st)));
   return MCRN_OK;
 }
 
 static int cell_forward(const Geo& g, const float* S, const CellW& w, const CellBufs& b, float* h_out, float* h_mma,
-                        cudaStream_t st, __half* x16_next = nullptr) {
+                        cudaStream_t st, __half* x16_next = nullptr, __half* x16T_next = nullptr) {
   const int Hs = w.Hs, NBX = g.NB + 1;
   const int rnd = tf32_mode();
   const int64_t nH = g.R * Hs;
@@ -178,8 +179,8 @@ static int cell_forward(const Geo& g, const float* S, const CellW& w, const Cell
     MCRN_LAUNCH(k_build_input_block, ew_grid(nH), 256, 0, st, b.xpin, b.xp_k, b.xp_n, g.NB, w.Cin, g.B, g.R, Hs, rnd,
                 save ? b.xpg + (int64_t)g.NB * nH : nullptr, save ? b.xpu + (int64_t)g.NB * nH : nullptr, b.ib16);
     const bool last = (h_mma == nullptr);
-    return Hs == 64 ? cell_forward_fused_h<64>(g, w, b, h_out, h_mma, last, x16_next, st)
-                    : cell_forward_fused_h<128>(g, w, b, h_out, h_mma, last, x16_next, st);
+    return Hs == 64 ? cell_forward_fused_h<64>(g, w, b, h_out, h_mma, last, x16_next, x16T_next, st)
+                    : cell_forward_fused_h<128>(g, w, b, h_out, h_mma, last, x16_next, x16T_next, st);
   }
   // input block (input channels + bias) of both AGCNs of this step
   MCRN_LAUNCH(k_build_input_block, ew_grid(nH), 256, 0, st, b.xpin, b.xp_k, b.xp_n, g.NB, w.Cin, g.B, g.R, Hs, rnd,
@@ -281,8 +282,9 @@ static CellBufs enc_bufs(const Geo& g, const Plan& p, float* ws, int t) {
   b.hc = p.save ? ws + p.enc_hc + p.enc_v_sz * s : nullptr;
   b.hx = ws + p.enc_hx + p.enc_v_sz * s;
   const int64_t hs = p.save ? (int64_t)t * g.R * g.H : 0;        // training: per-step row-major fp16 copies
-  b.x16 = reinterpret_cast<__half*>(ws + p.enc_x16) + hs; b.x16T = reinterpret_cast<__half*>(ws + p.enc_x16T);
-  b.zh16 = reinterpret_cast<__half*>(ws + p.enc_zh16) + hs; b.zh16T = reinterpret_cast<__half*>(ws + p.enc_zh16T);
+  const int64_t hT = p.save ? (int64_t)t * g.B * g.H * fusedh::ld_half(g.N) : 0;
+  b.x16 = reinterpret_cast<__half*>(ws + p.enc_x16) + hs; b.x16T = reinterpret_cast<__half*>(ws + p.enc_x16T) + hT;
+  b.zh16 = reinterpret_cast<__half*>(ws + p.enc_zh16) + hs; b.zh16T = reinterpret_cast<__half*>(ws + p.enc_zh16T) + hT;
   b.ib16 = reinterpret_cast<__half*>(ws + p.enc_ib16);
   b.ib16c = reinterpret_cast<__half*>(ws + p.enc_ib16c) + (int64_t)t * g.R * 64;
   b.ib32c = p.save ? ws + p.enc_ib32c + (int64_t)t * g.R * 16 : nullptr;
@@ -301,8 +303,9 @@ static CellBufs dec_bufs(const Geo& g, const Plan& p, float* ws, int t) {
   b.hc = p.save ? ws + p.dec_hc + p.dec_v_sz * s : nullptr;
   b.hx = ws + p.dec_hx + p.dec_v_sz * s;
   const int64_t hs = p.save ? (int64_t)t * g.R * g.D : 0;
-  b.x16 = reinterpret_cast<__half*>(ws + p.dec_x16) + hs; b.x16T = reinterpret_cast<__half*>(ws + p.dec_x16T);
-  b.zh16 = reinterpret_cast<__half*>(ws + p.dec_zh16) + hs; b.zh16T = reinterpret_cast<__half*>(ws + p.dec_zh16T);
+  const int64_t hT = p.save ? (int64_t)t * g.B * g.D * fusedh::ld_half(g.N) : 0;
+  b.x16 = reinterpret_cast<__half*>(ws + p.dec_x16) + hs; b.x16T = reinterpret_cast<__half*>(ws + p.dec_x16T) + hT;
+  b.zh16 = reinterpret_cast<__half*>(ws + p.dec_zh16) + hs; b.zh16T = reinterpret_cast<__half*>(ws + p.dec_zh16T) + hT;
   b.ib16 = reinterpret_cast<__half*>(ws + p.dec_ib16);
   b.ib16c = reinterpret_cast<__half*>(ws + p.dec_ib16c) + (int64_t)t * g.R * 64;
   b.ib32c = p.save ? ws + p.dec_ib32c + (int64_t)t * g.R * 16 : nullptr;
@@ -366,7 +369,8 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
       const bool last = (t + 1 == g.T_in);
       float* h_out = last ? ws + p.h_enc : enc_bufs(g, p, ws, t + 1).hx;
       float* h_mma = last ? nullptr : enc_bufs(g, p, ws, t + 1).xpg;
-      MCRN_TRY(cell_forward(g, S, w, b, h_out, h_mma, st, last ? nullptr : enc_bufs(g, p, ws, t + 1).x16));
+      MCRN_TRY(cell_forward(g, S, w, b, h_out, h_mma, st, last ? nullptr : enc_bufs(g, p, ws, t + 1).x16,
+                            last ? nullptr : enc_bufs(g, p, ws, t + 1).x16T));
     }
   }
   // ---- memory query (:159-166) + decoder initial state (:179) ----
@@ -423,7 +427,8 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
       const bool last = (t + 1 == g.T_out);
       float* h_out = last ? ws + p.h_dec_last : dec_bufs(g, p, ws, t + 1).hx;
       float* h_mma = last ? nullptr : dec_bufs(g, p, ws, t + 1).xpg;
-      MCRN_TRY(cell_forward(g, S, w, b, h_out, h_mma, st, last ? nullptr : dec_bufs(g, p, ws, t + 1).x16));
+      MCRN_TRY(cell_forward(g, S, w, b, h_out, h_mma, st, last ? nullptr : dec_bufs(g, p, ws, t + 1).x16,
+                            last ? nullptr : dec_bufs(g, p, ws, t + 1).x16T));
       // projection (:186): needed now only if the next step feeds on it; otherwise (training: every state is kept) all such
       // steps are projected by one launch after the loop
       const bool next_needs_it = !last && !((dec_tf_mask >> (t + 1)) & 1u);
@@ -608,7 +613,8 @@ struct BwdStep {
   float *dU, *dG;          // this step's slices of dU_all / dG_all
   float *Qu, *Qg;          // this step's Q blocks [KS][R][Hs] / [2 KS][R][Hs]
   float* dXPin;            // this step's [NB][R][Cin]
-  int t = 0;               // time step (parity selects the dG16 / dG16T operand buffers of the fp16 backward)
+  int t = 0;               // time step (selects the per-step fp16 operand buffers of the fp16 backward)
+  __half *Qu16T = nullptr, *Qg16T = nullptr;   // fp16 weight-gradient kernel: node-transposed Q blocks of this step (else null)
   // fp16 backward: glue of the next cell to process (step t-1) folded into this step's gate-AGCN epilogue (null = no)
   const float *ng_r = nullptr, *ng_hc = nullptr, *ng_hx = nullptr, *ng_dOut = nullptr, *ng_wp = nullptr;
   float *ng_dU = nullptr, *ng_dG = nullptr;
@@ -620,8 +626,17 @@ static inline __half* dg16_buf(const Geo& g, const Plan& p, float* ws, int Hs, i
 static inline __half* du16_buf(const Geo& g, const Plan& p, float* ws, int Hs, int t) {      // row-major, one per step
   return reinterpret_cast<__half*>(ws + (Hs == g.D ? p.dU16 : p.e_dU16)) + (size_t)t * g.R * Hs;
 }
-static inline __half* dg16T_buf(const Geo& g, const Plan& p, float* ws, int Hs, int t) {
-  return reinterpret_cast<__half*>(ws + p.dG16T) + (size_t)(t & 1) * g.B * 2 * Hs * fusedh::ld_half(g.N);
+static inline __half* dg16T_buf(const Geo& g, const Plan& p, float* ws, int Hs, int t) {     // node-transposed, one per step
+  return reinterpret_cast<__half*>(ws + (Hs == g.D ? p.dG16T : p.e_dG16T)) + (size_t)t * g.B * 2 * Hs * fusedh::ld_half(g.N);
+}
+static inline __half* du16T_buf(const Geo& g, const Plan& p, float* ws, int Hs, int t) {
+  return reinterpret_cast<__half*>(ws + (Hs == g.D ? p.dU16T : p.e_dU16T)) + (size_t)t * g.B * Hs * fusedh::ld_half(g.N);
+}
+// fp16 weight-gradient kernel (agcn_dw_fused_h.cuh): 1 = on where the fp16 forward + backward and the compact input block
+// provide its operands
+static int g_dw_fused = getenv("MCRN_DW_FUSED") ? atoi(getenv("MCRN_DW_FUSED")) : 1;
+static bool dw_h_shape(const Geo& g, int Hs, int Cin) {
+  return g_dw_fused && g_bwd_fused == 2 && fused_h_shape(g, Hs) && ib_compact_shape(g, Hs, Cin, true);
 }
 // dXP[1..KS] = dV * Wall[1..KS]^T for the dS accumulation (side stream)
 static int make_dxp_s(const Geo& g, const float* dv, int O, const float* wall, int Hs, float* dxp, cudaStream_t st) {
@@ -660,14 +675,14 @@ static int cell_backward_fused(const Geo& g, const Plan& p, float* ws, const flo
   }
   const bool h16 = (g_bwd_fused == 2);
   __half* dU16 = du16_buf(g, p, ws, HS, bs.t);
-  __half* dU16T = reinterpret_cast<__half*>(ws + p.dU16T);
+  __half* dU16T = du16T_buf(g, p, ws, HS, bs.t);
   __half* dG16 = dg16_buf(g, p, ws, HS, bs.t);
   __half* dG16T = dg16T_buf(g, p, ws, HS, bs.t);
   const __half* S16T = reinterpret_cast<const __half*>(ws + p.s16T);
   if (h16) {
     fusedbh::BHOperands ou{S16T, dU16T, dU16, w.wu16n, ws + p.gs};
     fusedbh::EpiBUH eu{HS, b.z, b.hx, ws + p.dHr, bs.dG, dHp, dG16, dG16T, fusedh::ld_half(g.N)};
-    MCRN_TRY((fusedbh::launch_agcn_bwd_h<HS>(g.N, g.B, g.KS, 1, ou, bs.Qu, ws + p.dIBu16, eu, st)));
+    MCRN_TRY((fusedbh::launch_agcn_bwd_h<HS>(g.N, g.B, g.KS, 1, ou, bs.Qu, ws + p.dIBu16, eu, st, nullptr, nullptr, 0, bs.Qu16T)));
   } else {
   fusedb::EpiBU eu{HS, b.z, b.hx, ws + p.dHr, bs.dG, dHp};
   MCRN_TRY((fusedb::launch_agcn_bwd<HS>(g.N, g.B, g.KS, g.ldS, 1, St, bs.dU, w.wu, bs.Qu, ws + p.dIBu16, eu, st)));
@@ -683,13 +698,13 @@ static int cell_backward_fused(const Geo& g, const Plan& p, float* ws, const flo
     // the gate-AGCN launch also sums both input-block gradients into dXPin (no repack kernel)
     if (bs.ng_r != nullptr) {     // ... and runs the glue of step t-1 in its epilogue
       fusedbh::EpiBGHG eg{HS, dHp, bs.ng_r, bs.ng_hc, bs.ng_hx, bs.ng_dOut, bs.ng_wp, g.B, bs.ng_T, g.N, bs.ng_Cout, bs.t - 1,
-                          bs.ng_dU, bs.ng_dG, ws + p.dHr, du16_buf(g, p, ws, HS, bs.t - 1), dU16T, dg16_buf(g, p, ws, HS, bs.t - 1),
+                          bs.ng_dU, bs.ng_dG, ws + p.dHr, du16_buf(g, p, ws, HS, bs.t - 1), du16T_buf(g, p, ws, HS, bs.t - 1), dg16_buf(g, p, ws, HS, bs.t - 1),
                           dg16T_buf(g, p, ws, HS, bs.t - 1),
                           fusedh::ld_half(g.N)};
-      MCRN_TRY((fusedbh::launch_agcn_bwd_h<HS>(g.N, g.B, g.KS, 2, og, bs.Qg, ws + p.dIBg16, eg, st, ws + p.dIBu16, bs.dXPin, w.Cin)));
+      MCRN_TRY((fusedbh::launch_agcn_bwd_h<HS>(g.N, g.B, g.KS, 2, og, bs.Qg, ws + p.dIBg16, eg, st, ws + p.dIBu16, bs.dXPin, w.Cin, bs.Qg16T)));
     } else {
       fusedbh::EpiBGH eg{HS, dHp, dH};
-      MCRN_TRY((fusedbh::launch_agcn_bwd_h<HS>(g.N, g.B, g.KS, 2, og, bs.Qg, ws + p.dIBg16, eg, st, ws + p.dIBu16, bs.dXPin, w.Cin)));
+      MCRN_TRY((fusedbh::launch_agcn_bwd_h<HS>(g.N, g.B, g.KS, 2, og, bs.Qg, ws + p.dIBg16, eg, st, ws + p.dIBu16, bs.dXPin, w.Cin, bs.Qg16T)));
     }
   } else {
   fusedb::EpiBG eg{HS, dHp, dH};
@@ -775,7 +790,7 @@ static int acc_ds_fused_all(const Geo& g, const Plan& p, float* ws, const CellW&
 //   blocks 0 and NB : dW = sum_t XP_t[blk]^T dV_t            (as acc_dw_all, two blocks)
 //   blocks 1..KS    : dW_k[:, half] = sum_t X_t^T Q_t[k, half]     (X_t = XP_t[0])
 static int acc_dw_fused(const Geo& g, const float* xp0, int64_t xp_step, int ta, int tb, int Hs, const float* dv_all, const float* q_all,
-                        int nhalf, float* dw, const float* ib32c, cudaStream_t st) {
+                        int nhalf, float* dw, const float* ib32c, cudaStream_t st, bool ib_only = false) {
   if (g_dbg_skip & 2) return MCRN_OK;
   const int O = nhalf * Hs;
   for (int t0 = ta; t0 < tb; t0 += 16) {
@@ -789,6 +804,7 @@ static int acc_dw_fused(const Geo& g, const float* xp0, int64_t xp_step, int ta,
       EpiAtomicAdd e{dw + (int64_t)g.NB * Hs * O, O, 0};
       MCRN_TRY(gemm(q, e, st));
     }
+    if (ib_only) continue;                 // blocks 0..KS: fp16 kernel (agcn_dw_fused_h.cuh)
     {
       GemmDesc q;
       q.A = xp0 + (int64_t)t0 * xp_step; q.a_row = 1; q.a_k = Hs; q.a_batch = (int64_t)g.NB * g.R * Hs; q.a_seg = xp_step;
@@ -940,8 +956,22 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
       }
       MCRN_TRY(side2_fork(st));
       const float* ibc = ib_compact_shape(g, g.D, g.Cdec, true) ? ws + p.dec_ib32c : nullptr;
-      MCRN_TRY(acc_dw_fused(g, ws + p.dec_xpu, (int64_t)p.dec_xp_sz, ta, tb, g.D, dU_all, ws + p.d_Qu, 1, ws + p.a_d_wu, ibc, g_side.s2));
-      MCRN_TRY(acc_dw_fused(g, ws + p.dec_xpg, (int64_t)p.dec_xp_sz, ta, tb, g.D, dG_all, ws + p.d_Qg, 2, ws + p.a_d_wg, ibc, g_side.s2));
+      const bool dwh = dw_h_shape(g, g.D, g.Cdec);
+      MCRN_TRY(acc_dw_fused(g, ws + p.dec_xpu, (int64_t)p.dec_xp_sz, ta, tb, g.D, dU_all, ws + p.d_Qu, 1, ws + p.a_d_wu, ibc, g_side.s2, dwh));
+      MCRN_TRY(acc_dw_fused(g, ws + p.dec_xpg, (int64_t)p.dec_xp_sz, ta, tb, g.D, dG_all, ws + p.d_Qg, 2, ws + p.a_d_wg, ibc, g_side.s2, dwh));
+      if (dwh) {
+        const int64_t sT = (int64_t)g.B * g.D * fusedh::ld_half(g.N);      // one [B][D][ldT] block
+        const __half* xT = reinterpret_cast<const __half*>(ws + p.dec_x16T) + ta * sT;
+        const __half* zT = reinterpret_cast<const __half*>(ws + p.dec_zh16T) + ta * sT;
+        const float* gs = ws + p.gs;
+        if (g.D == 64) {
+          MCRN_TRY((fusedwh::launch_agcn_dw_h<64>(g.N, g.B, tb - ta, g.KS, 1, zT, du16T_buf(g, p, ws, g.D, ta), reinterpret_cast<const __half*>(ws + p.d_Qu16T) + (int64_t)ta * g.KS * sT, gs, ws + p.a_d_wu, g_side.s2)));
+          MCRN_TRY((fusedwh::launch_agcn_dw_h<64>(g.N, g.B, tb - ta, g.KS, 2, xT, dg16T_buf(g, p, ws, g.D, ta), reinterpret_cast<const __half*>(ws + p.d_Qg16T) + (int64_t)ta * 2 * g.KS * sT, gs, ws + p.a_d_wg, g_side.s2)));
+        } else {
+          MCRN_TRY((fusedwh::launch_agcn_dw_h<128>(g.N, g.B, tb - ta, g.KS, 1, zT, du16T_buf(g, p, ws, g.D, ta), reinterpret_cast<const __half*>(ws + p.d_Qu16T) + (int64_t)ta * g.KS * sT, gs, ws + p.a_d_wu, g_side.s2)));
+          MCRN_TRY((fusedwh::launch_agcn_dw_h<128>(g.N, g.B, tb - ta, g.KS, 2, xT, dg16T_buf(g, p, ws, g.D, ta), reinterpret_cast<const __half*>(ws + p.d_Qg16T) + (int64_t)ta * 2 * g.KS * sT, gs, ws + p.a_d_wg, g_side.s2)));
+        }
+      }
       return MCRN_OK;
     };
     for (int t = g.T_out - 1; t >= 0; --t) {
@@ -959,7 +989,7 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
           const size_t gsm = ((size_t)(32 + g.D) * g.Cout + 2 * 32 * (g.D + 1)) * sizeof(float);
           MCRN_LAUNCH(fusedbh::k_bwd_glue_h, dim3(ceil_div(g.N, 32), g.B), 256, gsm, st, d_output, use_dgo ? dXin : nullptr, g.Cdec, h_t,
                       prm->proj_w, dH, (t == g.T_out - 1) ? 1 : 0, b.r, b.hc, b.hx, dU_t, dG_all + (int64_t)t * g.R * 2 * g.D,
-                      ws + p.dHr, du16_buf(g, p, ws, g.D, t), reinterpret_cast<__half*>(ws + p.dU16T),
+                      ws + p.dHr, du16_buf(g, p, ws, g.D, t), du16T_buf(g, p, ws, g.D, t),
                       dg16_buf(g, p, ws, g.D, t), dg16T_buf(g, p, ws, g.D, t), fusedh::ld_half(g.N),
                       ws + p.gs, grads->proj_w, grads->proj_b, g.B, g.T_out, g.N, g.D, g.Cout, t);
         } else if (g_bwd_fused != 2)
@@ -970,6 +1000,11 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
         BwdStep bs{dU_t, dG_all + (int64_t)t * g.R * 2 * g.D, ws + p.d_Qu + (int64_t)t * g.KS * g.R * g.D,
                    ws + p.d_Qg + (int64_t)t * 2 * g.KS * g.R * g.D, ws + p.dXPin_all + p.dXPin_sz * t};
         bs.t = t;
+        if (dw_h_shape(g, g.D, g.Cdec)) {
+          const int64_t sT = (int64_t)g.B * g.D * fusedh::ld_half(g.N);
+          bs.Qu16T = reinterpret_cast<__half*>(ws + p.d_Qu16T) + (int64_t)t * g.KS * sT;
+          bs.Qg16T = reinterpret_cast<__half*>(ws + p.d_Qg16T) + (int64_t)t * 2 * g.KS * sT;
+        }
         if (g_bwd_fused == 2 && g_glue_fuse && t > 0 && tf && tf[t - 1]) {     // step t-1 is teacher-forced: fold its glue in
           CellBufs bp = dec_bufs(g, p, ws, t - 1);
           bs.ng_r = bp.r; bs.ng_hc = bp.hc; bs.ng_hx = bp.hx; bs.ng_dOut = d_output; bs.ng_wp = prm->proj_w;
@@ -1056,8 +1091,22 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
       }
       MCRN_TRY(side2_fork(st));
       const float* ibc = ib_compact_shape(g, g.H, g.Cin, true) ? ws + p.enc_ib32c : nullptr;
-      MCRN_TRY(acc_dw_fused(g, ws + p.enc_xpu, (int64_t)p.enc_xp_sz, ta, tb, g.H, dU_all, ws + p.e_Qu, 1, ws + p.a_e_wu, ibc, g_side.s2));
-      MCRN_TRY(acc_dw_fused(g, ws + p.enc_xpg, (int64_t)p.enc_xp_sz, ta, tb, g.H, dG_all, ws + p.e_Qg, 2, ws + p.a_e_wg, ibc, g_side.s2));
+      const bool dwh = dw_h_shape(g, g.H, g.Cin);
+      MCRN_TRY(acc_dw_fused(g, ws + p.enc_xpu, (int64_t)p.enc_xp_sz, ta, tb, g.H, dU_all, ws + p.e_Qu, 1, ws + p.a_e_wu, ibc, g_side.s2, dwh));
+      MCRN_TRY(acc_dw_fused(g, ws + p.enc_xpg, (int64_t)p.enc_xp_sz, ta, tb, g.H, dG_all, ws + p.e_Qg, 2, ws + p.a_e_wg, ibc, g_side.s2, dwh));
+      if (dwh) {
+        const int64_t sT = (int64_t)g.B * g.H * fusedh::ld_half(g.N);
+        const __half* xT = reinterpret_cast<const __half*>(ws + p.enc_x16T) + ta * sT;
+        const __half* zT = reinterpret_cast<const __half*>(ws + p.enc_zh16T) + ta * sT;
+        const float* gs = ws + p.gs;
+        if (g.H == 64) {
+          MCRN_TRY((fusedwh::launch_agcn_dw_h<64>(g.N, g.B, tb - ta, g.KS, 1, zT, du16T_buf(g, p, ws, g.H, ta), reinterpret_cast<const __half*>(ws + p.e_Qu16T) + (int64_t)ta * g.KS * sT, gs, ws + p.a_e_wu, g_side.s2)));
+          MCRN_TRY((fusedwh::launch_agcn_dw_h<64>(g.N, g.B, tb - ta, g.KS, 2, xT, dg16T_buf(g, p, ws, g.H, ta), reinterpret_cast<const __half*>(ws + p.e_Qg16T) + (int64_t)ta * 2 * g.KS * sT, gs, ws + p.a_e_wg, g_side.s2)));
+        } else {
+          MCRN_TRY((fusedwh::launch_agcn_dw_h<128>(g.N, g.B, tb - ta, g.KS, 1, zT, du16T_buf(g, p, ws, g.H, ta), reinterpret_cast<const __half*>(ws + p.e_Qu16T) + (int64_t)ta * g.KS * sT, gs, ws + p.a_e_wu, g_side.s2)));
+          MCRN_TRY((fusedwh::launch_agcn_dw_h<128>(g.N, g.B, tb - ta, g.KS, 2, xT, dg16T_buf(g, p, ws, g.H, ta), reinterpret_cast<const __half*>(ws + p.e_Qg16T) + (int64_t)ta * 2 * g.KS * sT, gs, ws + p.a_e_wg, g_side.s2)));
+        }
+      }
       return MCRN_OK;
     };
     for (int t = g.T_in - 1; t >= 0; --t) {
@@ -1070,7 +1119,7 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
           const size_t gsm = (size_t)2 * 32 * (g.H + 1) * sizeof(float);
           MCRN_LAUNCH(fusedbh::k_bwd_glue_h, dim3(ceil_div(g.N, 32), g.B), 256, gsm, st, (const float*)nullptr, (const float*)nullptr, 0,
                       (const float*)nullptr, (const float*)nullptr, dHe, 0, b.r, b.hc, b.hx, dU_t, dG_all + (int64_t)t * g.R * 2 * g.H,
-                      ws + p.dHr, du16_buf(g, p, ws, g.H, t), reinterpret_cast<__half*>(ws + p.dU16T),
+                      ws + p.dHr, du16_buf(g, p, ws, g.H, t), du16T_buf(g, p, ws, g.H, t),
                       dg16_buf(g, p, ws, g.H, t), dg16T_buf(g, p, ws, g.H, t), fusedh::ld_half(g.N),
                       ws + p.gs, (float*)nullptr, (float*)nullptr, g.B, g.T_in, g.N, g.H, 0, t);
         } else if (g_bwd_fused != 2)
@@ -1080,6 +1129,11 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
         BwdStep bs{dU_t, dG_all + (int64_t)t * g.R * 2 * g.H, ws + p.e_Qu + (int64_t)t * g.KS * g.R * g.H,
                    ws + p.e_Qg + (int64_t)t * 2 * g.KS * g.R * g.H, ws + p.dXPin_all + p.dXPin_sz * t};
         bs.t = t;
+        if (dw_h_shape(g, g.H, g.Cin)) {
+          const int64_t sT = (int64_t)g.B * g.H * fusedh::ld_half(g.N);
+          bs.Qu16T = reinterpret_cast<__half*>(ws + p.e_Qu16T) + (int64_t)t * g.KS * sT;
+          bs.Qg16T = reinterpret_cast<__half*>(ws + p.e_Qg16T) + (int64_t)t * 2 * g.KS * sT;
+        }
         if (g_bwd_fused == 2 && g_glue_fuse && t > 0) {       // encoder: the glue of step t-1 always folds into this step's epilogue
           CellBufs bp = enc_bufs(g, p, ws, t - 1);
           bs.ng_r = bp.r; bs.ng_hc = bp.hc; bs.ng_hx = bp.hx;
@@ -1167,6 +1221,7 @@ bool set_option(const char* name, int value) {
   else if (n == "side_chunks") g_side_chunks = value > 0 ? value : 1;
   else if (n == "ds_fused") g_ds_fused = value;
   else if (n == "ib_compact") g_ib_compact = value;
+  else if (n == "dw_fused") g_dw_fused = value;
   else return false;
   return true;
 }

@@ -17,6 +17,7 @@ from oracle import megacrn_oracle as O
 
 pytestmark = pytest.mark.gpu
 
+DW_FUSED_DEFAULT = 1    # library default of the "dw_fused" option (fp16 weight-gradient kernel)
 FWD_TOL = 1e-3          # north_star: outputs within 1e-3 rel of the reference fp32 forward
 GRAD_TOL = 4e-3         # BPTT through ~300 TF32 contractions; the exact-fp32 SIMT engine is held to 5e-4 below
 
@@ -344,7 +345,7 @@ def test_fused_backward_kernel_matches_per_stage_backward(N, H, dm, B, T, defaul
                 assert rel_l2(res[bf][1][k], res[0][1][k]) < 1.5e-3, (bf, flags, k, rel_l2(res[bf][1][k], res[0][1][k]))
 
 
-@pytest.mark.parametrize("opt,val", [("glue_fuse", 1), ("side_chunks", 3), ("ds_fused", 0), ("ds_fused", 1), ("ib_compact", 0)])
+@pytest.mark.parametrize("opt,val", [("glue_fuse", 1), ("side_chunks", 3), ("ds_fused", 0), ("ds_fused", 1), ("ib_compact", 0), ("dw_fused", 1), ("dw_fused", 0)])
 def test_backward_variants_agree(opt, val, default_engine):
     """Non-default variants of the fused backward (glue inside the gate-AGCN epilogue, chunked dS / dW launches, per-step dS
     GEMMs / TF32 fused dS kernel, full-width input block) give the same gradients as the default."""
@@ -367,8 +368,8 @@ def test_backward_variants_agree(opt, val, default_engine):
             torch.autograd.backward([outs[0], outs[2]], ups)
             res[v] = {k: t.grad.cpu() for k, t in m.named_parameters()}
     finally:
-        lib.mcrn_set_option(opt.encode(), {"glue_fuse": 0, "side_chunks": 1, "ds_fused": 2, "ib_compact": 1}[opt])
-    tol = 1e-3 if opt in ("ds_fused", "ib_compact") else 2e-5      # different rounding points vs same arithmetic, atomics order
+        lib.mcrn_set_option(opt.encode(), {"glue_fuse": 0, "side_chunks": 1, "ds_fused": 2, "ib_compact": 1, "dw_fused": DW_FUSED_DEFAULT}[opt])
+    tol = 1e-3 if opt in ("ds_fused", "ib_compact", "dw_fused") else 2e-5      # different rounding points vs same arithmetic, atomics order
     for k in res[None]:
         assert rel_l2(res[val][k], res[None][k]) < tol, (opt, k, rel_l2(res[val][k], res[None][k]))
     assert lib.mcrn_set_option(b"no_such_option", 1) != 0
