@@ -312,12 +312,8 @@ agcn_bwd_h_kernel(const __grid_constant__ CUtensorMap tmST, const __grid_constan
 #pragma unroll
             for (int i = 0; i < 16; ++i) u[ci][i] = pack_h2(v[2 * i], v[2 * i + 1]);
             if (p.q16T != nullptr) {                     // node-transposed fp16 copy straight from the accumulator layout
-              const int node = node0 + lane;             // (lane = node row): 64 contiguous bytes per warp store
-              if (node < p.N) {
-                __half* dst = p.q16T + (((int64_t)ks * p.B + b) * HS + c * 32) * p.ldT + node;
-#pragma unroll 8
-                for (int j = 0; j < 32; ++j) dst[(int64_t)j * p.ldT] = __float2half_rn(v[j]);
-              }
+              // (lane = node row): pairs of adjacent nodes, 16 four-byte stores per lane
+              fusedh::store_T_pairs_regs(p.q16T + (((int64_t)ks * p.B + b) * HS + c * 32) * p.ldT + node0, p.ldT, v, lane, node0, p.N);
             } else if (node0 < p.N) {
               __syncwarp();
 #pragma unroll
@@ -388,16 +384,11 @@ agcn_bwd_h_kernel(const __grid_constant__ CUtensorMap tmST, const __grid_constan
         }
         if constexpr (Epi::NT >= 1) {                     // node-transposed scaled fp16 copies: X^T[b][c*32 + j][node0 + lane]
           __syncwarp();
-          const int node = node0 + lane;
 #pragma unroll
           for (int ti = 0; ti < Epi::NT; ++ti) {
             __half* base = epi.tdst(ti, b, c * 32);
             const float* src = ti == 0 ? scr : scr2;
-            if (base != nullptr && node < p.N) {
-              __half* dst = base + node;
-#pragma unroll 8
-              for (int j = 0; j < 32; ++j) dst[(int64_t)j * epi.ldT] = __float2half_rn(src[lane * 36 + j]);
-            }
+            if (base != nullptr) fusedh::store_T_pairs_smem(base + node0, epi.ldT, src, lane, node0, p.N);
           }
         }
       }
@@ -554,12 +545,13 @@ __global__ void __launch_bounds__(256) k_bwd_glue_h(const float* __restrict__ dO
   }
   __syncthreads();
   // node-transposed copies: for each column c, the 32 nodes of this block are contiguous
-  for (int e = threadIdx.x; e < 32 * D; e += blockDim.x) {
-    const int i = e & 31, c = e >> 5;
+  for (int e = threadIdx.x; e < 16 * D; e += blockDim.x) {          // pairs of adjacent nodes: one 4-byte store each
+    const int i = (e & 15) * 2, c = e >> 4;
     const int n = n0 + i;
     if (n >= N) continue;
-    u16T[((int64_t)b * D + c) * ldT + n] = __float2half_rn(sh_u[i * (D + 1) + c]);
-    g16T[((int64_t)b * 2 * D + D + c) * ldT + n] = __float2half_rn(sh_g[i * (D + 1) + c]);
+    const bool two = n + 1 < N;
+    *reinterpret_cast<uint32_t*>(u16T + ((int64_t)b * D + c) * ldT + n) = pack_h2(sh_u[i * (D + 1) + c], two ? sh_u[(i + 1) * (D + 1) + c] : 0.f);
+    *reinterpret_cast<uint32_t*>(g16T + ((int64_t)b * 2 * D + D + c) * ldT + n) = pack_h2(sh_g[i * (D + 1) + c], two ? sh_g[(i + 1) * (D + 1) + c] : 0.f);
   }
   if (proj) {
     for (int i = threadIdx.x; i < Cout * D; i += blockDim.x) atomicAdd(dwp + i, sh_w[i]);

@@ -105,6 +105,32 @@ __device__ __forceinline__ void for_each_item_h(int KS, int kb1, int nparts, int
   }
 }
 
+// Node-transposed fp16 store of a 32 (nodes = lanes) x 32 (columns) tile: column j goes to base[j * ld + lane] (base = address of
+// (column 0, node node0); node0 and ld even).  Each lane stores one 4-byte pair of adjacent nodes (even lanes the even columns, odd
+// lanes the odd ones): 16 four-byte stores per lane instead of 32 two-byte ones.  The partner of the last valid node of an odd N
+// lands in the row padding (columns N..ld-1 are never read: the tensor maps stop at N).
+__device__ __forceinline__ void store_T_pairs_smem(__half* base, int ld, const float* tile /* [32][36] */, int lane, int node0, int N) {
+  const int odd = lane & 1, re = lane & ~1;
+  if (node0 + re < N) {
+#pragma unroll 8
+    for (int j = 0; j < 32; j += 2) {
+      const int col = j + odd;
+      *reinterpret_cast<uint32_t*>(base + (int64_t)col * ld + re) = pack_h2(tile[re * 36 + col], tile[(re + 1) * 36 + col]);
+    }
+  }
+}
+// Same from registers (v = the 32 columns of this lane's node): lane pairs exchange with one shuffle per column pair.
+__device__ __forceinline__ void store_T_pairs_regs(__half* base, int ld, const float (&v)[32], int lane, int node0, int N) {
+  const int odd = lane & 1, re = lane & ~1;
+  const bool ok = node0 + re < N;
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    const float mine = odd ? v[j + 1] : v[j], give = odd ? v[j] : v[j + 1];
+    const float got = __shfl_xor_sync(0xffffffffu, give, 1);
+    if (ok) *reinterpret_cast<uint32_t*>(base + (int64_t)(j + odd) * ld + re) = odd ? pack_h2(got, mine) : pack_h2(mine, got);
+  }
+}
+
 template <int HS, int O>
 struct CfgH {
   static_assert(HS == 64 || HS == 128, "hidden width of the fused AGCN kernel: 64 or 128");
@@ -400,12 +426,7 @@ agcn_fused_h_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_consta
         // node-transposed fp16 copy of the new operand: X^T[b][c*32 + j][node0 + lane]
         if (epi.has_state(c * 32) && epi.x16T != nullptr) {
           __syncwarp();
-          const int node = node0 + lane;
-          if (node < p.N) {
-            __half* dst = epi.x16T + ((int64_t)b * HS + c * 32) * epi.ldT + node;
-#pragma unroll 8
-            for (int j = 0; j < 32; ++j) dst[(int64_t)j * epi.ldT] = __float2half_rn(scr[lane * 36 + j]);
-          }
+          store_T_pairs_smem(epi.x16T + ((int64_t)b * HS + c * 32) * epi.ldT + node0, epi.ldT, scr, lane, node0, p.N);
         }
       }
     }
