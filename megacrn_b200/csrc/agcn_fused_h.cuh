@@ -8,8 +8,9 @@
 //               fp16 operand copies (row-major and node-transposed) the next fused launch reads
 // -- but every tensor-core operand is stored in HALF precision.  fp16 has the same 11-bit significand as TF32, so the
 // numerics match the TF32 path (all forward operands are O(1): softmax supports, states in (-1,1), inputs, weights), while
-// each operand byte carries twice the work: the kernel is bound by the L2 -> shared-memory fill rate (~32 B/clk/SM
-// measured), and kind::f16 also runs at twice the kind::tf32 MMA rate.  The weights keep the hi + lo split
+// each operand byte carries twice the work: the kernel is bound by operand bytes through shared memory (every byte is
+// written by TMA and read by the MMA at 128 B/clk/SM; profiles/r1_summary.md), and kind::f16 also runs at twice the
+// kind::tf32 MMA rate.  The weights keep the hi + lo split
 // (hi = fp16(W), lo = fp16(W - hi)).  All operands are K-major with the 128-byte swizzle:
 //     S16  [KS][N][ld16]        supports                       A of MMA1   box [64 k][128 m]
 //     X16T [B][HS][ldT]         state, node index contiguous   B of MMA1   box [64 k][HS n]
