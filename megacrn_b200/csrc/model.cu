@@ -527,12 +527,21 @@ struct Side {
 static Side g_side;
 static int side_init() {
   if (g_side.s) return MCRN_OK;
+  // MCRN_SIDE_PRIO=1: side streams at the lowest priority, so that CTAs of the recurrent chain are scheduled before those
+  // of the dS / dW kernels whenever both are ready
+  int prio_lo = 0, prio_hi = 0;
+  const bool low = getenv("MCRN_SIDE_PRIO") && atoi(getenv("MCRN_SIDE_PRIO")) != 0;
+  if (low) MCRN_CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  if (low) MCRN_CUDA_OK(cudaStreamCreateWithPriority(&g_side.s, cudaStreamNonBlocking, prio_lo));
+  else
   MCRN_CUDA_OK(cudaStreamCreateWithFlags(&g_side.s, cudaStreamNonBlocking));
   for (int i = 0; i < 3; ++i) {
     MCRN_CUDA_OK(cudaEventCreateWithFlags(&g_side.ready[i], cudaEventDisableTiming));
     MCRN_CUDA_OK(cudaEventCreateWithFlags(&g_side.freed[i], cudaEventDisableTiming));
   }
   MCRN_CUDA_OK(cudaEventCreateWithFlags(&g_side.join, cudaEventDisableTiming));
+  if (low) MCRN_CUDA_OK(cudaStreamCreateWithPriority(&g_side.s2, cudaStreamNonBlocking, prio_lo));
+  else
   MCRN_CUDA_OK(cudaStreamCreateWithFlags(&g_side.s2, cudaStreamNonBlocking));
   MCRN_CUDA_OK(cudaEventCreateWithFlags(&g_side.fork2, cudaEventDisableTiming));
   MCRN_CUDA_OK(cudaEventCreateWithFlags(&g_side.join2, cudaEventDisableTiming));
