@@ -191,6 +191,11 @@ uint64_t mcrn_launch_count(void);
 /* 0 = default (tcgen05 TF32 where the shape allows, SIMT otherwise), 1 = force SIMT fp32. */
 int mcrn_set_engine(int engine);
 int mcrn_get_engine(void);
+/* Round-2 probe, not on the product path (csrc/probe_mn16.cuh, tools/probe_mn16.py): one 128 x 128 x 64 tcgen05 kind::f16 tile with
+ * an MN-major B operand whose shared-memory descriptor fields are given at run time.  A: device fp16 [128][64], B: device fp16
+ * [64][128] (N contiguous), C: device fp32 [128][128]. */
+int mcrn_debug_probe_mn16(const void* A, const void* B, float* C, unsigned lbo_bytes, unsigned sbo_bytes, unsigned layout,
+                          unsigned kstep_bytes, unsigned b_major, void* stream);
 /* Internal tuning knobs by name (tests / experiments): "glue_fuse" (step glue inside the gate-AGCN backward epilogue, default 0),
  * "side_chunks" (dS / dW launches per cell type, default 1), "ds_fused" (fused support-gradient kernel: 2 = fp16 operands (default), 1 = TF32, 0 = per-step GEMMs),
  * "ib_compact" (compact input block, default 1), "dw_fused" (fp16 weight-gradient kernel agcn_dw_fused_h.cuh, default 1). */

@@ -68,6 +68,8 @@ def load() -> C.CDLL:
     lib.mcrn_set_engine.argtypes = [C.c_int]
     lib.mcrn_get_engine.restype = C.c_int
     lib.mcrn_mode_epoch.restype = C.c_uint64
+    lib.mcrn_debug_probe_mn16.restype = C.c_int
+    lib.mcrn_debug_probe_mn16.argtypes = [vp, vp, vp, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, vp]
     lib.mcrn_set_option.restype = C.c_int
     lib.mcrn_set_option.argtypes = [C.c_char_p, C.c_int]
     lib.mcrn_debug_fused_timeline.restype = C.c_int

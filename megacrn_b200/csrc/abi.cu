@@ -27,6 +27,8 @@ int adam_step_impl(const Geo& g, const mcrn_params* prm, const mcrn_params* grad
                    float* state, float beta1, float beta2, float eps, float max_norm, cudaStream_t st);
 
 bool set_option(const char* name, int value);
+int probe_mn16_entry(const void* A, const void* B, float* C, unsigned lbo, unsigned sbo, unsigned layout, unsigned kstep,
+                     unsigned b_major, cudaStream_t st);
 static std::atomic<uint64_t> g_mode_epoch{0};
 static std::mutex g_mu;
 static std::unordered_map<const void*, uint64_t> g_saved;   // workspace -> dims hash of the last saving forward
@@ -82,6 +84,12 @@ int mcrn_set_engine(int engine) {
 int mcrn_get_engine(void) { return g_engine; }
 int mcrn_set_debug_mask(int mask) { g_simt_mask = mask; g_mode_epoch.fetch_add(1); return MCRN_OK; }
 uint64_t mcrn_mode_epoch(void) { return g_mode_epoch.load(); }
+int mcrn_debug_probe_mn16(const void* A, const void* B, float* C, unsigned lbo, unsigned sbo, unsigned layout, unsigned kstep,
+                          unsigned b_major, void* stream) {
+  if (!A || !B || !C) { set_error("mcrn_debug_probe_mn16: null pointer"); return MCRN_ERR_BAD_POINTER; }
+  MCRN_TRY(check_device());
+  return probe_mn16_entry(A, B, C, lbo, sbo, layout, kstep, b_major, static_cast<cudaStream_t>(stream));
+}
 int mcrn_set_option(const char* name, int value) {
   if (!set_option(name, value)) { set_error("mcrn_set_option: unknown option '%s'", name ? name : "(null)"); return MCRN_ERR_BAD_DIMS; }
   g_mode_epoch.fetch_add(1);

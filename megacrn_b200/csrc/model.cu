@@ -16,6 +16,7 @@
 #include "agcn_bwd_fused_h.cuh"
 #include "agcn_ds_fused_h.cuh"
 #include "agcn_dw_fused_h.cuh"
+#include "probe_mn16.cuh"
 #include "plan.cuh"
 #include "loss.cuh"
 #include "small_kernels.cuh"
@@ -1221,6 +1222,11 @@ int adam_step_impl(const Geo& g, const mcrn_params* prm, const mcrn_params* grad
   MCRN_LAUNCH(k_grad_sqnorm, grid, 256, 0, st, t, state);
   MCRN_LAUNCH(k_clip_adam, grid, 256, 0, st, t, state, beta1, beta2, eps, max_norm);
   return MCRN_OK;
+}
+
+int probe_mn16_entry(const void* A, const void* B, float* C, unsigned lbo, unsigned sbo, unsigned layout, unsigned kstep,
+                     unsigned b_major, cudaStream_t st) {
+  return probe::run_probe_mn16(static_cast<const __half*>(A), static_cast<const __half*>(B), C, lbo, sbo, layout, kstep, b_major, st);
 }
 
 // internal tuning knobs by name (tests / experiments); returns false for an unknown name
