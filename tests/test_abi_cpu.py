@@ -62,3 +62,32 @@ def test_module_keeps_reference_interface():
     assert abs(m.compute_sampling_threshold(0) - 2000 / 2001) < 1e-12
     with pytest.raises(RuntimeError, match="no CPU path"):
         m(torch.zeros(1, 2, 20, 1), torch.zeros(1, 3, 20, 1))
+
+
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """The boundary is a C ABI: include/megacrn_b200.h compiles as C99 (no C++ / torch types) and a C program links against
+    libmegacrn_b200.so and calls it (argument validation only -- no GPU here)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "host.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "megacrn_b200.h"
+int main(void) {
+  mcrn_dims d = {64, 207, 12, 12, 1, 1, 1, 64, 1, 3, 20, 64};
+  size_t fwd = mcrn_workspace_bytes(&d, 0), trn = mcrn_workspace_bytes(&d, MCRN_FWD_SAVE_FOR_BACKWARD);
+  d.num_layers = 2;
+  size_t bad = mcrn_workspace_bytes(&d, 0);
+  printf("%d %zu %zu %zu %d\n", mcrn_abi_version(), fwd, trn, bad, mcrn_support_ld(207));
+  return (mcrn_abi_version() == 1 && fwd > 0 && trn > fwd && bad == 0) ? 0 : 1;
+}
+''')
+    libdir = os.path.join(ROOT, "megacrn_b200")
+    exe = tmp_path / "host"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-l:libmegacrn_b200.so", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.split()[-1] == "208"
