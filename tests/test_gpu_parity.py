@@ -243,27 +243,6 @@ def test_large_graph_shapes_vs_oracle(cfg):
         assert rel_l2(prm.grad.cpu(), ref_grads[pname]) < 2.5 * GRAD_TOL, (pname, rel_l2(prm.grad.cpu(), ref_grads[pname]))
 
 
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: first execution of cheb_k != 3 at a fused "
-                                        "shape happens on the round-end box (DESIGN.md section 11); XPASS = the gap is closed")
-@pytest.mark.parametrize("cheb_k", [2, 4])
-def test_fused_kernels_other_chebyshev_orders_vs_oracle(cheb_k, default_engine):
-    """cheb_k = 2 / 4 (KS = 2 / 6 supports) through the fused forward / backward kernels against the CPU oracle."""
-    d = O.Dims(num_nodes=60, horizon=2, rnn_units=64, cheb_k=cheb_k)
-    p = O.init_params(d, seed=3)
-    x, y_cov, labels = O.synthetic_batch(d, 2, 2, seed=6)
-    flags = [True, False]
-    ref_loss, ref_outs, ref_grads = O.loss_and_grads(d, p, x, y_cov, labels, flags)
-    m = _model(d, p).train()
-    dv = _dev()
-    outs = m(x.to(dv), y_cov.to(dv), labels.to(dv), teacher_forcing=flags)
-    d_out, d_q = reference_upstream(ref_outs[0], ref_outs[2], ref_outs[3], ref_outs[4], labels)
-    torch.autograd.backward([outs[0], outs[2]], [d_out.to(dv), d_q.to(dv)])
-    for k, a, b in zip(OUT_NAMES[:3], outs[:3], ref_outs[:3]):
-        assert rel_l2(a.detach().cpu(), b) < FWD_TOL, (k, rel_l2(a.detach().cpu(), b))
-    for pname, prm in m.named_parameters():
-        assert rel_l2(prm.grad.cpu(), ref_grads[pname]) < 2.5 * GRAD_TOL, (pname, rel_l2(prm.grad.cpu(), ref_grads[pname]))
-
-
 def test_all_output_gradients_including_pos_neg(engine):
     """Upstream gradients on all five outputs (pos/neg are not detached by the model itself)."""
     d = O.Dims(num_nodes=40, horizon=3, rnn_units=16, mem_num=6, mem_dim=12)
@@ -530,3 +509,25 @@ def test_unsupported_configs_fail_loudly():
     m = _model(d, p)
     with pytest.raises(RuntimeError):
         m(x, y_cov)                           # CPU tensors: no fallback
+
+
+# ---- kept LAST in the file: never executed on a GPU before the round-end run; a device-side fault here cannot affect other tests ----
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: first execution of cheb_k != 3 at a fused "
+                                        "shape happens on the round-end box (DESIGN.md section 11); XPASS = the gap is closed")
+@pytest.mark.parametrize("cheb_k", [2, 4])
+def test_fused_kernels_other_chebyshev_orders_vs_oracle(cheb_k, default_engine):
+    """cheb_k = 2 / 4 (KS = 2 / 6 supports) through the fused forward / backward kernels against the CPU oracle."""
+    d = O.Dims(num_nodes=60, horizon=2, rnn_units=64, cheb_k=cheb_k)
+    p = O.init_params(d, seed=3)
+    x, y_cov, labels = O.synthetic_batch(d, 2, 2, seed=6)
+    flags = [True, False]
+    ref_loss, ref_outs, ref_grads = O.loss_and_grads(d, p, x, y_cov, labels, flags)
+    m = _model(d, p).train()
+    dv = _dev()
+    outs = m(x.to(dv), y_cov.to(dv), labels.to(dv), teacher_forcing=flags)
+    d_out, d_q = reference_upstream(ref_outs[0], ref_outs[2], ref_outs[3], ref_outs[4], labels)
+    torch.autograd.backward([outs[0], outs[2]], [d_out.to(dv), d_q.to(dv)])
+    for k, a, b in zip(OUT_NAMES[:3], outs[:3], ref_outs[:3]):
+        assert rel_l2(a.detach().cpu(), b) < FWD_TOL, (k, rel_l2(a.detach().cpu(), b))
+    for pname, prm in m.named_parameters():
+        assert rel_l2(prm.grad.cpu(), ref_grads[pname]) < 2.5 * GRAD_TOL, (pname, rel_l2(prm.grad.cpu(), ref_grads[pname]))
