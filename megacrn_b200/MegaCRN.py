@@ -103,7 +103,9 @@ class _MegaCRNFunction(torch.autograd.Function):
         ws = module._workspace(dims, flags, x.device)
         # eval fast path: supports, folded weights and their operand copies depend on the parameters only; they
         # are reused while no parameter has been modified in place or re-allocated and the library mode is unchanged
-        key = (tuple(getattr(dims, f) for f, _ in dims._fields_), flags, lib.mcrn_mode_epoch(),
+        # (`_param_epoch` counts the updates that go through raw pointers -- FusedClipAdam / a replayed CUDA graph -- and
+        # therefore bump no tensor version)
+        key = (tuple(getattr(dims, f) for f, _ in dims._fields_), flags, lib.mcrn_mode_epoch(), module._param_epoch,
                tuple((p.data_ptr(), p._version) for p in params))
         if not need_grad and not module.training and ws.prologue_key == key:
             flags |= _abi.MCRN_FWD_REUSE_PROLOGUE
@@ -125,6 +127,8 @@ class _MegaCRNFunction(torch.autograd.Function):
             ctx.ws, ctx.dims, ctx.tf = ws, dims, tf
             ctx.inputs = (x, y_cov, labels)
             ctx.params = params
+            ctx.param_versions = tuple(p._version for p in params)
+            ctx.done = False
         ctx.set_materialize_grads(False)
         return output, h_att, query, pos, neg
 
@@ -132,6 +136,12 @@ class _MegaCRNFunction(torch.autograd.Function):
     def backward(ctx, d_out, d_hatt, d_query, d_pos, d_neg):
         lib = _abi.load()
         params = ctx.params
+        if ctx.done:
+            raise RuntimeError("megacrn_b200: backward through this forward a second time -- the saved activations live in "
+                               "a workspace that is released (and its accumulators consumed) by the first backward; "
+                               "run the forward again (retain_graph is not supported)")
+        if tuple(p._version for p in params) != ctx.param_versions:
+            raise RuntimeError("megacrn_b200: a parameter was modified in place between forward and backward")
         x, y_cov, labels = ctx.inputs
         # one flat fp32 buffer aliased by all 14 gradients -> a single NCCL all-reduce per step (ddp.py)
         sizes = [p.numel() for p in params]
@@ -150,6 +160,7 @@ class _MegaCRNFunction(torch.autograd.Function):
                                    _abi.ptr(d_pos), _abi.ptr(d_neg), _abi.make_params(grads), ctx.ws.buf.data_ptr(),
                                    ctx.ws.nbytes, stream)
         _abi.check(st, "mcrn_backward")
+        ctx.done = True
         ctx.ws.busy = False
         return (None, None, None, None, None, None) + tuple(grads)
 
@@ -180,6 +191,7 @@ class MegaCRN(nn.Module):
         self.decoder = ADCRNN_Decoder(num_nodes, output_dim + ycov_dim, self.decoder_dim, cheb_k, num_layers)
         self.proj = nn.Sequential(nn.Linear(self.decoder_dim, output_dim, bias=True))
         self._ws_pool = {}
+        self._param_epoch = 0            # bumped by every parameter update that bypasses torch's version counters
         self.last_teacher_forcing = None
         if num_layers != 1:
             raise NotImplementedError("megacrn_b200 implements the reference default num_layers=1 only")
@@ -200,6 +212,20 @@ class MegaCRN(nn.Module):
         return memory_dict
 
     # ---- plumbing -----------------------------------------------------------------------
+    def note_parameter_update(self):
+        """Called by every updater that writes the parameters through raw pointers (FusedClipAdam.step, a replayed
+        CUDA graph that contains it): invalidates the eval fast path's cached prologue."""
+        self._param_epoch += 1
+
+    def train(self, mode=True):
+        # leaving / entering training drops every cached prologue: whatever happened to the weights in between, the
+        # next eval forward rebuilds supports, folded weights and operand copies from the live parameters
+        if mode != self.training:
+            for pool in self._ws_pool.values():
+                for ws in pool:
+                    ws.prologue_key = None
+        return super().train(mode)
+
     def _ordered_params(self):
         e, d = self.encoder.dcrnn_cells[0], self.decoder.dcrnn_cells[0]
         return (self.memory["Memory"], self.memory["Wq"], self.memory["We1"], self.memory["We2"],

@@ -40,10 +40,19 @@ static uint64_t dims_hash(const mcrn_dims* d) {
   return h;
 }
 
+// One device per process (one process per GPU is the deployment model): the side streams, events and
+// the per-kernel shared-memory attributes of the library are created for the device of the first call.  A later call with
+// another current device fails loudly instead of launching on streams of the wrong device.
+static std::atomic<int> g_bound_device{-1};
 static int check_device() {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) { set_error("no CUDA device: %s", cudaGetErrorString(e)); cudaGetLastError(); return MCRN_ERR_NO_DEVICE; }
+  int expected = -1;
+  if (!g_bound_device.compare_exchange_strong(expected, dev) && expected != dev) {
+    set_error("libmegacrn_b200 is bound to device %d by its first call; the current device is %d (one process per GPU)", expected, dev);
+    return MCRN_ERR_STATE;
+  }
   int major = 0;
   e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
   if (e != cudaSuccess || major != 10) {
@@ -210,8 +219,15 @@ int mcrn_backward(const mcrn_dims* dims, const mcrn_params* params, const float*
       return MCRN_ERR_STATE;
     }
   }
-  return backward_impl(g, p, params, teacher_forcing, d_output, d_h_att, d_query, d_pos, d_neg, grads,
-                       static_cast<float*>(workspace), static_cast<cudaStream_t>(stream));
+  const int s = backward_impl(g, p, params, teacher_forcing, d_output, d_h_att, d_query, d_pos, d_neg, grads,
+                              static_cast<float*>(workspace), static_cast<cudaStream_t>(stream));
+  {
+    // the backward consumes the saved state (accumulators are not idempotent): a second mcrn_backward on the same
+    // forward is an error, as it is for freed autograd buffers
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_saved.erase(workspace);
+  }
+  return s;
 }
 
 int mcrn_supports_fwd(const mcrn_dims* dims, const float* memory, const float* we1, const float* we2,

@@ -40,7 +40,9 @@ using fusedh::tcgen05_mma_f16;
 using fusedh::tcgen05_mma_f16_ts;
 using fusedh::tmem_st_32x32b_x16;
 
-constexpr int BHTHREADS = 320;
+constexpr int BH_EPI_WARPS = 8;
+constexpr int NPROD_B = 3;                      // TMA producer warps (see fusedh::NPROD): warp 0 and the last NPROD_B-1 warps
+constexpr int BHTHREADS = 64 + 32 * BH_EPI_WARPS + 32 * (NPROD_B - 1);
 
 struct BHParams {
   int N, B, KS, nhalf;
@@ -208,11 +210,15 @@ agcn_bwd_h_kernel(const __grid_constant__ CUtensorMap tmST, const __grid_constan
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_wait();                       // programmatic dependent launch: the prologue above overlapped the previous kernel's tail
+  pdl_launch_dependents();
 
-  if (warp == 0) {
-    if (lane == 0) {                                     // ===== TMA producer =====
+  const int pw = warp == 0 ? 0 : (warp >= 2 + BH_EPI_WARPS ? warp - (2 + BH_EPI_WARPS) + 1 : -1);   // producer index or -1
+  if (pw >= 0) {
+    if (lane == 0) {                                     // ===== TMA producers: item `it` belongs to producer it % NPROD_B =====
       int it = 0;
       fusedb::for_each_item_b<C::KB2>(nks, p.nhalf, kb1, [&](int type, int ks, int j) {
+        if (it % NPROD_B != pw) { ++it; return; }
         const int s = it % NST;
         if (it >= NST) mbar_wait_b(smem_u32(&empty_bar[s]), (((uint32_t)(it / NST)) & 1u) ^ 1u);
         const uint32_t fb = smem_u32(&full_bar[s]);
@@ -249,11 +255,14 @@ agcn_bwd_h_kernel(const __grid_constant__ CUtensorMap tmST, const __grid_constan
         const uint32_t a_addr = smem_base + (uint32_t)s * C::STAGE, b_addr = a_addr + C::A_SLOT, ib_addr = b_addr + C::B_SLOT;
         const uint32_t qbuf = tmem_base + ((ks & 1) ? C::TM_Q1 : C::TM_Q0);
         if (type == B_ITEM_P) {
+          const int nkk = min(BKH / 16, (p.N - j * BKH + 15) / 16);     // the last k-block stops at the node count
 #pragma unroll
           for (int kk = 0; kk < BKH / 16; ++kk) {
-            const uint64_t ad = make_smem_desc(a_addr + kk * 32, 16, 1024, 2);
-            const uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, 1024, 2);
-            tcgen05_mma_f16(qbuf, ad, bd, idesc_n, (j > 0 || kk > 0) ? 1u : 0u);
+            if (kk < nkk) {
+              const uint64_t ad = make_smem_desc(a_addr + kk * 32, 16, 1024, 2);
+              const uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, 1024, 2);
+              tcgen05_mma_f16(qbuf, ad, bd, idesc_n, (j > 0 || kk > 0) ? 1u : 0u);
+            }
           }
           tcgen05_commit(smem_u32(&empty_bar[s]));
           if (j == kb1 - 1) tcgen05_commit(smem_u32(&q_full_bar[ks & 1]));
@@ -285,7 +294,7 @@ agcn_bwd_h_kernel(const __grid_constant__ CUtensorMap tmST, const __grid_constan
       });
       tcgen05_commit(smem_u32(&acc_full_bar));
     }
-  } else {                                               // ===== rounding + epilogue warps =====
+  } else if (warp < 2 + BH_EPI_WARPS) {                  // ===== rounding + epilogue warps =====
     const int quarter = warp & 3;
     const int ew = warp - 2, half_id = ew >> 2;
     const int cq = (lane & 7) * 4, r0 = lane >> 3;
@@ -430,11 +439,16 @@ agcn_bwd_h_kernel(const __grid_constant__ CUtensorMap tmST, const __grid_constan
 }
 
 // ---- loss scale ---------------------------------------------------------------------------------
-// amax[0] = max |x| over both tensors (as the bit pattern of a non-negative float: integer max is float max)
-__global__ void k_grad_amax(const float* __restrict__ a, int64_t na, const float* __restrict__ b, int64_t nb, unsigned* __restrict__ amax) {
+// amax[0] = max |x| over all upstream gradient tensors (as the bit pattern of a non-negative float: integer max is float max)
+struct AmaxSrc { const float* p[5]; int64_t end[5]; };     // end[i] = cumulative element count
+__global__ void k_grad_amax(AmaxSrc a, unsigned* __restrict__ amax) {
   float m = 0.f;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < na + nb; i += (int64_t)gridDim.x * blockDim.x)
-    m = fmaxf(m, fabsf(i < na ? a[i] : b[i - na]));
+  const int64_t total = a.end[4];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int k = 0;
+    while (i >= a.end[k]) ++k;
+    m = fmaxf(m, fabsf(a.p[k][i - (k ? a.end[k - 1] : 0)]));
+  }
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0 && m > 0.f && m < INFINITY) atomicMax(amax, __float_as_uint(m));
 }
@@ -489,6 +503,8 @@ __global__ void __launch_bounds__(256) k_bwd_glue_h(const float* __restrict__ dO
                                                     float* __restrict__ dwp, float* __restrict__ dbp, int B, int T, int N,
                                                     int D, int Cout, int t) {
   extern __shared__ float sh[];                    // [32][Cout] d_out rows, [Cout][D] dwp partials, [2][32][D+1] transposition
+  pdl_wait();
+  pdl_launch_dependents();
   float* sh_do = sh;
   float* sh_w = sh + 32 * Cout;
   float* sh_u = sh_w + Cout * D;
@@ -664,7 +680,7 @@ int launch_agcn_bwd_h(int N, int B, int KS, int nhalf, const BHOperands& op, flo
   }
   dim3 grid(ceil_div(N, BM), B, 1);
   const int pi = fused::prof_begin(fused::prof_class(1, HS, nhalf == 2 ? 1 : 0), st);
-  MCRN_LAUNCH(kern, grid, BHTHREADS, C::SMEM, st, tST, tVT, tVA, tW, tWib, p, epi);
+  MCRN_TRY(launch_chain(kern, grid, dim3(BHTHREADS), C::SMEM, st, "agcn_bwd_h_kernel", tST, tVT, tVA, tW, tWib, p, epi));
   fused::prof_end(pi, st);
   return MCRN_OK;
 }

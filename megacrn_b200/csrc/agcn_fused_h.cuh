@@ -37,7 +37,11 @@ using fused::ITEM_SS;
 using fused::ITEM_TS;
 
 constexpr int EPI_WARPS = 16;                   // epilogue warps: 4 per TMEM lane quarter (latency-bound tail: more warps in flight)
-constexpr int FTHREADS = 64 + 32 * EPI_WARPS;
+// TMA producer warps: one elected thread issues one cp.async.bulk.tensor per ~190 cycles (measured, tools/probe_tma2.cu:
+// issue-bound, independent of the box size), so a single producer caps the ring at ~45 B/clk; the ring items are dealt
+// round-robin to NPROD producer warps (warp 0 and the last NPROD-1 warps of the CTA).
+constexpr int NPROD = 4;
+constexpr int FTHREADS = 64 + 32 * EPI_WARPS + 32 * (NPROD - 1);
 constexpr int BKH = 64;                         // halves per k-block = one 128-byte swizzle row
 
 struct HParams {
@@ -267,11 +271,16 @@ agcn_fused_h_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_consta
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_slot;
   if (threadIdx.x == 0) MCRN_TLH(1);
+  // programmatic dependent launch: everything above overlapped the previous kernel's tail; its results are read from here on
+  pdl_wait();
+  pdl_launch_dependents();
 
-  if (warp == 0) {
-    if (lane == 0) {                                     // ===== TMA producer =====
+  const int pw = warp == 0 ? 0 : (warp >= 2 + EPI_WARPS ? warp - (2 + EPI_WARPS) + 1 : -1);   // producer index or -1
+  if (pw >= 0) {
+    if (lane == 0) {                                     // ===== TMA producers: item `it` belongs to producer it % NPROD =====
       int it = 0;
       for_each_item_h<C::KB2>(p.KS, kb1, p.nparts, p.ib_blocks, [&](int type, int k, int j, int part) {
+        if (it % NPROD != pw) { ++it; return; }
         const int s = it % NST;
         if (it >= NST) mbar_wait_b(smem_u32(&empty_bar[s]), (((uint32_t)(it / NST)) & 1u) ^ 1u);
         if (it < 200) MCRN_TLH(240 + it);
@@ -293,7 +302,7 @@ agcn_fused_h_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_consta
         }
         ++it;
       });
-      MCRN_TLH(232);
+      if (pw == 0) MCRN_TLH(232);
     }
   } else if (warp == 1) {
     if (lane == 0) {                                     // ===== MMA issuer =====
@@ -309,11 +318,16 @@ agcn_fused_h_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_consta
         const uint32_t a_addr = smem_base + (uint32_t)s * C::STAGE, b_addr = a_addr + C::A_SLOT;
         const uint32_t pbuf = tmem_base + ((k & 1) ? C::TM_P1 : C::TM_P0);
         if (type == ITEM_P) {
+          // UMMA_K = 16 for fp16: 32 bytes along the swizzled row; the last k-block stops at the node count (the tensor
+          // maps zero-fill beyond N, so whole 16-node steps past it would only add zeros)
+          const int nkk = min(BKH / 16, (p.N - j * BKH + 15) / 16);
 #pragma unroll
-          for (int kk = 0; kk < BKH / 16; ++kk) {        // UMMA_K = 16 for fp16: 32 bytes along the swizzled row
-            const uint64_t ad = make_smem_desc(a_addr + kk * 32, 16, 1024, 2);
-            const uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, 1024, 2);
-            tcgen05_mma_f16(pbuf, ad, bd, idesc1, (j > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < BKH / 16; ++kk) {
+            if (kk < nkk) {
+              const uint64_t ad = make_smem_desc(a_addr + kk * 32, 16, 1024, 2);
+              const uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, 1024, 2);
+              tcgen05_mma_f16(pbuf, ad, bd, idesc1, (j > 0 || kk > 0) ? 1u : 0u);
+            }
           }
           tcgen05_commit(smem_u32(&empty_bar[s]));
           if (j == kb1 - 1) tcgen05_commit(smem_u32(&p_full_bar[k & 1]));
@@ -344,7 +358,7 @@ agcn_fused_h_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_consta
       tcgen05_commit(smem_u32(&acc_full_bar));
       MCRN_TLH(233);
     }
-  } else {                                               // ===== rounding + epilogue warps =====
+  } else if (warp < 2 + EPI_WARPS) {                     // ===== rounding + epilogue warps =====
     const int quarter = warp & 3;                        // TMEM lane quarter this warp may access
     const int ew = warp - 2, half_id = ew >> 2;          // ew 0..15; warps 2..5 (half_id 0) also do the P rounding
     const int cq = (lane & 7) * 4, r0 = lane >> 3;
@@ -697,7 +711,7 @@ int launch_agcn_fused_h(int N, int B, int KS, const HOperands& op, int nparts, c
   }
   dim3 grid(ceil_div(N, BM), B, 1);
   const int pi = fused::prof_begin(fused::prof_class(0, HS, O == HS ? 1 : 0), st);
-  MCRN_LAUNCH(kern, grid, FTHREADS, C::SMEM, st, tS, tXT, tXA, tIB, tW, p, epi);
+  MCRN_TRY(launch_chain(kern, grid, dim3(FTHREADS), C::SMEM, st, "agcn_fused_h_kernel", tS, tXT, tXA, tIB, tW, p, epi));
   fused::prof_end(pi, st);
   return MCRN_OK;
 }

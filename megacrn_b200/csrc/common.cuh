@@ -46,6 +46,31 @@ extern std::atomic<uint64_t> g_launches;
     }                                                                                      \
   } while (0)
 
+// Launch of a kernel of the recurrent chain (fused AGCN forward / backward, step glue) with programmatic dependent launch:
+// the next kernel of the chain is scheduled as soon as every CTA of this one has passed `griddepcontrol.launch_dependents`,
+// runs its prologue (barrier init, TMEM allocation, tensor-map prefetch) while this one drains, and blocks in
+// `griddepcontrol.wait` until this grid has completed and flushed.  Works eagerly and under stream capture (the edge
+// becomes a programmatic graph edge).  g_pdl_chain = 0 (MCRN_PDL_CHAIN=0 / mcrn_set_option("pdl", 0)): plain launches.
+extern int g_pdl_chain;
+template <class... KArgs, class... Args>
+int launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const char* name, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_pdl_chain ? 1 : 0;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (le != cudaSuccess) {
+    set_error("launch of %s failed: %s", name, cudaGetErrorString(le));
+    return MCRN_ERR_CUDA;
+  }
+  return MCRN_OK;
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

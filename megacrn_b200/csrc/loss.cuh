@@ -127,6 +127,12 @@ __global__ void __launch_bounds__(256) k_clip_adam(ParamTable t, float* __restri
                                                    float max_norm) {
   const float step = state[0], lr = state[1];
   const float norm = sqrtf(state[2]);
+  // a non-finite gradient norm (fp16 operand overflow upstream, exploding gradients) must not reach the weights: the step
+  // is skipped (clip coefficient reported as 0; the step counter has already advanced, as torch's GradScaler-style skips do not)
+  if (!(norm < INFINITY)) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) state[3] = 0.0f;
+    return;
+  }
   const float coef = max_norm > 0.f ? fminf(1.0f, max_norm / (norm + 1e-6f)) : 1.0f;
   const float bc1 = 1.0f - powf(beta1, step), bc2 = 1.0f - powf(beta2, step);
   const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);

@@ -93,6 +93,7 @@ static inline int tf32_mode() { return g_engine != 1 ? 1 : 0; }
 // Debug: bit i set -> GEMM call-site class i runs on the SIMT engine (operands stay as produced).
 // 0 propagate, 1 gate/update, 2 make_dxp, 3 acc_dw, 4 propagate_T, 5 acc_ds, 6 chebyshev
 int g_simt_mask = 0;
+int g_pdl_chain = getenv("MCRN_PDL_CHAIN") ? atoi(getenv("MCRN_PDL_CHAIN")) : 1;
 static inline int dbg_exact(int bit) { return (g_simt_mask >> bit) & 1; }
 
 // propagation  XP[1..KS] = S * XP[0]      (model/MegaCRN.py:24-25 for the KS real supports)
@@ -116,7 +117,9 @@ static inline void hilo(GemmDesc& q, int NBX) {
 namespace fused { long long* g_dbg_timeline = nullptr; int g_dbg_which = -1, g_dbg_count = 0; KernelProf g_prof; }
 // g_fused: 0 = per-stage GEMMs, 1 = fused kernel with TF32 operands, 2 = fused kernel with fp16 operands (default).
 int g_fused = getenv("MCRN_FUSED") ? atoi(getenv("MCRN_FUSED")) : 2;
-int g_fused_parts = getenv("MCRN_FUSED_PARTS") ? atoi(getenv("MCRN_FUSED_PARTS")) : 2;
+// Forward weights: 1 = the fp16 hi part only (default: forward error 5e-4 vs the reference, inside the 1e-3 bar, for half the
+// weight bytes and MMA2 work), 2 = hi + lo (2e-4).
+int g_fused_parts = getenv("MCRN_FUSED_PARTS") ? atoi(getenv("MCRN_FUSED_PARTS")) : 1;
 
 template <int HS>
 static int cell_forward_fused(const Geo& g, const float* S, const CellW& w, const CellBufs& b, float* h_out, float* h_mma,
@@ -150,6 +153,12 @@ static bool ib_compact_shape(const Geo& g, int Hs, int Cin, bool save) {
          fused_h_shape(g, Hs) && g.NB * Cin + 1 <= fusedh::IBF && (!save || bwd_fused_shape(g, Hs, Cin));
 }
 
+// fp32 copies of the fp16-rounded state operands (block 0 of the XP buffers): only the TF32 weight- / support-gradient paths
+// read them; with the fp16 dW and dS kernels (the default at hidden width 64 / 128, N <= 256) the fused forward skips them.
+static bool dw_h_shape(const Geo& g, int Hs, int Cin);
+static bool ds_h_shape(const Geo& g, int Hs);
+static bool need_xp0(const Geo& g, int Hs, int Cin) { return !(dw_h_shape(g, Hs, Cin) && ds_h_shape(g, Hs)); }
+
 // fp16-operand fused cell (agcn_fused_h.cuh).  last: no next step consumes the new state as a tensor-core operand.
 template <int HS>
 static int cell_forward_fused_h(const Geo& g, const CellW& w, const CellBufs& b, float* h_out, float* h_mma, bool last,
@@ -161,10 +170,11 @@ static int cell_forward_fused_h(const Geo& g, const CellW& w, const CellBufs& b,
   const __half* ib = ibc ? b.ib16c : b.ib16;
   const int ib_ld = ibc ? fusedh::IBC : 0;
   fusedh::HOperands og{w.S16, b.x16T, b.x16, ib, w.wg16, save_p ? b.xpg : nullptr, ib_ld};
-  fusedh::EpiGateH eg{HS, b.hx, b.z, b.r, save ? b.xpu : nullptr, b.zh16, b.zh16T, ldT};
+  const bool xp0 = save && need_xp0(g, HS, w.Cin);
+  fusedh::EpiGateH eg{HS, b.hx, b.z, b.r, xp0 ? b.xpu : nullptr, b.zh16, b.zh16T, ldT};
   MCRN_TRY((fusedh::launch_agcn_fused_h<HS, 2 * HS>(g.N, g.B, g.KS, og, g_fused_parts, eg, st)));
   fusedh::HOperands ou{w.S16, b.zh16T, b.zh16, ib, w.wu16, save_p ? b.xpu : nullptr, ib_ld};
-  fusedh::EpiUpdateH eu{HS, b.hx, b.r, b.hc, h_out, save ? h_mma : nullptr, last ? nullptr : x16_next, last ? nullptr : x16T_next, ldT};
+  fusedh::EpiUpdateH eu{HS, b.hx, b.r, b.hc, h_out, xp0 ? h_mma : nullptr, last ? nullptr : x16_next, last ? nullptr : x16T_next, ldT};
   MCRN_TRY((fusedh::launch_agcn_fused_h<HS, HS>(g.N, g.B, g.KS, ou, g_fused_parts, eu, st)));
   return MCRN_OK;
 }
@@ -662,6 +672,7 @@ static int g_side_chunks = getenv("MCRN_SIDE_CHUNKS") ? (atoi(getenv("MCRN_SIDE_
 // fused support-gradient kernel: 2 = fp16 operands where the fp16 forward + backward provide them (default), 1 = TF32, 0 = per step
 int g_ds_fused = getenv("MCRN_DS_FUSED") ? atoi(getenv("MCRN_DS_FUSED")) : 2;
 static bool ds_fused_shape(const Geo& g, int Hs) { return g_ds_fused && fusedd::ds_fused_eligible(g.N, Hs); }
+static bool ds_h_shape(const Geo& g, int Hs) { return ds_fused_shape(g, Hs) && g_bwd_fused == 2 && g_ds_fused == 2 && fused_h_shape(g, Hs); }
 // Step glue of the next cell inside the gate-AGCN epilogue (EpiBGHG): correct and tested, but measured slower at C2 (4.38 vs
 // 4.25 ms/step): the exposed, latency-bound epilogue grows by more than the 15 us HBM-rate glue kernel it replaces.  Off by default.
 static int g_glue_fuse = getenv("MCRN_GLUE_FUSE") ? atoi(getenv("MCRN_GLUE_FUSE")) : 0;
@@ -767,7 +778,7 @@ static int acc_ds_fused_all(const Geo& g, const Plan& p, float* ws, const CellW&
   float* dS = ws + p.dS;
   cudaStream_t sd = g_side.s;
   MCRN_TRY(side_begin(0, mainst));
-  if (g_bwd_fused == 2 && g_ds_fused == 2 && fused_h_shape(g, HS)) {
+  if (ds_h_shape(g, HS)) {
     // fp16 operands: the per-step scaled dV16 copies of the fp16 backward and the per-step state copies of the fp16 forward
     MCRN_TRY((fuseddh::launch_agcn_ds_h<HS>(g.N, g.B, tb - ta, g.KS, g.ldS, HS, du16_buf(g, p, ws, HS, ta), w.wu16n,
                                             zh16_0 + (int64_t)ta * g.R * HS, ws + p.gs, dS, sd)));
@@ -926,8 +937,16 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
     // loss scale from the upstream gradients, fp16 operand copies of the transposed supports and of the weights
     unsigned* amax = reinterpret_cast<unsigned*>(ws + p.gs + 2);
     MCRN_CUDA_OK(cudaMemsetAsync(amax, 0, sizeof(unsigned), st));
-    const int64_t n_out = d_output ? (int64_t)g.B * g.T_out * g.N * g.Cout : 0, n_q = d_query ? (int64_t)g.B * g.N * g.d : 0;
-    if (n_out + n_q > 0) MCRN_LAUNCH(fusedbh::k_grad_amax, ew_grid(n_out + n_q), 256, 0, st, d_output, n_out, d_query, n_q, amax);
+    // every upstream gradient that enters the fp16 chain: d_output, d_query and (through the memory query) d_h_att, d_pos, d_neg
+    {
+      const int64_t n_out = (int64_t)g.B * g.T_out * g.N * g.Cout, n_b = (int64_t)g.B * g.N * g.d;
+      const float* src[5] = {d_output, d_query, d_hatt, d_pos, d_neg};
+      const int64_t cnt[5] = {n_out, n_b, n_b, n_b, n_b};
+      fusedbh::AmaxSrc a;
+      int64_t acc = 0;
+      for (int i = 0; i < 5; ++i) { a.p[i] = src[i]; acc += src[i] ? cnt[i] : 0; a.end[i] = acc; }
+      if (acc > 0) MCRN_LAUNCH(fusedbh::k_grad_amax, ew_grid(acc), 256, 0, st, a, amax);
+    }
     MCRN_LAUNCH(fusedbh::k_grad_scale, 1, 1, 0, st, amax, ws + p.gs);
     const int ld16 = fusedh::ld_half(g.N);
     MCRN_LAUNCH(fusedbh::k_supports_to_half_T, dim3(ceil_div(g.N, 32), ceil_div(ld16, 32), g.KS), dim3(32, 8), 0, st, ws + p.S,
@@ -997,11 +1016,11 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
         dec_glue_fused = false;
         if (g_bwd_fused == 2 && !glue_fused_here) {
           const size_t gsm = ((size_t)(32 + g.D) * g.Cout + 2 * 32 * (g.D + 1)) * sizeof(float);
-          MCRN_LAUNCH(fusedbh::k_bwd_glue_h, dim3(ceil_div(g.N, 32), g.B), 256, gsm, st, d_output, use_dgo ? dXin : nullptr, g.Cdec, h_t,
+          MCRN_TRY(launch_chain(fusedbh::k_bwd_glue_h, dim3(ceil_div(g.N, 32), g.B), dim3(256), gsm, st, "k_bwd_glue_h", d_output, use_dgo ? dXin : nullptr, g.Cdec, h_t,
                       prm->proj_w, dH, (t == g.T_out - 1) ? 1 : 0, b.r, b.hc, b.hx, dU_t, dG_all + (int64_t)t * g.R * 2 * g.D,
                       ws + p.dHr, du16_buf(g, p, ws, g.D, t), du16T_buf(g, p, ws, g.D, t),
                       dg16_buf(g, p, ws, g.D, t), dg16T_buf(g, p, ws, g.D, t), fusedh::ld_half(g.N),
-                      ws + p.gs, grads->proj_w, grads->proj_b, g.B, g.T_out, g.N, g.D, g.Cout, t);
+                      ws + p.gs, grads->proj_w, grads->proj_b, g.B, g.T_out, g.N, g.D, g.Cout, t));
         } else if (g_bwd_fused != 2)
           MCRN_LAUNCH(fusedb::k_bwd_glue, (int)ceil_div64(g.R, 32), 256, (size_t)(32 + g.D) * g.Cout * sizeof(float), st, d_output,
                       use_dgo ? dXin : nullptr, g.Cdec, h_t, prm->proj_w, dH, (t == g.T_out - 1) ? 1 : 0, b.r, b.hc, b.hx, dU_t,
@@ -1127,11 +1146,11 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
         enc_glue_fused = false;
         if (g_bwd_fused == 2 && !glue_fused_here) {
           const size_t gsm = (size_t)2 * 32 * (g.H + 1) * sizeof(float);
-          MCRN_LAUNCH(fusedbh::k_bwd_glue_h, dim3(ceil_div(g.N, 32), g.B), 256, gsm, st, (const float*)nullptr, (const float*)nullptr, 0,
+          MCRN_TRY(launch_chain(fusedbh::k_bwd_glue_h, dim3(ceil_div(g.N, 32), g.B), dim3(256), gsm, st, "k_bwd_glue_h", (const float*)nullptr, (const float*)nullptr, 0,
                       (const float*)nullptr, (const float*)nullptr, dHe, 0, b.r, b.hc, b.hx, dU_t, dG_all + (int64_t)t * g.R * 2 * g.H,
                       ws + p.dHr, du16_buf(g, p, ws, g.H, t), du16T_buf(g, p, ws, g.H, t),
                       dg16_buf(g, p, ws, g.H, t), dg16T_buf(g, p, ws, g.H, t), fusedh::ld_half(g.N),
-                      ws + p.gs, (float*)nullptr, (float*)nullptr, g.B, g.T_in, g.N, g.H, 0, t);
+                      ws + p.gs, (float*)nullptr, (float*)nullptr, g.B, g.T_in, g.N, g.H, 0, t));
         } else if (g_bwd_fused != 2)
           MCRN_LAUNCH(fusedb::k_bwd_glue, (int)ceil_div64(g.R, 32), 256, 0, st, (const float*)nullptr, (const float*)nullptr, 0,
                       (const float*)nullptr, (const float*)nullptr, dHe, 0, b.r, b.hc, b.hx, dU_t,
@@ -1237,6 +1256,7 @@ bool set_option(const char* name, int value) {
   else if (n == "ds_fused") g_ds_fused = value;
   else if (n == "ib_compact") g_ib_compact = value;
   else if (n == "dw_fused") g_dw_fused = value;
+  else if (n == "pdl") g_pdl_chain = value;
   else return false;
   return true;
 }

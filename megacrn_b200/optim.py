@@ -78,6 +78,14 @@ class FusedClipAdam:
                                     self.max_grad_norm if self.max_grad_norm else 0.0,
                                     torch.cuda.current_stream(dev).cuda_stream)
         _abi.check(st, "mcrn_adam_step")
+        self.note_update()
+
+    def note_update(self):
+        """The update went through raw pointers: tell the module (eval fast-path cache) and torch's version counters.
+        Also called by GraphedTrainStep after replaying a graph that contains this optimiser."""
+        self.model.note_parameter_update()
+        for p in self.params:
+            torch.autograd.graph.increment_version(p)
 
     def state_dict(self):
         return {"exp_avg": [t.clone() for t in self.exp_avg], "exp_avg_sq": [t.clone() for t in self.exp_avg_sq],

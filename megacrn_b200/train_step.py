@@ -129,6 +129,8 @@ class GraphedTrainStep:
             entry = self.graphs[key] = self._capture(flags)
         g, loss, grads, kernels = entry
         g.replay()
+        if self.optimizer is not None:                     # the replayed graph updated the weights through raw pointers
+            self.optimizer.note_update()
         self.kernels_replayed += kernels
         for p, gr in zip(self.params, grads):              # static gradient tensors of this graph
             p.grad = gr
