@@ -136,6 +136,20 @@ int mcrn_trainer_loss(const mcrn_dims* dims, const float* output, const float* l
                       float* loss_out, float* d_output, float* d_query,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* Data-parallel form of the loss.  masked_mae's normaliser `mask.mean()`
+ * (model/utils.py:127-128) is a property of the GLOBAL batch: with the batch sharded over W ranks, the W-rank
+ * average of the per-rank losses equals the single-process loss only if every rank divides by
+ * (global count of labels != 0) / W instead of its local count.  mcrn_mask_count adds this rank's count of
+ * (labels*std+mean != 0) to count_out[0] (device; the caller zeroes it, all-reduces it and divides by W);
+ * mcrn_trainer_loss_dp is mcrn_trainer_loss with that device scalar as the normaliser (NULL: local count). */
+int mcrn_mask_count(const float* labels, int64_t n, float scaler_mean, float scaler_std, float* count_out, void* stream);
+int mcrn_trainer_loss_dp(const mcrn_dims* dims, const float* output, const float* labels,
+                         const float* query, const float* pos, const float* neg,
+                         float scaler_mean, float scaler_std, float lamb, float lamb1,
+                         const float* mask_count,
+                         float* loss_out, float* d_output, float* d_query,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 /* The optimiser half of the training step, fused over the 14 parameter tensors:
  * torch.nn.utils.clip_grad_norm_(parameters, max_grad_norm)   (model/traintest_MegaCRN.py:129; max_grad_norm <= 0: no clipping)
  * followed by torch.optim.Adam(lr, betas=(beta1, beta2), eps).step()   (:104, :130; no weight decay, no amsgrad).
@@ -158,7 +172,7 @@ int mcrn_forward_host(const mcrn_dims* dims, const mcrn_params* host_params,
                       void* device_workspace, size_t workspace_bytes, uint32_t flags, void* stream);
 
 /* Stage-level entries used by the unit tests (same arithmetic the whole-model entries
- * run; see tests/test_stage_kernels.py). */
+ * run; see tests/test_gpu_parity.py: test_gemm_engine, test_supports_stage_matches_spec). */
 
 /* Supports prologue: model/MegaCRN.py:169-173 and the Chebyshev set of :19-23 hoisted.
  * supports_out [KS, N, ld] with KS = 2*(cheb_k-1), ld = mcrn_support_ld(N). */
@@ -179,11 +193,6 @@ int mcrn_gemm(int M, int N, int K, const float* A, int lda, int trans_a,
               const float* B, int ldb, int trans_b, float* C, int ldc,
               int engine, void* stream);
 
-/* Debug aid: mcrn_gemm on the tcgen05 engine with shared-memory stage 0 of CTA (0,0,0) dumped to dbg
- * (at least 16 K floats + 2). */
-int mcrn_debug_tc_gemm(int M, int N, int K, const float* A, int lda, int trans_a,
-                       const float* B, int ldb, int trans_b, float* C, int ldc, float* dbg, void* stream);
-
 /* Number of kernels the library launched since process start (for bench.py's
  * `gpu_launches`). */
 uint64_t mcrn_launch_count(void);
@@ -191,38 +200,11 @@ uint64_t mcrn_launch_count(void);
 /* 0 = default (tcgen05 TF32 where the shape allows, SIMT otherwise), 1 = force SIMT fp32. */
 int mcrn_set_engine(int engine);
 int mcrn_get_engine(void);
-/* Round-2 probe, not on the product path (csrc/probe_mn16.cuh, tools/probe_mn16.py): one 128 x 128 x 64 tcgen05 kind::f16 tile with
- * an MN-major B operand whose shared-memory descriptor fields are given at run time.  A: device fp16 [128][64], B: device fp16
- * [64][128] (N contiguous), C: device fp32 [128][128]. */
-int mcrn_debug_probe_mn16(const void* A, const void* B, float* C, unsigned lbo_bytes, unsigned sbo_bytes, unsigned layout,
-                          unsigned kstep_bytes, unsigned b_major, void* stream);
-/* Internal tuning knobs by name (tests / experiments): "glue_fuse" (step glue inside the gate-AGCN backward epilogue, default 0),
- * "side_chunks" (dS / dW launches per cell type, default 1), "ds_fused" (fused support-gradient kernel: 2 = fp16 operands (default), 1 = TF32, 0 = per-step GEMMs),
- * "ib_compact" (compact input block, default 1), "dw_fused" (fp16 weight-gradient kernel agcn_dw_fused_h.cuh, default 1). */
-int mcrn_set_option(const char* name, int value);
 /* Counter incremented by every mcrn_set_* call: part of the validity key of MCRN_FWD_REUSE_PROLOGUE. */
 uint64_t mcrn_mode_epoch(void);
-/* Debug: bit i forces GEMM call-site class i onto the SIMT engine (see model.cu). */
-int mcrn_set_debug_mask(int mask);
-/* Forward AGCN as ONE fused kernel per AGCN call (graph convolution + weight contraction + gate/update tail) where the
- * hidden width is 64 or 128: fused = 2 (default) fp16 operands / fp32 accumulate (csrc/agcn_fused_h.cuh), 1 = TF32
- * operands (csrc/agcn_fused.cuh), 0 = per-stage GEMM kernels.
- * weight_parts: 2 = hi + lo residual of the weights (default), 1 = hi only. */
-int mcrn_set_fused(int fused, int weight_parts);
-/* Per-kernel timing for bench.py's roofline: while enabled, every EAGER launch of a fused AGCN kernel is bracketed by CUDA
- * events on its launching stream (launches under stream capture are not).  kernel_class = direction*8 + (HS==128 ? 4 : 0) +
- * variant; direction 0 = forward (variant 0 gate, 1 update), 1 = backward (variant 0 update-AGCN, 1 gate-AGCN).
- * mcrn_kernel_timing(1) also resets the record; _read synchronises the recorded events and returns their summed duration. */
-int mcrn_kernel_timing(int enable);
-int mcrn_kernel_timing_read(int kernel_class, float* ms_total, int* launches);
-/* Backward data path of every AGCN as one fused kernel where the hidden width is 64 or 128: 2 (default) = fp16 operands
- * with a per-backward power-of-two loss scale (csrc/agcn_bwd_fused_h.cuh), 1 = TF32 operands (csrc/agcn_bwd_fused.cuh),
- * 0 = per-stage GEMM kernels.  Set it before the forward whose backward it governs. */
-int mcrn_set_bwd_fused(int fused);
-/* Debug aid (tools/fused_timeline.py): while device_slots != NULL the `which`-th fused AGCN launch after this call
- * (-1 = every launch) records clock64 timestamps of CTA (0,0) into it (512 x int64; slot map in csrc/agcn_fused.cuh).
- * NULL switches the recording off. */
-int mcrn_debug_fused_timeline(long long* device_slots, int which);
+
+/* Debug, probe and tuning entries (mcrn_debug_*, mcrn_set_option, mcrn_set_fused, mcrn_kernel_timing, ...) are declared in
+ * megacrn_b200_debug.h: tests, tools and bench.py's roofline use them; a binding of the product path does not need them. */
 
 #ifdef __cplusplus
 }

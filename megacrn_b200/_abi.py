@@ -74,6 +74,8 @@ def load() -> C.CDLL:
     lib.mcrn_set_option.argtypes = [C.c_char_p, C.c_int]
     lib.mcrn_debug_fused_timeline.restype = C.c_int
     lib.mcrn_debug_fused_timeline.argtypes = [C.c_void_p, C.c_int]
+    lib.mcrn_debug_launch_spans.restype = C.c_int
+    lib.mcrn_debug_launch_spans.argtypes = [C.c_void_p, C.c_int]
     lib.mcrn_adam_step.restype = C.c_int
     lib.mcrn_adam_step.argtypes = [C.POINTER(Dims), C.POINTER(Params), C.POINTER(Params), C.POINTER(Params), C.POINTER(Params),
                                    fp, C.c_float, C.c_float, C.c_float, C.c_float, vp]
@@ -97,6 +99,11 @@ def load() -> C.CDLL:
     lib.mcrn_trainer_loss.restype = C.c_int
     lib.mcrn_trainer_loss.argtypes = [C.POINTER(Dims), fp, fp, fp, fp, fp, C.c_float, C.c_float, C.c_float,
                                       C.c_float, fp, fp, fp, vp, C.c_size_t, vp]
+    lib.mcrn_trainer_loss_dp.restype = C.c_int
+    lib.mcrn_trainer_loss_dp.argtypes = [C.POINTER(Dims), fp, fp, fp, fp, fp, C.c_float, C.c_float, C.c_float,
+                                         C.c_float, fp, fp, fp, fp, vp, C.c_size_t, vp]
+    lib.mcrn_mask_count.restype = C.c_int
+    lib.mcrn_mask_count.argtypes = [fp, C.c_int64, C.c_float, C.c_float, fp, vp]
     lib.mcrn_supports_fwd.restype = C.c_int
     lib.mcrn_supports_fwd.argtypes = [C.POINTER(Dims), fp, fp, fp, fp, vp, C.c_size_t, vp]
     lib.mcrn_supports_fwd2.restype = C.c_int

@@ -20,8 +20,9 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
 int supports_forward_entry(const Geo& g, const Plan& p, float* ws, const float* mem, const float* we1,
                            const float* we2, float* S, float* Sr, cudaStream_t st);
 int trainer_loss_impl(const Geo& g, const float* output, const float* labels, const float* query, const float* pos,
-                      const float* neg, float mean, float std, float lamb, float lamb1, float* loss_out,
+                      const float* neg, float mean, float std, float lamb, float lamb1, const float* mask_count, float* loss_out,
                       float* d_output, float* d_query, float* scratch, cudaStream_t st);
+int mask_count_impl(const float* labels, int64_t n, float mean, float std, float* count_out, cudaStream_t st);
 
 int adam_step_impl(const Geo& g, const mcrn_params* prm, const mcrn_params* grads, const mcrn_params* m, const mcrn_params* v,
                    float* state, float beta1, float beta2, float eps, float max_norm, cudaStream_t st);
@@ -106,6 +107,10 @@ int mcrn_set_option(const char* name, int value) {
 }
 int mcrn_debug_fused_timeline(long long* device_slots, int which) {
   fused::g_dbg_timeline = device_slots; fused::g_dbg_which = which; fused::g_dbg_count = 0;
+  return MCRN_OK;
+}
+int mcrn_debug_launch_spans(unsigned long long* device_slots, int max_launches) {
+  fused::g_dbg_span = device_slots; fused::g_dbg_span_n = 0; fused::g_dbg_span_cap = device_slots ? max_launches : 0;
   return MCRN_OK;
 }
 int mcrn_adam_step(const mcrn_dims* dims, const mcrn_params* params, const mcrn_params* grads, const mcrn_params* exp_avg,
@@ -279,13 +284,27 @@ int mcrn_trainer_loss(const mcrn_dims* dims, const float* output, const float* l
                       const float* pos, const float* neg, float scaler_mean, float scaler_std, float lamb,
                       float lamb1, float* loss_out, float* d_output, float* d_query, void* workspace,
                       size_t workspace_bytes, void* stream) {
+  return mcrn_trainer_loss_dp(dims, output, labels, query, pos, neg, scaler_mean, scaler_std, lamb, lamb1, nullptr, loss_out,
+                              d_output, d_query, workspace, workspace_bytes, stream);
+}
+
+int mcrn_trainer_loss_dp(const mcrn_dims* dims, const float* output, const float* labels, const float* query,
+                         const float* pos, const float* neg, float scaler_mean, float scaler_std, float lamb,
+                         float lamb1, const float* mask_count, float* loss_out, float* d_output, float* d_query,
+                         void* workspace, size_t workspace_bytes, void* stream) {
   Geo g;
   MCRN_TRY(make_geo(dims, &g));
   if (!output || !labels || !query || !pos || !neg || !loss_out || !workspace) { set_error("null pointer"); return MCRN_ERR_BAD_POINTER; }
   if (workspace_bytes < 256) { set_error("mcrn_trainer_loss needs 256 bytes of device scratch"); return MCRN_ERR_WORKSPACE; }
   MCRN_TRY(check_device());
-  return trainer_loss_impl(g, output, labels, query, pos, neg, scaler_mean, scaler_std, lamb, lamb1, loss_out,
+  return trainer_loss_impl(g, output, labels, query, pos, neg, scaler_mean, scaler_std, lamb, lamb1, mask_count, loss_out,
                            d_output, d_query, static_cast<float*>(workspace), static_cast<cudaStream_t>(stream));
+}
+
+int mcrn_mask_count(const float* labels, int64_t n, float scaler_mean, float scaler_std, float* count_out, void* stream) {
+  if (!labels || !count_out || n < 1) { set_error("mcrn_mask_count: bad arguments"); return MCRN_ERR_BAD_POINTER; }
+  MCRN_TRY(check_device());
+  return mask_count_impl(labels, n, scaler_mean, scaler_std, count_out, static_cast<cudaStream_t>(stream));
 }
 
 // ---- host-buffer entries ---------------------------------------------------------------

@@ -57,6 +57,8 @@ struct BHParams {
   const float* dib_in;
   float* dxpin;
   int nb, cin;
+  int pdl_late;          // see fusedh::HParams
+  unsigned long long* span;
 };
 
 template <int HS>
@@ -182,6 +184,7 @@ agcn_bwd_h_kernel(const __grid_constant__ CUtensorMap tmST, const __grid_constan
   const int kb1 = (p.N + BKH - 1) / BKH;
   const int nks = p.KS * p.nhalf;
   const int NBLK = p.KS + 1;
+  if (p.span != nullptr && threadIdx.x == 0) atomicMin(p.span, fused::globaltimer_ns());
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmST) : "memory");
@@ -211,7 +214,7 @@ agcn_bwd_h_kernel(const __grid_constant__ CUtensorMap tmST, const __grid_constan
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_slot;
   pdl_wait();                       // programmatic dependent launch: the prologue above overlapped the previous kernel's tail
-  pdl_launch_dependents();
+  if (!p.pdl_late) pdl_launch_dependents();
 
   const int pw = warp == 0 ? 0 : (warp >= 2 + BH_EPI_WARPS ? warp - (2 + BH_EPI_WARPS) + 1 : -1);   // producer index or -1
   if (pw >= 0) {
@@ -355,6 +358,7 @@ agcn_bwd_h_kernel(const __grid_constant__ CUtensorMap tmST, const __grid_constan
     }
     mbar_wait_b(smem_u32(&acc_full_bar), 0);
     tcgen05_fence_after();
+    if (p.pdl_late) pdl_launch_dependents();
     if (node0 < p.N) {
       float* scr = reinterpret_cast<float*>(smem_al) + ew * (32 * 36);      // the ring is idle now
 #pragma unroll 1
@@ -436,6 +440,7 @@ agcn_bwd_h_kernel(const __grid_constant__ CUtensorMap tmST, const __grid_constan
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
   }
+  if (p.span != nullptr && threadIdx.x == 0) atomicMax(p.span + 1, fused::globaltimer_ns());
 }
 
 // ---- loss scale ---------------------------------------------------------------------------------
@@ -672,6 +677,8 @@ int launch_agcn_bwd_h(int N, int B, int KS, int nhalf, const BHOperands& op, flo
   p.qsave = qsave; p.blk_stride = R * HS; p.dib = dib; p.gs = op.gs;
   p.q16T = q16T; p.ldT = ldn;
   p.dib_in = dib_in; p.dxpin = dxpin; p.nb = KS + 1; p.cin = cin;
+  p.pdl_late = (g_pdl_chain >> 3) & 1;
+  p.span = fused::next_span();
   auto kern = agcn_bwd_h_kernel<HS, Epi>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -680,7 +687,7 @@ int launch_agcn_bwd_h(int N, int B, int KS, int nhalf, const BHOperands& op, flo
   }
   dim3 grid(ceil_div(N, BM), B, 1);
   const int pi = fused::prof_begin(fused::prof_class(1, HS, nhalf == 2 ? 1 : 0), st);
-  MCRN_TRY(launch_chain(kern, grid, dim3(BHTHREADS), C::SMEM, st, "agcn_bwd_h_kernel", tST, tVT, tVA, tW, tWib, p, epi));
+  MCRN_TRY(launch_chain(2, kern, grid, dim3(BHTHREADS), C::SMEM, st, "agcn_bwd_h_kernel", tST, tVT, tVA, tW, tWib, p, epi));
   fused::prof_end(pi, st);
   return MCRN_OK;
 }

@@ -33,6 +33,10 @@ struct FusedParams {
 };
 extern long long* g_dbg_timeline;   // host side: non-null only while mcrn_debug_fused_timeline is armed
 extern int g_dbg_which, g_dbg_count;
+extern unsigned long long* g_dbg_span;   // per-launch wall-clock spans {min CTA start, max CTA end} (ns, %globaltimer), mcrn_debug_launch_spans
+extern int g_dbg_span_n, g_dbg_span_cap;
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+static inline unsigned long long* next_span() { return (g_dbg_span != nullptr && g_dbg_span_n < g_dbg_span_cap) ? g_dbg_span + 2 * (g_dbg_span_n++) : nullptr; }
 
 // timeline slots: [0] start, [1] after prologue, [2 + it] MMA issuer: operands of item `it` landed (up to 200 items),
 // [210 + 4k .. ] rounding warp 2: p_full seen / rounded+stored / (2 unused), [230] acc_full seen, [231] epilogue done,

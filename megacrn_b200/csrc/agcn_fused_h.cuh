@@ -50,6 +50,8 @@ struct HParams {
   float* xp_save;       // training: fp32 XP buffer [KS+2][R][HS]; the (fp16-rounded) P_k goes to block 1+k.  null = eval
   int64_t blk_stride;   // R * HS
   long long* dbg;       // debug timeline (see agcn_fused.cuh)
+  unsigned long long* span;   // debug: {min CTA start, max CTA end} of this launch (ns), or null
+  int pdl_late;         // programmatic dependent launch: 0 = let the dependents start right after the prologue, 1 = at the epilogue
 };
 
 __device__ __forceinline__ void tcgen05_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -242,6 +244,12 @@ agcn_fused_h_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_consta
   const int kb1 = (p.N + BKH - 1) / BKH;
   const int NSEG = p.KS + 2;                         // weight segments per part
   if (threadIdx.x == 0) MCRN_TLH(0);
+  if (p.span != nullptr && threadIdx.x == 0) atomicMin(p.span, fused::globaltimer_ns());
+  if (p.dbg != nullptr && threadIdx.x == 0) {        // per-CTA wall-clock stamps (ns): [512 + 2 cta] = start, [513 + 2 cta] = end
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.dbg[512 + 2 * (blockIdx.y * gridDim.x + blockIdx.x)] = (long long)gt;
+  }
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmS) : "memory");
@@ -273,7 +281,7 @@ agcn_fused_h_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_consta
   if (threadIdx.x == 0) MCRN_TLH(1);
   // programmatic dependent launch: everything above overlapped the previous kernel's tail; its results are read from here on
   pdl_wait();
-  pdl_launch_dependents();
+  if (!p.pdl_late) pdl_launch_dependents();
 
   const int pw = warp == 0 ? 0 : (warp >= 2 + EPI_WARPS ? warp - (2 + EPI_WARPS) + 1 : -1);   // producer index or -1
   if (pw >= 0) {
@@ -405,6 +413,7 @@ agcn_fused_h_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_consta
     // ---- epilogue: accumulator -> gate / update math; rows = (node, b); this warp takes chunks c = half_id (mod 4) ----
     mbar_wait_b(smem_u32(&acc_full_bar), 0);
     tcgen05_fence_after();
+    if (p.pdl_late) pdl_launch_dependents();
     if (warp == 2 && lane == 0) MCRN_TLH(230);
     if (node0 < p.N) {
       float* scr = reinterpret_cast<float*>(smem_al) + ew * (32 * 36);      // the ring is idle now
@@ -449,9 +458,15 @@ agcn_fused_h_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_consta
   if (warp == 2 && lane == 0) MCRN_TLH(231);
   tcgen05_fence_before();
   __syncthreads();
+  if (p.dbg != nullptr && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.dbg[513 + 2 * (blockIdx.y * gridDim.x + blockIdx.x)] = (long long)gt;
+  }
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
   }
+  if (p.span != nullptr && threadIdx.x == 0) atomicMax(p.span + 1, fused::globaltimer_ns());
 }
 
 // ---- operand conversion kernels ---------------------------------------------------------------
@@ -699,6 +714,8 @@ int launch_agcn_fused_h(int N, int B, int KS, const HOperands& op, int nparts, c
   p.xp_save = op.xp_save;
   p.blk_stride = R * HS;
   p.dbg = nullptr;
+  p.pdl_late = (g_pdl_chain >> 3) & 1;
+  p.span = fused::next_span();
   if (fused::g_dbg_timeline != nullptr) {
     if (fused::g_dbg_which < 0 || fused::g_dbg_count == fused::g_dbg_which) p.dbg = fused::g_dbg_timeline;
     ++fused::g_dbg_count;
@@ -711,7 +728,7 @@ int launch_agcn_fused_h(int N, int B, int KS, const HOperands& op, int nparts, c
   }
   dim3 grid(ceil_div(N, BM), B, 1);
   const int pi = fused::prof_begin(fused::prof_class(0, HS, O == HS ? 1 : 0), st);
-  MCRN_TRY(launch_chain(kern, grid, dim3(FTHREADS), C::SMEM, st, "agcn_fused_h_kernel", tS, tXT, tXA, tIB, tW, p, epi));
+  MCRN_TRY(launch_chain(1, kern, grid, dim3(FTHREADS), C::SMEM, st, "agcn_fused_h_kernel", tS, tXT, tXA, tIB, tW, p, epi));
   fused::prof_end(pi, st);
   return MCRN_OK;
 }

@@ -10,6 +10,7 @@
 #include <string>
 
 #include "../../include/megacrn_b200.h"
+#include "../../include/megacrn_b200_debug.h"
 
 namespace mcrn {
 
@@ -51,15 +52,15 @@ extern std::atomic<uint64_t> g_launches;
 // runs its prologue (barrier init, TMEM allocation, tensor-map prefetch) while this one drains, and blocks in
 // `griddepcontrol.wait` until this grid has completed and flushed.  Works eagerly and under stream capture (the edge
 // becomes a programmatic graph edge).  g_pdl_chain = 0 (MCRN_PDL_CHAIN=0 / mcrn_set_option("pdl", 0)): plain launches.
-extern int g_pdl_chain;
+extern int g_pdl_chain;     // bit 0: fused forward, bit 1: fused backward, bit 2: step glue; bit 3: trigger the dependents late (before the epilogue)
 template <class... KArgs, class... Args>
-int launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const char* name, Args&&... args) {
+int launch_chain(int pdl_bit, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const char* name, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = g_pdl_chain ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = (g_pdl_chain & pdl_bit) ? 1 : 0;
   cudaError_t le = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (le != cudaSuccess) {

@@ -44,18 +44,31 @@ __global__ void __launch_bounds__(256) k_loss_reduce_rows(const float* __restric
   if (threadIdx.x == 0) { atomicAdd(scratch + 2, trip); atomicAdd(scratch + 3, mse); }
 }
 
-__global__ void k_loss_finish(const float* __restrict__ scratch, int64_t rows, int d, float lamb, float lamb1,
-                              float* __restrict__ loss_out) {
+// this rank's count of labels whose inverse-scaled value is non-zero, added to out[0] (model/utils.py:127)
+__global__ void __launch_bounds__(256) k_mask_count(const float* __restrict__ lab, int64_t n, float mean, float std, float* __restrict__ out) {
+  __shared__ float sh[8];
+  float cnt = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (__fadd_rn(__fmul_rn(lab[i], std), mean) != 0.f) cnt += 1.f;
+  cnt = block_sum_256(cnt, sh);
+  if (threadIdx.x == 0) atomicAdd(out, cnt);
+}
+
+// cnt_override (device, or null): the masked-MAE normaliser to use instead of this batch's own count (data parallel:
+// global count / world size)
+__global__ void k_loss_finish(const float* __restrict__ scratch, const float* __restrict__ cnt_override, int64_t rows, int d, float lamb,
+                              float lamb1, float* __restrict__ loss_out) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    float cnt = scratch[0];
+    float cnt = cnt_override ? cnt_override[0] : scratch[0];
     float l1 = cnt > 0.f ? scratch[1] / cnt : 0.f;
     loss_out[0] = l1 + lamb * scratch[2] / (float)rows + lamb1 * scratch[3] / ((float)rows * (float)d);
   }
 }
 
 __global__ void k_loss_grad_out(const float* __restrict__ out, const float* __restrict__ lab, int64_t n, float mean,
-                                float std, const float* __restrict__ scratch, float* __restrict__ d_out) {
-  float cnt = scratch[0];
+                                float std, const float* __restrict__ scratch, const float* __restrict__ cnt_override,
+                                float* __restrict__ d_out) {
+  float cnt = cnt_override ? cnt_override[0] : scratch[0];
   float sc = cnt > 0.f ? std / cnt : 0.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float yt = __fadd_rn(__fmul_rn(lab[i], std), mean);

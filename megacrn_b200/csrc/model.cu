@@ -93,7 +93,7 @@ static inline int tf32_mode() { return g_engine != 1 ? 1 : 0; }
 // Debug: bit i set -> GEMM call-site class i runs on the SIMT engine (operands stay as produced).
 // 0 propagate, 1 gate/update, 2 make_dxp, 3 acc_dw, 4 propagate_T, 5 acc_ds, 6 chebyshev
 int g_simt_mask = 0;
-int g_pdl_chain = getenv("MCRN_PDL_CHAIN") ? atoi(getenv("MCRN_PDL_CHAIN")) : 1;
+int g_pdl_chain = getenv("MCRN_PDL_CHAIN") ? atoi(getenv("MCRN_PDL_CHAIN")) : 0;
 static inline int dbg_exact(int bit) { return (g_simt_mask >> bit) & 1; }
 
 // propagation  XP[1..KS] = S * XP[0]      (model/MegaCRN.py:24-25 for the KS real supports)
@@ -114,7 +114,8 @@ static inline void hilo(GemmDesc& q, int NBX) {
 
 // Fused AGCN kernel (agcn_fused.cuh): propagation + weight contraction + gate/update tail in one launch per AGCN.
 // g_fused_parts: 2 = hi + lo weights, 1 = hi only.
-namespace fused { long long* g_dbg_timeline = nullptr; int g_dbg_which = -1, g_dbg_count = 0; KernelProf g_prof; }
+namespace fused { long long* g_dbg_timeline = nullptr; int g_dbg_which = -1, g_dbg_count = 0; KernelProf g_prof;
+                  unsigned long long* g_dbg_span = nullptr; int g_dbg_span_n = 0, g_dbg_span_cap = 0; }
 // g_fused: 0 = per-stage GEMMs, 1 = fused kernel with TF32 operands, 2 = fused kernel with fp16 operands (default).
 int g_fused = getenv("MCRN_FUSED") ? atoi(getenv("MCRN_FUSED")) : 2;
 // Forward weights: 1 = the fp16 hi part only (default: forward error 5e-4 vs the reference, inside the 1e-3 bar, for half the
@@ -237,26 +238,37 @@ struct Ptrs {            // resolved workspace pointers
   float* at(size_t off) const { return w + off; }
 };
 
+struct Fork;
+static int fork_begin(Fork& f, cudaStream_t mainst);
+static int fork_join(Fork& f, cudaStream_t mainst);
+static Fork* fw_fork(int i);      // helper stream i of the forward (null: forks disabled / not initialised)
+static cudaStream_t fw_fork_stream(int i);
+
 static int supports_forward(const Geo& g, const Plan& p, float* ws, const float* mem, const float* we1, const float* we2,
                             float* S, float* Sr, cudaStream_t st) {
   float *E1 = ws + p.E1, *E2 = ws + p.E2, *L1 = ws + p.L1, *L2 = ws + p.L2;
+  // the g1 and g2 chains are independent once E1 and E2 exist: chain 1 runs on a helper stream
+  Fork* f = fw_fork(1);
+  cudaStream_t sx[2] = {st, st};
+  if (f) { MCRN_TRY(fork_begin(*f, st)); sx[1] = fw_fork_stream(1); }
   for (int i = 0; i < 2; ++i) {  // E_i = We_i * Memory                         model/MegaCRN.py:169-170
     GemmDesc q;
     q.A = i ? we2 : we1; q.a_row = g.M; q.a_k = 1; q.M = g.N; q.Kseg = g.M;
     q.B = mem; q.b_k = g.d; q.b_n = 1; q.N = g.d; q.prec_exact = 1;
     EpiStore e{i ? E2 : E1, g.d, 0, 1.0f, nullptr, nullptr};
-    MCRN_TRY(gemm(q, e, st));
+    MCRN_TRY(gemm(q, e, sx[i]));
   }
+  if (f) { MCRN_TRY(fork_join(*f, st)); MCRN_TRY(fork_begin(*f, st)); }
   const int per = g.cheb_k - 1;
   for (int i = 0; i < 2; ++i) {  // logits E1 E2^T / E2 E1^T, relu, row softmax   :171-172
     GemmDesc q;
     q.A = i ? E2 : E1; q.a_row = g.d; q.a_k = 1; q.M = g.N; q.Kseg = g.d;
     q.B = i ? E1 : E2; q.b_k = 1; q.b_n = g.d; q.N = g.N; q.prec_exact = 1;
     EpiStore e{i ? L2 : L1, g.ldS, 0, 1.0f, nullptr, nullptr};
-    MCRN_TRY(gemm(q, e, st));
+    MCRN_TRY(gemm(q, e, sx[i]));
     float* gi = S + (int64_t)i * per * g.N * g.ldS;
     float* gri = Sr + (int64_t)i * per * g.N * g.ldS;
-    MCRN_LAUNCH(k_relu_softmax_rows, g.N, 256, 0, st, i ? L2 : L1, gi, gri, g.N, g.ldS);
+    MCRN_LAUNCH(k_relu_softmax_rows, g.N, 256, 0, sx[i], i ? L2 : L1, gi, gri, g.N, g.ldS);
     for (int k = 2; k < g.cheb_k; ++k) {  // T_k = 2 g T_{k-1} - T_{k-2}          :21-22 (hoisted)
       float* tk = gi + (int64_t)(k - 1) * g.N * g.ldS;
       const float* tkm1 = gri + (int64_t)(k - 2) * g.N * g.ldS;      // tensor-core operands: rounded copies
@@ -265,13 +277,14 @@ static int supports_forward(const Geo& g, const Plan& p, float* ws, const float*
       c.A = gri; c.a_row = g.ldS; c.a_k = 1; c.M = g.N; c.Kseg = g.N;
       c.B = tkm1; c.b_k = g.ldS; c.b_n = 1; c.N = g.N; c.prec_exact = dbg_exact(6);
       EpiCheb e{tk, g.ldS, tkm2, gri + (int64_t)(k - 1) * g.N * g.ldS};
-      MCRN_TRY(gemm(c, e, st));
+      MCRN_TRY(gemm(c, e, sx[i]));
     }
   }
+  if (f) MCRN_TRY(fork_join(*f, st));
   return MCRN_OK;
 }
 
-static int fold_all_weights(const Geo& g, const Plan& p, float* ws, const mcrn_params* prm, cudaStream_t st) {
+[[maybe_unused]] static int fold_all_weights(const Geo& g, const Plan& p, float* ws, const mcrn_params* prm, cudaStream_t st) {
   const int sp = tf32_mode();
   MCRN_LAUNCH(k_fold_weights, 128, 256, 0, st, prm->enc_gate_w, prm->enc_gate_b, ws + p.e_wg, g.Cin, g.H, 2 * g.H, g.cheb_k, sp);
   MCRN_LAUNCH(k_fold_weights, 128, 256, 0, st, prm->enc_update_w, prm->enc_update_b, ws + p.e_wu, g.Cin, g.H, g.H, g.cheb_k, sp);
@@ -333,6 +346,66 @@ static CellW dec_w(const Geo& g, const Plan& p, float* ws) {
                p.save ? reinterpret_cast<const __half*>(ws + p.d_wg16n) : nullptr, p.save ? reinterpret_cast<const __half*>(ws + p.d_wu16n) : nullptr};
 }
 
+// ---- forward-side fork / join: work that does not sit on the recurrent chain runs on two helper streams ------------
+// (eagerly and under stream capture: the events become graph edges).  f0: weight folding and operand conversion, concurrent
+// with the supports prologue; f1: everything that needs the supports but not the encoder (decoder input blocks of the
+// teacher-forced steps, the backward's transposed operand copies), concurrent with the encoder loop.
+struct Fork { cudaStream_t s = nullptr; cudaEvent_t begin = nullptr, end = nullptr; };
+static Fork g_fw[2];
+static int fw_init() {
+  for (auto& f : g_fw) {
+    if (f.s) continue;
+    MCRN_CUDA_OK(cudaStreamCreateWithFlags(&f.s, cudaStreamNonBlocking));
+    MCRN_CUDA_OK(cudaEventCreateWithFlags(&f.begin, cudaEventDisableTiming));
+    MCRN_CUDA_OK(cudaEventCreateWithFlags(&f.end, cudaEventDisableTiming));
+  }
+  return MCRN_OK;
+}
+static int fork_begin(Fork& f, cudaStream_t mainst) {
+  MCRN_CUDA_OK(cudaEventRecord(f.begin, mainst));
+  MCRN_CUDA_OK(cudaStreamWaitEvent(f.s, f.begin, 0));
+  return MCRN_OK;
+}
+static int fork_join(Fork& f, cudaStream_t mainst) {
+  MCRN_CUDA_OK(cudaEventRecord(f.end, f.s));
+  MCRN_CUDA_OK(cudaStreamWaitEvent(mainst, f.end, 0));
+  return MCRN_OK;
+}
+static int g_fw_fork = getenv("MCRN_FWD_FORK") ? atoi(getenv("MCRN_FWD_FORK")) : 1;
+static Fork* fw_fork(int i) { return (g_fw_fork != 0 && g_fw[i].s != nullptr) ? &g_fw[i] : nullptr; }
+static cudaStream_t fw_fork_stream(int i) { return g_fw[i].s; }
+
+static bool bwd_fused_shape(const Geo& g, int Hs, int Cin);
+extern int g_bwd_fused;
+
+// Operand copies of the fused backward that depend on the forward's prologue only (transposed fp16 supports, fp16 weights
+// in [K][O] order, TF32 transposed supports of the TF32 variant): built at forward time, off the critical path.
+static int backward_operand_copies(const Geo& g, const Plan& p, float* ws, cudaStream_t st_w, cudaStream_t st_s, bool weights, bool supports) {
+  const bool fe = bwd_fused_shape(g, g.H, g.Cin), fd = bwd_fused_shape(g, g.D, g.Cdec);
+  if (!(fe || fd)) return MCRN_OK;
+  if (g_bwd_fused == 2) {
+    if (supports) {
+      const int ld16 = fusedh::ld_half(g.N);
+      MCRN_LAUNCH(fusedbh::k_supports_to_half_T, dim3(ceil_div(g.N, 32), ceil_div(ld16, 32), g.KS), dim3(32, 8), 0, st_s, ws + p.S,
+                  reinterpret_cast<__half*>(ws + p.s16T), g.N, g.ldS, ld16);
+    }
+    if (weights && fe) {
+      const int64_t ng = (int64_t)(g.NB + 1) * g.H * 2 * g.H, nu = (int64_t)(g.NB + 1) * g.H * g.H;
+      MCRN_LAUNCH(fusedbh::k_weights_to_half_n, ew_grid(ng), 256, 0, st_w, ws + p.e_wg, reinterpret_cast<__half*>(ws + p.e_wg16n), ng);
+      MCRN_LAUNCH(fusedbh::k_weights_to_half_n, ew_grid(nu), 256, 0, st_w, ws + p.e_wu, reinterpret_cast<__half*>(ws + p.e_wu16n), nu);
+    }
+    if (weights && fd) {
+      const int64_t ng = (int64_t)(g.NB + 1) * g.D * 2 * g.D, nu = (int64_t)(g.NB + 1) * g.D * g.D;
+      MCRN_LAUNCH(fusedbh::k_weights_to_half_n, ew_grid(ng), 256, 0, st_w, ws + p.d_wg, reinterpret_cast<__half*>(ws + p.d_wg16n), ng);
+      MCRN_LAUNCH(fusedbh::k_weights_to_half_n, ew_grid(nu), 256, 0, st_w, ws + p.d_wu, reinterpret_cast<__half*>(ws + p.d_wu16n), nu);
+    }
+  }
+  if (supports)
+    MCRN_LAUNCH(fusedb::k_transpose_supports, dim3(ceil_div(g.N, 32), ceil_div(g.N, 32), g.KS), dim3(32, 8), 0, st_s, ws + p.Sr, ws + p.St,
+                g.N, g.ldS);
+  return MCRN_OK;
+}
+
 // ======================================================================================
 // forward                                                        model/MegaCRN.py:168-194
 // ======================================================================================
@@ -340,24 +413,64 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
                  const float* labels, const uint8_t* tf, float* output, float* h_att, float* query, float* pos,
                  float* neg, float* ws, cudaStream_t st, bool reuse_prologue) {
   float* S = ws + p.Sr;     // the recurrent GEMMs read the tensor-core copy of the supports
+  MCRN_TRY(fw_init());
+  const bool fork = g_fw_fork != 0;
+  cudaStream_t s0 = fork ? g_fw[0].s : st, s1 = fork ? g_fw[1].s : st;
+  const bool enc_h = fused_h_shape(g, g.H), dec_h = fused_h_shape(g, g.D);
   // eval fast path (MCRN_FWD_REUSE_PROLOGUE): everything below that depends on the parameters only is still in the workspace
   if (!reuse_prologue) {
-  MCRN_TRY(supports_forward(g, p, ws, prm->memory, prm->we1, prm->we2, ws + p.S, ws + p.Sr, st));
-  MCRN_TRY(fold_all_weights(g, p, ws, prm, st));
+    // f0: folded weights + their fp16 operand copies (independent of the supports)
+    if (fork) MCRN_TRY(fork_begin(g_fw[0], st));
+    {
+      const int sp = tf32_mode();
+      MCRN_LAUNCH(k_fold_weights, 128, 256, 0, s0, prm->enc_gate_w, prm->enc_gate_b, ws + p.e_wg, g.Cin, g.H, 2 * g.H, g.cheb_k, sp);
+      MCRN_LAUNCH(k_fold_weights, 128, 256, 0, s0, prm->enc_update_w, prm->enc_update_b, ws + p.e_wu, g.Cin, g.H, g.H, g.cheb_k, sp);
+      MCRN_LAUNCH(k_fold_weights, 128, 256, 0, s0, prm->dec_gate_w, prm->dec_gate_b, ws + p.d_wg, g.Cdec, g.D, 2 * g.D, g.cheb_k, sp);
+      MCRN_LAUNCH(k_fold_weights, 128, 256, 0, s0, prm->dec_update_w, prm->dec_update_b, ws + p.d_wu, g.Cdec, g.D, g.D, g.cheb_k, sp);
+      if (enc_h) {
+        MCRN_LAUNCH(fusedh::k_weights_to_half, 128, 256, 0, s0, ws + p.e_wg, reinterpret_cast<__half*>(ws + p.e_wg16), g.NB + 1, g.H, 2 * g.H);
+        MCRN_LAUNCH(fusedh::k_weights_to_half, 128, 256, 0, s0, ws + p.e_wu, reinterpret_cast<__half*>(ws + p.e_wu16), g.NB + 1, g.H, g.H);
+      }
+      if (dec_h) {
+        MCRN_LAUNCH(fusedh::k_weights_to_half, 128, 256, 0, s0, ws + p.d_wg, reinterpret_cast<__half*>(ws + p.d_wg16), g.NB + 1, g.D, 2 * g.D);
+        MCRN_LAUNCH(fusedh::k_weights_to_half, 128, 256, 0, s0, ws + p.d_wu, reinterpret_cast<__half*>(ws + p.d_wu16), g.NB + 1, g.D, g.D);
+      }
+      if (p.save) MCRN_TRY(backward_operand_copies(g, p, ws, s0, s0, true, false));
+    }
+    MCRN_TRY(supports_forward(g, p, ws, prm->memory, prm->we1, prm->we2, ws + p.S, ws + p.Sr, st));
+    if (enc_h || dec_h) {  // fp16 operand copy of the supports for the fused forward (exact fp32 -> half)
+      const int ld16 = fusedh::ld_half(g.N);
+      MCRN_LAUNCH(fusedh::k_supports_to_half, ew_grid((int64_t)g.KS * g.N * ld16), 256, 0, st, ws + p.S,
+                  reinterpret_cast<__half*>(ws + p.s16), g.KS * g.N, g.N, g.ldS, ld16);
+    }
   }
-  const bool enc_h = fused_h_shape(g, g.H), dec_h = fused_h_shape(g, g.D);
-  if ((enc_h || dec_h) && !reuse_prologue) {  // fp16 operand copies for the fused forward: supports (exact fp32 -> half) and weights (hi/lo, transposed)
-    const int ld16 = fusedh::ld_half(g.N);
-    MCRN_LAUNCH(fusedh::k_supports_to_half, ew_grid((int64_t)g.KS * g.N * ld16), 256, 0, st, ws + p.S,
-                reinterpret_cast<__half*>(ws + p.s16), g.KS * g.N, g.N, g.ldS, ld16);
-    if (enc_h) {
-      MCRN_LAUNCH(fusedh::k_weights_to_half, 128, 256, 0, st, ws + p.e_wg, reinterpret_cast<__half*>(ws + p.e_wg16), g.NB + 1, g.H, 2 * g.H);
-      MCRN_LAUNCH(fusedh::k_weights_to_half, 128, 256, 0, st, ws + p.e_wu, reinterpret_cast<__half*>(ws + p.e_wu16), g.NB + 1, g.H, g.H);
+  // ---- f1: needs the supports, not the encoder: decoder input blocks of every step whose input is known up front
+  // (step 0: zeros; step t after a teacher-forced coin flip: labels[:, t-1]) in ONE launch; backward operand copies ----
+  const bool dec_compact = ib_compact_shape(g, g.D, g.Cdec, p.save);
+  unsigned dec_tf_mask = 0, proj_mask = 0;
+  auto launch_dec_input = [&](const float* go_src, unsigned mask, cudaStream_t sx) -> int {
+    const size_t shm = ((size_t)(g.N | 1) * fusedh::DI_COLS + (size_t)fusedh::DI_ROWS * (g.N + 1) +
+                        (size_t)fusedh::DI_NODES * fusedh::DI_COLS * (fusedh::IBF + 1)) * sizeof(float);
+    static bool di_attr = false;
+    if (!di_attr) {
+      MCRN_CUDA_OK(cudaFuncSetAttribute(fusedh::k_decoder_input_block, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      di_attr = true;
     }
-    if (dec_h) {
-      MCRN_LAUNCH(fusedh::k_weights_to_half, 128, 256, 0, st, ws + p.d_wg, reinterpret_cast<__half*>(ws + p.d_wg16), g.NB + 1, g.D, 2 * g.D);
-      MCRN_LAUNCH(fusedh::k_weights_to_half, 128, 256, 0, st, ws + p.d_wu, reinterpret_cast<__half*>(ws + p.d_wu16), g.NB + 1, g.D, g.D);
+    MCRN_LAUNCH(fusedh::k_decoder_input_block,
+                dim3(ceil_div(g.B * g.Cdec, fusedh::DI_COLS), ceil_div(g.N, fusedh::DI_NODES), __builtin_popcount(mask)), 256, shm, sx,
+                go_src, y_cov, ws + p.S, g.ldS, g.KS, g.N, g.B, g.T_out, g.Cout, g.Ycov, mask,
+                p.save ? ws + p.dec_xpin : nullptr, (int64_t)p.dec_xpin_sz, reinterpret_cast<__half*>(ws + p.dec_ib16c),
+                p.save ? ws + p.dec_ib32c : nullptr);
+    return MCRN_OK;
+  };
+  {
+    if (fork) MCRN_TRY(fork_begin(g_fw[1], st));
+    if (dec_compact && g.T_out <= 32) {
+      for (int t = 0; t < g.T_out; ++t)
+        if (t == 0 || (tf && tf[t - 1])) dec_tf_mask |= 1u << t;
+      MCRN_TRY(launch_dec_input(labels, dec_tf_mask, s1));
     }
+    if (p.save && !reuse_prologue) MCRN_TRY(backward_operand_copies(g, p, ws, s1, s1, false, true));
   }
   // ---- encoder (ADCRNN_Encoder.forward :65-83; zero initial state :50-51, :174) ----
   {
@@ -374,6 +487,7 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
       MCRN_CUDA_OK(cudaMemsetAsync(ws + p.enc_x16, 0, (size_t)g.R * g.H * sizeof(__half), st));
       MCRN_CUDA_OK(cudaMemsetAsync(ws + p.enc_x16T, 0, (size_t)g.B * g.H * fusedh::ld_half(g.N) * sizeof(__half), st));
     }
+    if (fork && !reuse_prologue) MCRN_TRY(fork_join(g_fw[0], st));      // the folded weights are needed from here on
     CellW w = enc_w(g, p, ws);
     for (int t = 0; t < g.T_in; ++t) {
       CellBufs b = enc_bufs(g, p, ws, t);
@@ -395,33 +509,10 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
       MCRN_LAUNCH(fusedh::k_state_to_half, ew_grid(g.R * g.D), 256, 0, st, b0.xpg, b0.x16, b0.x16T, g.N, g.B, g.D,
                   fusedh::ld_half(g.N));
   }
+  if (fork) MCRN_TRY(fork_join(g_fw[1], st));
   // ---- decoder loop (:181-192) ----
   {
     CellW w = dec_w(g, p, ws);
-    // compact input blocks: every step whose decoder input is known up front (step 0: zeros; step t after a teacher-forced
-    // coin flip: labels[:, t-1]) is built by ONE launch before the loop; free-running steps by a launch of their own
-    const bool dec_compact = ib_compact_shape(g, g.D, g.Cdec, p.save);
-    unsigned dec_tf_mask = 0, proj_mask = 0;
-    auto launch_dec_input = [&](const float* go_src, unsigned mask) -> int {
-      const size_t shm = ((size_t)(g.N | 1) * fusedh::DI_COLS + (size_t)fusedh::DI_ROWS * (g.N + 1) +
-                          (size_t)fusedh::DI_NODES * fusedh::DI_COLS * (fusedh::IBF + 1)) * sizeof(float);
-      static bool di_attr = false;
-      if (!di_attr) {
-        MCRN_CUDA_OK(cudaFuncSetAttribute(fusedh::k_decoder_input_block, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        di_attr = true;
-      }
-      MCRN_LAUNCH(fusedh::k_decoder_input_block,
-                  dim3(ceil_div(g.B * g.Cdec, fusedh::DI_COLS), ceil_div(g.N, fusedh::DI_NODES), __builtin_popcount(mask)), 256, shm, st,
-                  go_src, y_cov, ws + p.S, g.ldS, g.KS, g.N, g.B, g.T_out, g.Cout, g.Ycov, mask,
-                  p.save ? ws + p.dec_xpin : nullptr, (int64_t)p.dec_xpin_sz, reinterpret_cast<__half*>(ws + p.dec_ib16c),
-                  p.save ? ws + p.dec_ib32c : nullptr);
-      return MCRN_OK;
-    };
-    if (dec_compact && g.T_out <= 32) {
-      for (int t = 0; t < g.T_out; ++t)
-        if (t == 0 || (tf && tf[t - 1])) dec_tf_mask |= 1u << t;
-      MCRN_TRY(launch_dec_input(labels, dec_tf_mask));
-    }
     for (int t = 0; t < g.T_out; ++t) {
       CellBufs b = dec_bufs(g, p, ws, t);
       const float* go_src = nullptr;
@@ -429,7 +520,7 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
       int64_t n_in = (int64_t)g.R * g.Cdec;
       if (dec_compact) {
         if (!((dec_tf_mask >> t) & 1u))      // free-running step: its input is the previous prediction
-          MCRN_TRY(launch_dec_input(output, 1u << t));
+          MCRN_TRY(launch_dec_input(output, 1u << t, st));
       } else {
       MCRN_LAUNCH(k_stage_decoder_input, ew_grid(n_in), 256, 0, st, go_src, y_cov, const_cast<float*>(b.xpin), g.B,
                   g.T_out, g.N, g.Cout, g.Ycov, t, tf32_mode());
@@ -861,7 +952,12 @@ static int supports_backward(const Geo& g, const Plan& p, float* ws, const mcrn_
   float* dg[2] = {ws + p.dg1, ws + p.dg2};
   // N^3 work: exact fp32 on the SIMT engine for METR-LA/PEMS-BAY sizes (negligible FLOPs), tensor cores beyond.
   const int big_exact = (g.N <= 1024) ? 1 : 0;
+  // the two supports (i = 0: g1 chain, i = 1: g2 chain) are independent up to dL1: chain 1 runs on a helper stream
+  const bool fork = g_fw_fork != 0 && g_fw[1].s != nullptr;
+  float *dLa = ws + p.dLa, *dLb = ws + p.dLb, *dL1 = ws + p.dL1, *dE1 = ws + p.dE1, *dE2 = ws + p.dE2;
+  if (fork) MCRN_TRY(fork_begin(g_fw[1], st));
   for (int i = 0; i < 2; ++i) {
+    cudaStream_t sx = (i == 1 && fork) ? g_fw[1].s : st;
     float* gi = (big_exact ? S : ws + p.Sr) + (int64_t)i * per * mat;
     float* dt = dS + (int64_t)i * per * mat;                 // dt[k-1] = d T_k, k = 1..cheb_k-1
     for (int k = g.cheb_k - 1; k >= 2; --k) {
@@ -871,7 +967,7 @@ static int supports_backward(const Geo& g, const Plan& p, float* ws, const mcrn_
         q.A = dtk; q.a_row = g.ldS; q.a_k = 1; q.M = g.N; q.Kseg = g.N;
         q.B = gi + (int64_t)(k - 2) * mat; q.b_k = 1; q.b_n = g.ldS; q.N = g.N; q.prec_exact = big_exact;
         EpiStore e{dg[i], g.ldS, 0, 2.0f, dg[i], nullptr};
-        MCRN_TRY(gemm(q, e, st));
+        MCRN_TRY(gemm(q, e, sx));
       }
       {  // dT_{k-1} += 2 * g^T * dT_k
         float* dtm1 = dt + (int64_t)(k - 2) * mat;
@@ -879,38 +975,40 @@ static int supports_backward(const Geo& g, const Plan& p, float* ws, const mcrn_
         q.A = gi; q.a_row = 1; q.a_k = g.ldS; q.M = g.N; q.Kseg = g.N;
         q.B = dtk; q.b_k = g.ldS; q.b_n = 1; q.N = g.N; q.prec_exact = big_exact;
         EpiStore e{dtm1, g.ldS, 0, 2.0f, dtm1, nullptr};
-        MCRN_TRY(gemm(q, e, st));
+        MCRN_TRY(gemm(q, e, sx));
       }
       if (k - 2 >= 1) {  // dT_{k-2} -= dT_k
         float* dtm2 = dt + (int64_t)(k - 3) * mat;
-        MCRN_LAUNCH(k_axpy, ew_grid(mat), 256, 0, st, dtm2, dtk, -1.0f, mat);
+        MCRN_LAUNCH(k_axpy, ew_grid(mat), 256, 0, sx, dtm2, dtk, -1.0f, mat);
       }
     }
-    MCRN_LAUNCH(k_add_inplace, ew_grid(mat), 256, 0, st, dg[i], dt, mat);      // dg += dT_1
+    MCRN_LAUNCH(k_add_inplace, ew_grid(mat), 256, 0, sx, dg[i], dt, mat);      // dg += dT_1
+    MCRN_LAUNCH(k_relu_softmax_rows_bwd, g.N, 256, 0, sx, i ? ws + p.L2 : ws + p.L1, S + (int64_t)i * per * mat, dg[i], i ? dLb : dLa, g.N, g.ldS);
   }
-  float *dLa = ws + p.dLa, *dLb = ws + p.dLb, *dL1 = ws + p.dL1, *dE1 = ws + p.dE1, *dE2 = ws + p.dE2;
-  MCRN_LAUNCH(k_relu_softmax_rows_bwd, g.N, 256, 0, st, ws + p.L1, S, dg[0], dLa, g.N, g.ldS);
-  MCRN_LAUNCH(k_relu_softmax_rows_bwd, g.N, 256, 0, st, ws + p.L2, S + (int64_t)per * mat, dg[1], dLb, g.N, g.ldS);
+  if (fork) MCRN_TRY(fork_join(g_fw[1], st));
   MCRN_LAUNCH(k_add_transpose, dim3(ceil_div(g.N, 32), ceil_div(g.N, 32)), dim3(32, 8), 0, st, dLa, dLb, dL1, g.N, g.ldS);
-  {  // dE1 = dL1 * E2 ; dE2 = dL1^T * E1
-    GemmDesc q;
-    q.A = dL1; q.a_row = g.ldS; q.a_k = 1; q.M = g.N; q.Kseg = g.N;
-    q.B = ws + p.E2; q.b_k = g.d; q.b_n = 1; q.N = g.d; q.prec_exact = 1;
-    EpiStore e{dE1, g.d, 0, 1.0f, nullptr, nullptr};
-    MCRN_TRY(gemm(q, e, st));
-    q.A = dL1; q.a_row = 1; q.a_k = g.ldS; q.B = ws + p.E1;
-    EpiStore e2{dE2, g.d, 0, 1.0f, nullptr, nullptr};
-    MCRN_TRY(gemm(q, e2, st));
-  }
+  if (fork) MCRN_TRY(fork_begin(g_fw[1], st));
   for (int i = 0; i < 2; ++i) {
-    const float* dE = i ? dE2 : dE1;
+    cudaStream_t sx = (i == 1 && fork) ? g_fw[1].s : st;
+    {  // dE1 = dL1 * E2 ; dE2 = dL1^T * E1
+      GemmDesc q;
+      q.M = g.N; q.Kseg = g.N; q.A = dL1;
+      if (i == 0) { q.a_row = g.ldS; q.a_k = 1; } else { q.a_row = 1; q.a_k = g.ldS; }
+      q.B = i ? ws + p.E1 : ws + p.E2; q.b_k = g.d; q.b_n = 1; q.N = g.d; q.prec_exact = 1;
+      EpiStore e{i ? dE2 : dE1, g.d, 0, 1.0f, nullptr, nullptr};
+      MCRN_TRY(gemm(q, e, sx));
+    }
     {  // dWe_i = dE_i * Memory^T                     [N x M]
       GemmDesc q;
-      q.A = dE; q.a_row = g.d; q.a_k = 1; q.M = g.N; q.Kseg = g.d;
+      q.A = i ? dE2 : dE1; q.a_row = g.d; q.a_k = 1; q.M = g.N; q.Kseg = g.d;
       q.B = prm->memory; q.b_k = 1; q.b_n = g.d; q.N = g.M; q.prec_exact = 1;
       EpiStore e{i ? grads->we2 : grads->we1, g.M, 0, 1.0f, nullptr, nullptr};
-      MCRN_TRY(gemm(q, e, st));
+      MCRN_TRY(gemm(q, e, sx));
     }
+  }
+  if (fork) MCRN_TRY(fork_join(g_fw[1], st));
+  for (int i = 0; i < 2; ++i) {
+    const float* dE = i ? dE2 : dE1;
     {  // dMemory += We_i^T * dE_i                    [M x d]
       GemmDesc q;
       q.A = i ? prm->we2 : prm->we1; q.a_row = 1; q.a_k = g.M; q.M = g.M; q.Kseg = g.N;
@@ -927,6 +1025,7 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
                   const mcrn_params* grads, float* ws, cudaStream_t st) {
   const float* S = ws + p.Sr;     // tensor-core copy of the supports (equal to the exact ones in SIMT mode)
   MCRN_TRY(side_init());
+  MCRN_TRY(fw_init());
   // zero accumulators and the directly-accumulated outputs
   MCRN_CUDA_OK(cudaMemsetAsync(ws + p.acc_begin, 0, (p.acc_end - p.acc_begin) * sizeof(float), st));
   MCRN_CUDA_OK(cudaMemsetAsync(grads->memory, 0, (size_t)g.M * g.d * sizeof(float), st));
@@ -948,23 +1047,8 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
       if (acc > 0) MCRN_LAUNCH(fusedbh::k_grad_amax, ew_grid(acc), 256, 0, st, a, amax);
     }
     MCRN_LAUNCH(fusedbh::k_grad_scale, 1, 1, 0, st, amax, ws + p.gs);
-    const int ld16 = fusedh::ld_half(g.N);
-    MCRN_LAUNCH(fusedbh::k_supports_to_half_T, dim3(ceil_div(g.N, 32), ceil_div(ld16, 32), g.KS), dim3(32, 8), 0, st, ws + p.S,
-                reinterpret_cast<__half*>(ws + p.s16T), g.N, g.ldS, ld16);
-    if (bwd_fused_shape(g, g.H, g.Cin)) {
-      const int64_t ng = (int64_t)(g.NB + 1) * g.H * 2 * g.H, nu = (int64_t)(g.NB + 1) * g.H * g.H;
-      MCRN_LAUNCH(fusedbh::k_weights_to_half_n, ew_grid(ng), 256, 0, st, ws + p.e_wg, reinterpret_cast<__half*>(ws + p.e_wg16n), ng);
-      MCRN_LAUNCH(fusedbh::k_weights_to_half_n, ew_grid(nu), 256, 0, st, ws + p.e_wu, reinterpret_cast<__half*>(ws + p.e_wu16n), nu);
-    }
-    if (bwd_fused_shape(g, g.D, g.Cdec)) {
-      const int64_t ng = (int64_t)(g.NB + 1) * g.D * 2 * g.D, nu = (int64_t)(g.NB + 1) * g.D * g.D;
-      MCRN_LAUNCH(fusedbh::k_weights_to_half_n, ew_grid(ng), 256, 0, st, ws + p.d_wg, reinterpret_cast<__half*>(ws + p.d_wg16n), ng);
-      MCRN_LAUNCH(fusedbh::k_weights_to_half_n, ew_grid(nu), 256, 0, st, ws + p.d_wu, reinterpret_cast<__half*>(ws + p.d_wu16n), nu);
-    }
   }
-  if (bwd_fused_shape(g, g.D, g.Cdec) || bwd_fused_shape(g, g.H, g.Cin))
-    MCRN_LAUNCH(fusedb::k_transpose_supports, dim3(ceil_div(g.N, 32), ceil_div(g.N, 32), g.KS), dim3(32, 8), 0, st, S, ws + p.St,
-                g.N, g.ldS);
+  // (the transposed / fp16 operand copies of the supports and weights were built by the forward: backward_operand_copies)
   // ---- decoder, reverse time ----
   {
     CellW w = dec_w(g, p, ws);
@@ -1016,7 +1100,7 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
         dec_glue_fused = false;
         if (g_bwd_fused == 2 && !glue_fused_here) {
           const size_t gsm = ((size_t)(32 + g.D) * g.Cout + 2 * 32 * (g.D + 1)) * sizeof(float);
-          MCRN_TRY(launch_chain(fusedbh::k_bwd_glue_h, dim3(ceil_div(g.N, 32), g.B), dim3(256), gsm, st, "k_bwd_glue_h", d_output, use_dgo ? dXin : nullptr, g.Cdec, h_t,
+          MCRN_TRY(launch_chain(4, fusedbh::k_bwd_glue_h, dim3(ceil_div(g.N, 32), g.B), dim3(256), gsm, st, "k_bwd_glue_h", d_output, use_dgo ? dXin : nullptr, g.Cdec, h_t,
                       prm->proj_w, dH, (t == g.T_out - 1) ? 1 : 0, b.r, b.hc, b.hx, dU_t, dG_all + (int64_t)t * g.R * 2 * g.D,
                       ws + p.dHr, du16_buf(g, p, ws, g.D, t), du16T_buf(g, p, ws, g.D, t),
                       dg16_buf(g, p, ws, g.D, t), dg16T_buf(g, p, ws, g.D, t), fusedh::ld_half(g.N),
@@ -1070,6 +1154,7 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
     }
   }
   // ---- memory query ----
+  bool mq_forked = false;
   {
     size_t shm = (8 * (g.d + g.M) + (size_t)g.M * (g.d + 1)) * sizeof(float);
     float *dv = ws + p.mq_dv, *dsc = ws + p.mq_dsc, *dq = ws + p.mq_dq;
@@ -1077,23 +1162,29 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
                 prm->memory, ws + p.mq_att, reinterpret_cast<const int*>(ws + p.mq_ind), dv, dsc, dq, grads->memory,
                 g.B, g.N, g.H, g.M, g.d);
     int sp = split_for(1, g.R / 16);
+    // dMemory / dWq feed nothing on the recurrent chain: helper stream (joined before the supports backward, which also
+    // accumulates into grads->memory)
+    Fork* f0 = fw_fork(0);
+    cudaStream_t sq = f0 ? fw_fork_stream(0) : st;
+    if (f0) MCRN_TRY(fork_begin(*f0, st));
     {  // dMemory += att^T dv + dsc^T query            [M x d], K = R
       GemmDesc q;
       q.A = ws + p.mq_att; q.a_row = 1; q.a_k = g.M; q.M = g.M; q.Kseg = (int)g.R;
       q.B = dv; q.b_k = g.d; q.b_n = 1; q.N = g.d; q.splits = sp; q.prec_exact = 1;
       EpiAtomicAdd e{grads->memory, g.d, 0};
-      MCRN_TRY(gemm(q, e, st));
+      MCRN_TRY(gemm(q, e, sq));
       q.A = dsc; q.B = ws + p.mq_q;
-      MCRN_TRY(gemm(q, e, st));
+      MCRN_TRY(gemm(q, e, sq));
     }
     {  // dWq = h_enc^T dq                             [H x d], K = R
-      MCRN_CUDA_OK(cudaMemsetAsync(grads->wq, 0, (size_t)g.H * g.d * sizeof(float), st));
+      MCRN_CUDA_OK(cudaMemsetAsync(grads->wq, 0, (size_t)g.H * g.d * sizeof(float), sq));
       GemmDesc q;
       q.A = ws + p.h_enc; q.a_row = 1; q.a_k = g.H; q.M = g.H; q.Kseg = (int)g.R;
       q.B = dq; q.b_k = g.d; q.b_n = 1; q.N = g.d; q.splits = sp; q.prec_exact = 1;
       EpiAtomicAdd e{grads->wq, g.d, 0};
-      MCRN_TRY(gemm(q, e, st));
+      MCRN_TRY(gemm(q, e, sq));
     }
+    mq_forked = f0 != nullptr;
     {  // dH_enc = dH0[:, :H] + dq Wq^T                [R x H], K = d
       GemmDesc q;
       q.A = dq; q.a_row = g.d; q.a_k = 1; q.M = (int)g.R; q.Kseg = g.d;
@@ -1146,7 +1237,7 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
         enc_glue_fused = false;
         if (g_bwd_fused == 2 && !glue_fused_here) {
           const size_t gsm = (size_t)2 * 32 * (g.H + 1) * sizeof(float);
-          MCRN_TRY(launch_chain(fusedbh::k_bwd_glue_h, dim3(ceil_div(g.N, 32), g.B), dim3(256), gsm, st, "k_bwd_glue_h", (const float*)nullptr, (const float*)nullptr, 0,
+          MCRN_TRY(launch_chain(4, fusedbh::k_bwd_glue_h, dim3(ceil_div(g.N, 32), g.B), dim3(256), gsm, st, "k_bwd_glue_h", (const float*)nullptr, (const float*)nullptr, 0,
                       (const float*)nullptr, (const float*)nullptr, dHe, 0, b.r, b.hc, b.hx, dU_t, dG_all + (int64_t)t * g.R * 2 * g.H,
                       ws + p.dHr, du16_buf(g, p, ws, g.H, t), du16T_buf(g, p, ws, g.H, t),
                       dg16_buf(g, p, ws, g.H, t), dg16T_buf(g, p, ws, g.H, t), fusedh::ld_half(g.N),
@@ -1187,6 +1278,7 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
   }
   MCRN_TRY(side_join(st));        // all dS contributions have landed
   MCRN_TRY(side_join_fused(st));
+  if (mq_forked) MCRN_TRY(fork_join(*fw_fork(0), st));
   MCRN_TRY(supports_backward(g, p, ws, prm, grads, st));
   MCRN_TRY(side2_join(st));
   // ---- un-fold weight gradients into the reference layout ----
@@ -1205,16 +1297,21 @@ int supports_forward_entry(const Geo& g, const Plan& p, float* ws, const float* 
   return MCRN_OK;
 }
 
+int mask_count_impl(const float* labels, int64_t n, float mean, float std, float* count_out, cudaStream_t st) {
+  MCRN_LAUNCH(k_mask_count, ew_grid(n) > 296 ? 296 : ew_grid(n), 256, 0, st, labels, n, mean, std, count_out);
+  return MCRN_OK;
+}
+
 int trainer_loss_impl(const Geo& g, const float* output, const float* labels, const float* query, const float* pos,
-                      const float* neg, float mean, float std, float lamb, float lamb1, float* loss_out,
+                      const float* neg, float mean, float std, float lamb, float lamb1, const float* mask_count, float* loss_out,
                       float* d_output, float* d_query, float* scratch, cudaStream_t st) {
   const int64_t n_out = (int64_t)g.B * g.T_out * g.N * g.Cout, rows = (int64_t)g.B * g.N;
   MCRN_CUDA_OK(cudaMemsetAsync(scratch, 0, 4 * sizeof(float), st));
   MCRN_LAUNCH(k_loss_reduce_out, ew_grid(n_out) > 296 ? 296 : ew_grid(n_out), 256, 0, st, output, labels, n_out, mean, std, scratch);
   int rgrid = (int)(ceil_div64(rows, 8) > 296 ? 296 : ceil_div64(rows, 8));
   MCRN_LAUNCH(k_loss_reduce_rows, rgrid, 256, 0, st, query, pos, neg, rows, g.d, scratch);
-  MCRN_LAUNCH(k_loss_finish, 1, 32, 0, st, scratch, rows, g.d, lamb, lamb1, loss_out);
-  if (d_output) MCRN_LAUNCH(k_loss_grad_out, ew_grid(n_out), 256, 0, st, output, labels, n_out, mean, std, scratch, d_output);
+  MCRN_LAUNCH(k_loss_finish, 1, 32, 0, st, scratch, mask_count, rows, g.d, lamb, lamb1, loss_out);
+  if (d_output) MCRN_LAUNCH(k_loss_grad_out, ew_grid(n_out), 256, 0, st, output, labels, n_out, mean, std, scratch, mask_count, d_output);
   if (d_query) MCRN_LAUNCH(k_loss_grad_rows, (int)ceil_div64(rows, 8), 256, 0, st, query, pos, neg, rows, g.d, lamb, lamb1, d_query);
   return MCRN_OK;
 }
@@ -1257,6 +1354,7 @@ bool set_option(const char* name, int value) {
   else if (n == "ib_compact") g_ib_compact = value;
   else if (n == "dw_fused") g_dw_fused = value;
   else if (n == "pdl") g_pdl_chain = value;
+  else if (n == "fwd_fork") g_fw_fork = value;
   else return false;
   return true;
 }

@@ -26,6 +26,16 @@ def flat_grad_view(params: Iterable[torch.nn.Parameter]) -> Optional[torch.Tenso
     return torch.empty(0, dtype=torch.float32, device=grads[0].device).set_(st, 0, (n,), (1,))
 
 
+def _allreduce_mean(t: torch.Tensor, world: int, group) -> None:
+    """In-place mean over the group.  NCCL averages inside the collective (ncclAvg: no separate scaling kernel on the
+    critical path); other backends (gloo in the CPU tests) sum and scale."""
+    if t.is_cuda and dist.get_backend(group) == "nccl":
+        dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group)
+    else:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        t.mul_(1.0 / world)
+
+
 def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None) -> int:
     """Average gradients over the data-parallel group with a single collective.
     Returns the number of collectives issued (1, or 0 outside a process group)."""
@@ -37,18 +47,46 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None) -> int
     params = [p for p in params if p.grad is not None]
     flat = flat_grad_view(params)
     if flat is not None:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        flat.mul_(1.0 / world)
+        _allreduce_mean(flat, world, group)
         return 1
     buf = torch.cat([p.grad.reshape(-1) for p in params])
-    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
-    buf.mul_(1.0 / world)
+    _allreduce_mean(buf, world, group)
     off = 0
     for p in params:
         n = p.grad.numel()
         p.grad.copy_(buf[off:off + n].view_as(p.grad))
         off += n
     return 1
+
+
+def global_mask_count_begin(labels: torch.Tensor, scaler_mean: float, scaler_std: float, group=None):
+    """Start the all-reduce of the masked-MAE normaliser (model/utils.py:127-128: ``mask.mean()`` over the GLOBAL batch):
+    this rank's count of labels with ``labels * std + mean != 0`` (``mcrn_mask_count``), summed over the group.
+    Returns None outside a multi-rank process group, else an opaque handle for ``global_mask_count_end``.  The labels are
+    known before the forward, so the 4-byte collective overlaps it."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return None
+    from . import _abi
+    lib = _abi.load()
+    lab = labels.detach().to(torch.float32).contiguous()
+    cnt = torch.zeros(1, device=lab.device, dtype=torch.float32)
+    with torch.cuda.device(lab.device):
+        st = lib.mcrn_mask_count(lab.data_ptr(), lab.numel(), scaler_mean, scaler_std, cnt.data_ptr(),
+                                 torch.cuda.current_stream(lab.device).cuda_stream)
+    _abi.check(st, "mcrn_mask_count")
+    work = dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group, async_op=True)
+    return cnt, work, dist.get_world_size(group)
+
+
+def global_mask_count_end(pending):
+    """Wait for the collective started by ``global_mask_count_begin``; returns the per-rank normaliser
+    (global count / world size) as a 1-element device tensor, or None."""
+    if pending is None:
+        return None
+    cnt, work, world = pending
+    work.wait()
+    cnt.mul_(1.0 / world)
+    return cnt
 
 
 def shard_batch(t: torch.Tensor, rank: int, world: int) -> torch.Tensor:

@@ -16,9 +16,13 @@ def _dims_from(d_like, batch, t_in=1):
                      mem_dim=g("mem_dim"))
 
 
-def fused_trainer_loss(d_like, output, labels, query, pos, neg, scaler_mean=54.0, scaler_std=20.0,
-                       lamb=0.01, lamb1=0.01, want_grads=True):
-    """Returns (loss[1], d_output, d_query); pos/neg are constants (the trainer detaches them)."""
+def fused_trainer_loss(d_like, output, labels, query, pos, neg, *, scaler_mean, scaler_std,
+                       lamb=0.01, lamb1=0.01, want_grads=True, mask_count=None):
+    """Returns (loss[1], d_output, d_query); pos/neg are constants (the trainer detaches them).
+
+    ``scaler_mean`` / ``scaler_std``: the trainer's StandardScaler (model/traintest_MegaCRN.py:274-277, :118-119).
+    ``mask_count``: 1-element device tensor holding the masked-MAE normaliser to use instead of this batch's own count
+    of non-zero labels (data parallel: global count / world size, ``ddp.global_mask_count``)."""
     lib = _abi.load()
     dev = output.device
     dims = _dims_from(d_like, output.shape[0])
@@ -29,19 +33,31 @@ def fused_trainer_loss(d_like, output, labels, query, pos, neg, scaler_mean=54.0
     d_q = torch.empty_like(query) if want_grads else None
     scratch = torch.empty(64, device=dev, dtype=torch.float32)
     with torch.cuda.device(dev):
-        st = lib.mcrn_trainer_loss(dims, output.data_ptr(), labels.data_ptr(), query.data_ptr(), pos.data_ptr(),
-                                   neg.data_ptr(), scaler_mean, scaler_std, lamb, lamb1, loss.data_ptr(),
-                                   _abi.ptr(d_out), _abi.ptr(d_q), scratch.data_ptr(), 256,
-                                   torch.cuda.current_stream(dev).cuda_stream)
+        st = lib.mcrn_trainer_loss_dp(dims, output.data_ptr(), labels.data_ptr(), query.data_ptr(), pos.data_ptr(),
+                                      neg.data_ptr(), scaler_mean, scaler_std, lamb, lamb1, _abi.ptr(mask_count),
+                                      loss.data_ptr(), _abi.ptr(d_out), _abi.ptr(d_q), scratch.data_ptr(), 256,
+                                      torch.cuda.current_stream(dev).cuda_stream)
     _abi.check(st, "mcrn_trainer_loss")
     return loss, d_out, d_q
 
 
-def train_step(model, x, y_cov, labels, batches_seen=0, teacher_forcing=None, **loss_kw):
-    """forward + trainer loss + backward; leaves gradients in ``p.grad``; returns loss[1] (device)."""
+DEFAULT_SCALER = dict(scaler_mean=54.0, scaler_std=20.0)     # the synthetic scaler of SURVEY.md 8(d); a trainer passes its own
+
+
+def train_step(model, x, y_cov, labels, batches_seen=0, teacher_forcing=None, group=None, **loss_kw):
+    """forward + trainer loss + backward; leaves gradients in ``p.grad``; returns loss[1] (device).
+
+    Inside an initialised process group with more than one rank the masked-MAE normaliser is the global one
+    (``ddp.global_mask_count``: a 4-byte all-reduce issued before the forward and waited for only at the loss), so that
+    the rank-average of loss and gradients equals the single-process step on the concatenated batch."""
+    from . import ddp
+    for k, v in DEFAULT_SCALER.items():
+        loss_kw.setdefault(k, v)
+    pending = ddp.global_mask_count_begin(labels, loss_kw["scaler_mean"], loss_kw["scaler_std"], group)
     outs = model(x, y_cov, labels, batches_seen, teacher_forcing=teacher_forcing)
     output, _h_att, query, pos, neg = outs
-    loss, d_out, d_q = fused_trainer_loss(model, output, labels, query, pos, neg, **loss_kw)
+    loss, d_out, d_q = fused_trainer_loss(model, output, labels, query, pos, neg, mask_count=ddp.global_mask_count_end(pending),
+                                          **loss_kw)
     torch.autograd.backward([output, query], [d_out, d_q])
     return loss
 
@@ -58,9 +74,21 @@ class GraphedTrainStep:
     alias one flat buffer (``flat_grad``), the loss in ``loss`` (a 1-element device tensor).
     """
 
-    def __init__(self, model, batch, seq_len, max_graphs=16, optimizer=None, **loss_kw):
-        """optimizer: a ``megacrn_b200.optim.FusedClipAdam``; if given, clip + Adam are part of the captured step
-        (single-GPU; with data parallelism call ``optimizer.step()`` after the gradient all-reduce instead)."""
+    def __init__(self, model, batch, seq_len, max_graphs=16, optimizer=None, allreduce=None, group=None, **loss_kw):
+        """optimizer: a ``megacrn_b200.optim.FusedClipAdam``; if given, clip + Adam are part of the captured step.
+        allreduce: capture the data-parallel collectives (mask-count all-reduce, ONE gradient all-reduce with NCCL's
+        in-collective averaging) inside the graph, between backward and optimiser; default: on inside a process group
+        with more than one rank (``MCRN_GRAPH_ALLREDUCE=0`` keeps them outside: call ``ddp.allreduce_gradients`` after
+        the replay, and the optimiser after that)."""
+        import os
+        import torch.distributed as dist
+        in_group = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        if allreduce is None:
+            allreduce = in_group and os.environ.get("MCRN_GRAPH_ALLREDUCE", "1") != "0"
+        self.allreduce, self.group = bool(allreduce) and in_group, group
+        if in_group and optimizer is not None and not self.allreduce:
+            raise ValueError("data parallel: the optimiser must run after the gradient all-reduce -- capture both "
+                             "(allreduce=True) or call optimizer.step() yourself after ddp.allreduce_gradients")
         self.model, self.loss_kw, self.max_graphs, self.optimizer = model, loss_kw, max_graphs, optimizer
         dev = next(model.parameters()).device
         self.x = torch.zeros(batch, seq_len, model.num_nodes, model.input_dim, device=dev)
@@ -80,7 +108,14 @@ class GraphedTrainStep:
     def _eager(self, flags):
         for p in self.params:
             p.grad = None
-        loss = train_step(self.model, self.x, self.y_cov, self.labels, teacher_forcing=flags, **self.loss_kw)
+        loss = self._step_body(flags)
+        return loss
+
+    def _step_body(self, flags):
+        from .ddp import allreduce_gradients
+        loss = train_step(self.model, self.x, self.y_cov, self.labels, teacher_forcing=flags, group=self.group, **self.loss_kw)
+        if self.allreduce:
+            allreduce_gradients(self.params, self.group)
         if self.optimizer is not None:
             self.optimizer.step()
         return loss
@@ -94,12 +129,13 @@ class GraphedTrainStep:
         with torch.cuda.stream(side):                  # warm-up outside capture (lazy inits, allocator)
             for _ in range(2):
                 self._eager(flags)
+        torch.cuda.current_stream().wait_stream(side)      # the restore below must not overtake the warm-up updates
         if saved is not None:
             with torch.no_grad():
                 self.optimizer.load_state_dict(saved[0])
                 for p, q in zip(self.params, saved[1]):
                     p.copy_(q)
-        torch.cuda.current_stream().wait_stream(side)
+            self.optimizer.note_update()
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         for p in self.params:
@@ -107,9 +143,7 @@ class GraphedTrainStep:
         lib = _abi.load()
         n0 = lib.mcrn_launch_count()
         with torch.cuda.graph(g, pool=self.pool):
-            loss = train_step(self.model, self.x, self.y_cov, self.labels, teacher_forcing=flags, **self.loss_kw)
-            if self.optimizer is not None:
-                self.optimizer.step()
+            loss = self._step_body(flags)
         kernels = int(lib.mcrn_launch_count() - n0)       # library kernels recorded in this graph
         if self.pool is None:
             self.pool = g.pool()

@@ -10,8 +10,8 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
-    src = open(os.path.join(ROOT, "include", "megacrn_b200.h")).read()
+def _declared_symbols(header="megacrn_b200.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(mcrn_[a-z_0-9]+)\s*\(", src)))
 
@@ -24,6 +24,12 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), s
     assert lib.mcrn_abi_version() == 1
+    # the public header holds the drop-in boundary only; debug / probe / tuning entries live in megacrn_b200_debug.h
+    assert not [s for s in syms if "debug" in s or "probe" in s or s in ("mcrn_set_option", "mcrn_kernel_timing")], syms
+    dbg = _declared_symbols("megacrn_b200_debug.h")
+    assert "mcrn_debug_fused_timeline" in dbg and "mcrn_set_option" in dbg
+    for s in dbg:
+        assert hasattr(lib, s), s
 
 
 def test_workspace_and_dim_validation():

@@ -495,7 +495,7 @@ def test_fused_trainer_loss_matches_torch():
     ref = O.trainer_loss((o, None, q, ps, ng), lab)
     ref.backward()
     dv = _dev()
-    loss, d_out, d_q = fused_trainer_loss(d, out.to(dv), lab.to(dv), qy.to(dv), ps.to(dv), ng.to(dv))
+    loss, d_out, d_q = fused_trainer_loss(d, out.to(dv), lab.to(dv), qy.to(dv), ps.to(dv), ng.to(dv), scaler_mean=54.0, scaler_std=20.0)
     assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref))
     assert rel_l2(d_out.cpu(), o.grad) < 1e-5
     assert rel_l2(d_q.cpu(), q.grad) < 1e-4

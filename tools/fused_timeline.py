@@ -25,7 +25,7 @@ torch.cuda.synchronize()
 # the decoder gate launch is the 3rd fused launch of a forward, the decoder update the 4th: record all, keep per-launch
 # copies by running the forward with the buffer armed and reading it after each variant
 WHICH = int(os.environ.get("WHICH", "2"))      # 0 enc gate, 1 enc update, 2 dec gate, 3 dec update
-slots = torch.zeros(512, dtype=torch.int64, device=dev)
+slots = torch.zeros(512 + 2 * 1024, dtype=torch.int64, device=dev)
 lib.mcrn_debug_fused_timeline(slots.data_ptr(), WHICH)
 m(xs, ys, ls, teacher_forcing=[True])
 torch.cuda.synchronize()
@@ -47,3 +47,13 @@ for k in range(5):
     if a:
         print(f"P_{k}: full seen {rel(a)}  rounded {rel(b)}  (+{b - a})")
 print("producer done", rel(t[232]), " MMA issuer done", rel(t[233]), " acc_full seen", rel(t[230]), " epilogue done", rel(t[231]))
+
+import numpy as np
+ct = np.array(t[512:512 + 2 * 2 * B]).reshape(-1, 2)
+ct = ct[ct[:, 0] > 0]
+if len(ct):
+    s0 = ct[:, 0].min()
+    st, en = ct[:, 0] - s0, ct[:, 1] - s0
+    print(f"per-CTA wall clock (ns, {len(ct)} CTAs): start min/median/max {st.min()} {int(np.median(st))} {st.max()}   end min/median/max {en.min()} {int(np.median(en))} {en.max()}   duration min/median/max {(en-st).min()} {int(np.median(en-st))} {(en-st).max()}")
+    odd = ct[1::2]; even = ct[0::2]
+    print(f"  tile 0 CTAs duration median {int(np.median(even[:,1]-even[:,0]))}   tile 1 CTAs duration median {int(np.median(odd[:,1]-odd[:,0]))}")
