@@ -278,7 +278,7 @@ def main():
                 g2(batches_seen=0)
             ms, _ = timed(lambda: g2(batches_seen=0), args.steps)
             extras["with_optimizer"] = {"value": B * world * args.steps / (ms / 1e3), "unit": "sequences/s", "ms_per_step": ms / args.steps,
-                                        "what": "step + gradient all-reduce (N > 1) + fused clip_grad_norm_(5.0) + Adam(lr 0.01, eps 1e-3), one graph"}
+                                        "what": "step + gradient all-reduce (N > 1) + fused clip_grad_norm_(5.0) + Adam(lr 0.01, eps 1e-3); one graph at N = 1"}
             del g2
             # free-running decoder (no teacher forcing: what training looks like after ~10 k batches, tau(20000) = 0.083,
             # model/MegaCRN.py:146-147, :188-191): projection + input build + cell serialised per step
@@ -406,11 +406,11 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.engine == "simt" else "f16/tf32", "data": "synthetic",
-            "config": {"workload": f"{args.config}: {what}, train step = forward + trainer loss + backward"
-                                   + (" + 1 NCCL grad all-reduce" if world > 1 else ""),
+            "config": {"workload": f"{args.config}: {what}, train step = forward + trainer loss + backward",
+                       "collective": "1 NCCL gradient all-reduce (+ a 4-byte normaliser all-reduce) per step" if world > 1 else "none",
                        "global_batch": gB, "parallelism": f"dp{world}", "engine": args.engine,
                        "launch": "eager" if args.no_graph else "cuda-graph replay (one graph per teacher-forcing pattern"
-                                 + (", collectives captured in the graph)" if collectives_in_graph else ")"),
+                                 + ("; normaliser and gradient all-reduce issued around the replay)" if collectives_in_graph else ")"),
                        "l2": "256 MiB memset between timed steps (flush) + >1 GB/step activation working set",
                        "final_loss": final_loss},
             "e2e": {"value": e2e_value, "unit": "sequences/s", "ms_per_step": e2e_ms / args.steps,

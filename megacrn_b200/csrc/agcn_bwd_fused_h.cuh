@@ -11,7 +11,7 @@
 // the 11-bit significand of the TF32 path; the power-of-two scale changes no mantissa.
 // All operands K-major, 128-byte swizzle:
 //     S16T [KS][N][ld16]  transposed supports      A of MMA1   box [64 k][128 m]
-//     dV16T [B][O][ldT]   node index contiguous    B of MMA1   box [64 k][HS n]      (O = HS or 2 HS columns, half = column block)
+//     dV16 [R][O]         rows (node, b)           B of MMA1, MN-major: HS/64 boxes [64 n][1][64 k] at column half * HS  (see agcn_fused_h.cuh)
 //     dV16 [R][O]         rows                     A of MMA2 (identity segment)      box [64 k][1][128 m]
 //     W16n [KS+2][HS][O]  folded weights, fp16     B of MMA2   box [64 k][HS n] and [64 k][16 n] (input block rows)
 #pragma once
@@ -48,7 +48,7 @@ struct BHParams {
   int N, B, KS, nhalf;
   float* qsave;          // [KS * nhalf][R][HS] fp32, unscaled (TF32 weight-gradient GEMMs); null when q16T is used
   int64_t blk_stride;    // R * HS
-  __half* q16T;          // [KS * nhalf][B][HS][ldT] scaled fp16, node index contiguous (fp16 weight-gradient kernel); or null
+  __half* q16T;          // [KS * nhalf][R][HS] scaled fp16, ROW-major (operand of the fp16 weight-gradient kernel, read MN-major); or null
   int ldT;
   float* dib;            // [R][IBW], unscaled (written when dxpin == null)
   const float* gs;       // device: {scale, 1 / scale}
@@ -165,7 +165,7 @@ struct EpiBGHG {
 
 template <int HS, class Epi>
 __global__ void __launch_bounds__(BHTHREADS, 1)
-agcn_bwd_h_kernel(const __grid_constant__ CUtensorMap tmST, const __grid_constant__ CUtensorMap tmVT,
+agcn_bwd_h_kernel(const __grid_constant__ CUtensorMap tmST, const __grid_constant__ CUtensorMap tmVB,
                   const __grid_constant__ CUtensorMap tmVA, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ CUtensorMap tmWib, BHParams p, Epi epi) {
   using C = CfgBH<HS>;
@@ -188,7 +188,7 @@ agcn_bwd_h_kernel(const __grid_constant__ CUtensorMap tmST, const __grid_constan
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmST) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmVT) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmVB) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmVA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWib) : "memory");
@@ -230,7 +230,9 @@ agcn_bwd_h_kernel(const __grid_constant__ CUtensorMap tmST, const __grid_constan
           const int k = ks / p.nhalf, half = ks - k * p.nhalf;
           mbar_expect_tx(fb, C::A_SLOT + C::B_SLOT);
           tma_load_4d(a_dst, &tmST, fb, j * BKH, m0, k, 0);                        // S_k^T[m0.., 64 j..]
-          tma_load_4d(b_dst, &tmVT, fb, j * BKH, half * HS, b, 0);                 // dV^T[b][half*HS..][64 j..]
+#pragma unroll
+          for (int q = 0; q < HS / 64; ++q)                                        // dV rows (64 j.., b), columns half*HS + 64 q..  (MN-major B)
+            tma_load_4d(b_dst + q * 8192, &tmVB, fb, half * HS + q * 64, b, j * BKH, 0);
         } else if (type == B_ITEM_SS) {
           const int half = ks;
           mbar_expect_tx(fb, C::A_SLOT + C::B_SLOT + C::IB_SLOT);
@@ -248,6 +250,7 @@ agcn_bwd_h_kernel(const __grid_constant__ CUtensorMap tmST, const __grid_constan
   } else if (warp == 1) {
     if (lane == 0) {                                     // ===== MMA issuer =====
       constexpr uint32_t idesc_n = make_idesc_f16<HS>();
+      constexpr uint32_t idesc_p = make_idesc_f16<HS>() | (1u << 16);      // MMA1: B is MN-major (row-major dV rows)
       constexpr uint32_t idesc_ib = make_idesc_f16<IBW>();
       int it = 0;
       bool acc_on = false, ib_on = false;
@@ -263,8 +266,8 @@ agcn_bwd_h_kernel(const __grid_constant__ CUtensorMap tmST, const __grid_constan
           for (int kk = 0; kk < BKH / 16; ++kk) {
             if (kk < nkk) {
               const uint64_t ad = make_smem_desc(a_addr + kk * 32, 16, 1024, 2);
-              const uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, 1024, 2);
-              tcgen05_mma_f16(qbuf, ad, bd, idesc_n, (j > 0 || kk > 0) ? 1u : 0u);
+              const uint64_t bd = make_smem_desc(b_addr + kk * 2048, 8192, 1024, 2);
+              tcgen05_mma_f16(qbuf, ad, bd, idesc_p, (j > 0 || kk > 0) ? 1u : 0u);
             }
           }
           tcgen05_commit(smem_u32(&empty_bar[s]));
@@ -323,9 +326,14 @@ agcn_bwd_h_kernel(const __grid_constant__ CUtensorMap tmST, const __grid_constan
             tmem_ld_32x32b_x32(qbuf + (uint32_t)(c * 32), v);
 #pragma unroll
             for (int i = 0; i < 16; ++i) u[ci][i] = pack_h2(v[2 * i], v[2 * i + 1]);
-            if (p.q16T != nullptr) {                     // node-transposed fp16 copy straight from the accumulator layout
-              // (lane = node row): pairs of adjacent nodes, 16 four-byte stores per lane
-              fusedh::store_T_pairs_regs(p.q16T + (((int64_t)ks * p.B + b) * HS + c * 32) * p.ldT + node0, p.ldT, v, lane, node0, p.N);
+            if (p.q16T != nullptr) {                     // row-major fp16 copy straight from the accumulator layout (lane = node row):
+              // 32 consecutive columns = 64 contiguous bytes per lane
+              const int node = node0 + lane;
+              if (node < p.N) {
+                uint4* dst = reinterpret_cast<uint4*>(p.q16T + ((int64_t)ks * p.N * p.B + (int64_t)node * p.B + b) * HS + c * 32);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dst[i] = make_uint4(u[ci][4 * i], u[ci][4 * i + 1], u[ci][4 * i + 2], u[ci][4 * i + 3]);
+              }
             } else if (node0 < p.N) {
               __syncwarp();
 #pragma unroll
@@ -645,7 +653,7 @@ int launch_agcn_bwd_h(int N, int B, int KS, int nhalf, const BHOperands& op, flo
   using C = CfgBH<HS>;
   const int64_t R = (int64_t)N * B;
   const int O = nhalf * HS, ldn = fusedh::ld_half(N);
-  CUtensorMap tST, tVT, tVA, tW, tWib;
+  CUtensorMap tST, tVB, tVA, tW, tWib;
   {
     uint64_t dims[4] = {(uint64_t)N, (uint64_t)N, (uint64_t)KS, 1};
     uint64_t str[3] = {(uint64_t)ldn * 2, (uint64_t)N * ldn * 2, (uint64_t)KS * N * ldn * 2};
@@ -653,16 +661,12 @@ int launch_agcn_bwd_h(int N, int B, int KS, int nhalf, const BHOperands& op, flo
     MCRN_TRY(fusedh::encode_tensor_map_h(&tST, op.S16T, dims, str, box));
   }
   {
-    uint64_t dims[4] = {(uint64_t)N, (uint64_t)O, (uint64_t)B, 1};
-    uint64_t str[3] = {(uint64_t)ldn * 2, (uint64_t)O * ldn * 2, (uint64_t)B * O * ldn * 2};
-    uint32_t box[4] = {BKH, (uint32_t)HS, 1, 1};
-    MCRN_TRY(fusedh::encode_tensor_map_h(&tVT, op.V16T, dims, str, box));
-  }
-  {
     uint64_t dims[4] = {(uint64_t)O, (uint64_t)B, (uint64_t)N, 1};
     uint64_t str[3] = {(uint64_t)O * 2, (uint64_t)B * O * 2, (uint64_t)R * O * 2};
     uint32_t box[4] = {BKH, 1, BM, 1};
     MCRN_TRY(fusedh::encode_tensor_map_h(&tVA, op.V16, dims, str, box));
+    uint32_t boxb[4] = {64, 1, BKH, 1};                  // MN-major B of MMA1: 64 columns x 64 node rows of batch element b
+    MCRN_TRY(fusedh::encode_tensor_map_h(&tVB, op.V16, dims, str, boxb));
   }
   {
     uint64_t dims[4] = {(uint64_t)O, (uint64_t)HS, (uint64_t)(KS + 2), 1};
@@ -687,7 +691,7 @@ int launch_agcn_bwd_h(int N, int B, int KS, int nhalf, const BHOperands& op, flo
   }
   dim3 grid(ceil_div(N, BM), B, 1);
   const int pi = fused::prof_begin(fused::prof_class(1, HS, nhalf == 2 ? 1 : 0), st);
-  MCRN_TRY(launch_chain(2, kern, grid, dim3(BHTHREADS), C::SMEM, st, "agcn_bwd_h_kernel", tST, tVT, tVA, tW, tWib, p, epi));
+  MCRN_TRY(launch_chain(2, kern, grid, dim3(BHTHREADS), C::SMEM, st, "agcn_bwd_h_kernel", tST, tVB, tVA, tW, tWib, p, epi));
   fused::prof_end(pi, st);
   return MCRN_OK;
 }

@@ -1,10 +1,12 @@
 // Weight gradients of ONE AGCN over all time steps and batch elements, fp16 operands (tcgen05 kind::f16, fp32 accumulate):
 //     dW[blk][c][h*HS + o] = sum_{t,b,n} X_t[n,b,c] * Y_t[n,b,o]
 // with Y = dV (blk = 0, the folded identity block) or Y = Q_{k,h} = S_k^T dV (blk = 1 + k; agcn_bwd_fused_h.cuh).  Both
-// operands are the node-transposed fp16 copies the fused forward / backward write anyway:
-//     X16T [T][B][HS][ldT]          A: rows c, K = node (box [64 k][128 m]; rows >= HS are out of bounds = 0)
-//     dV16T [T][B][O][ldT]          B for blk 0: rows o
-//     Q16T [T * nks][B][HS][ldT]    B for blk >= 1: rows o, block ks = k * nhalf + h
+// operands are the ROW-MAJOR fp16 copies the fused forward / backward write anyway, read as MN-major tcgen05 operands
+// (the contraction index -- the node -- is the strided one; descriptor: LBO 8192 / SBO 1024 / SWIZZLE_128B, 2048 B per
+// K = 16 step, a_major = b_major = 1; tools/probe_mn16.py), so no node-transposed copy exists anywhere:
+//     X16  [T][R][HS]               A: 2 boxes [64 c][1][64 nodes] (the second is out of bounds = 0 when HS = 64)
+//     dV16 [T][R][O]                B for blk 0: HS/64 boxes at column half * HS
+//     Q16  [T * nks][R][HS]         B for blk >= 1: block ks = k * nhalf + h
 // A plain split-K GEMM: CTA = (output tile (blk, h), group g) loops over its (t, b) units, ceil(N / 64) ring items each,
 // accumulator [128 x HS] in TMEM, one red.global.add.v4.f32 pass at the end (times 1 / loss scale: dV16T and Q16T carry it).
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
@@ -92,14 +94,18 @@ agcn_dw_h_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const int i = it / kb, j = it - i * kb;
         const int u = grp + i * G, t = u / p.B, b = u - t * p.B;
         mbar_expect_tx(fb, C::A_SLOT + C::B_SLOT);
-        tma_load_4d(a_dst, &tmX, fb, j * BKH, 0, b, t);                                   // X^T_t[b][0..128 (HS valid)][64 j..]
-        if (blk == 0) tma_load_4d(b_dst, &tmV, fb, j * BKH, half * HS, b, t);             // dV^T_t[b][half*HS..][64 j..]
-        else tma_load_4d(b_dst, &tmQ, fb, j * BKH, 0, b, t * nks + (blk - 1) * p.nhalf + half);   // Q^T_t[ks][b][0..HS][64 j..]
+        tma_load_4d(a_dst, &tmX, fb, 0, b, j * BKH, t);                                   // X_t rows (64 j.., b), channels 0..63
+        tma_load_4d(a_dst + 8192, &tmX, fb, 64, b, j * BKH, t);                           // channels 64..127 (zero fill when HS = 64)
+#pragma unroll
+        for (int q = 0; q < HS / 64; ++q) {
+          if (blk == 0) tma_load_4d(b_dst + q * 8192, &tmV, fb, half * HS + q * 64, b, j * BKH, t);      // dV_t rows, columns half*HS + 64 q..
+          else tma_load_4d(b_dst + q * 8192, &tmQ, fb, q * 64, b, j * BKH, t * nks + (blk - 1) * p.nhalf + half);   // Q_t[ks] rows
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {                                     // ===== MMA issuer =====
-      constexpr uint32_t idesc = make_idesc_f16<HS>();
+      constexpr uint32_t idesc = make_idesc_f16<HS>() | (1u << 15) | (1u << 16);     // A and B MN-major
       for (int it = 0; it < nit; ++it) {
         const int s = it % NST;
         mbar_wait_b(smem_u32(&full_bar[s]), ((uint32_t)(it / NST)) & 1u);
@@ -107,8 +113,8 @@ agcn_dw_h_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const uint32_t a_addr = smem_base + (uint32_t)s * C::STAGE, b_addr = a_addr + C::A_SLOT;
 #pragma unroll
         for (int kk = 0; kk < BKH / 16; ++kk) {
-          const uint64_t ad = make_smem_desc(a_addr + kk * 32, 16, 1024, 2);
-          const uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, 1024, 2);
+          const uint64_t ad = make_smem_desc(a_addr + kk * 2048, 8192, 1024, 2);
+          const uint64_t bd = make_smem_desc(b_addr + kk * 2048, 8192, 1024, 2);
           tcgen05_mma_f16(tmem_base, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
         }
         tcgen05_commit(smem_u32(&empty_bar[s]));
@@ -152,30 +158,29 @@ agcn_dw_h_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   }
 }
 
-// x16T_all [T][B][HS][ldT], v16T_all [T][B][O][ldT], q16T_all [T * KS * nhalf][B][HS][ldT] (steps [0, T) of the launch)
+// x16_all [T][R][HS], v16_all [T][R][O], q16_all [T * KS * nhalf][R][HS]: row-major, rows (node, b)  (steps [0, T) of the launch)
 template <int HS>
-int launch_agcn_dw_h(int N, int B, int T, int KS, int nhalf, const __half* x16T_all, const __half* v16T_all, const __half* q16T_all,
+int launch_agcn_dw_h(int N, int B, int T, int KS, int nhalf, const __half* x16_all, const __half* v16_all, const __half* q16_all,
                      const float* gs, float* dw, cudaStream_t st) {
   using C = CfgW<HS>;
-  const int O = nhalf * HS, ldn = fusedh::ld_half(N), nks = KS * nhalf;
+  const int O = nhalf * HS, nks = KS * nhalf;
+  const uint64_t R = (uint64_t)N * B;
   CUtensorMap tX, tV, tQ;
+  uint32_t box[4] = {64, 1, BKH, 1};                     // 64 channels x 64 node rows of one batch element
   {
-    uint64_t dims[4] = {(uint64_t)N, (uint64_t)HS, (uint64_t)B, (uint64_t)T};
-    uint64_t str[3] = {(uint64_t)ldn * 2, (uint64_t)HS * ldn * 2, (uint64_t)B * HS * ldn * 2};
-    uint32_t box[4] = {BKH, BM, 1, 1};                   // 128 rows: rows >= HS are out of bounds (zero) when HS = 64
-    MCRN_TRY(fusedh::encode_tensor_map_h(&tX, x16T_all, dims, str, box));
+    uint64_t dims[4] = {(uint64_t)HS, (uint64_t)B, (uint64_t)N, (uint64_t)T};
+    uint64_t str[3] = {(uint64_t)HS * 2, (uint64_t)B * HS * 2, R * HS * 2};
+    MCRN_TRY(fusedh::encode_tensor_map_h(&tX, x16_all, dims, str, box));
   }
   {
-    uint64_t dims[4] = {(uint64_t)N, (uint64_t)O, (uint64_t)B, (uint64_t)T};
-    uint64_t str[3] = {(uint64_t)ldn * 2, (uint64_t)O * ldn * 2, (uint64_t)B * O * ldn * 2};
-    uint32_t box[4] = {BKH, (uint32_t)HS, 1, 1};
-    MCRN_TRY(fusedh::encode_tensor_map_h(&tV, v16T_all, dims, str, box));
+    uint64_t dims[4] = {(uint64_t)O, (uint64_t)B, (uint64_t)N, (uint64_t)T};
+    uint64_t str[3] = {(uint64_t)O * 2, (uint64_t)B * O * 2, R * O * 2};
+    MCRN_TRY(fusedh::encode_tensor_map_h(&tV, v16_all, dims, str, box));
   }
   {
-    uint64_t dims[4] = {(uint64_t)N, (uint64_t)HS, (uint64_t)B, (uint64_t)T * nks};
-    uint64_t str[3] = {(uint64_t)ldn * 2, (uint64_t)HS * ldn * 2, (uint64_t)B * HS * ldn * 2};
-    uint32_t box[4] = {BKH, (uint32_t)HS, 1, 1};
-    MCRN_TRY(fusedh::encode_tensor_map_h(&tQ, q16T_all, dims, str, box));
+    uint64_t dims[4] = {(uint64_t)HS, (uint64_t)B, (uint64_t)N, (uint64_t)T * nks};
+    uint64_t str[3] = {(uint64_t)HS * 2, (uint64_t)B * HS * 2, R * HS * 2};
+    MCRN_TRY(fusedh::encode_tensor_map_h(&tQ, q16_all, dims, str, box));
   }
   WParams p;
   p.N = N; p.B = B; p.T = T; p.KS = KS; p.nhalf = nhalf; p.O = O; p.dw = dw; p.gs = gs;

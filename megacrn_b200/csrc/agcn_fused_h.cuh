@@ -13,7 +13,8 @@
 // kind::tf32 MMA rate.  The weights keep the hi + lo split
 // (hi = fp16(W), lo = fp16(W - hi)).  All operands are K-major with the 128-byte swizzle:
 //     S16  [KS][N][ld16]        supports                       A of MMA1   box [64 k][128 m]
-//     X16T [B][HS][ldT]         state, node index contiguous   B of MMA1   box [64 k][HS n]
+//     X16  [R][HS]              state rows (node, b)           B of MMA1, MN-major: HS/64 boxes [64 n][1][64 k]  (no transposed copy:
+//                                                              descriptor LBO 8192 / SBO 1024 / SWIZZLE_128B, K step 2048 B; tools/probe_mn16.py)
 //     X16  [R][HS], IB16 [R][HS] state / input block rows      A of MMA2 (identity + input segments)  box [64 k][1][128 m]
 //     W16  [parts][KS+2][O][HS] folded weights, transposed     B of MMA2   box [64 k][O n]
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = P rounding + epilogue,
@@ -51,6 +52,7 @@ struct HParams {
   int64_t blk_stride;   // R * HS
   long long* dbg;       // debug timeline (see agcn_fused.cuh)
   unsigned long long* span;   // debug: {min CTA start, max CTA end} of this launch (ns), or null
+  int epi_skip;         // timing experiments only (MCRN_EPI_SKIP): 1 no epilogue global loads, 2 no fp32 stores, 4 no transposed fp16 copy, 8 no row-major fp16 copy, 16 cheap activation
   int pdl_late;         // programmatic dependent launch: 0 = let the dependents start right after the prologue, 1 = at the epilogue
 };
 
@@ -161,6 +163,7 @@ struct CfgH {
 // Gate AGCN (model/MegaCRN.py:43-45): zr = sigmoid(acc); columns [0,H) = z, [H,2H) = r; writes z, r, z*h.
 struct EpiGateH {
   static constexpr int NP = 1;
+  int skip = 0;
   int H;
   const float* h;       // [R][H] exact state
   float* z;             // null in eval
@@ -171,18 +174,20 @@ struct EpiGateH {
   int ldT;
   __device__ __forceinline__ bool has_state(int n0) const { return n0 < H; }
   __device__ __forceinline__ void load4(int row, int n0, float4 (&p)[NP]) const {
-    p[0] = (n0 < H) ? ldg4(h + (int64_t)row * H + n0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    p[0] = (n0 < H && !(skip & 1)) ? ldg4(h + (int64_t)row * H + n0) : make_float4(0.5f, 0.5f, 0.5f, 0.5f);
   }
   __device__ __forceinline__ void fin4(int row, int n0, const float4 (&p)[NP], const float (&acc)[4], float (&st)[4]) const {
-    const float s0 = sigmoid_fast(acc[0]), s1 = sigmoid_fast(acc[1]), s2 = sigmoid_fast(acc[2]), s3 = sigmoid_fast(acc[3]);
+    float s0, s1, s2, s3;
+    if (skip & 16) { s0 = acc[0] * 0.01f + 0.5f; s1 = acc[1] * 0.01f + 0.5f; s2 = acc[2] * 0.01f + 0.5f; s3 = acc[3] * 0.01f + 0.5f; }
+    else { s0 = sigmoid_fast(acc[0]); s1 = sigmoid_fast(acc[1]); s2 = sigmoid_fast(acc[2]); s3 = sigmoid_fast(acc[3]); }
     if (n0 < H) {
       const int64_t o = (int64_t)row * H + n0;
-      if (z) st4(z + o, s0, s1, s2, s3);
+      if (z && !(skip & 2)) st4(z + o, s0, s1, s2, s3);
       st[0] = round_h(s0 * p[0].x); st[1] = round_h(s1 * p[0].y); st[2] = round_h(s2 * p[0].z); st[3] = round_h(s3 * p[0].w);
       if (zh32) st4(zh32 + o, st[0], st[1], st[2], st[3]);
-      *reinterpret_cast<uint2*>(x16 + o) = make_uint2(pack_h2(st[0], st[1]), pack_h2(st[2], st[3]));
+      if (!(skip & 8)) *reinterpret_cast<uint2*>(x16 + o) = make_uint2(pack_h2(st[0], st[1]), pack_h2(st[2], st[3]));
     } else {
-      st4(r + (int64_t)row * H + (n0 - H), s0, s1, s2, s3);
+      if (!(skip & 2)) st4(r + (int64_t)row * H + (n0 - H), s0, s1, s2, s3);
     }
   }
 };
@@ -225,7 +230,7 @@ struct EpiUpdateH {
 
 template <int HS, int O, class Epi>
 __global__ void __launch_bounds__(FTHREADS, 1)
-agcn_fused_h_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmXT,
+agcn_fused_h_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmXB,
                     const __grid_constant__ CUtensorMap tmXA, const __grid_constant__ CUtensorMap tmIB,
                     const __grid_constant__ CUtensorMap tmW, HParams p, Epi epi) {
   using C = CfgH<HS, O>;
@@ -253,7 +258,7 @@ agcn_fused_h_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_consta
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmS) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmXT) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmXB) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmXA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmIB) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
@@ -297,7 +302,9 @@ agcn_fused_h_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_consta
         if (type == ITEM_P) {
           mbar_expect_tx(fb, C::A_SLOT + (uint32_t)HS * 128);
           tma_load_4d(a_dst, &tmS, fb, j * BKH, m0, k, 0);                      // S_k[m0.., 64 j..]
-          tma_load_4d(b_dst, &tmXT, fb, j * BKH, 0, b, 0);                      // X^T[b][0..HS][64 j..]
+#pragma unroll
+          for (int q = 0; q < HS / 64; ++q)                                     // X rows (64 j.., b), channels 64 q..  (MN-major B)
+            tma_load_4d(b_dst + q * 8192, &tmXB, fb, q * 64, b, j * BKH, 0);
         } else {
           const int wseg = (type == ITEM_SS ? k : 1 + k) + part * NSEG;
           if (type == ITEM_SS) {
@@ -314,7 +321,7 @@ agcn_fused_h_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_consta
     }
   } else if (warp == 1) {
     if (lane == 0) {                                     // ===== MMA issuer =====
-      constexpr uint32_t idesc1 = make_idesc_f16<HS>();
+      constexpr uint32_t idesc1 = make_idesc_f16<HS>() | (1u << 16);     // B of MMA1 is MN-major (row-major X rows)
       constexpr uint32_t idesc2 = make_idesc_f16<O>();
       int it = 0;
       bool acc_on = false;
@@ -333,7 +340,7 @@ agcn_fused_h_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_consta
           for (int kk = 0; kk < BKH / 16; ++kk) {
             if (kk < nkk) {
               const uint64_t ad = make_smem_desc(a_addr + kk * 32, 16, 1024, 2);
-              const uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, 1024, 2);
+              const uint64_t bd = make_smem_desc(b_addr + kk * 2048, 8192, 1024, 2);     // 16 node rows per step, 64-channel blocks 8 KB apart
               tcgen05_mma_f16(pbuf, ad, bd, idesc1, (j > 0 || kk > 0) ? 1u : 0u);
             }
           }
@@ -448,7 +455,7 @@ agcn_fused_h_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_consta
           }
         }
         // node-transposed fp16 copy of the new operand: X^T[b][c*32 + j][node0 + lane]
-        if (epi.has_state(c * 32) && epi.x16T != nullptr) {
+        if (epi.has_state(c * 32) && epi.x16T != nullptr && !(p.epi_skip & 4)) {
           __syncwarp();
           store_T_pairs_smem(epi.x16T + ((int64_t)b * HS + c * 32) * epi.ldT + node0, epi.ldT, scr, lane, node0, p.N);
         }
@@ -514,14 +521,16 @@ __global__ void k_weights_to_half(const float* __restrict__ wall, __half* __rest
 constexpr int IBC = 64, IBF = 16;
 
 // Encoder, all steps at once.  xpin: [NB][N][T][B][Cin] (block 0 = staged input, 1.. = propagated).
+// steps [t0, t0 + nt): step 0 is built on the main stream, the others beside the first encoder cell
 __global__ void k_encoder_input_blocks(const float* __restrict__ xpin, int NB, int N, int T, int B, int Cin,
-                                       __half* __restrict__ ib16c, float* __restrict__ ib32c) {
-  const int64_t R = (int64_t)N * B, total = (int64_t)T * R * IBC;
+                                       __half* __restrict__ ib16c, float* __restrict__ ib32c, int t0, int nt) {
+  const int64_t R = (int64_t)N * B, total = (int64_t)nt * R * IBC;
   const int nin = NB * Cin;
+  ib16c += (int64_t)t0 * R * IBC;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int j = (int)(i % IBC);
     const int64_t row = (i / IBC) % R;
-    const int t = (int)(i / ((int64_t)IBC * R));
+    const int t = t0 + (int)(i / ((int64_t)IBC * R));
     float v = 0.f;
     if (j < nin) {
       const int k = j / Cin, ci = j - k * Cin;
@@ -679,7 +688,7 @@ int launch_agcn_fused_h(int N, int B, int KS, const HOperands& op, int nparts, c
   using C = CfgH<HS, O>;
   const int64_t R = (int64_t)N * B;
   const int ldn = ld_half(N);
-  CUtensorMap tS, tXT, tXA, tIB, tW;
+  CUtensorMap tS, tXB, tXA, tIB, tW;
   {
     uint64_t dims[4] = {(uint64_t)N, (uint64_t)N, (uint64_t)KS, 1};
     uint64_t str[3] = {(uint64_t)ldn * 2, (uint64_t)N * ldn * 2, (uint64_t)KS * N * ldn * 2};
@@ -687,16 +696,12 @@ int launch_agcn_fused_h(int N, int B, int KS, const HOperands& op, int nparts, c
     MCRN_TRY(encode_tensor_map_h(&tS, op.S16, dims, str, box));
   }
   {
-    uint64_t dims[4] = {(uint64_t)N, (uint64_t)HS, (uint64_t)B, 1};
-    uint64_t str[3] = {(uint64_t)ldn * 2, (uint64_t)HS * ldn * 2, (uint64_t)B * HS * ldn * 2};
-    uint32_t box[4] = {BKH, (uint32_t)HS, 1, 1};
-    MCRN_TRY(encode_tensor_map_h(&tXT, op.X16T, dims, str, box));
-  }
-  {
     uint64_t dims[4] = {(uint64_t)HS, (uint64_t)B, (uint64_t)N, 1};
     uint64_t str[3] = {(uint64_t)HS * 2, (uint64_t)B * HS * 2, (uint64_t)R * HS * 2};
     uint32_t box[4] = {BKH, 1, BM, 1};
     MCRN_TRY(encode_tensor_map_h(&tXA, op.X16, dims, str, box));
+    uint32_t boxb[4] = {64, 1, BKH, 1};                  // MN-major B of MMA1: 64 channels x 64 node rows of batch element b
+    MCRN_TRY(encode_tensor_map_h(&tXB, op.X16, dims, str, boxb));
     const uint64_t il = op.ib_ld ? (uint64_t)op.ib_ld : (uint64_t)HS;
     uint64_t dimi[4] = {il, (uint64_t)B, (uint64_t)N, 1};
     uint64_t stri[3] = {il * 2, (uint64_t)B * il * 2, (uint64_t)R * il * 2};
@@ -716,6 +721,7 @@ int launch_agcn_fused_h(int N, int B, int KS, const HOperands& op, int nparts, c
   p.dbg = nullptr;
   p.pdl_late = (g_pdl_chain >> 3) & 1;
   p.span = fused::next_span();
+  { static const int es = getenv("MCRN_EPI_SKIP") ? atoi(getenv("MCRN_EPI_SKIP")) : 0; p.epi_skip = es; }
   if (fused::g_dbg_timeline != nullptr) {
     if (fused::g_dbg_which < 0 || fused::g_dbg_count == fused::g_dbg_which) p.dbg = fused::g_dbg_timeline;
     ++fused::g_dbg_count;
@@ -728,7 +734,7 @@ int launch_agcn_fused_h(int N, int B, int KS, const HOperands& op, int nparts, c
   }
   dim3 grid(ceil_div(N, BM), B, 1);
   const int pi = fused::prof_begin(fused::prof_class(0, HS, O == HS ? 1 : 0), st);
-  MCRN_TRY(launch_chain(1, kern, grid, dim3(FTHREADS), C::SMEM, st, "agcn_fused_h_kernel", tS, tXT, tXA, tIB, tW, p, epi));
+  MCRN_TRY(launch_chain(1, kern, grid, dim3(FTHREADS), C::SMEM, st, "agcn_fused_h_kernel", tS, tXB, tXA, tIB, tW, p, epi));
   fused::prof_end(pi, st);
   return MCRN_OK;
 }

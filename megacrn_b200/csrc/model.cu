@@ -172,7 +172,8 @@ static int cell_forward_fused_h(const Geo& g, const CellW& w, const CellBufs& b,
   const int ib_ld = ibc ? fusedh::IBC : 0;
   fusedh::HOperands og{w.S16, b.x16T, b.x16, ib, w.wg16, save_p ? b.xpg : nullptr, ib_ld};
   const bool xp0 = save && need_xp0(g, HS, w.Cin);
-  fusedh::EpiGateH eg{HS, b.hx, b.z, b.r, xp0 ? b.xpu : nullptr, b.zh16, b.zh16T, ldT};
+  static const int epi_skip = getenv("MCRN_EPI_SKIP") ? atoi(getenv("MCRN_EPI_SKIP")) : 0;
+  fusedh::EpiGateH eg{epi_skip, HS, b.hx, b.z, b.r, xp0 ? b.xpu : nullptr, b.zh16, b.zh16T, ldT};
   MCRN_TRY((fusedh::launch_agcn_fused_h<HS, 2 * HS>(g.N, g.B, g.KS, og, g_fused_parts, eg, st)));
   fusedh::HOperands ou{w.S16, b.zh16T, b.zh16, ib, w.wu16, save_p ? b.xpu : nullptr, ib_ld};
   fusedh::EpiUpdateH eu{HS, b.hx, b.r, b.hc, h_out, xp0 ? h_mma : nullptr, last ? nullptr : x16_next, last ? nullptr : x16T_next, ldT};
@@ -478,18 +479,32 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
     MCRN_LAUNCH(k_stage_encoder_input, ew_grid(n_in), 256, 0, st, x, ws + p.enc_xpin, g.B, g.T_in, g.N, g.Cin, tf32_mode());
     MCRN_TRY(propagate_in(g, S, ws + p.enc_xpin, (int64_t)g.N * g.T_in * g.B * g.Cin, (int64_t)g.T_in * g.B * g.Cin,
                           g.T_in * g.B * g.Cin, st));
-    if (ib_compact_shape(g, g.H, g.Cin, p.save))
-      MCRN_LAUNCH(fusedh::k_encoder_input_blocks, ew_grid((int64_t)g.T_in * g.R * 64), 256, 0, st, ws + p.enc_xpin, g.NB, g.N, g.T_in,
-                  g.B, g.Cin, reinterpret_cast<__half*>(ws + p.enc_ib16c), p.save ? ws + p.enc_ib32c : nullptr);
+    bool enc_ib_forked = false;
+    if (ib_compact_shape(g, g.H, g.Cin, p.save)) {
+      // step 0 now; steps 1.. on helper stream f0's successor (joined before the second cell), beside the first cell
+      MCRN_LAUNCH(fusedh::k_encoder_input_blocks, ew_grid((int64_t)g.R * 64), 256, 0, st, ws + p.enc_xpin, g.NB, g.N, g.T_in,
+                  g.B, g.Cin, reinterpret_cast<__half*>(ws + p.enc_ib16c), p.save ? ws + p.enc_ib32c : nullptr, 0, 1);
+      if (g.T_in > 1) {
+        cudaStream_t sx = st;
+        if (fork) {
+          if (!reuse_prologue) MCRN_TRY(fork_join(g_fw[0], st));          // f0's earlier work (weights) is needed by cell 0 anyway
+          MCRN_TRY(fork_begin(g_fw[0], st));
+          sx = g_fw[0].s; enc_ib_forked = true;
+        }
+        MCRN_LAUNCH(fusedh::k_encoder_input_blocks, ew_grid((int64_t)(g.T_in - 1) * g.R * 64), 256, 0, sx, ws + p.enc_xpin, g.NB, g.N,
+                    g.T_in, g.B, g.Cin, reinterpret_cast<__half*>(ws + p.enc_ib16c), p.save ? ws + p.enc_ib32c : nullptr, 1, g.T_in - 1);
+      }
+    }
     MCRN_CUDA_OK(cudaMemsetAsync(ws + p.enc_xpg, 0, (size_t)g.R * g.H * sizeof(float), st));
     MCRN_CUDA_OK(cudaMemsetAsync(ws + p.enc_hx, 0, (size_t)g.R * g.H * sizeof(float), st));
     if (enc_h) {
       MCRN_CUDA_OK(cudaMemsetAsync(ws + p.enc_x16, 0, (size_t)g.R * g.H * sizeof(__half), st));
       MCRN_CUDA_OK(cudaMemsetAsync(ws + p.enc_x16T, 0, (size_t)g.B * g.H * fusedh::ld_half(g.N) * sizeof(__half), st));
     }
-    if (fork && !reuse_prologue) MCRN_TRY(fork_join(g_fw[0], st));      // the folded weights are needed from here on
+    if (fork && !reuse_prologue && !enc_ib_forked) MCRN_TRY(fork_join(g_fw[0], st));      // the folded weights are needed from here on
     CellW w = enc_w(g, p, ws);
     for (int t = 0; t < g.T_in; ++t) {
+      if (t == 1 && enc_ib_forked) MCRN_TRY(fork_join(g_fw[0], st));      // input blocks of steps 1..
       CellBufs b = enc_bufs(g, p, ws, t);
       const bool last = (t + 1 == g.T_in);
       float* h_out = last ? ws + p.h_enc : enc_bufs(g, p, ws, t + 1).hx;
@@ -1073,16 +1088,18 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
       MCRN_TRY(acc_dw_fused(g, ws + p.dec_xpu, (int64_t)p.dec_xp_sz, ta, tb, g.D, dU_all, ws + p.d_Qu, 1, ws + p.a_d_wu, ibc, g_side.s2, dwh));
       MCRN_TRY(acc_dw_fused(g, ws + p.dec_xpg, (int64_t)p.dec_xp_sz, ta, tb, g.D, dG_all, ws + p.d_Qg, 2, ws + p.a_d_wg, ibc, g_side.s2, dwh));
       if (dwh) {
-        const int64_t sT = (int64_t)g.B * g.D * fusedh::ld_half(g.N);      // one [B][D][ldT] block
-        const __half* xT = reinterpret_cast<const __half*>(ws + p.dec_x16T) + ta * sT;
-        const __half* zT = reinterpret_cast<const __half*>(ws + p.dec_zh16T) + ta * sT;
+        const int64_t sR = g.R * g.D;                                      // one row-major [R][D] block
+        const __half* x16 = reinterpret_cast<const __half*>(ws + p.dec_x16) + ta * sR;
+        const __half* zh16 = reinterpret_cast<const __half*>(ws + p.dec_zh16) + ta * sR;
+        const __half* qu = reinterpret_cast<const __half*>(ws + p.d_Qu16T) + (int64_t)ta * g.KS * sR;
+        const __half* qg = reinterpret_cast<const __half*>(ws + p.d_Qg16T) + (int64_t)ta * 2 * g.KS * sR;
         const float* gs = ws + p.gs;
         if (g.D == 64) {
-          MCRN_TRY((fusedwh::launch_agcn_dw_h<64>(g.N, g.B, tb - ta, g.KS, 1, zT, du16T_buf(g, p, ws, g.D, ta), reinterpret_cast<const __half*>(ws + p.d_Qu16T) + (int64_t)ta * g.KS * sT, gs, ws + p.a_d_wu, g_side.s2)));
-          MCRN_TRY((fusedwh::launch_agcn_dw_h<64>(g.N, g.B, tb - ta, g.KS, 2, xT, dg16T_buf(g, p, ws, g.D, ta), reinterpret_cast<const __half*>(ws + p.d_Qg16T) + (int64_t)ta * 2 * g.KS * sT, gs, ws + p.a_d_wg, g_side.s2)));
+          MCRN_TRY((fusedwh::launch_agcn_dw_h<64>(g.N, g.B, tb - ta, g.KS, 1, zh16, du16_buf(g, p, ws, g.D, ta), qu, gs, ws + p.a_d_wu, g_side.s2)));
+          MCRN_TRY((fusedwh::launch_agcn_dw_h<64>(g.N, g.B, tb - ta, g.KS, 2, x16, dg16_buf(g, p, ws, g.D, ta), qg, gs, ws + p.a_d_wg, g_side.s2)));
         } else {
-          MCRN_TRY((fusedwh::launch_agcn_dw_h<128>(g.N, g.B, tb - ta, g.KS, 1, zT, du16T_buf(g, p, ws, g.D, ta), reinterpret_cast<const __half*>(ws + p.d_Qu16T) + (int64_t)ta * g.KS * sT, gs, ws + p.a_d_wu, g_side.s2)));
-          MCRN_TRY((fusedwh::launch_agcn_dw_h<128>(g.N, g.B, tb - ta, g.KS, 2, xT, dg16T_buf(g, p, ws, g.D, ta), reinterpret_cast<const __half*>(ws + p.d_Qg16T) + (int64_t)ta * 2 * g.KS * sT, gs, ws + p.a_d_wg, g_side.s2)));
+          MCRN_TRY((fusedwh::launch_agcn_dw_h<128>(g.N, g.B, tb - ta, g.KS, 1, zh16, du16_buf(g, p, ws, g.D, ta), qu, gs, ws + p.a_d_wu, g_side.s2)));
+          MCRN_TRY((fusedwh::launch_agcn_dw_h<128>(g.N, g.B, tb - ta, g.KS, 2, x16, dg16_buf(g, p, ws, g.D, ta), qg, gs, ws + p.a_d_wg, g_side.s2)));
         }
       }
       return MCRN_OK;
@@ -1114,9 +1131,9 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
                    ws + p.d_Qg + (int64_t)t * 2 * g.KS * g.R * g.D, ws + p.dXPin_all + p.dXPin_sz * t};
         bs.t = t;
         if (dw_h_shape(g, g.D, g.Cdec)) {
-          const int64_t sT = (int64_t)g.B * g.D * fusedh::ld_half(g.N);
-          bs.Qu16T = reinterpret_cast<__half*>(ws + p.d_Qu16T) + (int64_t)t * g.KS * sT;
-          bs.Qg16T = reinterpret_cast<__half*>(ws + p.d_Qg16T) + (int64_t)t * 2 * g.KS * sT;
+          const int64_t sR = g.R * g.D;                 // row-major [R][D] blocks
+          bs.Qu16T = reinterpret_cast<__half*>(ws + p.d_Qu16T) + (int64_t)t * g.KS * sR;
+          bs.Qg16T = reinterpret_cast<__half*>(ws + p.d_Qg16T) + (int64_t)t * 2 * g.KS * sR;
         }
         if (g_bwd_fused == 2 && g_glue_fuse && t > 0 && tf && tf[t - 1]) {     // step t-1 is teacher-forced: fold its glue in
           CellBufs bp = dec_bufs(g, p, ws, t - 1);
@@ -1215,16 +1232,18 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
       MCRN_TRY(acc_dw_fused(g, ws + p.enc_xpu, (int64_t)p.enc_xp_sz, ta, tb, g.H, dU_all, ws + p.e_Qu, 1, ws + p.a_e_wu, ibc, g_side.s2, dwh));
       MCRN_TRY(acc_dw_fused(g, ws + p.enc_xpg, (int64_t)p.enc_xp_sz, ta, tb, g.H, dG_all, ws + p.e_Qg, 2, ws + p.a_e_wg, ibc, g_side.s2, dwh));
       if (dwh) {
-        const int64_t sT = (int64_t)g.B * g.H * fusedh::ld_half(g.N);
-        const __half* xT = reinterpret_cast<const __half*>(ws + p.enc_x16T) + ta * sT;
-        const __half* zT = reinterpret_cast<const __half*>(ws + p.enc_zh16T) + ta * sT;
+        const int64_t sR = g.R * g.H;
+        const __half* x16 = reinterpret_cast<const __half*>(ws + p.enc_x16) + ta * sR;
+        const __half* zh16 = reinterpret_cast<const __half*>(ws + p.enc_zh16) + ta * sR;
+        const __half* qu = reinterpret_cast<const __half*>(ws + p.e_Qu16T) + (int64_t)ta * g.KS * sR;
+        const __half* qg = reinterpret_cast<const __half*>(ws + p.e_Qg16T) + (int64_t)ta * 2 * g.KS * sR;
         const float* gs = ws + p.gs;
         if (g.H == 64) {
-          MCRN_TRY((fusedwh::launch_agcn_dw_h<64>(g.N, g.B, tb - ta, g.KS, 1, zT, du16T_buf(g, p, ws, g.H, ta), reinterpret_cast<const __half*>(ws + p.e_Qu16T) + (int64_t)ta * g.KS * sT, gs, ws + p.a_e_wu, g_side.s2)));
-          MCRN_TRY((fusedwh::launch_agcn_dw_h<64>(g.N, g.B, tb - ta, g.KS, 2, xT, dg16T_buf(g, p, ws, g.H, ta), reinterpret_cast<const __half*>(ws + p.e_Qg16T) + (int64_t)ta * 2 * g.KS * sT, gs, ws + p.a_e_wg, g_side.s2)));
+          MCRN_TRY((fusedwh::launch_agcn_dw_h<64>(g.N, g.B, tb - ta, g.KS, 1, zh16, du16_buf(g, p, ws, g.H, ta), qu, gs, ws + p.a_e_wu, g_side.s2)));
+          MCRN_TRY((fusedwh::launch_agcn_dw_h<64>(g.N, g.B, tb - ta, g.KS, 2, x16, dg16_buf(g, p, ws, g.H, ta), qg, gs, ws + p.a_e_wg, g_side.s2)));
         } else {
-          MCRN_TRY((fusedwh::launch_agcn_dw_h<128>(g.N, g.B, tb - ta, g.KS, 1, zT, du16T_buf(g, p, ws, g.H, ta), reinterpret_cast<const __half*>(ws + p.e_Qu16T) + (int64_t)ta * g.KS * sT, gs, ws + p.a_e_wu, g_side.s2)));
-          MCRN_TRY((fusedwh::launch_agcn_dw_h<128>(g.N, g.B, tb - ta, g.KS, 2, xT, dg16T_buf(g, p, ws, g.H, ta), reinterpret_cast<const __half*>(ws + p.e_Qg16T) + (int64_t)ta * 2 * g.KS * sT, gs, ws + p.a_e_wg, g_side.s2)));
+          MCRN_TRY((fusedwh::launch_agcn_dw_h<128>(g.N, g.B, tb - ta, g.KS, 1, zh16, du16_buf(g, p, ws, g.H, ta), qu, gs, ws + p.a_e_wu, g_side.s2)));
+          MCRN_TRY((fusedwh::launch_agcn_dw_h<128>(g.N, g.B, tb - ta, g.KS, 2, x16, dg16_buf(g, p, ws, g.H, ta), qg, gs, ws + p.a_e_wg, g_side.s2)));
         }
       }
       return MCRN_OK;
@@ -1250,9 +1269,9 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
                    ws + p.e_Qg + (int64_t)t * 2 * g.KS * g.R * g.H, ws + p.dXPin_all + p.dXPin_sz * t};
         bs.t = t;
         if (dw_h_shape(g, g.H, g.Cin)) {
-          const int64_t sT = (int64_t)g.B * g.H * fusedh::ld_half(g.N);
-          bs.Qu16T = reinterpret_cast<__half*>(ws + p.e_Qu16T) + (int64_t)t * g.KS * sT;
-          bs.Qg16T = reinterpret_cast<__half*>(ws + p.e_Qg16T) + (int64_t)t * 2 * g.KS * sT;
+          const int64_t sR = g.R * g.H;
+          bs.Qu16T = reinterpret_cast<__half*>(ws + p.e_Qu16T) + (int64_t)t * g.KS * sR;
+          bs.Qg16T = reinterpret_cast<__half*>(ws + p.e_Qg16T) + (int64_t)t * 2 * g.KS * sR;
         }
         if (g_bwd_fused == 2 && g_glue_fuse && t > 0) {       // encoder: the glue of step t-1 always folds into this step's epilogue
           CellBufs bp = enc_bufs(g, p, ws, t - 1);

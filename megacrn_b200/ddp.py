@@ -78,6 +78,20 @@ def global_mask_count_begin(labels: torch.Tensor, scaler_mean: float, scaler_std
     return cnt, work, dist.get_world_size(group)
 
 
+def global_mask_count_into(labels: torch.Tensor, scaler_mean: float, scaler_std: float, out: torch.Tensor, group=None) -> None:
+    """Synchronous form: ``out[0]`` (a static 1-element device tensor, e.g. one a captured graph reads) = global count of
+    non-masked labels / world size."""
+    from . import _abi
+    lib = _abi.load()
+    lab = labels.detach().to(torch.float32).contiguous()
+    out.zero_()
+    with torch.cuda.device(lab.device):
+        st = lib.mcrn_mask_count(lab.data_ptr(), lab.numel(), scaler_mean, scaler_std, out.data_ptr(),
+                                 torch.cuda.current_stream(lab.device).cuda_stream)
+    _abi.check(st, "mcrn_mask_count")
+    _allreduce_mean(out, dist.get_world_size(group), group)
+
+
 def global_mask_count_end(pending):
     """Wait for the collective started by ``global_mask_count_begin``; returns the per-rank normaliser
     (global count / world size) as a 1-element device tensor, or None."""

@@ -44,20 +44,25 @@ def fused_trainer_loss(d_like, output, labels, query, pos, neg, *, scaler_mean, 
 DEFAULT_SCALER = dict(scaler_mean=54.0, scaler_std=20.0)     # the synthetic scaler of SURVEY.md 8(d); a trainer passes its own
 
 
-def train_step(model, x, y_cov, labels, batches_seen=0, teacher_forcing=None, group=None, **loss_kw):
+def train_step(model, x, y_cov, labels, batches_seen=0, teacher_forcing=None, group=None, mask_count=None, **loss_kw):
     """forward + trainer loss + backward; leaves gradients in ``p.grad``; returns loss[1] (device).
 
     Inside an initialised process group with more than one rank the masked-MAE normaliser is the global one
     (``ddp.global_mask_count``: a 4-byte all-reduce issued before the forward and waited for only at the loss), so that
-    the rank-average of loss and gradients equals the single-process step on the concatenated batch."""
+    the rank-average of loss and gradients equals the single-process step on the concatenated batch.  ``mask_count``: a
+    1-element device tensor that already holds that normaliser (``GraphedTrainStep`` computes it before replaying its
+    graph); no collective is issued here then."""
     from . import ddp
     for k, v in DEFAULT_SCALER.items():
         loss_kw.setdefault(k, v)
-    pending = ddp.global_mask_count_begin(labels, loss_kw["scaler_mean"], loss_kw["scaler_std"], group)
+    pending = None
+    if mask_count is None:
+        pending = ddp.global_mask_count_begin(labels, loss_kw["scaler_mean"], loss_kw["scaler_std"], group)
     outs = model(x, y_cov, labels, batches_seen, teacher_forcing=teacher_forcing)
     output, _h_att, query, pos, neg = outs
-    loss, d_out, d_q = fused_trainer_loss(model, output, labels, query, pos, neg, mask_count=ddp.global_mask_count_end(pending),
-                                          **loss_kw)
+    if pending is not None:
+        mask_count = ddp.global_mask_count_end(pending)
+    loss, d_out, d_q = fused_trainer_loss(model, output, labels, query, pos, neg, mask_count=mask_count, **loss_kw)
     torch.autograd.backward([output, query], [d_out, d_q])
     return loss
 
@@ -74,21 +79,16 @@ class GraphedTrainStep:
     alias one flat buffer (``flat_grad``), the loss in ``loss`` (a 1-element device tensor).
     """
 
-    def __init__(self, model, batch, seq_len, max_graphs=16, optimizer=None, allreduce=None, group=None, **loss_kw):
-        """optimizer: a ``megacrn_b200.optim.FusedClipAdam``; if given, clip + Adam are part of the captured step.
-        allreduce: capture the data-parallel collectives (mask-count all-reduce, ONE gradient all-reduce with NCCL's
-        in-collective averaging) inside the graph, between backward and optimiser; default: on inside a process group
-        with more than one rank (``MCRN_GRAPH_ALLREDUCE=0`` keeps them outside: call ``ddp.allreduce_gradients`` after
-        the replay, and the optimiser after that)."""
-        import os
+    def __init__(self, model, batch, seq_len, max_graphs=16, optimizer=None, group=None, **loss_kw):
+        """optimizer: a ``megacrn_b200.optim.FusedClipAdam``.  Single process: clip + Adam are part of the captured step.
+        Inside a process group with more than one rank the graph holds forward + loss + backward only; every call then
+        runs, around the replay: the 4-byte all-reduce of the masked-MAE normaliser (before), ONE gradient all-reduce
+        (NCCL averages inside the collective) and the optimiser (after).  Collectives are not captured: graph capture of
+        the NCCL calls hung on the 2-GPU box of this round (profiles/r2_summary.md)."""
         import torch.distributed as dist
-        in_group = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
-        if allreduce is None:
-            allreduce = in_group and os.environ.get("MCRN_GRAPH_ALLREDUCE", "1") != "0"
-        self.allreduce, self.group = bool(allreduce) and in_group, group
-        if in_group and optimizer is not None and not self.allreduce:
-            raise ValueError("data parallel: the optimiser must run after the gradient all-reduce -- capture both "
-                             "(allreduce=True) or call optimizer.step() yourself after ddp.allreduce_gradients")
+        self.group = group
+        self.dp = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.allreduce = self.dp            # the gradient all-reduce is issued by __call__
         self.model, self.loss_kw, self.max_graphs, self.optimizer = model, loss_kw, max_graphs, optimizer
         dev = next(model.parameters()).device
         self.x = torch.zeros(batch, seq_len, model.num_nodes, model.input_dim, device=dev)
@@ -99,26 +99,43 @@ class GraphedTrainStep:
         self.loss = None
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.pool = None
+        self.mask_count = torch.zeros(1, device=dev) if self.dp else None      # static: read by the captured loss kernel
 
     def load(self, x, y_cov, labels, non_blocking=True):
         self.x.copy_(x, non_blocking=non_blocking)
         self.y_cov.copy_(y_cov, non_blocking=non_blocking)
         self.labels.copy_(labels, non_blocking=non_blocking)
 
-    def _eager(self, flags):
+    def _eager(self, flags, complete=True):
         for p in self.params:
             p.grad = None
+        if complete:
+            self._before()
         loss = self._step_body(flags)
+        if complete:
+            self._after()
         return loss
 
     def _step_body(self, flags):
-        from .ddp import allreduce_gradients
-        loss = train_step(self.model, self.x, self.y_cov, self.labels, teacher_forcing=flags, group=self.group, **self.loss_kw)
-        if self.allreduce:
-            allreduce_gradients(self.params, self.group)
-        if self.optimizer is not None:
+        """What is captured: forward + loss + backward, and (single process only) the optimiser."""
+        loss = train_step(self.model, self.x, self.y_cov, self.labels, teacher_forcing=flags, group=self.group,
+                          mask_count=self.mask_count, **self.loss_kw)
+        if self.optimizer is not None and not self.dp:
             self.optimizer.step()
         return loss
+
+    def _before(self):
+        if self.dp:
+            from .ddp import global_mask_count_into
+            kw = {**DEFAULT_SCALER, **self.loss_kw}
+            global_mask_count_into(self.labels, kw["scaler_mean"], kw["scaler_std"], self.mask_count, self.group)
+
+    def _after(self):
+        if self.dp:
+            from .ddp import allreduce_gradients
+            allreduce_gradients(self.params, self.group)
+            if self.optimizer is not None:
+                self.optimizer.step()
 
     def _capture(self, flags):
         side = torch.cuda.Stream()
@@ -126,9 +143,10 @@ class GraphedTrainStep:
         saved = None
         if self.optimizer is not None:                 # the warm-up steps must not advance the optimiser / the weights
             saved = (self.optimizer.state_dict(), [p.detach().clone() for p in self.params])
-        with torch.cuda.stream(side):                  # warm-up outside capture (lazy inits, allocator)
+        self._before()                                 # (data parallel: a valid normaliser for the warm-up steps)
+        with torch.cuda.stream(side):                  # warm-up outside capture (lazy inits, allocator); no collectives
             for _ in range(2):
-                self._eager(flags)
+                self._eager(flags, complete=False)
         torch.cuda.current_stream().wait_stream(side)      # the restore below must not overtake the warm-up updates
         if saved is not None:
             with torch.no_grad():
@@ -162,12 +180,14 @@ class GraphedTrainStep:
                 return self.loss
             entry = self.graphs[key] = self._capture(flags)
         g, loss, grads, kernels = entry
+        self._before()
         g.replay()
-        if self.optimizer is not None:                     # the replayed graph updated the weights through raw pointers
+        if self.optimizer is not None and not self.dp:     # the replayed graph updated the weights through raw pointers
             self.optimizer.note_update()
         self.kernels_replayed += kernels
         for p, gr in zip(self.params, grads):              # static gradient tensors of this graph
             p.grad = gr
+        self._after()
         self.loss = loss
         return loss
 

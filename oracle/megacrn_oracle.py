@@ -112,7 +112,7 @@ def chebyshev_support_set(supports: Sequence[Tensor], cheb_k: int) -> List[Tenso
     """[I, S, 2 S T_{k-1} - T_{k-2}, ...] for each support (model/MegaCRN.py:19-23)."""
     out: List[Tensor] = []
     for s in supports:
-        ks = [torch.eye(s.shape[0], dtype=s.dtype), s]
+        ks = [torch.eye(s.shape[0], dtype=s.dtype, device=s.device), s]
         for _ in range(2, cheb_k):
             ks.append(torch.matmul(2 * s, ks[-1]) - ks[-2])
         out.extend(ks)
@@ -195,7 +195,7 @@ def forward(d: Dims, p: Dict[str, Tensor], x: Tensor, y_cov: Tensor, labels: Opt
     cur = x
     last_states = []
     for i in range(d.num_layers):                                                           # :71
-        state = torch.zeros(bsz, d.num_nodes, d.rnn_units, dtype=x.dtype)                   # :50-51, :174
+        state = torch.zeros(bsz, d.num_nodes, d.rnn_units, dtype=x.dtype, device=x.device)                # :50-51, :174
         inner = []
         for t in range(cur.shape[1]):                                                       # :74
             state = agcrn_cell(cur[:, t], state, supports, p, f"encoder.dcrnn_cells.{i}.", d.cheb_k)
@@ -206,7 +206,7 @@ def forward(d: Dims, p: Dict[str, Tensor], x: Tensor, y_cov: Tensor, labels: Opt
     h_att, query, pos, neg, att, ind = query_memory(h_t, p)                                 # :178
     h_t = torch.cat([h_t, h_att], dim=-1)                                                   # :179
     ht_list = [h_t] * d.num_layers                                                          # :181
-    go = torch.zeros(bsz, d.num_nodes, d.output_dim, dtype=x.dtype)                         # :182
+    go = torch.zeros(bsz, d.num_nodes, d.output_dim, dtype=x.dtype, device=x.device)                     # :182
     out = []
     for t in range(d.horizon):                                                              # :184
         cur_in = torch.cat([go, y_cov[:, t]], dim=-1)                                       # :185

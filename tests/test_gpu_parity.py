@@ -243,6 +243,33 @@ def test_large_graph_shapes_vs_oracle(cfg):
         assert rel_l2(prm.grad.cpu(), ref_grads[pname]) < 2.5 * GRAD_TOL, (pname, rel_l2(prm.grad.cpu(), ref_grads[pname]))
 
 
+@pytest.mark.parametrize("cfg", ["c4_full_T", "c5_full_T"])
+def test_large_graph_full_sequence_vs_oracle(cfg, default_engine):
+    """One sequence through the FULL recurrence of BASELINE.json configs[3] (N=1843, T=6+6, H=64) and configs[4] (N=2841,
+    T=12+12, H=128): error compounding over all steps with 1843- / 2841-term sums over the supports in 16-bit operands
+    (VERDICT r1 weak #3).  The CPU oracle needs ~10 s / ~1 min on 16 cores for these (96 N^3 Chebyshev products)."""
+    if cfg == "c4_full_T":
+        d, B, t_in = O.Dims(num_nodes=1843, horizon=6, rnn_units=64), 1, 6
+    else:
+        d, B, t_in = O.Dims(num_nodes=2841, horizon=12, rnn_units=128), 1, 12
+    p = O.init_params(d, seed=0)
+    x, y_cov, labels = O.synthetic_batch(d, B, t_in, seed=78)
+    flags = [t % 3 == 0 for t in range(d.horizon)]
+    torch.set_num_threads(min(16, torch.get_num_threads()))
+    ref_loss, ref_outs, ref_grads = O.loss_and_grads(d, p, x, y_cov, labels, flags)
+    m = _model(d, p).train()
+    dv = _dev()
+    outs = m(x.to(dv), y_cov.to(dv), labels.to(dv), teacher_forcing=flags)
+    d_out, d_q = reference_upstream(ref_outs[0], ref_outs[2], ref_outs[3], ref_outs[4], labels)
+    torch.autograd.backward([outs[0], outs[2]], [d_out.to(dv), d_q.to(dv)])
+    for k, a, b in zip(OUT_NAMES[:3], outs[:3], ref_outs[:3]):
+        assert rel_l2(a.detach().cpu(), b) < FWD_TOL, (k, rel_l2(a.detach().cpu(), b))
+    errs = {pname: rel_l2(prm.grad.cpu(), ref_grads[pname]) for pname, prm in m.named_parameters()}
+    print(cfg, "forward rel-L2", rel_l2(outs[0].detach().cpu(), ref_outs[0]), "grad rel-L2", {k: f"{v:.1e}" for k, v in errs.items()})
+    for pname, e in errs.items():      # a single sequence: no batch averaging of the rounding noise
+        assert e < 2.5 * GRAD_TOL, (pname, e)
+
+
 def test_all_output_gradients_including_pos_neg(engine):
     """Upstream gradients on all five outputs (pos/neg are not detached by the model itself)."""
     d = O.Dims(num_nodes=40, horizon=3, rnn_units=16, mem_num=6, mem_dim=12)

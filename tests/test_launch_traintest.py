@@ -1,6 +1,7 @@
 """CPU: the reference trainer, unmodified, resolves `from MegaCRN import MegaCRN` to this repo's module when started
 through megacrn_b200.launch_traintest.  Without a GPU the run must stop at the module's explicit no-CPU-path error --
-which proves the wiring (and that there is no silent fallback).  Needs the reference checkout; skipped on the GPU box."""
+which proves the wiring (and that there is no silent fallback).  Needs the reference checkout; on a GPU box the same
+launcher is run for a full epoch by tests/test_trainer_gpu.py::test_reference_trainer_one_epoch_on_gpu."""
 import os
 import subprocess
 import sys
