@@ -49,7 +49,6 @@ struct BHParams {
   float* qsave;          // [KS * nhalf][R][HS] fp32, unscaled (TF32 weight-gradient GEMMs); null when q16T is used
   int64_t blk_stride;    // R * HS
   __half* q16T;          // [KS * nhalf][R][HS] scaled fp16, ROW-major (operand of the fp16 weight-gradient kernel, read MN-major); or null
-  int ldT;
   float* dib;            // [R][IBW], unscaled (written when dxpin == null)
   const float* gs;       // device: {scale, 1 / scale}
   // gate-AGCN launch: the input-block gradient of the update AGCN (dib_in, written by the previous launch) is added and the
@@ -69,7 +68,7 @@ struct CfgBH {
   static constexpr uint32_t IB_SLOT = IBW * 128;                  // [16 rows][64 halves]
   static constexpr uint32_t STAGE = A_SLOT + B_SLOT + IB_SLOT;
   static constexpr int NST = HS >= 128 ? 5 : 6;
-  static constexpr uint32_t SCRATCH = 8 * 32 * 36 * 4;
+  static constexpr uint32_t SCRATCH = 8 * 32 * 36 * 4;     // (rounding-phase staging of the fp32 Q path)
   static constexpr size_t SMEM = (size_t)NST * STAGE + SCRATCH + 1024;
   static constexpr uint32_t TM_ACC = 0, TM_IB = HS, TM_Q0 = HS + 32, TM_Q1 = 2 * HS + 32;
   static constexpr uint32_t TMEM_COLS = pow2_cols(3 * HS + 32);
@@ -77,25 +76,20 @@ struct CfgBH {
 };
 
 // ---- epilogue functors: load4 / fin4 on 4 consecutive columns of one (node, b) row; acc is already unscaled ----------
-// NT = number of node-transposed fp16 operand copies the functor produces; fin4 returns their (scaled, fp16-rounded)
-// values in st[0..NT); tdst(i, b, col) = address of element (b, column col, node 0) of copy i (null: not wanted).
 
 // Update-AGCN tail (the cell's gate backward): dZH = acc; dG[:, :H] = dZH*h*z(1-z); dh_part = dHr + dZH*z.
 struct EpiBUH {
-  static constexpr int NP = 3, NT = 1;
+  static constexpr int NP = 3;
   int H;
   const float *z, *h, *dHr;
   float *dG, *dh_part;     // dG: fp32 [R][2H] (columns [0, H) written here)
-  __half* g16;             // [R][2H] scaled fp16 copy (columns [0, H))
-  __half* g16T;            // [B][2H][ldT]
-  int ldT;
-  __device__ __forceinline__ __half* tdst(int, int b, int col) const { return g16T + ((int64_t)b * 2 * H + col) * ldT; }
+  __half* g16;             // [R][2H] scaled fp16 copy (columns [0, H)): operand of the gate-AGCN launch
   __device__ __forceinline__ void load4(int row, int, int, int n0, float4 (&p)[NP]) const {
     const int64_t f = (int64_t)row * H + n0;
     p[0] = ldg4(z + f); p[1] = ldg4(h + f); p[2] = ldg4(dHr + f);
   }
-  __device__ __forceinline__ void fin4(int row, int, int, int n0, const float4 (&p)[NP], const float (&acc)[4], float s, float inv_s,
-                                       float (&st)[1][4]) const {
+  __device__ __forceinline__ void fin4(int row, int, int, int n0, const float4 (&p)[NP], const float (&acc)[4], float s, float inv_s) const {
+    float st[1][4];
     const float4 zz = p[0], hh = p[1], dr = p[2];
     const float d0 = acc[0], d1 = acc[1], d2 = acc[2], d3 = acc[3];
     st[0][0] = round_h(d0 * hh.x * zz.x * (1.0f - zz.x) * s); st[0][1] = round_h(d1 * hh.y * zz.y * (1.0f - zz.y) * s);
@@ -107,14 +101,12 @@ struct EpiBUH {
 };
 // Gate-AGCN tail: dH_prev = acc + dh_part
 struct EpiBGH {
-  static constexpr int NP = 1, NT = 0;
+  static constexpr int NP = 1;
   int H;
   const float* dh_part;
   float* dH_out;
-  __device__ __forceinline__ __half* tdst(int, int, int) const { return nullptr; }
   __device__ __forceinline__ void load4(int row, int, int, int n0, float4 (&p)[NP]) const { p[0] = ldg4(dh_part + (int64_t)row * H + n0); }
-  __device__ __forceinline__ void fin4(int row, int, int, int n0, const float4 (&p)[NP], const float (&acc)[4], float, float,
-                                       float (&)[1][4]) const {
+  __device__ __forceinline__ void fin4(int row, int, int, int n0, const float4 (&p)[NP], const float (&acc)[4], float, float) const {
     st4(dH_out + (int64_t)row * H + n0, acc[0] + p[0].x, acc[1] + p[0].y, acc[2] + p[0].z, acc[3] + p[0].w);
   }
 };
@@ -123,24 +115,21 @@ struct EpiBGH {
 //   dH' = acc + dh_part + d_out_{t-1} . wp ;  dU' = dH'(1-r')(1-hc'^2) ;  dG'[:, H:] = dH'(h'-hc')r'(1-r') ;  dHr' = dH' r'
 // with r', hc', h' the saved activations of step t-1.  Replaces k_bwd_glue_h for that step (dwp / dbp: k_proj_wgrad).
 struct EpiBGHG {
-  static constexpr int NP = 4, NT = 2;
+  static constexpr int NP = 4;
   int H;
   const float *dh_part, *r, *hc, *hx;      // r, hc, hx: step t-1
   const float* dOut;                       // [B][T][N][Cout] upstream gradient or null
   const float* wp;                         // [Cout][H]
   int B, T, N, Cout, tprev;
   float *dU, *dG, *dHr;                    // step t-1: dU [R][H], dG [R][2H] (columns [H, 2H)), dHr [R][H]
-  __half *u16, *u16T, *g16, *g16T;         // scaled fp16 operand copies of step t-1
-  int ldT;
-  __device__ __forceinline__ __half* tdst(int i, int b, int col) const {
-    return i == 0 ? u16T + ((int64_t)b * H + col) * ldT : g16T + ((int64_t)b * 2 * H + H + col) * ldT;
-  }
+  __half *u16, *g16;                       // scaled fp16 operand copies of step t-1 (row-major)
   __device__ __forceinline__ void load4(int row, int, int, int n0, float4 (&p)[NP]) const {
     const int64_t f = (int64_t)row * H + n0;
     p[0] = ldg4(dh_part + f); p[1] = ldg4(r + f); p[2] = ldg4(hc + f); p[3] = ldg4(hx + f);
   }
   __device__ __forceinline__ void fin4(int row, int node, int b, int n0, const float4 (&p)[NP], const float (&acc)[4], float s,
-                                       float inv_s, float (&st)[2][4]) const {
+                                       float inv_s) const {
+    float st[2][4];
     const float4 rr = p[1], cc = p[2], hh = p[3];
     float4 v = make_float4(acc[0] + p[0].x, acc[1] + p[0].y, acc[2] + p[0].z, acc[3] + p[0].w);
     if (dOut != nullptr) {
@@ -380,8 +369,6 @@ agcn_bwd_h_kernel(const __grid_constant__ CUtensorMap tmST, const __grid_constan
         __syncwarp();
         const int col = c * 32 + cq;
         constexpr int RB = Epi::NP <= 2 ? 8 : 4;
-        constexpr int NTS = Epi::NT > 0 ? Epi::NT : 1;
-        float* scr2 = scr + 8 * (32 * 36);               // second staging area (second transposed copy)
 #pragma unroll
         for (int b0 = 0; b0 < 8; b0 += RB) {
           float4 pre[RB][Epi::NP];
@@ -396,22 +383,11 @@ agcn_bwd_h_kernel(const __grid_constant__ CUtensorMap tmST, const __grid_constan
             if (node < p.N) {
               const float4 t = *reinterpret_cast<const float4*>(&scr[rr * 36 + cq]);
               const float a4[4] = {t.x, t.y, t.z, t.w};
-              float st[NTS][4];
-              epi.fin4(node * p.B + b, node, b, col, pre[i], a4, gs, inv_gs, st);
-              if constexpr (Epi::NT >= 1) *reinterpret_cast<float4*>(&scr[rr * 36 + cq]) = make_float4(st[0][0], st[0][1], st[0][2], st[0][3]);
-              if constexpr (Epi::NT >= 2) *reinterpret_cast<float4*>(&scr2[rr * 36 + cq]) = make_float4(st[1][0], st[1][1], st[1][2], st[1][3]);
+              epi.fin4(node * p.B + b, node, b, col, pre[i], a4, gs, inv_gs);
             }
           }
         }
-        if constexpr (Epi::NT >= 1) {                     // node-transposed scaled fp16 copies: X^T[b][c*32 + j][node0 + lane]
-          __syncwarp();
-#pragma unroll
-          for (int ti = 0; ti < Epi::NT; ++ti) {
-            __half* base = epi.tdst(ti, b, c * 32);
-            const float* src = ti == 0 ? scr : scr2;
-            if (base != nullptr) fusedh::store_T_pairs_smem(base + node0, epi.ldT, src, lane, node0, p.N);
-          }
-        }
+        __syncwarp();                                    // the staging tile is reused by the next chunk
       }
       if (half_id == 1) {                                // input-block gradient: 16 columns, one row per thread
         float v[16];
@@ -504,24 +480,20 @@ __global__ void k_weights_to_half_n(const float* __restrict__ wall, __half* __re
 }
 
 // ---- step glue, fp16 version ----------------------------------------------------------------------
-// As fusedb::k_bwd_glue, plus the scaled fp16 operand copies of dU and of the r-half of dG (row-major and
-// node-transposed).  Block = one batch element b x 32 consecutive nodes (rows n*B + b), thread = 4 columns.
+// As fusedb::k_bwd_glue, plus the scaled fp16 operand copies (row-major) of dU and of the r-half of dG.  Block = one batch element b x 32 consecutive nodes (rows n*B + b), thread = 4 columns.
 __global__ void __launch_bounds__(256) k_bwd_glue_h(const float* __restrict__ dOut, const float* __restrict__ dxin, int dxin_stride,
                                                     const float* __restrict__ h_t, const float* __restrict__ wp,
                                                     const float* __restrict__ dH, int dh_init, const float* __restrict__ r,
                                                     const float* __restrict__ hc, const float* __restrict__ hx,
                                                     float* __restrict__ dU, float* __restrict__ dG, float* __restrict__ dHr,
-                                                    __half* __restrict__ u16, __half* __restrict__ u16T, __half* __restrict__ g16,
-                                                    __half* __restrict__ g16T, int ldT, const float* __restrict__ gsp,
+                                                    __half* __restrict__ u16, __half* __restrict__ g16, const float* __restrict__ gsp,
                                                     float* __restrict__ dwp, float* __restrict__ dbp, int B, int T, int N,
                                                     int D, int Cout, int t) {
-  extern __shared__ float sh[];                    // [32][Cout] d_out rows, [Cout][D] dwp partials, [2][32][D+1] transposition
+  extern __shared__ float sh[];                    // [32][Cout] d_out rows, [Cout][D] dwp partials
   pdl_wait();
   pdl_launch_dependents();
   float* sh_do = sh;
   float* sh_w = sh + 32 * Cout;
-  float* sh_u = sh_w + Cout * D;
-  float* sh_g = sh_u + 32 * (D + 1);
   const int b = blockIdx.y, n0 = blockIdx.x * 32;
   const bool proj = (dOut != nullptr) || (dxin != nullptr);
   const float s = __ldg(gsp), inv_s = __ldg(gsp + 1);
@@ -567,21 +539,8 @@ __global__ void __launch_bounds__(256) k_bwd_glue_h(const float* __restrict__ dO
     st4(dHr + o, v.x * rr.x, v.y * rr.y, v.z * rr.z, v.w * rr.w);
     *reinterpret_cast<uint2*>(u16 + o) = make_uint2(pack_h2(u0, u1), pack_h2(u2, u3));
     *reinterpret_cast<uint2*>(g16 + row * 2 * D + D + q4) = make_uint2(pack_h2(g0, g1), pack_h2(g2, g3));
-    float* su = sh_u + i * (D + 1) + q4;
-    su[0] = u0; su[1] = u1; su[2] = u2; su[3] = u3;
-    float* sg = sh_g + i * (D + 1) + q4;
-    sg[0] = g0; sg[1] = g1; sg[2] = g2; sg[3] = g3;
   }
   __syncthreads();
-  // node-transposed copies: for each column c, the 32 nodes of this block are contiguous
-  for (int e = threadIdx.x; e < 16 * D; e += blockDim.x) {          // pairs of adjacent nodes: one 4-byte store each
-    const int i = (e & 15) * 2, c = e >> 4;
-    const int n = n0 + i;
-    if (n >= N) continue;
-    const bool two = n + 1 < N;
-    *reinterpret_cast<uint32_t*>(u16T + ((int64_t)b * D + c) * ldT + n) = pack_h2(sh_u[i * (D + 1) + c], two ? sh_u[(i + 1) * (D + 1) + c] : 0.f);
-    *reinterpret_cast<uint32_t*>(g16T + ((int64_t)b * 2 * D + D + c) * ldT + n) = pack_h2(sh_g[i * (D + 1) + c], two ? sh_g[(i + 1) * (D + 1) + c] : 0.f);
-  }
   if (proj) {
     for (int i = threadIdx.x; i < Cout * D; i += blockDim.x) atomicAdd(dwp + i, sh_w[i]);
     if (threadIdx.x < Cout) {
@@ -641,7 +600,6 @@ __global__ void __launch_bounds__(256) k_proj_wgrad(const float* __restrict__ dO
 // ---- host side ----------------------------------------------------------------------------------
 struct BHOperands {
   const __half* S16T;    // [KS][N][ld_half(N)]
-  const __half* V16T;    // [B][O][ld_half(N)]
   const __half* V16;     // [R][O]
   const __half* W16n;    // [KS+2][HS][O]
   const float* gs;       // device {scale, 1/scale}
@@ -679,7 +637,7 @@ int launch_agcn_bwd_h(int N, int B, int KS, int nhalf, const BHOperands& op, flo
   BHParams p;
   p.N = N; p.B = B; p.KS = KS; p.nhalf = nhalf;
   p.qsave = qsave; p.blk_stride = R * HS; p.dib = dib; p.gs = op.gs;
-  p.q16T = q16T; p.ldT = ldn;
+  p.q16T = q16T;
   p.dib_in = dib_in; p.dxpin = dxpin; p.nb = KS + 1; p.cin = cin;
   p.pdl_late = (g_pdl_chain >> 3) & 1;
   p.span = fused::next_span();

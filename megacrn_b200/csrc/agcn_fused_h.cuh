@@ -5,7 +5,7 @@
 //     round  P_k -> fp16 pairs, packed IN PLACE in TMEM (tcgen05.ld / cvt.rn.f16x2 / tcgen05.st)
 //     MMA2   acc[128 x O] += P_k * W_k   (A = packed P_k straight from TMEM)  + X_tile * W_0 + IB_tile * W_NB  (A in smem)
 //     epilogue: sigmoid / tanh / GRU algebra (model/MegaCRN.py:43-47), writes the fp32 tensors the backward needs and the
-//               fp16 operand copies (row-major and node-transposed) the next fused launch reads
+//               row-major fp16 operand copy the next fused launch reads
 // -- but every tensor-core operand is stored in HALF precision.  fp16 has the same 11-bit significand as TF32, so the
 // numerics match the TF32 path (all forward operands are O(1): softmax supports, states in (-1,1), inputs, weights), while
 // each operand byte carries twice the work: the kernel is bound by operand bytes through shared memory (every byte is
@@ -52,7 +52,6 @@ struct HParams {
   int64_t blk_stride;   // R * HS
   long long* dbg;       // debug timeline (see agcn_fused.cuh)
   unsigned long long* span;   // debug: {min CTA start, max CTA end} of this launch (ns), or null
-  int epi_skip;         // timing experiments only (MCRN_EPI_SKIP): 1 no epilogue global loads, 2 no fp32 stores, 4 no transposed fp16 copy, 8 no row-major fp16 copy, 16 cheap activation
   int pdl_late;         // programmatic dependent launch: 0 = let the dependents start right after the prologue, 1 = at the epilogue
 };
 
@@ -114,32 +113,6 @@ __device__ __forceinline__ void for_each_item_h(int KS, int kb1, int nparts, int
   }
 }
 
-// Node-transposed fp16 store of a 32 (nodes = lanes) x 32 (columns) tile: column j goes to base[j * ld + lane] (base = address of
-// (column 0, node node0); node0 and ld even).  Each lane stores one 4-byte pair of adjacent nodes (even lanes the even columns, odd
-// lanes the odd ones): 16 four-byte stores per lane instead of 32 two-byte ones.  The partner of the last valid node of an odd N
-// lands in the row padding (columns N..ld-1 are never read: the tensor maps stop at N).
-__device__ __forceinline__ void store_T_pairs_smem(__half* base, int ld, const float* tile /* [32][36] */, int lane, int node0, int N) {
-  const int odd = lane & 1, re = lane & ~1;
-  if (node0 + re < N) {
-#pragma unroll 8
-    for (int j = 0; j < 32; j += 2) {
-      const int col = j + odd;
-      *reinterpret_cast<uint32_t*>(base + (int64_t)col * ld + re) = pack_h2(tile[re * 36 + col], tile[(re + 1) * 36 + col]);
-    }
-  }
-}
-// Same from registers (v = the 32 columns of this lane's node): lane pairs exchange with one shuffle per column pair.
-__device__ __forceinline__ void store_T_pairs_regs(__half* base, int ld, const float (&v)[32], int lane, int node0, int N) {
-  const int odd = lane & 1, re = lane & ~1;
-  const bool ok = node0 + re < N;
-#pragma unroll
-  for (int j = 0; j < 32; j += 2) {
-    const float mine = odd ? v[j + 1] : v[j], give = odd ? v[j] : v[j + 1];
-    const float got = __shfl_xor_sync(0xffffffffu, give, 1);
-    if (ok) *reinterpret_cast<uint32_t*>(base + (int64_t)(j + odd) * ld + re) = odd ? pack_h2(got, mine) : pack_h2(mine, got);
-  }
-}
-
 template <int HS, int O>
 struct CfgH {
   static_assert(HS == 64 || HS == 128, "hidden width of the fused AGCN kernel: 64 or 128");
@@ -157,37 +130,33 @@ struct CfgH {
 };
 
 // ---- epilogue functors ------------------------------------------------------------------------
-// load4 / fin4 work on 4 consecutive columns of one (node, b) row.  fin4 returns in `st` the value the next fused
-// launch consumes as a tensor-core operand (already fp16-rounded), or leaves it untouched for columns without one.
+// load4 / fin4 work on 4 consecutive columns of one (node, b) row; fin4 also writes the fp16 operand copy the next fused
+// launch consumes (row-major only: the propagation reads it as an MN-major operand).
 
 // Gate AGCN (model/MegaCRN.py:43-45): zr = sigmoid(acc); columns [0,H) = z, [H,2H) = r; writes z, r, z*h.
 struct EpiGateH {
   static constexpr int NP = 1;
-  int skip = 0;
   int H;
   const float* h;       // [R][H] exact state
   float* z;             // null in eval
   float* r;
   float* zh32;          // fp32 copy of the fp16-rounded z*h (XPu block 0, read by the backward); null in eval
-  __half* x16;          // [R][H]        z*h, A operand of the update AGCN's identity segment
-  __half* x16T;         // [B][H][ldT]   z*h, B operand of the update AGCN's propagation
-  int ldT;
-  __device__ __forceinline__ bool has_state(int n0) const { return n0 < H; }
+  __half* x16;          // [R][H]  z*h: A operand of the update AGCN's identity segment and (MN-major) B operand of its propagation
   __device__ __forceinline__ void load4(int row, int n0, float4 (&p)[NP]) const {
-    p[0] = (n0 < H && !(skip & 1)) ? ldg4(h + (int64_t)row * H + n0) : make_float4(0.5f, 0.5f, 0.5f, 0.5f);
+    p[0] = (n0 < H) ? ldg4(h + (int64_t)row * H + n0) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  __device__ __forceinline__ void fin4(int row, int n0, const float4 (&p)[NP], const float (&acc)[4], float (&st)[4]) const {
+  __device__ __forceinline__ void fin4(int row, int n0, const float4 (&p)[NP], const float (&acc)[4]) const {
+    float st[4];
     float s0, s1, s2, s3;
-    if (skip & 16) { s0 = acc[0] * 0.01f + 0.5f; s1 = acc[1] * 0.01f + 0.5f; s2 = acc[2] * 0.01f + 0.5f; s3 = acc[3] * 0.01f + 0.5f; }
-    else { s0 = sigmoid_fast(acc[0]); s1 = sigmoid_fast(acc[1]); s2 = sigmoid_fast(acc[2]); s3 = sigmoid_fast(acc[3]); }
+    s0 = sigmoid_fast(acc[0]); s1 = sigmoid_fast(acc[1]); s2 = sigmoid_fast(acc[2]); s3 = sigmoid_fast(acc[3]);
     if (n0 < H) {
       const int64_t o = (int64_t)row * H + n0;
-      if (z && !(skip & 2)) st4(z + o, s0, s1, s2, s3);
+      if (z) st4(z + o, s0, s1, s2, s3);
       st[0] = round_h(s0 * p[0].x); st[1] = round_h(s1 * p[0].y); st[2] = round_h(s2 * p[0].z); st[3] = round_h(s3 * p[0].w);
       if (zh32) st4(zh32 + o, st[0], st[1], st[2], st[3]);
-      if (!(skip & 8)) *reinterpret_cast<uint2*>(x16 + o) = make_uint2(pack_h2(st[0], st[1]), pack_h2(st[2], st[3]));
+      *reinterpret_cast<uint2*>(x16 + o) = make_uint2(pack_h2(st[0], st[1]), pack_h2(st[2], st[3]));
     } else {
-      if (!(skip & 2)) st4(r + (int64_t)row * H + (n0 - H), s0, s1, s2, s3);
+      st4(r + (int64_t)row * H + (n0 - H), s0, s1, s2, s3);
     }
   }
 };
@@ -200,16 +169,14 @@ struct EpiUpdateH {
   float* hc;            // null in eval
   float* h_out;         // exact new state
   float* h32;           // fp32 copy of the fp16-rounded new state (next step's XPg block 0); null in eval / last step
-  __half* x16;          // next step's operand copies; null after the last step
-  __half* x16T;
-  int ldT;
-  __device__ __forceinline__ bool has_state(int) const { return x16 != nullptr; }
+  __half* x16;          // next step's operand copy [R][H]; null after the last step
   __device__ __forceinline__ void load4(int row, int n0, float4 (&p)[NP]) const {
     const int64_t o = (int64_t)row * H + n0;
     p[0] = ldg4(h + o);
     p[1] = ldg4(r + o);
   }
-  __device__ __forceinline__ void fin4(int row, int n0, const float4 (&p)[NP], const float (&acc)[4], float (&st)[4]) const {
+  __device__ __forceinline__ void fin4(int row, int n0, const float4 (&p)[NP], const float (&acc)[4]) const {
+    float st[4];
     const int64_t o = (int64_t)row * H + n0;
     const float4 hv = p[0], rv = p[1];
     const float c0 = tanh_fast(acc[0]), c1 = tanh_fast(acc[1]), c2 = tanh_fast(acc[2]), c3 = tanh_fast(acc[3]);
@@ -448,17 +415,11 @@ agcn_fused_h_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_consta
             if (node < p.N) {
               const float4 t = *reinterpret_cast<const float4*>(&scr[rr * 36 + cq]);
               const float a4[4] = {t.x, t.y, t.z, t.w};
-              float st[4] = {0.f, 0.f, 0.f, 0.f};
-              epi.fin4(node * p.B + b, col, pre[i], a4, st);
-              *reinterpret_cast<float4*>(&scr[rr * 36 + cq]) = make_float4(st[0], st[1], st[2], st[3]);
+              epi.fin4(node * p.B + b, col, pre[i], a4);
             }
           }
         }
-        // node-transposed fp16 copy of the new operand: X^T[b][c*32 + j][node0 + lane]
-        if (epi.has_state(c * 32) && epi.x16T != nullptr && !(p.epi_skip & 4)) {
-          __syncwarp();
-          store_T_pairs_smem(epi.x16T + ((int64_t)b * HS + c * 32) * epi.ldT + node0, epi.ldT, scr, lane, node0, p.N);
-        }
+        __syncwarp();                                    // the staging tile is reused by the next chunk
       }
     }
   }
@@ -486,18 +447,10 @@ __global__ void k_supports_to_half(const float* __restrict__ S, __half* __restri
     S16[i] = __float2half_rn(c < n ? S[r * ld + c] : 0.f);
   }
 }
-// state fp32 [N][B][HS] -> fp16 row-major [N][B][HS] and node-transposed [B][HS][ldT]
-__global__ void k_state_to_half(const float* __restrict__ x, __half* __restrict__ x16, __half* __restrict__ x16T, int N, int B,
-                                int HS, int ldT) {
-  const int64_t total = (int64_t)N * B * HS;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % HS);
-    const int64_t row = i / HS;
-    const int n = (int)(row / B), b = (int)(row - (int64_t)n * B);
-    const __half v = __float2half_rn(x[i]);
-    x16[i] = v;
-    x16T[((int64_t)b * HS + c) * ldT + n] = v;
-  }
+// state fp32 [N][B][HS] -> fp16 row-major [N][B][HS]
+__global__ void k_state_to_half(const float* __restrict__ x, __half* __restrict__ x16, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    x16[i] = __float2half_rn(x[i]);
 }
 // folded weights fp32 [2 (TF32 hi, lo)][KS+2][HS][O] -> fp16 hi / lo, transposed: [2][KS+2][O][HS]
 __global__ void k_weights_to_half(const float* __restrict__ wall, __half* __restrict__ w16, int nseg, int HS, int O) {
@@ -675,7 +628,6 @@ static inline int ld_half(int n) { return (n + 7) / 8 * 8; }     // 16-byte row 
 
 struct HOperands {
   const __half* S16;      // [KS][N][ld_half(N)]
-  const __half* X16T;     // [B][HS][ld_half(N)]
   const __half* X16;      // [R][HS]
   const __half* IB16;     // [R][ib_ld]: ib_ld = HS (full input block) or 64 (compact: only the first k-block is non-zero)
   const __half* W16;      // [nparts][KS+2][O][HS]
@@ -721,7 +673,6 @@ int launch_agcn_fused_h(int N, int B, int KS, const HOperands& op, int nparts, c
   p.dbg = nullptr;
   p.pdl_late = (g_pdl_chain >> 3) & 1;
   p.span = fused::next_span();
-  { static const int es = getenv("MCRN_EPI_SKIP") ? atoi(getenv("MCRN_EPI_SKIP")) : 0; p.epi_skip = es; }
   if (fused::g_dbg_timeline != nullptr) {
     if (fused::g_dbg_which < 0 || fused::g_dbg_count == fused::g_dbg_which) p.dbg = fused::g_dbg_timeline;
     ++fused::g_dbg_count;

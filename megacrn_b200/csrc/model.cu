@@ -80,7 +80,7 @@ struct CellBufs {        // per-step activations
   float *xpg, *xpu, *z, *r, *hc;
   float* hx;             // exact fp32 input state of the step (xpg block 0 is its tensor-core copy)
   // fp16 operand copies (fused fp16 forward): state h (row-major, node-transposed), z*h, input block
-  __half *x16 = nullptr, *x16T = nullptr, *zh16 = nullptr, *zh16T = nullptr, *ib16 = nullptr;
+  __half *x16 = nullptr, *zh16 = nullptr, *ib16 = nullptr;      // row-major [R][Hs] (MMA operands: A of the identity segment, MN-major B of the propagation)
   __half* ib16c = nullptr;   // compact input block of this step [R][64] (fused fp16 forward + fused backward / eval)
   float* ib32c = nullptr;    // [R][16] fp32 copy (training)
 };
@@ -163,26 +163,24 @@ static bool need_xp0(const Geo& g, int Hs, int Cin) { return !(dw_h_shape(g, Hs,
 // fp16-operand fused cell (agcn_fused_h.cuh).  last: no next step consumes the new state as a tensor-core operand.
 template <int HS>
 static int cell_forward_fused_h(const Geo& g, const CellW& w, const CellBufs& b, float* h_out, float* h_mma, bool last,
-                                __half* x16_next, __half* x16T_next, cudaStream_t st) {
+                                __half* x16_next, cudaStream_t st) {
   const bool save = b.z != nullptr;
   const bool save_p = save && !bwd_fused_shape(g, HS, w.Cin);     // the fused backward recomputes nothing from P_k: dW_k = X^T Q_k
-  const int ldT = fusedh::ld_half(g.N);
   const bool ibc = ib_compact_shape(g, HS, w.Cin, save);
   const __half* ib = ibc ? b.ib16c : b.ib16;
   const int ib_ld = ibc ? fusedh::IBC : 0;
-  fusedh::HOperands og{w.S16, b.x16T, b.x16, ib, w.wg16, save_p ? b.xpg : nullptr, ib_ld};
+  fusedh::HOperands og{w.S16, b.x16, ib, w.wg16, save_p ? b.xpg : nullptr, ib_ld};
   const bool xp0 = save && need_xp0(g, HS, w.Cin);
-  static const int epi_skip = getenv("MCRN_EPI_SKIP") ? atoi(getenv("MCRN_EPI_SKIP")) : 0;
-  fusedh::EpiGateH eg{epi_skip, HS, b.hx, b.z, b.r, xp0 ? b.xpu : nullptr, b.zh16, b.zh16T, ldT};
+  fusedh::EpiGateH eg{HS, b.hx, b.z, b.r, xp0 ? b.xpu : nullptr, b.zh16};
   MCRN_TRY((fusedh::launch_agcn_fused_h<HS, 2 * HS>(g.N, g.B, g.KS, og, g_fused_parts, eg, st)));
-  fusedh::HOperands ou{w.S16, b.zh16T, b.zh16, ib, w.wu16, save_p ? b.xpu : nullptr, ib_ld};
-  fusedh::EpiUpdateH eu{HS, b.hx, b.r, b.hc, h_out, xp0 ? h_mma : nullptr, last ? nullptr : x16_next, last ? nullptr : x16T_next, ldT};
+  fusedh::HOperands ou{w.S16, b.zh16, ib, w.wu16, save_p ? b.xpu : nullptr, ib_ld};
+  fusedh::EpiUpdateH eu{HS, b.hx, b.r, b.hc, h_out, xp0 ? h_mma : nullptr, last ? nullptr : x16_next};
   MCRN_TRY((fusedh::launch_agcn_fused_h<HS, HS>(g.N, g.B, g.KS, ou, g_fused_parts, eu, st)));
   return MCRN_OK;
 }
 
 static int cell_forward(const Geo& g, const float* S, const CellW& w, const CellBufs& b, float* h_out, float* h_mma,
-                        cudaStream_t st, __half* x16_next = nullptr, __half* x16T_next = nullptr) {
+                        cudaStream_t st, __half* x16_next = nullptr) {
   const int Hs = w.Hs, NBX = g.NB + 1;
   const int rnd = tf32_mode();
   const int64_t nH = g.R * Hs;
@@ -192,8 +190,8 @@ static int cell_forward(const Geo& g, const float* S, const CellW& w, const Cell
     MCRN_LAUNCH(k_build_input_block, ew_grid(nH), 256, 0, st, b.xpin, b.xp_k, b.xp_n, g.NB, w.Cin, g.B, g.R, Hs, rnd,
                 save ? b.xpg + (int64_t)g.NB * nH : nullptr, save ? b.xpu + (int64_t)g.NB * nH : nullptr, b.ib16);
     const bool last = (h_mma == nullptr);
-    return Hs == 64 ? cell_forward_fused_h<64>(g, w, b, h_out, h_mma, last, x16_next, x16T_next, st)
-                    : cell_forward_fused_h<128>(g, w, b, h_out, h_mma, last, x16_next, x16T_next, st);
+    return Hs == 64 ? cell_forward_fused_h<64>(g, w, b, h_out, h_mma, last, x16_next, st)
+                    : cell_forward_fused_h<128>(g, w, b, h_out, h_mma, last, x16_next, st);
   }
   // input block (input channels + bias) of both AGCNs of this step
   MCRN_LAUNCH(k_build_input_block, ew_grid(nH), 256, 0, st, b.xpin, b.xp_k, b.xp_n, g.NB, w.Cin, g.B, g.R, Hs, rnd,
@@ -307,9 +305,8 @@ static CellBufs enc_bufs(const Geo& g, const Plan& p, float* ws, int t) {
   b.hc = p.save ? ws + p.enc_hc + p.enc_v_sz * s : nullptr;
   b.hx = ws + p.enc_hx + p.enc_v_sz * s;
   const int64_t hs = p.save ? (int64_t)t * g.R * g.H : 0;        // training: per-step row-major fp16 copies
-  const int64_t hT = p.save ? (int64_t)t * g.B * g.H * fusedh::ld_half(g.N) : 0;
-  b.x16 = reinterpret_cast<__half*>(ws + p.enc_x16) + hs; b.x16T = reinterpret_cast<__half*>(ws + p.enc_x16T) + hT;
-  b.zh16 = reinterpret_cast<__half*>(ws + p.enc_zh16) + hs; b.zh16T = reinterpret_cast<__half*>(ws + p.enc_zh16T) + hT;
+  b.x16 = reinterpret_cast<__half*>(ws + p.enc_x16) + hs;
+  b.zh16 = reinterpret_cast<__half*>(ws + p.enc_zh16) + hs;
   b.ib16 = reinterpret_cast<__half*>(ws + p.enc_ib16);
   b.ib16c = reinterpret_cast<__half*>(ws + p.enc_ib16c) + (int64_t)t * g.R * 64;
   b.ib32c = p.save ? ws + p.enc_ib32c + (int64_t)t * g.R * 16 : nullptr;
@@ -328,9 +325,8 @@ static CellBufs dec_bufs(const Geo& g, const Plan& p, float* ws, int t) {
   b.hc = p.save ? ws + p.dec_hc + p.dec_v_sz * s : nullptr;
   b.hx = ws + p.dec_hx + p.dec_v_sz * s;
   const int64_t hs = p.save ? (int64_t)t * g.R * g.D : 0;
-  const int64_t hT = p.save ? (int64_t)t * g.B * g.D * fusedh::ld_half(g.N) : 0;
-  b.x16 = reinterpret_cast<__half*>(ws + p.dec_x16) + hs; b.x16T = reinterpret_cast<__half*>(ws + p.dec_x16T) + hT;
-  b.zh16 = reinterpret_cast<__half*>(ws + p.dec_zh16) + hs; b.zh16T = reinterpret_cast<__half*>(ws + p.dec_zh16T) + hT;
+  b.x16 = reinterpret_cast<__half*>(ws + p.dec_x16) + hs;
+  b.zh16 = reinterpret_cast<__half*>(ws + p.dec_zh16) + hs;
   b.ib16 = reinterpret_cast<__half*>(ws + p.dec_ib16);
   b.ib16c = reinterpret_cast<__half*>(ws + p.dec_ib16c) + (int64_t)t * g.R * 64;
   b.ib32c = p.save ? ws + p.dec_ib32c + (int64_t)t * g.R * 16 : nullptr;
@@ -499,7 +495,6 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
     MCRN_CUDA_OK(cudaMemsetAsync(ws + p.enc_hx, 0, (size_t)g.R * g.H * sizeof(float), st));
     if (enc_h) {
       MCRN_CUDA_OK(cudaMemsetAsync(ws + p.enc_x16, 0, (size_t)g.R * g.H * sizeof(__half), st));
-      MCRN_CUDA_OK(cudaMemsetAsync(ws + p.enc_x16T, 0, (size_t)g.B * g.H * fusedh::ld_half(g.N) * sizeof(__half), st));
     }
     if (fork && !reuse_prologue && !enc_ib_forked) MCRN_TRY(fork_join(g_fw[0], st));      // the folded weights are needed from here on
     CellW w = enc_w(g, p, ws);
@@ -509,8 +504,7 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
       const bool last = (t + 1 == g.T_in);
       float* h_out = last ? ws + p.h_enc : enc_bufs(g, p, ws, t + 1).hx;
       float* h_mma = last ? nullptr : enc_bufs(g, p, ws, t + 1).xpg;
-      MCRN_TRY(cell_forward(g, S, w, b, h_out, h_mma, st, last ? nullptr : enc_bufs(g, p, ws, t + 1).x16,
-                            last ? nullptr : enc_bufs(g, p, ws, t + 1).x16T));
+      MCRN_TRY(cell_forward(g, S, w, b, h_out, h_mma, st, last ? nullptr : enc_bufs(g, p, ws, t + 1).x16));
     }
   }
   // ---- memory query (:159-166) + decoder initial state (:179) ----
@@ -521,8 +515,7 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
                 ws + p.mq_q, ws + p.mq_att, reinterpret_cast<int*>(ws + p.mq_ind), h_att, query, pos, neg, b0.hx,
                 b0.xpg, tf32_mode(), g.B, g.N, g.H, g.M, g.d);
     if (dec_h)
-      MCRN_LAUNCH(fusedh::k_state_to_half, ew_grid(g.R * g.D), 256, 0, st, b0.xpg, b0.x16, b0.x16T, g.N, g.B, g.D,
-                  fusedh::ld_half(g.N));
+      MCRN_LAUNCH(fusedh::k_state_to_half, ew_grid(g.R * g.D), 256, 0, st, b0.xpg, b0.x16, (int64_t)g.R * g.D);
   }
   if (fork) MCRN_TRY(fork_join(g_fw[1], st));
   // ---- decoder loop (:181-192) ----
@@ -544,8 +537,7 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
       const bool last = (t + 1 == g.T_out);
       float* h_out = last ? ws + p.h_dec_last : dec_bufs(g, p, ws, t + 1).hx;
       float* h_mma = last ? nullptr : dec_bufs(g, p, ws, t + 1).xpg;
-      MCRN_TRY(cell_forward(g, S, w, b, h_out, h_mma, st, last ? nullptr : dec_bufs(g, p, ws, t + 1).x16,
-                            last ? nullptr : dec_bufs(g, p, ws, t + 1).x16T));
+      MCRN_TRY(cell_forward(g, S, w, b, h_out, h_mma, st, last ? nullptr : dec_bufs(g, p, ws, t + 1).x16));
       // projection (:186): needed now only if the next step feeds on it; otherwise (training: every state is kept) all such
       // steps are projected by one launch after the loop
       const bool next_needs_it = !last && !((dec_tf_mask >> (t + 1)) & 1u);
@@ -752,12 +744,6 @@ static inline __half* dg16_buf(const Geo& g, const Plan& p, float* ws, int Hs, i
 static inline __half* du16_buf(const Geo& g, const Plan& p, float* ws, int Hs, int t) {      // row-major, one per step
   return reinterpret_cast<__half*>(ws + (Hs == g.D ? p.dU16 : p.e_dU16)) + (size_t)t * g.R * Hs;
 }
-static inline __half* dg16T_buf(const Geo& g, const Plan& p, float* ws, int Hs, int t) {     // node-transposed, one per step
-  return reinterpret_cast<__half*>(ws + (Hs == g.D ? p.dG16T : p.e_dG16T)) + (size_t)t * g.B * 2 * Hs * fusedh::ld_half(g.N);
-}
-static inline __half* du16T_buf(const Geo& g, const Plan& p, float* ws, int Hs, int t) {
-  return reinterpret_cast<__half*>(ws + (Hs == g.D ? p.dU16T : p.e_dU16T)) + (size_t)t * g.B * Hs * fusedh::ld_half(g.N);
-}
 // fp16 weight-gradient kernel (agcn_dw_fused_h.cuh): 1 = on where the fp16 forward + backward and the compact input block
 // provide its operands
 static int g_dw_fused = getenv("MCRN_DW_FUSED") ? atoi(getenv("MCRN_DW_FUSED")) : 1;
@@ -802,13 +788,11 @@ static int cell_backward_fused(const Geo& g, const Plan& p, float* ws, const flo
   }
   const bool h16 = (g_bwd_fused == 2);
   __half* dU16 = du16_buf(g, p, ws, HS, bs.t);
-  __half* dU16T = du16T_buf(g, p, ws, HS, bs.t);
   __half* dG16 = dg16_buf(g, p, ws, HS, bs.t);
-  __half* dG16T = dg16T_buf(g, p, ws, HS, bs.t);
   const __half* S16T = reinterpret_cast<const __half*>(ws + p.s16T);
   if (h16) {
-    fusedbh::BHOperands ou{S16T, dU16T, dU16, w.wu16n, ws + p.gs};
-    fusedbh::EpiBUH eu{HS, b.z, b.hx, ws + p.dHr, bs.dG, dHp, dG16, dG16T, fusedh::ld_half(g.N)};
+    fusedbh::BHOperands ou{S16T, dU16, w.wu16n, ws + p.gs};
+    fusedbh::EpiBUH eu{HS, b.z, b.hx, ws + p.dHr, bs.dG, dHp, dG16};
     MCRN_TRY((fusedbh::launch_agcn_bwd_h<HS>(g.N, g.B, g.KS, 1, ou, bs.Qu, ws + p.dIBu16, eu, st, nullptr, nullptr, 0, bs.Qu16T)));
   } else {
   fusedb::EpiBU eu{HS, b.z, b.hx, ws + p.dHr, bs.dG, dHp};
@@ -821,13 +805,11 @@ static int cell_backward_fused(const Geo& g, const Plan& p, float* ws, const flo
   MCRN_TRY(acc_ds(g, dXP2 + nH, (int64_t)g.B * HS, b.xpg, (int64_t)g.B * HS, g.B * HS, dS, sd));
   }
   if (h16) {
-    fusedbh::BHOperands og{S16T, dG16T, dG16, w.wg16n, ws + p.gs};
+    fusedbh::BHOperands og{S16T, dG16, w.wg16n, ws + p.gs};
     // the gate-AGCN launch also sums both input-block gradients into dXPin (no repack kernel)
     if (bs.ng_r != nullptr) {     // ... and runs the glue of step t-1 in its epilogue
       fusedbh::EpiBGHG eg{HS, dHp, bs.ng_r, bs.ng_hc, bs.ng_hx, bs.ng_dOut, bs.ng_wp, g.B, bs.ng_T, g.N, bs.ng_Cout, bs.t - 1,
-                          bs.ng_dU, bs.ng_dG, ws + p.dHr, du16_buf(g, p, ws, HS, bs.t - 1), du16T_buf(g, p, ws, HS, bs.t - 1), dg16_buf(g, p, ws, HS, bs.t - 1),
-                          dg16T_buf(g, p, ws, HS, bs.t - 1),
-                          fusedh::ld_half(g.N)};
+                          bs.ng_dU, bs.ng_dG, ws + p.dHr, du16_buf(g, p, ws, HS, bs.t - 1), dg16_buf(g, p, ws, HS, bs.t - 1)};
       MCRN_TRY((fusedbh::launch_agcn_bwd_h<HS>(g.N, g.B, g.KS, 2, og, bs.Qg, ws + p.dIBg16, eg, st, ws + p.dIBu16, bs.dXPin, w.Cin, bs.Qg16T)));
     } else {
       fusedbh::EpiBGH eg{HS, dHp, dH};
@@ -1116,11 +1098,10 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
         const bool glue_fused_here = (g_bwd_fused == 2) && dec_glue_fused;
         dec_glue_fused = false;
         if (g_bwd_fused == 2 && !glue_fused_here) {
-          const size_t gsm = ((size_t)(32 + g.D) * g.Cout + 2 * 32 * (g.D + 1)) * sizeof(float);
+          const size_t gsm = (size_t)(32 + g.D) * g.Cout * sizeof(float);
           MCRN_TRY(launch_chain(4, fusedbh::k_bwd_glue_h, dim3(ceil_div(g.N, 32), g.B), dim3(256), gsm, st, "k_bwd_glue_h", d_output, use_dgo ? dXin : nullptr, g.Cdec, h_t,
                       prm->proj_w, dH, (t == g.T_out - 1) ? 1 : 0, b.r, b.hc, b.hx, dU_t, dG_all + (int64_t)t * g.R * 2 * g.D,
-                      ws + p.dHr, du16_buf(g, p, ws, g.D, t), du16T_buf(g, p, ws, g.D, t),
-                      dg16_buf(g, p, ws, g.D, t), dg16T_buf(g, p, ws, g.D, t), fusedh::ld_half(g.N),
+                      ws + p.dHr, du16_buf(g, p, ws, g.D, t), dg16_buf(g, p, ws, g.D, t),
                       ws + p.gs, grads->proj_w, grads->proj_b, g.B, g.T_out, g.N, g.D, g.Cout, t));
         } else if (g_bwd_fused != 2)
           MCRN_LAUNCH(fusedb::k_bwd_glue, (int)ceil_div64(g.R, 32), 256, (size_t)(32 + g.D) * g.Cout * sizeof(float), st, d_output,
@@ -1255,11 +1236,10 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
         const bool glue_fused_here = (g_bwd_fused == 2) && enc_glue_fused;
         enc_glue_fused = false;
         if (g_bwd_fused == 2 && !glue_fused_here) {
-          const size_t gsm = (size_t)2 * 32 * (g.H + 1) * sizeof(float);
+          const size_t gsm = 0;
           MCRN_TRY(launch_chain(4, fusedbh::k_bwd_glue_h, dim3(ceil_div(g.N, 32), g.B), dim3(256), gsm, st, "k_bwd_glue_h", (const float*)nullptr, (const float*)nullptr, 0,
                       (const float*)nullptr, (const float*)nullptr, dHe, 0, b.r, b.hc, b.hx, dU_t, dG_all + (int64_t)t * g.R * 2 * g.H,
-                      ws + p.dHr, du16_buf(g, p, ws, g.H, t), du16T_buf(g, p, ws, g.H, t),
-                      dg16_buf(g, p, ws, g.H, t), dg16T_buf(g, p, ws, g.H, t), fusedh::ld_half(g.N),
+                      ws + p.dHr, du16_buf(g, p, ws, g.H, t), dg16_buf(g, p, ws, g.H, t),
                       ws + p.gs, (float*)nullptr, (float*)nullptr, g.B, g.T_in, g.N, g.H, 0, t));
         } else if (g_bwd_fused != 2)
           MCRN_LAUNCH(fusedb::k_bwd_glue, (int)ceil_div64(g.R, 32), 256, 0, st, (const float*)nullptr, (const float*)nullptr, 0,

@@ -23,8 +23,8 @@ struct Plan {
   size_t h_dec_last;                     // [R][D]
   // fp16 operand copies of the fused forward (agcn_fused_h.cuh); offsets in floats, contents are halves
   size_t s16, e_wg16, e_wu16, d_wg16, d_wu16;
-  size_t enc_x16, enc_x16T, enc_zh16, enc_zh16T, enc_ib16;
-  size_t dec_x16, dec_x16T, dec_zh16, dec_zh16T, dec_ib16;
+  size_t enc_x16, enc_zh16, enc_ib16;     // row-major [R][Hs]; read as K-major A and as MN-major B operands
+  size_t dec_x16, dec_zh16, dec_ib16;
   size_t enc_ib16c, dec_ib16c;           // compact input blocks: [T_in][R][64] / [T_out][R][64] halves
   size_t enc_ib32c, dec_ib32c;           // [T][R][16] floats (training: operand of the input-block weight gradient)
   // per-slot sizes (floats)
@@ -41,9 +41,9 @@ struct Plan {
   size_t St, e_Qu, e_Qg, d_Qu, d_Qg, dIBu16, dIBg16, dXPin_all, dHr;
   // fp16 fused backward (agcn_bwd_fused_h.cuh): loss scale {s, 1/s, amax bits}, transposed fp16 supports, fp16 weights,
   // scaled fp16 operand copies of dU / dG (row-major and node-transposed)
-  size_t gs, s16T, e_wg16n, e_wu16n, d_wg16n, d_wu16n, dU16, dU16T, dG16, dG16T, e_dU16, e_dG16;
-  // fp16 weight-gradient kernel (agcn_dw_fused_h.cuh): node-transposed copies of every step
-  size_t e_dU16T, e_dG16T, e_Qu16T, e_Qg16T, d_Qu16T, d_Qg16T;
+  size_t gs, s16T, e_wg16n, e_wu16n, d_wg16n, d_wu16n, dU16, dG16, e_dU16, e_dG16;
+  // fp16 weight-gradient kernel (agcn_dw_fused_h.cuh): row-major fp16 Q blocks of every step
+  size_t e_Qu16T, e_Qg16T, d_Qu16T, d_Qg16T;
   size_t dXPin_sz;
   // loss scratch
   size_t loss_scratch;                   // 8 floats
@@ -106,11 +106,11 @@ static inline int make_plan(const Geo& g, bool save, Plan* p) {
     p->d_wu16 = halves(2 * (NB + 1) * g.D * g.D);
     // training: the row-major fp16 state copies of EVERY step are kept (operands of the fp16 support-gradient kernel)
     const size_t es = save ? (size_t)g.T_in : 1, ds = save ? (size_t)g.T_out : 1;
-    p->enc_x16 = halves(es * R * g.H);  p->enc_x16T = halves(es * (size_t)g.B * g.H * ld16);
-    p->enc_zh16 = halves(es * R * g.H); p->enc_zh16T = halves(es * (size_t)g.B * g.H * ld16);
+    p->enc_x16 = halves(es * R * g.H);
+    p->enc_zh16 = halves(es * R * g.H);
     p->enc_ib16 = halves(R * g.H);
-    p->dec_x16 = halves(ds * R * g.D);  p->dec_x16T = halves(ds * (size_t)g.B * g.D * ld16);
-    p->dec_zh16 = halves(ds * R * g.D); p->dec_zh16T = halves(ds * (size_t)g.B * g.D * ld16);
+    p->dec_x16 = halves(ds * R * g.D);
+    p->dec_zh16 = halves(ds * R * g.D);
     p->dec_ib16 = halves(R * g.D);
     p->enc_ib16c = halves((size_t)g.T_in * R * 64);
     p->dec_ib16c = halves((size_t)g.T_out * R * 64);
@@ -155,17 +155,14 @@ static inline int make_plan(const Geo& g, bool save, Plan* p) {
       // row-major copies of every step (fp16 support-gradient kernel); decoder and encoder separately: the decoder's
       // support-gradient kernels run on the side stream while the encoder backward proceeds
       p->dU16 = halves((size_t)g.T_out * R * g.D);
-      p->dU16T = halves((size_t)g.T_out * g.B * g.D * ld16);
       p->dG16 = halves((size_t)g.T_out * R * 2 * g.D);
       p->e_dU16 = halves((size_t)g.T_in * R * g.H);
       p->e_dG16 = halves((size_t)g.T_in * R * 2 * g.H);
-      p->e_dU16T = halves((size_t)g.T_in * g.B * g.H * ld16);
-      p->e_dG16T = halves((size_t)g.T_in * g.B * 2 * g.H * ld16);
-      p->e_Qu16T = halves(eq ? (size_t)g.T_in * KS * g.B * g.H * ld16 : 0);
-      p->e_Qg16T = halves(eq ? (size_t)g.T_in * 2 * KS * g.B * g.H * ld16 : 0);
-      p->d_Qu16T = halves(dq ? (size_t)g.T_out * KS * g.B * g.D * ld16 : 0);
-      p->d_Qg16T = halves(dq ? (size_t)g.T_out * 2 * KS * g.B * g.D * ld16 : 0);
-      p->dG16T = halves((size_t)g.T_out * g.B * 2 * g.D * ld16);
+      // row-major fp16 Q blocks of every step (operand of the fp16 weight-gradient kernel)
+      p->e_Qu16T = halves(eq ? (size_t)g.T_in * KS * R * g.H : 0);
+      p->e_Qg16T = halves(eq ? (size_t)g.T_in * 2 * KS * R * g.H : 0);
+      p->d_Qu16T = halves(dq ? (size_t)g.T_out * KS * R * g.D : 0);
+      p->d_Qg16T = halves(dq ? (size_t)g.T_out * 2 * KS * R * g.D : 0);
     }
     p->dIBu16 = take(R * 16);
     p->dIBg16 = take(R * 16);
