@@ -82,7 +82,7 @@ struct EpiBUH {
   static constexpr int NP = 3;
   int H;
   const float *z, *h, *dHr;
-  float *dG, *dh_part;     // dG: fp32 [R][2H] (columns [0, H) written here)
+  float *dG, *dh_part;     // dG: fp32 [R][2H] (columns [0, H) written here), or null when only the fp16 copy is consumed
   __half* g16;             // [R][2H] scaled fp16 copy (columns [0, H)): operand of the gate-AGCN launch
   __device__ __forceinline__ void load4(int row, int, int, int n0, float4 (&p)[NP]) const {
     const int64_t f = (int64_t)row * H + n0;
@@ -94,7 +94,7 @@ struct EpiBUH {
     const float d0 = acc[0], d1 = acc[1], d2 = acc[2], d3 = acc[3];
     st[0][0] = round_h(d0 * hh.x * zz.x * (1.0f - zz.x) * s); st[0][1] = round_h(d1 * hh.y * zz.y * (1.0f - zz.y) * s);
     st[0][2] = round_h(d2 * hh.z * zz.z * (1.0f - zz.z) * s); st[0][3] = round_h(d3 * hh.w * zz.w * (1.0f - zz.w) * s);
-    st4(dG + (int64_t)row * 2 * H + n0, st[0][0] * inv_s, st[0][1] * inv_s, st[0][2] * inv_s, st[0][3] * inv_s);
+    if (dG) st4(dG + (int64_t)row * 2 * H + n0, st[0][0] * inv_s, st[0][1] * inv_s, st[0][2] * inv_s, st[0][3] * inv_s);
     *reinterpret_cast<uint2*>(g16 + (int64_t)row * 2 * H + n0) = make_uint2(pack_h2(st[0][0], st[0][1]), pack_h2(st[0][2], st[0][3]));
     st4(dh_part + (int64_t)row * H + n0, dr.x + d0 * zz.x, dr.y + d1 * zz.y, dr.z + d2 * zz.z, dr.w + d3 * zz.w);
   }
@@ -534,8 +534,10 @@ __global__ void __launch_bounds__(256) k_bwd_glue_h(const float* __restrict__ dO
     const float u2 = round_h(v.z * (1.0f - rr.z) * (1.0f - cc.z * cc.z) * s), u3 = round_h(v.w * (1.0f - rr.w) * (1.0f - cc.w * cc.w) * s);
     const float g0 = round_h(v.x * (hh.x - cc.x) * rr.x * (1.0f - rr.x) * s), g1 = round_h(v.y * (hh.y - cc.y) * rr.y * (1.0f - rr.y) * s);
     const float g2 = round_h(v.z * (hh.z - cc.z) * rr.z * (1.0f - rr.z) * s), g3 = round_h(v.w * (hh.w - cc.w) * rr.w * (1.0f - rr.w) * s);
-    st4(dU + o, u0 * inv_s, u1 * inv_s, u2 * inv_s, u3 * inv_s);
-    st4(dG + row * 2 * D + D + q4, g0 * inv_s, g1 * inv_s, g2 * inv_s, g3 * inv_s);
+    if (dU) {                                        // fp32 copies: only the TF32 weight- / support-gradient paths read them
+      st4(dU + o, u0 * inv_s, u1 * inv_s, u2 * inv_s, u3 * inv_s);
+      st4(dG + row * 2 * D + D + q4, g0 * inv_s, g1 * inv_s, g2 * inv_s, g3 * inv_s);
+    }
     st4(dHr + o, v.x * rr.x, v.y * rr.y, v.z * rr.z, v.w * rr.w);
     *reinterpret_cast<uint2*>(u16 + o) = make_uint2(pack_h2(u0, u1), pack_h2(u2, u3));
     *reinterpret_cast<uint2*>(g16 + row * 2 * D + D + q4) = make_uint2(pack_h2(g0, g1), pack_h2(g2, g3));

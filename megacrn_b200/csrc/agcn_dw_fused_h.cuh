@@ -7,6 +7,8 @@
 //     X16  [T][R][HS]               A: 2 boxes [64 c][1][64 nodes] (the second is out of bounds = 0 when HS = 64)
 //     dV16 [T][R][O]                B for blk 0: HS/64 boxes at column half * HS
 //     Q16  [T * nks][R][HS]         B for blk >= 1: block ks = k * nhalf + h
+//     IB16 [T][R][64]               A of the input-block tiles (blk = KS + 1: rows = input-channel / bias columns of the compact
+//                                   input block, 16 used), with Y = dV: dW_NB = sum IB^T dV  (replaces a TF32 GEMM over fp32 dV)
 // A plain split-K GEMM: CTA = (output tile (blk, h), group g) loops over its (t, b) units, ceil(N / 64) ring items each,
 // accumulator [128 x HS] in TMEM, one red.global.add.v4.f32 pass at the end (times 1 / loss scale: dV16T and Q16T carry it).
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
@@ -42,7 +44,7 @@ struct CfgW {
 template <int HS>
 __global__ void __launch_bounds__(WTHREADS, 1)
 agcn_dw_h_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmV,
-                 const __grid_constant__ CUtensorMap tmQ, WParams p) {
+                 const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmIB, WParams p) {
   using C = CfgW<HS>;
   constexpr int NST = C::NST;
   extern __shared__ uint8_t smem_raw[];
@@ -54,7 +56,8 @@ agcn_dw_h_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x, grp = blockIdx.y, G = gridDim.y;
-  const int blk = tile / p.nhalf, half = tile - blk * p.nhalf;      // blk 0 = identity block, 1 + k = support k
+  const int blk = tile / p.nhalf, half = tile - blk * p.nhalf;      // blk 0 = identity block, 1 + k = support k, KS + 1 = input block
+  const bool ib_tile = blk == p.KS + 1;
   const int U = p.T * p.B;
   const int nu = (U - grp + G - 1) / G;
   const int kb = (p.N + BKH - 1) / BKH;
@@ -66,6 +69,7 @@ agcn_dw_h_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmIB) : "memory");
 #pragma unroll
     for (int s = 0; s < NST; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
@@ -94,11 +98,12 @@ agcn_dw_h_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const int i = it / kb, j = it - i * kb;
         const int u = grp + i * G, t = u / p.B, b = u - t * p.B;
         mbar_expect_tx(fb, C::A_SLOT + C::B_SLOT);
-        tma_load_4d(a_dst, &tmX, fb, 0, b, j * BKH, t);                                   // X_t rows (64 j.., b), channels 0..63
-        tma_load_4d(a_dst + 8192, &tmX, fb, 64, b, j * BKH, t);                           // channels 64..127 (zero fill when HS = 64)
+        const CUtensorMap* ta = ib_tile ? &tmIB : &tmX;
+        tma_load_4d(a_dst, ta, fb, 0, b, j * BKH, t);                                     // X_t / IB_t rows (64 j.., b), channels 0..63
+        tma_load_4d(a_dst + 8192, ta, fb, 64, b, j * BKH, t);                             // channels 64..127 (out of bounds = zero fill when the operand is 64 wide)
 #pragma unroll
         for (int q = 0; q < HS / 64; ++q) {
-          if (blk == 0) tma_load_4d(b_dst + q * 8192, &tmV, fb, half * HS + q * 64, b, j * BKH, t);      // dV_t rows, columns half*HS + 64 q..
+          if (blk == 0 || ib_tile) tma_load_4d(b_dst + q * 8192, &tmV, fb, half * HS + q * 64, b, j * BKH, t);      // dV_t rows, columns half*HS + 64 q..
           else tma_load_4d(b_dst + q * 8192, &tmQ, fb, q * 64, b, j * BKH, t * nks + (blk - 1) * p.nhalf + half);   // Q_t[ks] rows
         }
       }
@@ -126,7 +131,8 @@ agcn_dw_h_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     mbar_wait_b(smem_u32(&acc_full_bar), 0);
     tcgen05_fence_after();
     const int c0 = quarter * 32;                         // accumulator rows = weight rows c
-    if (c0 < HS) {
+    const int rows = ib_tile ? fusedh::IBF : HS;         // input-block tile: only the first 16 rows exist
+    if (c0 < rows) {
       const float inv_gs = __ldg(p.gs + 1);
       float* scr = reinterpret_cast<float*>(smem_al) + (warp - 2) * (32 * 36);     // the ring is idle now
       const int cq = (lane & 7) * 4, r0 = lane >> 3;
@@ -143,7 +149,7 @@ agcn_dw_h_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int rr = r0 + 4 * e, c = c0 + rr;
-          if (c < HS) {
+          if (c < rows) {
             const float4 t4 = *reinterpret_cast<const float4*>(&scr[rr * 36 + cq]);
             atomicAdd(reinterpret_cast<float4*>(dst + (int64_t)c * p.O + ch * 32 + cq), t4);
           }
@@ -161,12 +167,17 @@ agcn_dw_h_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 // x16_all [T][R][HS], v16_all [T][R][O], q16_all [T * KS * nhalf][R][HS]: row-major, rows (node, b)  (steps [0, T) of the launch)
 template <int HS>
 int launch_agcn_dw_h(int N, int B, int T, int KS, int nhalf, const __half* x16_all, const __half* v16_all, const __half* q16_all,
-                     const float* gs, float* dw, cudaStream_t st) {
+                     const __half* ib16_all /* [T][R][64] compact input blocks, or null */, const float* gs, float* dw, cudaStream_t st) {
   using C = CfgW<HS>;
   const int O = nhalf * HS, nks = KS * nhalf;
   const uint64_t R = (uint64_t)N * B;
-  CUtensorMap tX, tV, tQ;
+  CUtensorMap tX, tV, tQ, tIB;
   uint32_t box[4] = {64, 1, BKH, 1};                     // 64 channels x 64 node rows of one batch element
+  {
+    uint64_t dims[4] = {(uint64_t)fusedh::IBC, (uint64_t)B, (uint64_t)N, (uint64_t)T};
+    uint64_t str[3] = {(uint64_t)fusedh::IBC * 2, (uint64_t)B * fusedh::IBC * 2, R * fusedh::IBC * 2};
+    MCRN_TRY(fusedh::encode_tensor_map_h(&tIB, ib16_all ? ib16_all : x16_all, dims, str, box));
+  }
   {
     uint64_t dims[4] = {(uint64_t)HS, (uint64_t)B, (uint64_t)N, (uint64_t)T};
     uint64_t str[3] = {(uint64_t)HS * 2, (uint64_t)B * HS * 2, R * HS * 2};
@@ -190,11 +201,11 @@ int launch_agcn_dw_h(int N, int B, int T, int KS, int nhalf, const __half* x16_a
     MCRN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     attr_set = true;
   }
-  const int tiles = (1 + KS) * nhalf;
+  const int tiles = (1 + KS + (ib16_all ? 1 : 0)) * nhalf;
   int G = 148 / tiles;
   if (G < 1) G = 1;
   if (G > T * B) G = T * B;
-  MCRN_LAUNCH(kern, dim3(tiles, G), WTHREADS, C::SMEM, st, tX, tV, tQ, p);
+  MCRN_LAUNCH(kern, dim3(tiles, G), WTHREADS, C::SMEM, st, tX, tV, tQ, tIB, p);
   return MCRN_OK;
 }
 

@@ -89,10 +89,14 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ float round_h(float v) { return __half2float(__float2half_rn(v)); }
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// Gate activations: one ex2 and one rcp (MUFU) each, flush-to-zero forms -- no range-check code around them (the epilogue
+// issues 2 x 32 K of these per tile).  ex2.approx: max rel. error 2^-22; |x| large: e -> 0 or +inf, rcp(inf) = 0: exact limits.
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float tanh_fast(float x) {
-  const float t = __expf(-2.0f * fabsf(x));
-  return copysignf(__fdividef(1.0f - t, 1.0f + t), x);
+  const float t = ex2_ftz(-2.8853900817779268f * fabsf(x));
+  return copysignf((1.0f - t) * rcp_ftz(1.0f + t), x);
 }
 
 // ring items of one CTA, in issue order (as fused::for_each_item, but the input-block segment has `ibk` k-blocks)

@@ -457,7 +457,7 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
                 dim3(ceil_div(g.B * g.Cdec, fusedh::DI_COLS), ceil_div(g.N, fusedh::DI_NODES), __builtin_popcount(mask)), 256, shm, sx,
                 go_src, y_cov, ws + p.S, g.ldS, g.KS, g.N, g.B, g.T_out, g.Cout, g.Ycov, mask,
                 p.save ? ws + p.dec_xpin : nullptr, (int64_t)p.dec_xpin_sz, reinterpret_cast<__half*>(ws + p.dec_ib16c),
-                p.save ? ws + p.dec_ib32c : nullptr);
+                (p.save && need_xp0(g, g.D, g.Cdec)) ? ws + p.dec_ib32c : nullptr);
     return MCRN_OK;
   };
   {
@@ -479,7 +479,7 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
     if (ib_compact_shape(g, g.H, g.Cin, p.save)) {
       // step 0 now; steps 1.. on helper stream f0's successor (joined before the second cell), beside the first cell
       MCRN_LAUNCH(fusedh::k_encoder_input_blocks, ew_grid((int64_t)g.R * 64), 256, 0, st, ws + p.enc_xpin, g.NB, g.N, g.T_in,
-                  g.B, g.Cin, reinterpret_cast<__half*>(ws + p.enc_ib16c), p.save ? ws + p.enc_ib32c : nullptr, 0, 1);
+                  g.B, g.Cin, reinterpret_cast<__half*>(ws + p.enc_ib16c), (p.save && need_xp0(g, g.H, g.Cin)) ? ws + p.enc_ib32c : nullptr, 0, 1);
       if (g.T_in > 1) {
         cudaStream_t sx = st;
         if (fork) {
@@ -488,7 +488,7 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
           sx = g_fw[0].s; enc_ib_forked = true;
         }
         MCRN_LAUNCH(fusedh::k_encoder_input_blocks, ew_grid((int64_t)(g.T_in - 1) * g.R * 64), 256, 0, sx, ws + p.enc_xpin, g.NB, g.N,
-                    g.T_in, g.B, g.Cin, reinterpret_cast<__half*>(ws + p.enc_ib16c), p.save ? ws + p.enc_ib32c : nullptr, 1, g.T_in - 1);
+                    g.T_in, g.B, g.Cin, reinterpret_cast<__half*>(ws + p.enc_ib16c), (p.save && need_xp0(g, g.H, g.Cin)) ? ws + p.enc_ib32c : nullptr, 1, g.T_in - 1);
       }
     }
     MCRN_CUDA_OK(cudaMemsetAsync(ws + p.enc_xpg, 0, (size_t)g.R * g.H * sizeof(float), st));
@@ -792,7 +792,7 @@ static int cell_backward_fused(const Geo& g, const Plan& p, float* ws, const flo
   const __half* S16T = reinterpret_cast<const __half*>(ws + p.s16T);
   if (h16) {
     fusedbh::BHOperands ou{S16T, dU16, w.wu16n, ws + p.gs};
-    fusedbh::EpiBUH eu{HS, b.z, b.hx, ws + p.dHr, bs.dG, dHp, dG16};
+    fusedbh::EpiBUH eu{HS, b.z, b.hx, ws + p.dHr, need_xp0(g, HS, w.Cin) ? bs.dG : nullptr, dHp, dG16};
     MCRN_TRY((fusedbh::launch_agcn_bwd_h<HS>(g.N, g.B, g.KS, 1, ou, bs.Qu, ws + p.dIBu16, eu, st, nullptr, nullptr, 0, bs.Qu16T)));
   } else {
   fusedb::EpiBU eu{HS, b.z, b.hx, ws + p.dHr, bs.dG, dHp};
@@ -1067,8 +1067,10 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
       MCRN_TRY(side2_fork(st));
       const float* ibc = ib_compact_shape(g, g.D, g.Cdec, true) ? ws + p.dec_ib32c : nullptr;
       const bool dwh = dw_h_shape(g, g.D, g.Cdec);
-      MCRN_TRY(acc_dw_fused(g, ws + p.dec_xpu, (int64_t)p.dec_xp_sz, ta, tb, g.D, dU_all, ws + p.d_Qu, 1, ws + p.a_d_wu, ibc, g_side.s2, dwh));
-      MCRN_TRY(acc_dw_fused(g, ws + p.dec_xpg, (int64_t)p.dec_xp_sz, ta, tb, g.D, dG_all, ws + p.d_Qg, 2, ws + p.a_d_wg, ibc, g_side.s2, dwh));
+      if (!dwh) {
+      MCRN_TRY(acc_dw_fused(g, ws + p.dec_xpu, (int64_t)p.dec_xp_sz, ta, tb, g.D, dU_all, ws + p.d_Qu, 1, ws + p.a_d_wu, ibc, g_side.s2, false));
+      MCRN_TRY(acc_dw_fused(g, ws + p.dec_xpg, (int64_t)p.dec_xp_sz, ta, tb, g.D, dG_all, ws + p.d_Qg, 2, ws + p.a_d_wg, ibc, g_side.s2, false));
+      }
       if (dwh) {
         const int64_t sR = g.R * g.D;                                      // one row-major [R][D] block
         const __half* x16 = reinterpret_cast<const __half*>(ws + p.dec_x16) + ta * sR;
@@ -1076,12 +1078,13 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
         const __half* qu = reinterpret_cast<const __half*>(ws + p.d_Qu16T) + (int64_t)ta * g.KS * sR;
         const __half* qg = reinterpret_cast<const __half*>(ws + p.d_Qg16T) + (int64_t)ta * 2 * g.KS * sR;
         const float* gs = ws + p.gs;
+        const __half* ib16 = reinterpret_cast<const __half*>(ws + p.dec_ib16c) + (int64_t)ta * g.R * fusedh::IBC;
         if (g.D == 64) {
-          MCRN_TRY((fusedwh::launch_agcn_dw_h<64>(g.N, g.B, tb - ta, g.KS, 1, zh16, du16_buf(g, p, ws, g.D, ta), qu, gs, ws + p.a_d_wu, g_side.s2)));
-          MCRN_TRY((fusedwh::launch_agcn_dw_h<64>(g.N, g.B, tb - ta, g.KS, 2, x16, dg16_buf(g, p, ws, g.D, ta), qg, gs, ws + p.a_d_wg, g_side.s2)));
+          MCRN_TRY((fusedwh::launch_agcn_dw_h<64>(g.N, g.B, tb - ta, g.KS, 1, zh16, du16_buf(g, p, ws, g.D, ta), qu, ib16, gs, ws + p.a_d_wu, g_side.s2)));
+          MCRN_TRY((fusedwh::launch_agcn_dw_h<64>(g.N, g.B, tb - ta, g.KS, 2, x16, dg16_buf(g, p, ws, g.D, ta), qg, ib16, gs, ws + p.a_d_wg, g_side.s2)));
         } else {
-          MCRN_TRY((fusedwh::launch_agcn_dw_h<128>(g.N, g.B, tb - ta, g.KS, 1, zh16, du16_buf(g, p, ws, g.D, ta), qu, gs, ws + p.a_d_wu, g_side.s2)));
-          MCRN_TRY((fusedwh::launch_agcn_dw_h<128>(g.N, g.B, tb - ta, g.KS, 2, x16, dg16_buf(g, p, ws, g.D, ta), qg, gs, ws + p.a_d_wg, g_side.s2)));
+          MCRN_TRY((fusedwh::launch_agcn_dw_h<128>(g.N, g.B, tb - ta, g.KS, 1, zh16, du16_buf(g, p, ws, g.D, ta), qu, ib16, gs, ws + p.a_d_wu, g_side.s2)));
+          MCRN_TRY((fusedwh::launch_agcn_dw_h<128>(g.N, g.B, tb - ta, g.KS, 2, x16, dg16_buf(g, p, ws, g.D, ta), qg, ib16, gs, ws + p.a_d_wg, g_side.s2)));
         }
       }
       return MCRN_OK;
@@ -1094,13 +1097,15 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
       if (fb) {
         bool need_dxin = (t > 0) && !(tf && tf[t - 1]);
         float* dU_t = dU_all + (int64_t)t * g.R * g.D;
+        const bool dv32 = need_xp0(g, g.D, g.Cdec);      // fp32 dU / dG: read by the TF32 weight- / support-gradient paths only
         // fp16 backward: the glue of a teacher-forced step (no gradient through go) runs in the previous launch's epilogue
         const bool glue_fused_here = (g_bwd_fused == 2) && dec_glue_fused;
         dec_glue_fused = false;
         if (g_bwd_fused == 2 && !glue_fused_here) {
           const size_t gsm = (size_t)(32 + g.D) * g.Cout * sizeof(float);
           MCRN_TRY(launch_chain(4, fusedbh::k_bwd_glue_h, dim3(ceil_div(g.N, 32), g.B), dim3(256), gsm, st, "k_bwd_glue_h", d_output, use_dgo ? dXin : nullptr, g.Cdec, h_t,
-                      prm->proj_w, dH, (t == g.T_out - 1) ? 1 : 0, b.r, b.hc, b.hx, dU_t, dG_all + (int64_t)t * g.R * 2 * g.D,
+                      prm->proj_w, dH, (t == g.T_out - 1) ? 1 : 0, b.r, b.hc, b.hx, dv32 ? dU_t : nullptr,
+                      dv32 ? dG_all + (int64_t)t * g.R * 2 * g.D : nullptr,
                       ws + p.dHr, du16_buf(g, p, ws, g.D, t), dg16_buf(g, p, ws, g.D, t),
                       ws + p.gs, grads->proj_w, grads->proj_b, g.B, g.T_out, g.N, g.D, g.Cout, t));
         } else if (g_bwd_fused != 2)
@@ -1210,8 +1215,10 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
       MCRN_TRY(side2_fork(st));
       const float* ibc = ib_compact_shape(g, g.H, g.Cin, true) ? ws + p.enc_ib32c : nullptr;
       const bool dwh = dw_h_shape(g, g.H, g.Cin);
-      MCRN_TRY(acc_dw_fused(g, ws + p.enc_xpu, (int64_t)p.enc_xp_sz, ta, tb, g.H, dU_all, ws + p.e_Qu, 1, ws + p.a_e_wu, ibc, g_side.s2, dwh));
-      MCRN_TRY(acc_dw_fused(g, ws + p.enc_xpg, (int64_t)p.enc_xp_sz, ta, tb, g.H, dG_all, ws + p.e_Qg, 2, ws + p.a_e_wg, ibc, g_side.s2, dwh));
+      if (!dwh) {
+      MCRN_TRY(acc_dw_fused(g, ws + p.enc_xpu, (int64_t)p.enc_xp_sz, ta, tb, g.H, dU_all, ws + p.e_Qu, 1, ws + p.a_e_wu, ibc, g_side.s2, false));
+      MCRN_TRY(acc_dw_fused(g, ws + p.enc_xpg, (int64_t)p.enc_xp_sz, ta, tb, g.H, dG_all, ws + p.e_Qg, 2, ws + p.a_e_wg, ibc, g_side.s2, false));
+      }
       if (dwh) {
         const int64_t sR = g.R * g.H;
         const __half* x16 = reinterpret_cast<const __half*>(ws + p.enc_x16) + ta * sR;
@@ -1219,12 +1226,13 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
         const __half* qu = reinterpret_cast<const __half*>(ws + p.e_Qu16T) + (int64_t)ta * g.KS * sR;
         const __half* qg = reinterpret_cast<const __half*>(ws + p.e_Qg16T) + (int64_t)ta * 2 * g.KS * sR;
         const float* gs = ws + p.gs;
+        const __half* ib16 = reinterpret_cast<const __half*>(ws + p.enc_ib16c) + (int64_t)ta * g.R * fusedh::IBC;
         if (g.H == 64) {
-          MCRN_TRY((fusedwh::launch_agcn_dw_h<64>(g.N, g.B, tb - ta, g.KS, 1, zh16, du16_buf(g, p, ws, g.H, ta), qu, gs, ws + p.a_e_wu, g_side.s2)));
-          MCRN_TRY((fusedwh::launch_agcn_dw_h<64>(g.N, g.B, tb - ta, g.KS, 2, x16, dg16_buf(g, p, ws, g.H, ta), qg, gs, ws + p.a_e_wg, g_side.s2)));
+          MCRN_TRY((fusedwh::launch_agcn_dw_h<64>(g.N, g.B, tb - ta, g.KS, 1, zh16, du16_buf(g, p, ws, g.H, ta), qu, ib16, gs, ws + p.a_e_wu, g_side.s2)));
+          MCRN_TRY((fusedwh::launch_agcn_dw_h<64>(g.N, g.B, tb - ta, g.KS, 2, x16, dg16_buf(g, p, ws, g.H, ta), qg, ib16, gs, ws + p.a_e_wg, g_side.s2)));
         } else {
-          MCRN_TRY((fusedwh::launch_agcn_dw_h<128>(g.N, g.B, tb - ta, g.KS, 1, zh16, du16_buf(g, p, ws, g.H, ta), qu, gs, ws + p.a_e_wu, g_side.s2)));
-          MCRN_TRY((fusedwh::launch_agcn_dw_h<128>(g.N, g.B, tb - ta, g.KS, 2, x16, dg16_buf(g, p, ws, g.H, ta), qg, gs, ws + p.a_e_wg, g_side.s2)));
+          MCRN_TRY((fusedwh::launch_agcn_dw_h<128>(g.N, g.B, tb - ta, g.KS, 1, zh16, du16_buf(g, p, ws, g.H, ta), qu, ib16, gs, ws + p.a_e_wu, g_side.s2)));
+          MCRN_TRY((fusedwh::launch_agcn_dw_h<128>(g.N, g.B, tb - ta, g.KS, 2, x16, dg16_buf(g, p, ws, g.H, ta), qg, ib16, gs, ws + p.a_e_wg, g_side.s2)));
         }
       }
       return MCRN_OK;
@@ -1233,12 +1241,14 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
       CellBufs b = enc_bufs(g, p, ws, t);
       if (fb) {
         float* dU_t = dU_all + (int64_t)t * g.R * g.H;
+        const bool dv32 = need_xp0(g, g.H, g.Cin);
         const bool glue_fused_here = (g_bwd_fused == 2) && enc_glue_fused;
         enc_glue_fused = false;
         if (g_bwd_fused == 2 && !glue_fused_here) {
           const size_t gsm = 0;
           MCRN_TRY(launch_chain(4, fusedbh::k_bwd_glue_h, dim3(ceil_div(g.N, 32), g.B), dim3(256), gsm, st, "k_bwd_glue_h", (const float*)nullptr, (const float*)nullptr, 0,
-                      (const float*)nullptr, (const float*)nullptr, dHe, 0, b.r, b.hc, b.hx, dU_t, dG_all + (int64_t)t * g.R * 2 * g.H,
+                      (const float*)nullptr, (const float*)nullptr, dHe, 0, b.r, b.hc, b.hx, dv32 ? dU_t : nullptr,
+                      dv32 ? dG_all + (int64_t)t * g.R * 2 * g.H : nullptr,
                       ws + p.dHr, du16_buf(g, p, ws, g.H, t), dg16_buf(g, p, ws, g.H, t),
                       ws + p.gs, (float*)nullptr, (float*)nullptr, g.B, g.T_in, g.N, g.H, 0, t));
         } else if (g_bwd_fused != 2)

@@ -29,7 +29,17 @@ def arm():
     lib.mcrn_debug_launch_spans(slots.data_ptr(), NL)
 
 
+step_mode = mode == "step"
+if step_mode:
+    from megacrn_b200.train_step import train_step
+    m.train(); flags = [True] * d.horizon; mode = "eager"
+
+
 def fwd():
+    if step_mode:
+        for q in m.parameters():
+            q.grad = None
+        return train_step(m, x, y_cov, labels, teacher_forcing=flags, scaler_mean=54.0, scaler_std=20.0)
     with torch.no_grad():
         return m(x, y_cov, labels if train else None, teacher_forcing=flags)
 
@@ -68,5 +78,8 @@ dur = sp[:, 1] - sp[:, 0]
 gap = sp[1:, 0] - sp[:-1, 1]
 print(f"{cfg} {mode} {'train' if train else 'eval'} forward: {e0.elapsed_time(e1) * 1e3:.1f} us by CUDA events; {len(sp)} fused launches")
 print(f"  first CTA start -> last CTA end: {(sp[:, 1].max() - t0) / 1e3:.1f} us; sum of launch spans {dur.sum() / 1e3:.1f} us; sum of gaps between consecutive fused launches {gap.sum() / 1e3:.1f} us")
-print("  span us per launch:", " ".join(f"{v / 1e3:.1f}" for v in dur))
-print("  gap  us after launch:", " ".join(f"{v / 1e3:.1f}" for v in gap))
+try:
+    print("  span us per launch:", " ".join(f"{v / 1e3:.1f}" for v in dur))
+    print("  gap  us after launch:", " ".join(f"{v / 1e3:.1f}" for v in gap))
+except BrokenPipeError:
+    pass
