@@ -2,8 +2,8 @@
 vectors produced by the reference and vs the CPU oracle on identical seeded inputs.
 
 Tolerance: north_star asks for 1e-3 relative in fp32.  We check rel-L2 <= 1e-3 and the mixed
-elementwise bound |a-b| <= 1e-3*(|b| + rms(b)); gradients rel-L2 <= 2e-3
-(the backward compounds the TF32 rounding of ~3x as many contractions).
+elementwise bound |a-b| <= 2e-3*(|b| + rms(b)); gradients: per-parameter rel-L2 bounds at 2x the
+measured error, all <= 2e-3 (GRAD_TOL_BY_PARAM below).
 """
 import ctypes as C
 
@@ -18,12 +18,26 @@ from oracle import megacrn_oracle as O
 pytestmark = pytest.mark.gpu
 
 DW_FUSED_DEFAULT = 1    # library default of the "dw_fused" option (fp16 weight-gradient kernel)
-FWD_TOL = 1e-3          # north_star: outputs within 1e-3 rel of the reference fp32 forward
-GRAD_TOL = 4e-3         # BPTT through ~300 TF32 contractions; the exact-fp32 SIMT engine is held to 5e-4 below
+FWD_TOL = 1e-3          # north_star: outputs within 1e-3 rel of the reference fp32 forward (measured: <= 5.4e-4, profiles/r2_grad_errors.txt)
+# Gradient bounds = 2x the largest rel-L2 error measured on B200 over the six reference goldens, full C2 (B=64), C3 (B=8) and
+# the C4 / C5 node counts (mini and full-sequence cases): profiles/r2_grad_errors.txt, tools/grad_errors.py.  Every measured
+# value is <= 1.0e-3 (BPTT through ~300 contractions with 11-bit operands, fp32 accumulation).
+GRAD_TOL = 2e-3
+GRAD_TOL_BY_PARAM = {
+    "memory.Memory": 1.0e-3, "memory.Wq": 1.5e-3, "memory.We1": 2.0e-3, "memory.We2": 2.0e-3,
+    "encoder.dcrnn_cells.0.gate.weights": 2.0e-3, "encoder.dcrnn_cells.0.gate.bias": 2.0e-3,
+    "encoder.dcrnn_cells.0.update.weights": 2.0e-3, "encoder.dcrnn_cells.0.update.bias": 1.2e-3,
+    "decoder.dcrnn_cells.0.gate.weights": 1.3e-3, "decoder.dcrnn_cells.0.gate.bias": 1.0e-3,
+    "decoder.dcrnn_cells.0.update.weights": 1.0e-3, "decoder.dcrnn_cells.0.update.bias": 6e-4,
+    "proj.0.weight": 8e-4, "proj.0.bias": 4e-4,
+}
 
 
-def grad_tol(engine):
-    return 1e-3 if engine == "simt" else GRAD_TOL
+def grad_tol(engine, pname=None):
+    """Exact-fp32 SIMT engine: 1e-3 (summation order only).  Default engine: the per-parameter bound above."""
+    if engine == "simt":
+        return 1e-3
+    return GRAD_TOL_BY_PARAM.get(pname, GRAD_TOL)
 
 
 def reference_upstream(ref_output, ref_query, ref_pos, ref_neg, labels):
@@ -164,11 +178,11 @@ def test_train_forward_and_grads_vs_reference_golden(name, engine):
         g = prm.grad.detach().cpu()
         if full:
             ref = gold["grad_" + pname]
-            assert rel_l2(g, ref) < grad_tol(engine), (pname, rel_l2(g, ref))
+            assert rel_l2(g, ref) < grad_tol(engine, pname), (pname, rel_l2(g, ref))
         else:
             flat = g.reshape(-1).numpy()
             ref = gold["gsample_" + pname]
-            assert rel_l2(flat[sample_index(flat.size)], ref) < grad_tol(engine), (pname, rel_l2(flat[sample_index(flat.size)], ref))
+            assert rel_l2(flat[sample_index(flat.size)], ref) < grad_tol(engine, pname), (pname, rel_l2(flat[sample_index(flat.size)], ref))
             nrm = np.linalg.norm(flat.astype(np.float64))
             assert abs(nrm - gold["gnorm_" + pname]) < grad_tol(engine) * gold["gnorm_" + pname], pname
 
@@ -215,7 +229,7 @@ def test_full_size_vs_oracle(cfg, engine):
     mae = (outs[0].detach().cpu() - ref_outs[0]).abs().mean().item()
     assert mae < 1e-3, mae
     for pname, prm in m.named_parameters():
-        assert rel_l2(prm.grad.cpu(), ref_grads[pname]) < grad_tol(engine), (pname, rel_l2(prm.grad.cpu(), ref_grads[pname]))
+        assert rel_l2(prm.grad.cpu(), ref_grads[pname]) < grad_tol(engine, pname), (pname, rel_l2(prm.grad.cpu(), ref_grads[pname]))
 
 
 @pytest.mark.parametrize("cfg", ["c4_mini", "c5_mini"])
@@ -238,9 +252,8 @@ def test_large_graph_shapes_vs_oracle(cfg):
     torch.autograd.backward([outs[0], outs[2]], [d_out.to(dv), d_q.to(dv)])
     for k, a, b in zip(OUT_NAMES[:3], outs[:3], ref_outs[:3]):
         assert rel_l2(a.detach().cpu(), b) < FWD_TOL, (k, rel_l2(a.detach().cpu(), b))
-    # 1-2 sequences only: no batch averaging of the TF32 noise, hence the looser gradient bound here
     for pname, prm in m.named_parameters():
-        assert rel_l2(prm.grad.cpu(), ref_grads[pname]) < 2.5 * GRAD_TOL, (pname, rel_l2(prm.grad.cpu(), ref_grads[pname]))
+        assert rel_l2(prm.grad.cpu(), ref_grads[pname]) < grad_tol("default", pname), (pname, rel_l2(prm.grad.cpu(), ref_grads[pname]))
 
 
 @pytest.mark.parametrize("cfg", ["c4_full_T", "c5_full_T"])
@@ -266,8 +279,8 @@ def test_large_graph_full_sequence_vs_oracle(cfg, default_engine):
         assert rel_l2(a.detach().cpu(), b) < FWD_TOL, (k, rel_l2(a.detach().cpu(), b))
     errs = {pname: rel_l2(prm.grad.cpu(), ref_grads[pname]) for pname, prm in m.named_parameters()}
     print(cfg, "forward rel-L2", rel_l2(outs[0].detach().cpu(), ref_outs[0]), "grad rel-L2", {k: f"{v:.1e}" for k, v in errs.items()})
-    for pname, e in errs.items():      # a single sequence: no batch averaging of the rounding noise
-        assert e < 2.5 * GRAD_TOL, (pname, e)
+    for pname, e in errs.items():
+        assert e < grad_tol("default", pname), (pname, e)
 
 
 def test_all_output_gradients_including_pos_neg(engine):
@@ -538,9 +551,6 @@ def test_unsupported_configs_fail_loudly():
         m(x, y_cov)                           # CPU tensors: no fallback
 
 
-# ---- kept LAST in the file: never executed on a GPU before the round-end run; a device-side fault here cannot affect other tests ----
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: first execution of cheb_k != 3 at a fused "
-                                        "shape happens on the round-end box (DESIGN.md section 11); XPASS = the gap is closed")
 @pytest.mark.parametrize("cheb_k", [2, 4])
 def test_fused_kernels_other_chebyshev_orders_vs_oracle(cheb_k, default_engine):
     """cheb_k = 2 / 4 (KS = 2 / 6 supports) through the fused forward / backward kernels against the CPU oracle."""
@@ -556,5 +566,8 @@ def test_fused_kernels_other_chebyshev_orders_vs_oracle(cheb_k, default_engine):
     torch.autograd.backward([outs[0], outs[2]], [d_out.to(dv), d_q.to(dv)])
     for k, a, b in zip(OUT_NAMES[:3], outs[:3], ref_outs[:3]):
         assert rel_l2(a.detach().cpu(), b) < FWD_TOL, (k, rel_l2(a.detach().cpu(), b))
+    # cheb_k = 4 adds the third-order supports T3 = 2 g T2 - g (signed entries, larger dynamic range in 16 bits): measured
+    # 5.0e-3 on the encoder gate weights at this 2-sequence shape; cheb_k = 2 sits with the default order
+    tol = GRAD_TOL if cheb_k == 2 else 1e-2
     for pname, prm in m.named_parameters():
-        assert rel_l2(prm.grad.cpu(), ref_grads[pname]) < 2.5 * GRAD_TOL, (pname, rel_l2(prm.grad.cpu(), ref_grads[pname]))
+        assert rel_l2(prm.grad.cpu(), ref_grads[pname]) < tol, (pname, rel_l2(prm.grad.cpu(), ref_grads[pname]))
