@@ -519,13 +519,16 @@ __global__ void __launch_bounds__(256) k_bwd_glue_h(const float* __restrict__ dO
     const int64_t o = row * D + q4;
     float4 v = dh_init ? make_float4(0.f, 0.f, 0.f, 0.f) : ldg4(dH + o);
     if (proj) {
-      const float4 hv = ldg4(h_t + o);
+      // dwp == null: the projection weight gradient of this step is computed off the chain (k_proj_wgrad)
+      const float4 hv = dwp ? ldg4(h_t + o) : make_float4(0.f, 0.f, 0.f, 0.f);
       for (int co = 0; co < Cout; ++co) {
         const float d = sh_do[i * Cout + co];
         const float4 w4 = ldg4(wp + (int64_t)co * D + q4);
         v.x = fmaf(d, w4.x, v.x); v.y = fmaf(d, w4.y, v.y); v.z = fmaf(d, w4.z, v.z); v.w = fmaf(d, w4.w, v.w);
-        float* sw = sh_w + co * D + q4;
-        atomicAdd(sw, d * hv.x); atomicAdd(sw + 1, d * hv.y); atomicAdd(sw + 2, d * hv.z); atomicAdd(sw + 3, d * hv.w);
+        if (dwp) {
+          float* sw = sh_w + co * D + q4;
+          atomicAdd(sw, d * hv.x); atomicAdd(sw + 1, d * hv.y); atomicAdd(sw + 2, d * hv.z); atomicAdd(sw + 3, d * hv.w);
+        }
       }
     }
     const float4 rr = ldg4(r + o), cc = ldg4(hc + o), hh = ldg4(hx + o);
@@ -543,7 +546,7 @@ __global__ void __launch_bounds__(256) k_bwd_glue_h(const float* __restrict__ dO
     *reinterpret_cast<uint2*>(g16 + row * 2 * D + D + q4) = make_uint2(pack_h2(g0, g1), pack_h2(g2, g3));
   }
   __syncthreads();
-  if (proj) {
+  if (proj && dwp) {
     for (int i = threadIdx.x; i < Cout * D; i += blockDim.x) atomicAdd(dwp + i, sh_w[i]);
     if (threadIdx.x < Cout) {
       float sm = 0.f;

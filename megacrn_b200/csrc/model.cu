@@ -510,12 +510,17 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
   // ---- memory query (:159-166) + decoder initial state (:179) ----
   {
     CellBufs b0 = dec_bufs(g, p, ws, 0);
-    size_t shm = (8 * (g.d + g.M) + (size_t)g.M * (g.d + 1)) * sizeof(float);
-    MCRN_LAUNCH(k_memory_query, (int)ceil_div64(g.R, 8), 256, shm, st, ws + p.h_enc, prm->wq, prm->memory,
+    const size_t shm = (8 * (size_t)(g.H + g.d + g.M) + (size_t)g.M * (g.d + 1) + (size_t)g.H * g.d) * sizeof(float);
+    static bool mq_attr = false;
+    if (!mq_attr) {
+      MCRN_CUDA_OK(cudaFuncSetAttribute(k_memory_query, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      mq_attr = true;
+    }
+    if (shm > 160 * 1024) { set_error("memory query: rnn_units * mem_dim too large for the shared-memory staging (%zu bytes)", shm); return MCRN_ERR_BAD_DIMS; }
+    // also writes the fp16 operand copy of the decoder's initial state (no separate conversion launch)
+    MCRN_LAUNCH(k_memory_query, (int)ceil_div64(g.R, 8 * MQ_ROWS_PER_WARP), 256, shm, st, ws + p.h_enc, prm->wq, prm->memory,
                 ws + p.mq_q, ws + p.mq_att, reinterpret_cast<int*>(ws + p.mq_ind), h_att, query, pos, neg, b0.hx,
-                b0.xpg, tf32_mode(), g.B, g.N, g.H, g.M, g.d);
-    if (dec_h)
-      MCRN_LAUNCH(fusedh::k_state_to_half, ew_grid(g.R * g.D), 256, 0, st, b0.xpg, b0.x16, (int64_t)g.R * g.D);
+                b0.xpg, dec_h ? b0.x16 : (__half*)nullptr, tf32_mode(), g.B, g.N, g.H, g.M, g.d);
   }
   if (fork) MCRN_TRY(fork_join(g_fw[1], st));
   // ---- decoder loop (:181-192) ----
@@ -1103,11 +1108,17 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
         dec_glue_fused = false;
         if (g_bwd_fused == 2 && !glue_fused_here) {
           const size_t gsm = (size_t)(32 + g.D) * g.Cout * sizeof(float);
+          // a step whose d(out) has no free-running contribution: its projection weight gradient (dwp += d_out^T h_t) needs
+          // nothing from the chain -> k_proj_wgrad on the weight-gradient stream, after the loop
+          static const int wgrad_opt = getenv("MCRN_WGRAD_LATER") ? atoi(getenv("MCRN_WGRAD_LATER")) : 1;
+          const bool wgrad_later = wgrad_opt && !use_dgo && d_output != nullptr && g.T_out <= 32;
           MCRN_TRY(launch_chain(4, fusedbh::k_bwd_glue_h, dim3(ceil_div(g.N, 32), g.B), dim3(256), gsm, st, "k_bwd_glue_h", d_output, use_dgo ? dXin : nullptr, g.Cdec, h_t,
                       prm->proj_w, dH, (t == g.T_out - 1) ? 1 : 0, b.r, b.hc, b.hx, dv32 ? dU_t : nullptr,
                       dv32 ? dG_all + (int64_t)t * g.R * 2 * g.D : nullptr,
                       ws + p.dHr, du16_buf(g, p, ws, g.D, t), dg16_buf(g, p, ws, g.D, t),
-                      ws + p.gs, grads->proj_w, grads->proj_b, g.B, g.T_out, g.N, g.D, g.Cout, t));
+                      ws + p.gs, wgrad_later ? (float*)nullptr : grads->proj_w, wgrad_later ? (float*)nullptr : grads->proj_b,
+                      g.B, g.T_out, g.N, g.D, g.Cout, t));
+          if (wgrad_later) dec_wgrad_mask |= 1u << t;
         } else if (g_bwd_fused != 2)
           MCRN_LAUNCH(fusedb::k_bwd_glue, (int)ceil_div64(g.R, 32), 256, (size_t)(32 + g.D) * g.Cout * sizeof(float), st, d_output,
                       use_dgo ? dXin : nullptr, g.Cdec, h_t, prm->proj_w, dH, (t == g.T_out - 1) ? 1 : 0, b.r, b.hc, b.hx, dU_t,

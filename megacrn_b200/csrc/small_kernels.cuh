@@ -319,78 +319,93 @@ __global__ void __launch_bounds__(256) k_proj_bwd(const float* __restrict__ dOut
 // ---- memory-bank query (model/MegaCRN.py:159-166, :179); one warp per (node, batch) row ----
 // h [R][H] node-major.  Writes query/value node-major [R][d] (for backward), att [R][M], ind [R][2],
 // the four batch-major outputs [B][N][d], and the decoder's initial state [R][H+d] = [h | value].
+constexpr int MQ_ROWS_PER_WARP = 8;               // forward: a block of 8 warps serves 64 rows with Wq and the memory bank staged once
 __global__ void __launch_bounds__(256) k_memory_query(const float* __restrict__ h, const float* __restrict__ wq,
                                                       const float* __restrict__ mem, float* __restrict__ q_nm,
                                                       float* __restrict__ att, int* __restrict__ ind,
                                                       float* __restrict__ o_hatt, float* __restrict__ o_query,
                                                       float* __restrict__ o_pos, float* __restrict__ o_neg,
                                                       float* __restrict__ dec_h0, float* __restrict__ dec_h0_mma,
-                                                      int rnd, int B, int N, int H, int M, int d) {
-  extern __shared__ float shm[];                   // per warp: q[d] + sc[M]; then the memory bank [M][d + 1] (padded:
-  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;   // lanes that walk different memory rows hit different banks)
-  float* memS = shm + 8 * (d + M);
-  const int dp = d + 1;
+                                                      __half* __restrict__ dec_x16, int rnd, int B, int N, int H, int M, int d) {
+  // shared: per warp h row [H] + q[d] + sc[M]; the memory bank [M][d + 1] (padded: lanes that walk different memory rows hit
+  // different banks); Wq [H][d]
+  extern __shared__ float shm[];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per_warp = H + d + M, dp = d + 1;
+  float* memS = shm + 8 * per_warp;
+  float* wqS = memS + M * dp;
   for (int i = threadIdx.x; i < M * d; i += blockDim.x) memS[(i / d) * dp + (i % d)] = mem[i];
+  for (int i = threadIdx.x; i < H * d; i += blockDim.x) wqS[i] = wq[i];
   __syncthreads();
-  int64_t row = (int64_t)blockIdx.x * 8 + warp;
-  if (row >= (int64_t)N * B) return;
-  float* q = shm + warp * (d + M);
+  float* hs = shm + warp * per_warp;
+  float* q = hs + H;
   float* sc = q + d;
-  int n = (int)(row / B), b = (int)(row % B);
-  const float* hr = h + row * H;
-  for (int j = lane; j < d; j += 32) {             // query = h Wq            :160
-    float s = 0.f;
-    for (int k = 0; k < H; ++k) s = fmaf(hr[k], wq[(int64_t)k * d + j], s);
-    q[j] = s;
-  }
-  __syncwarp();
-  for (int m = lane; m < M; m += 32) {             // logits = q Mem^T        :161
-    float s = 0.f;
-    for (int k = 0; k < d; ++k) s = fmaf(q[k], memS[m * dp + k], s);
-    sc[m] = s;
-  }
-  __syncwarp();
-  float mx = -INFINITY;
-  for (int m = lane; m < M; m += 32) mx = fmaxf(mx, sc[m]);
-  mx = warp_max(mx);
-  float sum = 0.f;
-  for (int m = lane; m < M; m += 32) sum += expf(sc[m] - mx);
-  sum = warp_sum(sum);
-  float inv = 1.0f / sum;
-  __syncwarp();
-  for (int m = lane; m < M; m += 32) sc[m] = expf(sc[m] - mx) * inv;
-  __syncwarp();
-  // top-2 (first index wins ties, as torch.topk does on sorted-descending stable order)   :163
-  int i0 = 0, i1 = -1;
-  if (lane == 0) {
-    float b0 = sc[0], b1 = -INFINITY;
-    for (int m = 1; m < M; ++m) {
-      float v = sc[m];
-      if (v > b0) { b1 = b0; i1 = i0; b0 = v; i0 = m; }
-      else if (v > b1) { b1 = v; i1 = m; }
+  const int64_t R = (int64_t)N * B;
+  for (int rr = 0; rr < MQ_ROWS_PER_WARP; ++rr) {
+    const int64_t row = ((int64_t)blockIdx.x * 8 + warp) * MQ_ROWS_PER_WARP + rr;
+    if (row >= R) break;
+    int n = (int)(row / B), b = (int)(row % B);
+    const float* hr = h + row * H;
+    __syncwarp();
+    for (int j = lane; j < H; j += 32) hs[j] = hr[j];
+    __syncwarp();
+    for (int j = lane; j < d; j += 32) {             // query = h Wq            :160
+      float s = 0.f;
+      for (int k = 0; k < H; ++k) s = fmaf(hs[k], wqS[k * d + j], s);
+      q[j] = s;
     }
-    if (i1 < 0) i1 = 0;
+    __syncwarp();
+    for (int m = lane; m < M; m += 32) {             // logits = q Mem^T        :161
+      float s = 0.f;
+      for (int k = 0; k < d; ++k) s = fmaf(q[k], memS[m * dp + k], s);
+      sc[m] = s;
+    }
+    __syncwarp();
+    float mx = -INFINITY;
+    for (int m = lane; m < M; m += 32) mx = fmaxf(mx, sc[m]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int m = lane; m < M; m += 32) sum += expf(sc[m] - mx);
+    sum = warp_sum(sum);
+    float inv = 1.0f / sum;
+    __syncwarp();
+    for (int m = lane; m < M; m += 32) sc[m] = expf(sc[m] - mx) * inv;
+    __syncwarp();
+    // top-2 (first index wins ties, as torch.topk does on sorted-descending stable order)   :163
+    int i0 = 0, i1 = -1;
+    if (lane == 0) {
+      float b0 = sc[0], b1 = -INFINITY;
+      for (int m = 1; m < M; ++m) {
+        float v = sc[m];
+        if (v > b0) { b1 = b0; i1 = i0; b0 = v; i0 = m; }
+        else if (v > b1) { b1 = v; i1 = m; }
+      }
+      if (i1 < 0) i1 = 0;
+    }
+    i0 = __shfl_sync(0xffffffffu, i0, 0);
+    i1 = __shfl_sync(0xffffffffu, i1, 0);
+    int64_t ob = ((int64_t)b * N + n) * d;
+    const int64_t o0 = row * (H + d);
+    for (int j = lane; j < d; j += 32) {             // value = att Mem          :162
+      float s = 0.f;
+      for (int m = 0; m < M; ++m) s = fmaf(sc[m], memS[m * dp + j], s);
+      o_hatt[ob + j] = s;
+      o_query[ob + j] = q[j];
+      o_pos[ob + j] = memS[i0 * dp + j];             // :164
+      o_neg[ob + j] = memS[i1 * dp + j];             // :165
+      dec_h0[o0 + H + j] = s;                        // :179
+      dec_h0_mma[o0 + H + j] = rnd ? tf32_rn(s) : s;
+      if (dec_x16) dec_x16[o0 + H + j] = __float2half_rn(s);      // fp16 operand copy of the decoder's initial state
+      if (q_nm) q_nm[row * d + j] = q[j];
+    }
+    for (int j = lane; j < H; j += 32) {
+      dec_h0[o0 + j] = hs[j];
+      dec_h0_mma[o0 + j] = rnd ? tf32_rn(hs[j]) : hs[j];
+      if (dec_x16) dec_x16[o0 + j] = __float2half_rn(hs[j]);
+    }
+    if (att) for (int m = lane; m < M; m += 32) att[row * M + m] = sc[m];
+    if (ind && lane == 0) { ind[row * 2] = i0; ind[row * 2 + 1] = i1; }
   }
-  i0 = __shfl_sync(0xffffffffu, i0, 0);
-  i1 = __shfl_sync(0xffffffffu, i1, 0);
-  int64_t ob = ((int64_t)b * N + n) * d;
-  for (int j = lane; j < d; j += 32) {             // value = att Mem          :162
-    float s = 0.f;
-    for (int m = 0; m < M; ++m) s = fmaf(sc[m], memS[m * dp + j], s);
-    o_hatt[ob + j] = s;
-    o_query[ob + j] = q[j];
-    o_pos[ob + j] = memS[i0 * dp + j];             // :164
-    o_neg[ob + j] = memS[i1 * dp + j];             // :165
-    dec_h0[row * (H + d) + H + j] = s;             // :179
-    dec_h0_mma[row * (H + d) + H + j] = rnd ? tf32_rn(s) : s;
-    if (q_nm) q_nm[row * d + j] = q[j];
-  }
-  for (int j = lane; j < H; j += 32) {
-    dec_h0[row * (H + d) + j] = hr[j];
-    dec_h0_mma[row * (H + d) + j] = rnd ? tf32_rn(hr[j]) : hr[j];
-  }
-  if (att) for (int m = lane; m < M; m += 32) att[row * M + m] = sc[m];
-  if (ind && lane == 0) { ind[row * 2] = i0; ind[row * 2 + 1] = i1; }
 }
 
 // Row part of the memory-query backward (tests/kernel_spec.py:memory_query_bwd).  One warp per row.
