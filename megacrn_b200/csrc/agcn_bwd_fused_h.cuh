@@ -430,7 +430,8 @@ agcn_bwd_h_kernel(const __grid_constant__ CUtensorMap tmST, const __grid_constan
 // ---- loss scale ---------------------------------------------------------------------------------
 // amax[0] = max |x| over all upstream gradient tensors (as the bit pattern of a non-negative float: integer max is float max)
 struct AmaxSrc { const float* p[5]; int64_t end[5]; };     // end[i] = cumulative element count
-__global__ void k_grad_amax(AmaxSrc a, unsigned* __restrict__ amax) {
+__global__ void __launch_bounds__(256) k_grad_amax(AmaxSrc a, unsigned* __restrict__ amax) {
+  __shared__ float sh[8];
   float m = 0.f;
   const int64_t total = a.end[4];
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -439,7 +440,13 @@ __global__ void k_grad_amax(AmaxSrc a, unsigned* __restrict__ amax) {
     m = fmaxf(m, fabsf(a.p[k][i - (k ? a.end[k - 1] : 0)]));
   }
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0 && m > 0.f && m < INFINITY) atomicMax(amax, __float_as_uint(m));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 8) {                          // one atomic per block (the old one-per-warp version spent 20 us in contention)
+    m = sh[threadIdx.x];
+    for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffu, m, o));
+    if (threadIdx.x == 0 && m > 0.f && m < INFINITY) atomicMax(amax, __float_as_uint(m));
+  }
 }
 // gs = {2^e, 2^-e} with amax * 2^e in [2^7, 2^8): x2600 of head-room below fp16's 65504, full fp16 precision down to 2^-22 amax
 __global__ void k_grad_scale(const unsigned* __restrict__ amax, float* __restrict__ gs) {

@@ -445,6 +445,7 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
   // (step 0: zeros; step t after a teacher-forced coin flip: labels[:, t-1]) in ONE launch; backward operand copies ----
   const bool dec_compact = ib_compact_shape(g, g.D, g.Cdec, p.save);
   unsigned dec_tf_mask = 0, proj_mask = 0;
+  bool proj_forked = false;
   auto launch_dec_input = [&](const float* go_src, unsigned mask, cudaStream_t sx) -> int {
     const size_t shm = ((size_t)(g.N | 1) * fusedh::DI_COLS + (size_t)fusedh::DI_ROWS * (g.N + 1) +
                         (size_t)fusedh::DI_NODES * fusedh::DI_COLS * (fusedh::IBF + 1)) * sizeof(float);
@@ -552,7 +553,16 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
         MCRN_LAUNCH(k_proj_fwd, (int)ceil_div64(g.R, 8), 256, 0, st, h_out, prm->proj_w, prm->proj_b, output, g.B,
                     g.T_out, g.N, g.D, g.Cout, t);
       }
+      // the deferred projections of the steps done so far run beside the last cell (helper stream), not after the loop
+      if (fork && t + 2 == g.T_out && proj_mask) {
+        MCRN_TRY(fork_begin(g_fw[1], st));
+        MCRN_LAUNCH(k_proj_fwd_steps, dim3((int)ceil_div64(g.R, 8), __builtin_popcount(proj_mask)), 256, 0, g_fw[1].s, ws + p.dec_hx,
+                    (int64_t)p.dec_v_sz, ws + p.h_dec_last, prm->proj_w, prm->proj_b, output, proj_mask, g.B, g.T_out, g.N, g.D, g.Cout);
+        proj_mask = 0;
+        proj_forked = true;
+      }
     }
+    if (proj_forked) MCRN_TRY(fork_join(g_fw[1], st));
     if (proj_mask)
       MCRN_LAUNCH(k_proj_fwd_steps, dim3((int)ceil_div64(g.R, 8), __builtin_popcount(proj_mask)), 256, 0, st, ws + p.dec_hx,
                   (int64_t)p.dec_v_sz, ws + p.h_dec_last, prm->proj_w, prm->proj_b, output, proj_mask, g.B, g.T_out, g.N, g.D, g.Cout);
@@ -1046,7 +1056,7 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
       fusedbh::AmaxSrc a;
       int64_t acc = 0;
       for (int i = 0; i < 5; ++i) { a.p[i] = src[i]; acc += src[i] ? cnt[i] : 0; a.end[i] = acc; }
-      if (acc > 0) MCRN_LAUNCH(fusedbh::k_grad_amax, ew_grid(acc), 256, 0, st, a, amax);
+      if (acc > 0) MCRN_LAUNCH(fusedbh::k_grad_amax, ew_grid(acc) > 296 ? 296 : ew_grid(acc), 256, 0, st, a, amax);
     }
     MCRN_LAUNCH(fusedbh::k_grad_scale, 1, 1, 0, st, amax, ws + p.gs);
   }
