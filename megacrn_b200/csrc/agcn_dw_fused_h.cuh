@@ -11,7 +11,7 @@
 //                                   input block, 16 used), with Y = dV: dW_NB = sum IB^T dV  (replaces a TF32 GEMM over fp32 dV)
 // A plain split-K GEMM: CTA = (output tile (blk, h), group g) loops over its (t, b) units, ceil(N / 64) ring items each,
 // accumulator [128 x HS] in TMEM, one red.global.add.v4.f32 pass at the end (times 1 / loss scale: dV16T and Q16T carry it).
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+// Warp roles: warps 0, 6, 7 = TMA producers (ring items round-robin), warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
 #pragma once
 
 #include "agcn_bwd_fused_h.cuh"
@@ -25,7 +25,8 @@ using fusedh::BKH;
 using fusedh::make_idesc_f16;
 using fusedh::tcgen05_mma_f16;
 
-constexpr int WTHREADS = 192;
+constexpr int NPROD_W = 3;                      // TMA producer warps (one thread issues ~1 bulk-tensor copy per 190 cycles; an item is 3-4 of them)
+constexpr int WTHREADS = 192 + 32 * (NPROD_W - 1);
 
 struct WParams {
   int N, B, T, KS, nhalf, O;
@@ -88,9 +89,10 @@ agcn_dw_h_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
-  if (warp == 0) {
-    if (lane == 0) {                                     // ===== TMA producer =====
-      for (int it = 0; it < nit; ++it) {
+  const int pw = warp == 0 ? 0 : (warp >= 6 ? warp - 5 : -1);      // producer index or -1
+  if (pw >= 0) {
+    if (lane == 0) {                                     // ===== TMA producers: item `it` belongs to producer it % NPROD_W =====
+      for (int it = pw; it < nit; it += NPROD_W) {
         const int s = it % NST;
         if (it >= NST) mbar_wait_b(smem_u32(&empty_bar[s]), (((uint32_t)(it / NST)) & 1u) ^ 1u);
         const uint32_t fb = smem_u32(&full_bar[s]);
@@ -126,7 +128,7 @@ agcn_dw_h_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       }
       tcgen05_commit(smem_u32(&acc_full_bar));
     }
-  } else {                                               // ===== epilogue warps =====
+  } else if (warp < 6) {                                 // ===== epilogue warps =====
     const int quarter = warp & 3;
     mbar_wait_b(smem_u32(&acc_full_bar), 0);
     tcgen05_fence_after();

@@ -511,7 +511,7 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
   // ---- memory query (:159-166) + decoder initial state (:179) ----
   {
     CellBufs b0 = dec_bufs(g, p, ws, 0);
-    const size_t shm = (8 * (size_t)(g.H + g.d + g.M) + (size_t)g.M * (g.d + 1) + (size_t)g.H * g.d) * sizeof(float);
+    const size_t shm = (8 * (size_t)(g.H + g.d + g.M) + (size_t)g.M * (g.d + 1)) * sizeof(float);
     static bool mq_attr = false;
     if (!mq_attr) {
       MCRN_CUDA_OK(cudaFuncSetAttribute(k_memory_query, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));

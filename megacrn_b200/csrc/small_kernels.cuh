@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(256) k_proj_bwd(const float* __restrict__ dOut
 // ---- memory-bank query (model/MegaCRN.py:159-166, :179); one warp per (node, batch) row ----
 // h [R][H] node-major.  Writes query/value node-major [R][d] (for backward), att [R][M], ind [R][2],
 // the four batch-major outputs [B][N][d], and the decoder's initial state [R][H+d] = [h | value].
-constexpr int MQ_ROWS_PER_WARP = 8;               // forward: a block of 8 warps serves 64 rows with Wq and the memory bank staged once
+constexpr int MQ_ROWS_PER_WARP = 1;               // (a 64-rows-per-block variant with Wq staged in shared memory measured slower: 70 vs 53 us)
 __global__ void __launch_bounds__(256) k_memory_query(const float* __restrict__ h, const float* __restrict__ wq,
                                                       const float* __restrict__ mem, float* __restrict__ q_nm,
                                                       float* __restrict__ att, int* __restrict__ ind,
@@ -328,14 +328,12 @@ __global__ void __launch_bounds__(256) k_memory_query(const float* __restrict__ 
                                                       float* __restrict__ dec_h0, float* __restrict__ dec_h0_mma,
                                                       __half* __restrict__ dec_x16, int rnd, int B, int N, int H, int M, int d) {
   // shared: per warp h row [H] + q[d] + sc[M]; the memory bank [M][d + 1] (padded: lanes that walk different memory rows hit
-  // different banks); Wq [H][d]
+  // different banks)
   extern __shared__ float shm[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per_warp = H + d + M, dp = d + 1;
   float* memS = shm + 8 * per_warp;
-  float* wqS = memS + M * dp;
   for (int i = threadIdx.x; i < M * d; i += blockDim.x) memS[(i / d) * dp + (i % d)] = mem[i];
-  for (int i = threadIdx.x; i < H * d; i += blockDim.x) wqS[i] = wq[i];
   __syncthreads();
   float* hs = shm + warp * per_warp;
   float* q = hs + H;
@@ -351,7 +349,7 @@ __global__ void __launch_bounds__(256) k_memory_query(const float* __restrict__ 
     __syncwarp();
     for (int j = lane; j < d; j += 32) {             // query = h Wq            :160
       float s = 0.f;
-      for (int k = 0; k < H; ++k) s = fmaf(hs[k], wqS[k * d + j], s);
+      for (int k = 0; k < H; ++k) s = fmaf(hs[k], wq[(int64_t)k * d + j], s);
       q[j] = s;
     }
     __syncwarp();
