@@ -20,6 +20,7 @@
 #include "plan.cuh"
 #include "loss.cuh"
 #include "small_kernels.cuh"
+#include "supports_coop.cuh"
 
 namespace mcrn {
 
@@ -243,9 +244,23 @@ static int fork_join(Fork& f, cudaStream_t mainst);
 static Fork* fw_fork(int i);      // helper stream i of the forward (null: forks disabled / not initialised)
 static cudaStream_t fw_fork_stream(int i);
 
+// Supports prologue / backward as one cooperative launch each where they are latency-bound (supports_coop.cuh); 0 = per-stage kernels.
+static int g_supports_coop = getenv("MCRN_SUPPORTS_COOP") ? atoi(getenv("MCRN_SUPPORTS_COOP")) : 1;
+static bool supports_coop_shape(const Geo& g) {
+  return g_supports_coop && tf32_mode() && !g_simt_mask && scoop::eligible(g.N, g.cheb_k, g.d, g.M);
+}
+
+// s16 (optional): fp16 copy [KS][N][ld_half(N)] of the supports; *s16_done tells the caller whether this call wrote it.
 static int supports_forward(const Geo& g, const Plan& p, float* ws, const float* mem, const float* we1, const float* we2,
-                            float* S, float* Sr, cudaStream_t st) {
+                            float* S, float* Sr, cudaStream_t st, __half* s16 = nullptr, bool* s16_done = nullptr) {
   float *E1 = ws + p.E1, *E2 = ws + p.E2, *L1 = ws + p.L1, *L2 = ws + p.L2;
+  if (s16_done) *s16_done = false;
+  if (supports_coop_shape(g)) {
+    scoop::FwdArgs a{we1, we2, mem, E1, E2, L1, L2, S, Sr, s16, g.N, g.M, g.d, g.ldS, fusedh::ld_half(g.N)};
+    MCRN_TRY(scoop::launch_fwd(a, st));
+    if (s16_done) *s16_done = s16 != nullptr;
+    return MCRN_OK;
+  }
   // the g1 and g2 chains are independent once E1 and E2 exist: chain 1 runs on a helper stream
   Fork* f = fw_fork(1);
   cudaStream_t sx[2] = {st, st};
@@ -434,8 +449,10 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
       }
       if (p.save) MCRN_TRY(backward_operand_copies(g, p, ws, s0, s0, true, false));
     }
-    MCRN_TRY(supports_forward(g, p, ws, prm->memory, prm->we1, prm->we2, ws + p.S, ws + p.Sr, st));
-    if (enc_h || dec_h) {  // fp16 operand copy of the supports for the fused forward (exact fp32 -> half)
+    bool s16_done = false;
+    MCRN_TRY(supports_forward(g, p, ws, prm->memory, prm->we1, prm->we2, ws + p.S, ws + p.Sr, st,
+                              (enc_h || dec_h) ? reinterpret_cast<__half*>(ws + p.s16) : nullptr, &s16_done));
+    if ((enc_h || dec_h) && !s16_done) {  // fp16 operand copy of the supports for the fused forward (exact fp32 -> half)
       const int ld16 = fusedh::ld_half(g.N);
       MCRN_LAUNCH(fusedh::k_supports_to_half, ew_grid((int64_t)g.KS * g.N * ld16), 256, 0, st, ws + p.S,
                   reinterpret_cast<__half*>(ws + p.s16), g.KS * g.N, g.N, g.ldS, ld16);
@@ -962,6 +979,11 @@ static int supports_backward(const Geo& g, const Plan& p, float* ws, const mcrn_
   float* S = ws + p.S;
   float* dS = ws + p.dS;
   float* dg[2] = {ws + p.dg1, ws + p.dg2};
+  if (supports_coop_shape(g)) {
+    scoop::BwdArgs a{prm->we1, prm->we2, prm->memory, ws + p.E1, ws + p.E2, ws + p.L1, ws + p.L2, S, dS, ws + p.dLa, ws + p.dLb,
+                     ws + p.dE1, ws + p.dE2, grads->we1, grads->we2, grads->memory, g.N, g.M, g.d, g.ldS};
+    return scoop::launch_bwd(a, st);
+  }
   // N^3 work: exact fp32 on the SIMT engine for METR-LA/PEMS-BAY sizes (negligible FLOPs), tensor cores beyond.
   const int big_exact = (g.N <= 1024) ? 1 : 0;
   // the two supports (i = 0: g1 chain, i = 1: g2 chain) are independent up to dL1: chain 1 runs on a helper stream
@@ -1385,6 +1407,7 @@ bool set_option(const char* name, int value) {
   else if (n == "dw_fused") g_dw_fused = value;
   else if (n == "pdl") g_pdl_chain = value;
   else if (n == "fwd_fork") g_fw_fork = value;
+  else if (n == "supports_coop") g_supports_coop = value;
   else return false;
   return true;
 }
