@@ -106,7 +106,8 @@ __global__ void __launch_bounds__(THREADS) k_supports_fwd_coop(FwdArgs a) {
     __half* t16 = a.S16 ? a.S16 + ((int64_t)(2 * i + 1) * N + n) * a.ld16 : nullptr;
     for (int c = threadIdx.x; c < N; c += THREADS) {
       float s = 0.f;
-      for (int m = 0; m < N; ++m) s = fmaf(smem[m], g[(int64_t)m * ld + c], s);
+#pragma unroll 16
+      for (int m = 0; m < N; ++m) s = fmaf(smem[m], g[(int64_t)m * ld + c], s);      // independent L2 loads: keep 16 in flight
       const float v = 2.0f * s - (c == n ? 1.0f : 0.0f);
       t2[c] = v;
       t2r[c] = tf32_rn(v);
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(THREADS) k_supports_bwd_coop(BwdArgs a) {
     int q = 0;
     for (int c = threadIdx.x; c < N; c += THREADS, ++q) {
       float s2 = 0.f;
+#pragma unroll 16
       for (int m = 0; m < N; ++m) s2 = fmaf(col[m], dT2[(int64_t)m * ld + c], s2);     // (g^T dT2)[n][c], coalesced over c
       const float v = dT1[(int64_t)n * ld + c] + 2.0f * (s1v[c] + s2);
       dgv[q] = v;
@@ -183,6 +185,7 @@ __global__ void __launch_bounds__(THREADS) k_supports_bwd_coop(BwdArgs a) {
     const float* E = i == 0 ? a.E2 : a.E1;
     for (int j = threadIdx.x; j < d; j += THREADS) {
       float s = 0.f;
+#pragma unroll 16
       for (int m = 0; m < N; ++m) s = fmaf(v[m], E[(int64_t)m * d + j], s);
       (i == 0 ? a.dE1 : a.dE2)[(int64_t)n * d + j] = s;
     }
@@ -225,7 +228,7 @@ static inline int coop_grid(const void* kern, size_t smem) {
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, THREADS, smem) != cudaSuccess || per < 1) return 0;
-  return sms * (per > 2 ? 2 : per);
+  return sms * (per > 6 ? 6 : per);      // as many resident blocks as there are rows to work on: one row per block and phase
 }
 
 static inline int launch_fwd(const FwdArgs& a, cudaStream_t st) {

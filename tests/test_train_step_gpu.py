@@ -207,3 +207,35 @@ def test_forward_host_entry_matches_module():
     assert st == 0, lib.mcrn_last_error()
     for k, a, b in zip(OUT_NAMES, [out] + aux, want):
         assert np.array_equal(a, b.numpy()), k
+
+
+def test_mask_count_and_dp_loss_normaliser():
+    """mcrn_mask_count counts the labels whose inverse-scaled value is non-zero (model/utils.py:127); mcrn_trainer_loss_dp with
+    that count reproduces mcrn_trainer_loss, and with another normaliser rescales exactly the masked-MAE term and d(output)."""
+    from megacrn_b200 import _abi
+    from megacrn_b200.train_step import fused_trainer_loss
+    lib = _abi.load()
+    d = O.Dims(num_nodes=30, horizon=4, rnn_units=64, mem_num=6, mem_dim=64)
+    g = torch.Generator().manual_seed(2)
+    B = 5
+    out = torch.randn(B, d.horizon, d.num_nodes, 1, generator=g)
+    lab = torch.randn(B, d.horizon, d.num_nodes, 1, generator=g)
+    lab[1, :, :7] = -2.0                     # (-2) * 25 + 50 == 0 exactly -> masked
+    qy, ps, ng = (torch.randn(B, d.num_nodes, d.mem_dim, generator=g) for _ in range(3))
+    dv = _dev()
+    kw = dict(scaler_mean=50.0, scaler_std=25.0)
+    cnt = torch.zeros(1, device=dv)
+    st = lib.mcrn_mask_count(lab.to(dv).data_ptr(), lab.numel(), 50.0, 25.0, cnt.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert st == 0, lib.mcrn_last_error()
+    n_valid = int((lab * 25.0 + 50.0 != 0).sum())
+    assert int(cnt.item()) == n_valid == lab.numel() - d.horizon * 7
+    args = (d, out.to(dv), lab.to(dv), qy.to(dv), ps.to(dv), ng.to(dv))
+    l0, do0, dq0 = fused_trainer_loss(*args, **kw)
+    l1, do1, dq1 = fused_trainer_loss(*args, mask_count=cnt, **kw)
+    assert torch.equal(l0, l1) and torch.equal(do0, do1) and torch.equal(dq0, dq1)
+    ref = O.trainer_loss((out, None, qy, ps, ng), lab, **kw)
+    assert abs(float(l0) - float(ref)) < 1e-5 * abs(float(ref))
+    l2, do2, dq2 = fused_trainer_loss(*args, mask_count=cnt * 2, **kw)
+    assert rel_l2(do2.cpu(), 0.5 * do0.cpu()) < 1e-6 and torch.equal(dq2, dq0)
+    mae = float(O.masked_mae_loss(out * 25.0 + 50.0, lab * 25.0 + 50.0))
+    assert abs((float(l0) - float(l2)) - 0.5 * mae) < 1e-4 * mae
