@@ -100,11 +100,15 @@ class GraphedTrainStep:
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.pool = None
         self.mask_count = torch.zeros(1, device=dev) if self.dp else None      # static: read by the captured loss kernel
+        self._count_valid = False          # the normaliser depends on the labels only: recomputed after every load()
 
     def load(self, x, y_cov, labels, non_blocking=True):
+        """Copy a batch into the static input buffers (the only supported way to change them: the data-parallel
+        normaliser is recomputed when, and only when, new labels have been loaded)."""
         self.x.copy_(x, non_blocking=non_blocking)
         self.y_cov.copy_(y_cov, non_blocking=non_blocking)
         self.labels.copy_(labels, non_blocking=non_blocking)
+        self._count_valid = False
 
     def _eager(self, flags, complete=True):
         for p in self.params:
@@ -125,7 +129,8 @@ class GraphedTrainStep:
         return loss
 
     def _before(self):
-        if self.dp:
+        if self.dp and not self._count_valid:
+            self._count_valid = True
             from .ddp import global_mask_count_into
             kw = {**DEFAULT_SCALER, **self.loss_kw}
             global_mask_count_into(self.labels, kw["scaler_mean"], kw["scaler_std"], self.mask_count, self.group)
