@@ -13,6 +13,11 @@ The reference script (model/traintest_MegaCRN.py) imports ``MegaCRN`` and ``util
   * provides a ``torchsummary`` stub if that package is absent (imported at :11, never used by the script);
   * executes the reference file with ``runpy.run_path(..., run_name="__main__")`` with the shim directory first on
     ``sys.path``.  Nothing of the reference is modified or copied into this repository.
+
+``--harness model_EXPYTKY`` runs the EXPY-TKY harness (model_EXPYTKY/traintest_MegaCRN.py) the same way: it also reads
+``params.txt`` from the CWD (:182) and copies ``metrics.py`` / ``params.txt`` next to the model (:205-206), its data directory
+is always ``../EXPYTKY`` (params.txt), it calls ``torchsummary.summary`` (:27, stubbed to a no-op when the package is absent)
+and its ``utils.py`` imports ``jpholiday`` for a helper the trainer never calls (utils.py:5, :113; stubbed when absent).
 """
 from __future__ import annotations
 
@@ -28,17 +33,39 @@ SHIM = '"""Shim written by megacrn_b200.launch_traintest: the reference trainer 
        "from megacrn_b200.MegaCRN import MegaCRN, print_params  # noqa: F401\n"
 
 
-def prepare(reference: str, workdir: str, dataset: str, data: str | None) -> str:
-    model_dir = os.path.join(workdir, "model")
+# plumbing files each harness expects in its CWD (data handling / metrics / the month table: out of the hot path, used as is)
+HARNESS_FILES = {"model": ("utils.py",), "model_EXPYTKY": ("utils.py", "metrics.py", "params.txt")}
+
+
+def prepare(reference: str, workdir: str, dataset: str, data: str | None, harness: str = "model") -> str:
+    model_dir = os.path.join(workdir, harness)
     os.makedirs(model_dir, exist_ok=True)
     with open(os.path.join(model_dir, "MegaCRN.py"), "w") as f:
         f.write(SHIM)
-    shutil.copy2(os.path.join(reference, "model", "utils.py"), os.path.join(model_dir, "utils.py"))
+    for name in HARNESS_FILES[harness]:
+        shutil.copy2(os.path.join(reference, harness, name), os.path.join(model_dir, name))
     src = os.path.abspath(data or os.path.join(reference, dataset))
     dst = os.path.join(workdir, dataset)
     if not os.path.exists(dst):
         os.symlink(src, dst, target_is_directory=True)
     return model_dir
+
+
+def _writable_dataframe_values():
+    """pandas >= 3 hands out read-only arrays from ``DataFrame.values`` (copy-on-write); the EXPY-TKY ``utils.get_data``
+    clips them in place (model_EXPYTKY/utils.py:56-57, written for pandas 1.x).  Return a writable copy instead."""
+    try:
+        import pandas as pd
+    except ImportError:
+        return
+    if int(pd.__version__.split(".")[0]) < 3:
+        return
+    orig = pd.DataFrame.values
+
+    def values(self):
+        v = orig.fget(self)
+        return v if v.flags.writeable else v.copy()
+    pd.DataFrame.values = property(values, doc=orig.__doc__)
 
 
 def main(argv=None):
@@ -47,21 +74,31 @@ def main(argv=None):
     ap.add_argument("--workdir", default="run")
     ap.add_argument("--data", default=None, help="directory holding train/val/test.npz (default <reference>/<DATASET>)")
     ap.add_argument("--script", default="traintest_MegaCRN.py")
+    ap.add_argument("--harness", default="model", choices=sorted(HARNESS_FILES), help="reference directory holding the trainer")
     ap.add_argument("rest", nargs=argparse.REMAINDER, help="arguments after -- go to the reference script")
     args = ap.parse_args(argv)
     rest = [a for a in args.rest if a != "--"]
     dataset = "METRLA"
     if "--dataset" in rest:
         dataset = rest[rest.index("--dataset") + 1]
+    if args.harness == "model_EXPYTKY":
+        dataset = "EXPYTKY"                    # 'EXPYTKY' and 'EXPYTKY*' both live in ../EXPYTKY (params.txt)
     workdir = os.path.abspath(args.workdir)
-    model_dir = prepare(os.path.abspath(args.reference), workdir, dataset, args.data)
-    script = os.path.join(os.path.abspath(args.reference), "model", args.script)
+    model_dir = prepare(os.path.abspath(args.reference), workdir, dataset, args.data, args.harness)
+    script = os.path.join(os.path.abspath(args.reference), args.harness, args.script)
     try:
         import torchsummary  # noqa: F401
     except ImportError:
         stub = types.ModuleType("torchsummary")
         stub.summary = lambda *a, **k: None
         sys.modules["torchsummary"] = stub
+    try:
+        import jpholiday  # noqa: F401
+    except ImportError:
+        stub = types.ModuleType("jpholiday")
+        stub.is_holiday = lambda *a, **k: False
+        sys.modules["jpholiday"] = stub
+    _writable_dataframe_values()
     repo_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for p in (repo_root, model_dir):
         if p in sys.path:

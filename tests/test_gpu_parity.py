@@ -261,13 +261,15 @@ def test_large_graph_shapes_vs_oracle(cfg):
         assert rel_l2(prm.grad.cpu(), ref_grads[pname]) < grad_tol("default", pname), (pname, rel_l2(prm.grad.cpu(), ref_grads[pname]))
 
 
-@pytest.mark.parametrize("cfg", ["c4_full_T", "c5_full_T"])
+@pytest.mark.parametrize("cfg", ["c4_full_T", "c5_full_T", "expytky_harness"])
 def test_large_graph_full_sequence_vs_oracle(cfg, default_engine):
     """One sequence through the FULL recurrence of BASELINE.json configs[3] (N=1843, T=6+6, H=64) and configs[4] (N=2841,
     T=12+12, H=128): error compounding over all steps with 1843- / 2841-term sums over the supports in 16-bit operands
     (VERDICT r1 weak #3).  The CPU oracle needs ~10 s / ~1 min on 16 cores for these (96 N^3 Chebyshev products)."""
     if cfg == "c4_full_T":
         d, B, t_in = O.Dims(num_nodes=1843, horizon=6, rnn_units=64), 1, 6
+    elif cfg == "expytky_harness":     # the EXPY-TKY trainer's defaults (model_EXPYTKY/traintest_MegaCRN.py:155-164): encoder H=32 on
+        d, B, t_in = O.Dims(num_nodes=1843, horizon=6, rnn_units=32, mem_num=10, mem_dim=32), 2, 6   # the per-stage path, decoder D=64 fused
     else:
         d, B, t_in = O.Dims(num_nodes=2841, horizon=12, rnn_units=128), 1, 12
     p = O.init_params(d, seed=0)
