@@ -295,3 +295,181 @@ def model_bwd(d, p, saved, d_output, d_hatt, d_query, d_pos, d_neg) -> Dict[str,
         q + "update.bias": acc_d["bu"],
         "proj.0.weight": d_wp, "proj.0.bias": d_bp,
     }
+
+
+# ----------------------------------------------------------------------------
+# stacked cells (num_layers > 1)                 model/MegaCRN.py:62-63, :71-78, :100-101, :109-112
+# ----------------------------------------------------------------------------
+# The cells of layers >= 1 take the H- (D-) wide state of the layer below as their input.  The CUDA path runs them as an
+# AGCN over the concatenated operand V = [x_in | h] of width 2*Hs with NO separate input channels: the reference's weight
+# rows are already ordered (support block, [input channels | state channels]) (model/MegaCRN.py:42, :24-27), so
+# fold_agcn_weights(w, cin=0, hid=2*Hs) is the folded weight of that operand and the bias rides in the input block.
+def cell_fwd_wide(s, h, x_in, wg, bg, wu, bu):
+    """h, x_in [N,B,Hs]; wg [1+KS, 2Hs, 2Hs], wu [1+KS, 2Hs, Hs] (folded with cin = 0)."""
+    hid = h.shape[-1]
+    v0g = torch.cat([x_in, h], -1)
+    xp_g = torch.cat([v0g[None], propagate(s, v0g)], 0)                  # [1+KS,N,B,2Hs]
+    zr = torch.sigmoid(torch.einsum("knbc,kco->nbo", xp_g, wg) + bg)
+    z, r = zr[..., :hid], zr[..., hid:]
+    v0u = torch.cat([x_in, z * h], -1)
+    xp_u = torch.cat([v0u[None], propagate(s, v0u)], 0)
+    hc = torch.tanh(torch.einsum("knbc,kco->nbo", xp_u, wu) + bu)
+    h_new = r * h + (1 - r) * hc
+    return h_new, dict(xp_g=xp_g, xp_u=xp_u, z=z, r=r, hc=hc, h=h)
+
+
+def cell_bwd_wide(s, sv, d_hnew, wg, wu, acc):
+    """Returns (d_h, d_x_in); accumulates wg / wu / bg / bu / s into ``acc``.  Step order = csrc/model.cu:cell_backward_wide."""
+    h, z, r, hc = sv["h"], sv["z"], sv["r"], sv["hc"]
+    hid = h.shape[-1]
+    d_u = d_hnew * (1 - r) * (1 - hc * hc)
+    acc["wu"] += torch.einsum("knbc,nbo->kco", sv["xp_u"], d_u)
+    acc["bu"] += d_u.sum((0, 1))
+    d_xp = torch.einsum("nbo,kco->knbc", d_u, wu)
+    acc["s"] += d_supports(d_xp[1:], sv["xp_u"][0])
+    d_v0 = d_xp[0] + propagate_t(s, d_xp[1:])                            # [N,B,2Hs]
+    d_zh, d_xa = d_v0[..., hid:], d_v0[..., :hid]
+    d_g = torch.cat([d_zh * h * z * (1 - z), d_hnew * (h - hc) * r * (1 - r)], -1)
+    d_hp = d_hnew * r + d_zh * z
+    acc["wg"] += torch.einsum("knbc,nbo->kco", sv["xp_g"], d_g)
+    acc["bg"] += d_g.sum((0, 1))
+    d_xp2 = torch.einsum("nbo,kco->knbc", d_g, wg)
+    acc["s"] += d_supports(d_xp2[1:], sv["xp_g"][0])
+    d_v0 = d_xp2[0] + propagate_t(s, d_xp2[1:])
+    return d_hp + d_v0[..., hid:], d_xa + d_v0[..., :hid]
+
+
+def model_fwd_layers(d, p: Dict[str, Tensor], x, y_cov, labels, tf: Sequence[bool]):
+    """Layer-major encoder, step-major decoder: the data flow of csrc/model.cu:forward_impl_layers."""
+    hid, dd, ck, L = d.rnn_units, d.decoder_dim, d.cheb_k, d.num_layers
+    s, s_saved = supports_fwd(p, ck)
+    cin_d = d.output_dim + d.ycov_dim
+    e0, q0 = "encoder.dcrnn_cells.0.", "decoder.dcrnn_cells.0."
+    ew = fold_agcn_weights(p[e0 + "gate.weights"], d.input_dim, hid, ck) + fold_agcn_weights(p[e0 + "update.weights"], d.input_dim, hid, ck)
+    dw = fold_agcn_weights(p[q0 + "gate.weights"], cin_d, dd, ck) + fold_agcn_weights(p[q0 + "update.weights"], cin_d, dd, ck)
+    ewl = [(fold_agcn_weights(p[f"encoder.dcrnn_cells.{i}.gate.weights"], 0, 2 * hid, ck)[0],
+            fold_agcn_weights(p[f"encoder.dcrnn_cells.{i}.update.weights"], 0, 2 * hid, ck)[0]) for i in range(1, L)]
+    dwl = [(fold_agcn_weights(p[f"decoder.dcrnn_cells.{i}.gate.weights"], 0, 2 * dd, ck)[0],
+            fold_agcn_weights(p[f"decoder.dcrnn_cells.{i}.update.weights"], 0, 2 * dd, ck)[0]) for i in range(1, L)]
+    bsz, t_in = x.shape[0], x.shape[1]
+    kw = dict(dtype=x.dtype, device=x.device)
+    # encoder, layer by layer (:71-78)
+    seq = []
+    h = torch.zeros(d.num_nodes, bsz, hid, **kw)
+    enc_saved = [[]]
+    for t in range(t_in):
+        h, sv = cell_fwd(s, h, _nm(x[:, t]), ew[0], ew[1], p[e0 + "gate.bias"], ew[2], ew[3], p[e0 + "update.bias"])
+        enc_saved[0].append(sv)
+        seq.append(h)
+    for i in range(1, L):
+        pre = f"encoder.dcrnn_cells.{i}."
+        h = torch.zeros(d.num_nodes, bsz, hid, **kw)
+        nxt, svs = [], []
+        for t in range(t_in):
+            h, sv = cell_fwd_wide(s, h, seq[t], ewl[i - 1][0], p[pre + "gate.bias"], ewl[i - 1][1], p[pre + "update.bias"])
+            svs.append(sv)
+            nxt.append(h)
+        enc_saved.append(svs)
+        seq = nxt
+    h_enc = seq[-1]
+    value, query, att, ind = memory_query_fwd(h_enc, p["memory.Memory"], p["memory.Wq"])
+    mem = p["memory.Memory"]
+    pos, neg = mem[ind[..., 0]], mem[ind[..., 1]]
+    states = [torch.cat([h_enc, value], -1)] * L                       # :179-181
+    go = torch.zeros(d.num_nodes, bsz, d.output_dim, **kw)
+    wp, bp = p["proj.0.weight"], p["proj.0.bias"]
+    dec_saved, outs, h_top = [], [], []
+    for t in range(d.horizon):
+        xin = torch.cat([go, _nm(y_cov[:, t])], -1)
+        new_states, svs = [], []
+        h, sv = cell_fwd(s, states[0], xin, dw[0], dw[1], p[q0 + "gate.bias"], dw[2], dw[3], p[q0 + "update.bias"])
+        new_states.append(h)
+        svs.append(sv)
+        for i in range(1, L):
+            pre = f"decoder.dcrnn_cells.{i}."
+            h, sv = cell_fwd_wide(s, states[i], h, dwl[i - 1][0], p[pre + "gate.bias"], dwl[i - 1][1], p[pre + "update.bias"])
+            new_states.append(h)
+            svs.append(sv)
+        states = new_states
+        dec_saved.append(svs)
+        h_top.append(h)
+        go = h @ wp.T + bp
+        outs.append(go)
+        if tf[t]:
+            go = _nm(labels[:, t])
+    output = torch.stack([o.permute(1, 0, 2) for o in outs], 1)
+    res = (output, value.permute(1, 0, 2), query.permute(1, 0, 2), pos.permute(1, 0, 2), neg.permute(1, 0, 2))
+    saved = dict(s=s, s_saved=s_saved, ew=ew, dw=dw, ewl=ewl, dwl=dwl, enc=enc_saved, dec=dec_saved, h_top=h_top, h_enc=h_enc,
+                 query=query, att=att, ind=ind, tf=list(tf))
+    return res, saved
+
+
+def model_bwd_layers(d, p, saved, d_output, d_hatt, d_query, d_pos, d_neg) -> Dict[str, Tensor]:
+    """BPTT over the stack: the data flow of csrc/model.cu:backward_impl_layers."""
+    hid, dd, ck, L = d.rnn_units, d.decoder_dim, d.cheb_k, d.num_layers
+    cin_d = d.output_dim + d.ycov_dim
+    s, ew, dw, ewl, dwl = saved["s"], saved["ew"], saved["dw"], saved["ewl"], saved["dwl"]
+    wp = p["proj.0.weight"]
+    z = torch.zeros_like
+    kw = dict(dtype=s.dtype, device=s.device)
+
+    def acc0(w4):
+        return dict(wg_st=z(w4[0]), wg_in=z(w4[1]), wu_st=z(w4[2]), wu_in=z(w4[3]), bg=torch.zeros(w4[0].shape[-1], **kw),
+                    bu=torch.zeros(w4[2].shape[-1], **kw), s=z(s))
+
+    def accw(w2):
+        return dict(wg=z(w2[0]), wu=z(w2[1]), bg=torch.zeros(w2[0].shape[-1], **kw), bu=torch.zeros(w2[1].shape[-1], **kw), s=z(s))
+    acc_d, acc_e = acc0(dw), acc0(ew)
+    acc_dl, acc_el = [accw(w) for w in dwl], [accw(w) for w in ewl]
+    d_wp, d_bp = z(wp), z(p["proj.0.bias"])
+    n, bsz = saved["h_enc"].shape[0], saved["h_enc"].shape[1]
+    d_hl = [torch.zeros(n, bsz, dd, **kw) for _ in range(L)]            # recurrent gradient of every decoder layer
+    d_go_next = None
+    for t in range(d.horizon - 1, -1, -1):
+        d_out_t = _nm(d_output[:, t]).clone()
+        if d_go_next is not None and not saved["tf"][t]:
+            d_out_t = d_out_t + d_go_next
+        d_wp += torch.einsum("nbo,nbd->od", d_out_t, saved["h_top"][t])
+        d_bp += d_out_t.sum((0, 1))
+        d_hl[L - 1] = d_hl[L - 1] + d_out_t @ wp
+        for i in range(L - 1, 0, -1):
+            d_hl[i], d_x = cell_bwd_wide(s, saved["dec"][t][i], d_hl[i], dwl[i - 1][0], dwl[i - 1][1], acc_dl[i - 1])
+            d_hl[i - 1] = d_hl[i - 1] + d_x
+        d_hl[0], d_xin = cell_bwd(s, saved["dec"][t][0], d_hl[0], dw[0], dw[1], dw[2], dw[3], acc_d)
+        d_go_next = d_xin[..., :d.output_dim]
+    d_h = sum(d_hl)                                                      # every layer started from the same state (:181)
+    d_value = d_h[..., hid:] + _nm(d_hatt)
+    d_henc, d_mem, d_wq = memory_query_bwd(saved["h_enc"], p["memory.Memory"], p["memory.Wq"], saved["query"],
+                                           saved["att"], saved["ind"], d_value, _nm(d_query), _nm(d_pos), _nm(d_neg))
+    t_in = len(saved["enc"][0])
+    d_h = d_h[..., :hid] + d_henc                                        # gradient of the top layer's last state
+    d_seq = [None] * t_in                                                # gradient w.r.t. the outputs of the layer below
+    for i in range(L - 1, 0, -1):
+        for t in range(t_in - 1, -1, -1):
+            if d_seq[t] is not None:
+                d_h = d_h + d_seq[t]
+            d_h, d_seq[t] = cell_bwd_wide(s, saved["enc"][i][t], d_h, ewl[i - 1][0], ewl[i - 1][1], acc_el[i - 1])
+        d_h = torch.zeros(n, bsz, hid, **kw)
+    for t in range(t_in - 1, -1, -1):
+        if d_seq[t] is not None:
+            d_h = d_h + d_seq[t]
+        d_h, _ = cell_bwd(s, saved["enc"][0][t], d_h, ew[0], ew[1], ew[2], ew[3], acc_e)
+    d_s = acc_d["s"] + acc_e["s"] + sum(a["s"] for a in acc_dl) + sum(a["s"] for a in acc_el)
+    sg = supports_bwd(p, ck, saved["s_saved"], d_s)
+    e, q = "encoder.dcrnn_cells.0.", "decoder.dcrnn_cells.0."
+    out = {
+        "memory.Memory": d_mem + sg["Memory"], "memory.Wq": d_wq, "memory.We1": sg["We1"], "memory.We2": sg["We2"],
+        e + "gate.weights": unfold_agcn_grads(acc_e["wg_st"], acc_e["wg_in"], d.input_dim, hid, ck), e + "gate.bias": acc_e["bg"],
+        e + "update.weights": unfold_agcn_grads(acc_e["wu_st"], acc_e["wu_in"], d.input_dim, hid, ck), e + "update.bias": acc_e["bu"],
+        q + "gate.weights": unfold_agcn_grads(acc_d["wg_st"], acc_d["wg_in"], cin_d, dd, ck), q + "gate.bias": acc_d["bg"],
+        q + "update.weights": unfold_agcn_grads(acc_d["wu_st"], acc_d["wu_in"], cin_d, dd, ck), q + "update.bias": acc_d["bu"],
+        "proj.0.weight": d_wp, "proj.0.bias": d_bp,
+    }
+    for i in range(1, L):
+        for pre, a, w in ((f"encoder.dcrnn_cells.{i}.", acc_el[i - 1], 2 * hid), (f"decoder.dcrnn_cells.{i}.", acc_dl[i - 1], 2 * dd)):
+            empty = a["wg"][:, :0, :]
+            out[pre + "gate.weights"] = unfold_agcn_grads(a["wg"], empty, 0, w, ck)
+            out[pre + "gate.bias"] = a["bg"]
+            out[pre + "update.weights"] = unfold_agcn_grads(a["wu"], a["wu"][:, :0, :], 0, w, ck)
+            out[pre + "update.bias"] = a["bu"]
+    return out

@@ -42,6 +42,37 @@ def test_forward_and_backward_match_autograd(cheb_k, tf):
         assert err <= 1e-9 * scale + 1e-12, (name, err, scale)
 
 
+@pytest.mark.parametrize("layers,cheb_k", [(2, 3), (3, 2)])
+@pytest.mark.parametrize("tf", [[False] * 4, [True, False, True, False]])
+def test_stacked_cells_match_autograd(layers, cheb_k, tf):
+    """num_layers > 1 (model/MegaCRN.py:71-78, :109-112): the wide-operand cells of layers >= 1 ([x_in | h] as one AGCN operand,
+    weights folded with cin = 0) and the layer-wise BPTT of csrc/model.cu against autograd of the reference formulation."""
+    d = O.Dims(num_nodes=13, horizon=4, rnn_units=8, mem_num=5, mem_dim=12, cheb_k=cheb_k, num_layers=layers)
+    p = {k: v.double() for k, v in O.init_params(d, seed=2).items()}
+    g = torch.Generator().manual_seed(5)
+    for k in p:
+        if k.endswith("bias"):
+            p[k] = torch.randn(p[k].shape, generator=g, dtype=torch.float64) * 0.1
+    x, y_cov, labels = O.synthetic_batch(d, 3, 5, seed=98, dtype=torch.float64)
+    q = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    ref = O.forward(d, q, x, y_cov, labels, tf)
+    with torch.no_grad():
+        got, saved = K.model_fwd_layers(d, p, x, y_cov, labels, tf)
+    for a, b in zip(got, ref):
+        assert torch.allclose(a, b.detach(), rtol=1e-10, atol=1e-12)
+    gen = torch.Generator().manual_seed(3)
+    ups = [torch.randn(r.shape, generator=gen, dtype=torch.float64) for r in ref]
+    auto = torch.autograd.grad(sum((r * u).sum() for r, u in zip(ref, ups)), list(q.values()))
+    with torch.no_grad():
+        mine = K.model_bwd_layers(d, p, saved, *ups)
+    assert set(mine) == set(q)
+    for (name, _), ga in zip(q.items(), auto):
+        assert mine[name].shape == ga.shape, name
+        err = (mine[name] - ga).abs().max().item()
+        scale = ga.abs().max().item() + 1e-30
+        assert err <= 1e-9 * scale + 1e-12, (name, err, scale)
+
+
 def test_fold_unfold_roundtrip():
     w = torch.arange(6 * 5 * 3, dtype=torch.float64).reshape(30, 3)
     st, win = K.fold_agcn_weights(w, 2, 3, 3)
