@@ -50,7 +50,7 @@ typedef struct mcrn_dims {
   int32_t output_dim;   /* Cout                                                      */
   int32_t ycov_dim;
   int32_t rnn_units;    /* H                                                         */
-  int32_t num_layers;   /* only 1 is implemented                                     */
+  int32_t num_layers;   /* L, 1..MCRN_MAX_LAYERS; L > 1 goes through mcrn_forward_layers / mcrn_backward_layers */
   int32_t cheb_k;       /* >= 2                                                      */
   int32_t mem_num;      /* M                                                         */
   int32_t mem_dim;      /* d                                                         */
@@ -75,6 +75,21 @@ typedef struct mcrn_params {
   float* proj_w;        /* proj.0.weight                       [Cout, D]             */
   float* proj_b;        /* proj.0.bias                         [Cout]                */
 } mcrn_params;
+
+/* Stacked cells (num_layers > 1; model/MegaCRN.py:62-63, :71-78, :100-101, :109-112): the parameters of
+ * encoder.dcrnn_cells.{i} / decoder.dcrnn_cells.{i} for ONE layer i >= 1.  Their input is the state of the layer below, so
+ * dim_in = H for the encoder cell and D = H + d for the decoder cell.  The same struct carries their gradients. */
+#define MCRN_MAX_LAYERS 4
+typedef struct mcrn_layer_params {
+  float* enc_gate_w;    /* encoder.dcrnn_cells.{i}.gate.weights    [2k(H+H), 2H]   */
+  float* enc_gate_b;    /*                      ...gate.bias      [2H]            */
+  float* enc_update_w;  /*                      ...update.weights [2k(H+H), H]    */
+  float* enc_update_b;  /*                      ...update.bias    [H]             */
+  float* dec_gate_w;    /* decoder.dcrnn_cells.{i}.gate.weights    [2k(D+D), 2D]   */
+  float* dec_gate_b;    /*                                        [2D]            */
+  float* dec_update_w;  /*                                        [2k(D+D), D]    */
+  float* dec_update_b;  /*                                        [D]             */
+} mcrn_layer_params;
 
 /* Flags for mcrn_forward. */
 #define MCRN_FWD_SAVE_FOR_BACKWARD 1u   /* keep per-step activations in the workspace */
@@ -122,6 +137,26 @@ int mcrn_backward(const mcrn_dims* dims, const mcrn_params* params,
                   const float* d_pos, const float* d_neg,
                   const mcrn_params* grads,
                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* num_layers >= 1: mcrn_forward / mcrn_backward with the stacked cells of layers 1 .. num_layers-1 in `upper`
+ * (an array of num_layers-1 structs; NULL when num_layers == 1, in which case these ARE mcrn_forward / mcrn_backward).
+ * ADCRNN_Encoder.forward runs layer by layer over the whole sequence (model/MegaCRN.py:71-78), ADCRNN_Decoder.forward
+ * runs the stack once per step (:109-112), every decoder layer starts from the same [h_T | h_att] (:181) and the
+ * projection reads the top layer (:186).  Layers >= 1 run on the per-stage GEMM engine (their AGCN operand is the
+ * 2*width concatenation [state below | own state]); with num_layers > 1 layer 0 does too.  MCRN_FWD_REUSE_PROLOGUE is
+ * ignored for num_layers > 1.  mcrn_forward / mcrn_backward themselves reject num_layers > 1. */
+int mcrn_forward_layers(const mcrn_dims* dims, const mcrn_params* params, const mcrn_layer_params* upper,
+                        const float* x, const float* y_cov, const float* labels,
+                        const uint8_t* teacher_forcing,
+                        float* output, float* h_att, float* query, float* pos, float* neg,
+                        void* workspace, size_t workspace_bytes, uint32_t flags, void* stream);
+int mcrn_backward_layers(const mcrn_dims* dims, const mcrn_params* params, const mcrn_layer_params* upper,
+                         const float* x, const float* y_cov, const float* labels,
+                         const uint8_t* teacher_forcing,
+                         const float* d_output, const float* d_h_att, const float* d_query,
+                         const float* d_pos, const float* d_neg,
+                         const mcrn_params* grads, const mcrn_layer_params* upper_grads,
+                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* The caller-side loss of the training step, fused:
  * loss = masked_mae(output*std+mean, labels*std+mean)            (model/utils.py:126-133)

@@ -3,7 +3,8 @@
 ``from MegaCRN import MegaCRN`` (model/traintest_MegaCRN.py:15) resolves to this file when
 ``megacrn_b200`` is first on ``sys.path`` (see megacrn_b200/launch_traintest.py).  Same
 constructor (model/MegaCRN.py:117-118), same ``forward(x, y_cov, labels, batches_seen)``
--> ``(output, h_att, query, pos, neg)`` (:168, :194), same 14 ``state_dict`` keys and shapes,
+-> ``(output, h_att, query, pos, neg)`` (:168, :194), same ``state_dict`` keys and shapes (14 for the default
+``num_layers=1``, 8 more per stacked layer),
 same consumption of ``np.random.uniform`` for scheduled sampling (:188-191).
 
 All arithmetic runs in hand-written sm_100a kernels behind the C ABI of
@@ -113,12 +114,19 @@ class _MegaCRNFunction(torch.autograd.Function):
         B, N, d = x.shape[0], module.num_nodes, module.mem_dim
         output = torch.empty(B, module.horizon, N, module.output_dim, device=x.device, dtype=torch.float32)
         h_att, query, pos, neg = (torch.empty(B, N, d, device=x.device, dtype=torch.float32) for _ in range(4))
-        prm = _abi.make_params(params)
+        prm = _abi.make_params(params[:14])
+        upper = _abi.make_layer_params(params[14:])          # stacked cells of layers >= 1 (None for num_layers == 1)
         stream = torch.cuda.current_stream(x.device).cuda_stream
         with torch.cuda.device(x.device):
-            st = lib.mcrn_forward(dims, prm, x.data_ptr(), y_cov.data_ptr(), _abi.ptr(labels), tf,
-                                  output.data_ptr(), h_att.data_ptr(), query.data_ptr(), pos.data_ptr(),
-                                  neg.data_ptr(), ws.buf.data_ptr(), ws.nbytes, flags, stream)
+            if upper is None:
+                st = lib.mcrn_forward(dims, prm, x.data_ptr(), y_cov.data_ptr(), _abi.ptr(labels), tf,
+                                      output.data_ptr(), h_att.data_ptr(), query.data_ptr(), pos.data_ptr(),
+                                      neg.data_ptr(), ws.buf.data_ptr(), ws.nbytes, flags, stream)
+            else:
+                st = lib.mcrn_forward_layers(dims, prm, _abi.layer_ptr(upper), x.data_ptr(), y_cov.data_ptr(), _abi.ptr(labels),
+                                             tf, output.data_ptr(), h_att.data_ptr(), query.data_ptr(), pos.data_ptr(),
+                                             neg.data_ptr(), ws.buf.data_ptr(), ws.nbytes,
+                                             flags & ~_abi.MCRN_FWD_REUSE_PROLOGUE, stream)
         _abi.check(st, "mcrn_forward")
         ws.prologue_key = key
         if need_grad:
@@ -143,7 +151,7 @@ class _MegaCRNFunction(torch.autograd.Function):
         if tuple(p._version for p in params) != ctx.param_versions:
             raise RuntimeError("megacrn_b200: a parameter was modified in place between forward and backward")
         x, y_cov, labels = ctx.inputs
-        # one flat fp32 buffer aliased by all 14 gradients -> a single NCCL all-reduce per step (ddp.py)
+        # one flat fp32 buffer aliased by all the gradients -> a single NCCL all-reduce per step (ddp.py)
         sizes = [p.numel() for p in params]
         padded = [(s + 63) // 64 * 64 for s in sizes]
         flat = torch.empty(sum(padded), device=x.device, dtype=torch.float32)
@@ -154,11 +162,19 @@ class _MegaCRNFunction(torch.autograd.Function):
         cont = lambda t: None if t is None else t.contiguous()
         d_out, d_hatt, d_query, d_pos, d_neg = map(cont, (d_out, d_hatt, d_query, d_pos, d_neg))
         stream = torch.cuda.current_stream(x.device).cuda_stream
+        upper, upper_grads = _abi.make_layer_params(params[14:]), _abi.make_layer_params(grads[14:])
         with torch.cuda.device(x.device):
-            st = lib.mcrn_backward(ctx.dims, _abi.make_params(params), x.data_ptr(), y_cov.data_ptr(),
-                                   _abi.ptr(labels), ctx.tf, _abi.ptr(d_out), _abi.ptr(d_hatt), _abi.ptr(d_query),
-                                   _abi.ptr(d_pos), _abi.ptr(d_neg), _abi.make_params(grads), ctx.ws.buf.data_ptr(),
-                                   ctx.ws.nbytes, stream)
+            if upper is None:
+                st = lib.mcrn_backward(ctx.dims, _abi.make_params(params), x.data_ptr(), y_cov.data_ptr(),
+                                       _abi.ptr(labels), ctx.tf, _abi.ptr(d_out), _abi.ptr(d_hatt), _abi.ptr(d_query),
+                                       _abi.ptr(d_pos), _abi.ptr(d_neg), _abi.make_params(grads), ctx.ws.buf.data_ptr(),
+                                       ctx.ws.nbytes, stream)
+            else:
+                st = lib.mcrn_backward_layers(ctx.dims, _abi.make_params(params[:14]), _abi.layer_ptr(upper), x.data_ptr(),
+                                              y_cov.data_ptr(), _abi.ptr(labels), ctx.tf, _abi.ptr(d_out), _abi.ptr(d_hatt),
+                                              _abi.ptr(d_query), _abi.ptr(d_pos), _abi.ptr(d_neg),
+                                              _abi.make_params(grads[:14]), _abi.layer_ptr(upper_grads),
+                                              ctx.ws.buf.data_ptr(), ctx.ws.nbytes, stream)
         _abi.check(st, "mcrn_backward")
         ctx.done = True
         ctx.ws.busy = False
@@ -193,8 +209,8 @@ class MegaCRN(nn.Module):
         self._ws_pool = {}
         self._param_epoch = 0            # bumped by every parameter update that bypasses torch's version counters
         self.last_teacher_forcing = None
-        if num_layers != 1:
-            raise NotImplementedError("megacrn_b200 implements the reference default num_layers=1 only")
+        if not 1 <= num_layers <= _abi.MAX_LAYERS:
+            raise NotImplementedError(f"megacrn_b200 implements num_layers 1..{_abi.MAX_LAYERS} (got {num_layers})")
 
     def compute_sampling_threshold(self, batches_seen):
         """model/MegaCRN.py:146-147."""
@@ -227,11 +243,14 @@ class MegaCRN(nn.Module):
         return super().train(mode)
 
     def _ordered_params(self):
-        e, d = self.encoder.dcrnn_cells[0], self.decoder.dcrnn_cells[0]
-        return (self.memory["Memory"], self.memory["Wq"], self.memory["We1"], self.memory["We2"],
-                e.gate.weights, e.gate.bias, e.update.weights, e.update.bias,
-                d.gate.weights, d.gate.bias, d.update.weights, d.update.bias,
-                self.proj[0].weight, self.proj[0].bias)
+        """The tensors in C-ABI order (_abi.param_keys): the 14 of ``mcrn_params``, then 8 per stacked layer."""
+        def cell(c):
+            return (c.gate.weights, c.gate.bias, c.update.weights, c.update.bias)
+        out = (self.memory["Memory"], self.memory["Wq"], self.memory["We1"], self.memory["We2"]) + \
+            cell(self.encoder.dcrnn_cells[0]) + cell(self.decoder.dcrnn_cells[0]) + (self.proj[0].weight, self.proj[0].bias)
+        for i in range(1, self.num_layers):
+            out += cell(self.encoder.dcrnn_cells[i]) + cell(self.decoder.dcrnn_cells[i])
+        return out
 
     def _dims(self, x):
         return _abi.Dims(batch=x.shape[0], num_nodes=self.num_nodes, seq_len=x.shape[1], horizon=self.horizon,

@@ -33,6 +33,28 @@ STATE_DICT_KEYS = (
 )
 
 
+# stacked cells of one layer i >= 1 (mcrn_layer_params): field -> state_dict key template
+LAYER_FIELDS = (
+    "enc_gate_w", "enc_gate_b", "enc_update_w", "enc_update_b",
+    "dec_gate_w", "dec_gate_b", "dec_update_w", "dec_update_b",
+)
+LAYER_KEYS = (
+    "encoder.dcrnn_cells.{i}.gate.weights", "encoder.dcrnn_cells.{i}.gate.bias",
+    "encoder.dcrnn_cells.{i}.update.weights", "encoder.dcrnn_cells.{i}.update.bias",
+    "decoder.dcrnn_cells.{i}.gate.weights", "decoder.dcrnn_cells.{i}.gate.bias",
+    "decoder.dcrnn_cells.{i}.update.weights", "decoder.dcrnn_cells.{i}.update.bias",
+)
+MAX_LAYERS = 4
+
+
+def param_keys(num_layers: int = 1):
+    """state_dict keys in the order the C ABI takes the tensors: the 14 of mcrn_params, then 8 per stacked layer."""
+    keys = list(STATE_DICT_KEYS)
+    for i in range(1, num_layers):
+        keys += [k.format(i=i) for k in LAYER_KEYS]
+    return tuple(keys)
+
+
 class Dims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "batch", "num_nodes", "seq_len", "horizon", "input_dim", "output_dim", "ycov_dim",
@@ -41,6 +63,10 @@ class Dims(C.Structure):
 
 class Params(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in PARAM_FIELDS]
+
+
+class LayerParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in LAYER_FIELDS]
 
 
 class MegaCRNLibraryError(RuntimeError):
@@ -96,6 +122,12 @@ def load() -> C.CDLL:
     lib.mcrn_backward.restype = C.c_int
     lib.mcrn_backward.argtypes = [C.POINTER(Dims), C.POINTER(Params), fp, fp, fp, u8p,
                                   fp, fp, fp, fp, fp, C.POINTER(Params), vp, C.c_size_t, vp]
+    lib.mcrn_forward_layers.restype = C.c_int
+    lib.mcrn_forward_layers.argtypes = [C.POINTER(Dims), C.POINTER(Params), vp, fp, fp, fp, u8p,
+                                        fp, fp, fp, fp, fp, vp, C.c_size_t, C.c_uint32, vp]
+    lib.mcrn_backward_layers.restype = C.c_int
+    lib.mcrn_backward_layers.argtypes = [C.POINTER(Dims), C.POINTER(Params), vp, fp, fp, fp, u8p,
+                                         fp, fp, fp, fp, fp, C.POINTER(Params), vp, vp, C.c_size_t, vp]
     lib.mcrn_trainer_loss.restype = C.c_int
     lib.mcrn_trainer_loss.argtypes = [C.POINTER(Dims), fp, fp, fp, fp, fp, C.c_float, C.c_float, C.c_float,
                                       C.c_float, fp, fp, fp, vp, C.c_size_t, vp]
@@ -140,6 +172,24 @@ def make_params(tensors: Sequence) -> Params:
     for name, t in zip(PARAM_FIELDS, tensors):
         setattr(p, name, t.data_ptr())
     return p
+
+
+def make_layer_params(tensors: Sequence):
+    """``tensors``: 8 per stacked layer in LAYER_FIELDS order -> a ctypes array of mcrn_layer_params (None if empty).
+    Keep the returned object alive across the call that takes ``C.addressof`` / ``C.byref`` of it."""
+    n = len(tensors) // len(LAYER_FIELDS)
+    assert n * len(LAYER_FIELDS) == len(tensors) and n <= MAX_LAYERS - 1
+    if n == 0:
+        return None
+    arr = (LayerParams * n)()
+    for l in range(n):
+        for j, name in enumerate(LAYER_FIELDS):
+            setattr(arr[l], name, tensors[l * len(LAYER_FIELDS) + j].data_ptr())
+    return arr
+
+
+def layer_ptr(arr) -> Optional[int]:
+    return None if arr is None else C.addressof(arr)
 
 
 def tf_bytes(flags: Optional[Sequence[bool]], horizon: int) -> bytes:

@@ -17,6 +17,13 @@ int forward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const floa
 int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uint8_t* tf, const float* d_output,
                   const float* d_hatt, const float* d_query, const float* d_pos, const float* d_neg,
                   const mcrn_params* grads, float* ws, cudaStream_t st);
+int forward_impl_layers(const Geo& g, const Plan& p, const mcrn_params* prm, const mcrn_layer_params* up, const float* x,
+                        const float* y_cov, const float* labels, const uint8_t* tf, float* output, float* h_att, float* query,
+                        float* pos, float* neg, float* ws, cudaStream_t st);
+int backward_impl_layers(const Geo& g, const Plan& p, const mcrn_params* prm, const mcrn_layer_params* up, const uint8_t* tf,
+                         const float* d_output, const float* d_hatt, const float* d_query, const float* d_pos,
+                         const float* d_neg, const mcrn_params* grads, const mcrn_layer_params* ugrads, float* ws,
+                         cudaStream_t st);
 int supports_forward_entry(const Geo& g, const Plan& p, float* ws, const float* mem, const float* we1,
                            const float* we2, float* S, float* Sr, cudaStream_t st);
 int trainer_loss_impl(const Geo& g, const float* output, const float* labels, const float* query, const float* pos,
@@ -75,6 +82,20 @@ static int check_params(const mcrn_params* p, const char* what) {
   }
   return MCRN_OK;
 }
+static int check_layer_params(const mcrn_layer_params* up, int layers, const char* what) {
+  if (layers <= 1) return MCRN_OK;
+  if (!up) { set_error("%s is null but num_layers = %d", what, layers); return MCRN_ERR_BAD_POINTER; }
+  for (int l = 0; l + 1 < layers; ++l) {
+    const float* const* v = reinterpret_cast<const float* const*>(up + l);
+    for (size_t i = 0; i < sizeof(mcrn_layer_params) / sizeof(float*); ++i)
+      if (!v[i]) { set_error("%s[%d]: tensor #%zu is null", what, l, i); return MCRN_ERR_BAD_POINTER; }
+  }
+  return MCRN_OK;
+}
+static int single_layer_only(const Geo& g, const char* what) {
+  if (g.L != 1) { set_error("%s: num_layers = %d needs the *_layers entry (mcrn_forward_layers / mcrn_backward_layers)", what, g.L); return MCRN_ERR_BAD_DIMS; }
+  return MCRN_OK;
+}
 }  // namespace mcrn
 
 using namespace mcrn;
@@ -118,6 +139,7 @@ int mcrn_adam_step(const mcrn_dims* dims, const mcrn_params* params, const mcrn_
                    void* stream) {
   Geo g;
   MCRN_TRY(make_geo(dims, &g));
+  MCRN_TRY(single_layer_only(g, "mcrn_adam_step"));
   MCRN_TRY(check_params(params, "params"));
   MCRN_TRY(check_params(grads, "grads"));
   MCRN_TRY(check_params(exp_avg, "exp_avg"));
@@ -173,6 +195,7 @@ int mcrn_forward(const mcrn_dims* dims, const mcrn_params* params, const float* 
                  float* pos, float* neg, void* workspace, size_t workspace_bytes, uint32_t flags, void* stream) {
   Geo g;
   MCRN_TRY(make_geo(dims, &g));
+  MCRN_TRY(single_layer_only(g, "mcrn_forward"));
   MCRN_TRY(check_params(params, "params"));
   if (!x || !y_cov || !output || !h_att || !query || !pos || !neg || !workspace) {
     set_error("mcrn_forward: null tensor pointer");
@@ -209,6 +232,7 @@ int mcrn_backward(const mcrn_dims* dims, const mcrn_params* params, const float*
   (void)x; (void)y_cov; (void)labels;
   Geo g;
   MCRN_TRY(make_geo(dims, &g));
+  MCRN_TRY(single_layer_only(g, "mcrn_backward"));
   MCRN_TRY(check_params(params, "params"));
   MCRN_TRY(check_params(grads, "grads"));
   if (!workspace) { set_error("workspace is null"); return MCRN_ERR_BAD_POINTER; }
@@ -229,6 +253,77 @@ int mcrn_backward(const mcrn_dims* dims, const mcrn_params* params, const float*
   {
     // the backward consumes the saved state (accumulators are not idempotent): a second mcrn_backward on the same
     // forward is an error, as it is for freed autograd buffers
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_saved.erase(workspace);
+  }
+  return s;
+}
+
+int mcrn_forward_layers(const mcrn_dims* dims, const mcrn_params* params, const mcrn_layer_params* upper, const float* x,
+                        const float* y_cov, const float* labels, const uint8_t* teacher_forcing, float* output, float* h_att,
+                        float* query, float* pos, float* neg, void* workspace, size_t workspace_bytes, uint32_t flags,
+                        void* stream) {
+  Geo g;
+  MCRN_TRY(make_geo(dims, &g));
+  if (g.L == 1)
+    return mcrn_forward(dims, params, x, y_cov, labels, teacher_forcing, output, h_att, query, pos, neg, workspace,
+                        workspace_bytes, flags, stream);
+  MCRN_TRY(check_params(params, "params"));
+  MCRN_TRY(check_layer_params(upper, g.L, "upper"));
+  if (!x || !y_cov || !output || !h_att || !query || !pos || !neg || !workspace) {
+    set_error("mcrn_forward_layers: null tensor pointer");
+    return MCRN_ERR_BAD_POINTER;
+  }
+  bool any_tf = false;
+  if (teacher_forcing)
+    for (int t = 0; t < g.T_out; ++t) any_tf |= teacher_forcing[t] != 0;
+  if (any_tf && !labels) { set_error("teacher forcing requested but labels is null"); return MCRN_ERR_BAD_POINTER; }
+  if (!aligned16(workspace)) { set_error("workspace must be 16-byte aligned"); return MCRN_ERR_BAD_POINTER; }
+  MCRN_TRY(check_device());
+  Plan p;
+  const bool save = (flags & MCRN_FWD_SAVE_FOR_BACKWARD) != 0;
+  make_plan(g, save, &p);
+  if (workspace_bytes < p.bytes) { set_error("workspace too small: %zu < %zu", workspace_bytes, p.bytes); return MCRN_ERR_WORKSPACE; }
+  const int s = forward_impl_layers(g, p, params, upper, x, y_cov, labels, teacher_forcing, output, h_att, query, pos, neg,
+                                    static_cast<float*>(workspace), static_cast<cudaStream_t>(stream));
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (s == MCRN_OK && save) g_saved[workspace] = dims_hash(dims);
+    else g_saved.erase(workspace);
+  }
+  return s;
+}
+
+int mcrn_backward_layers(const mcrn_dims* dims, const mcrn_params* params, const mcrn_layer_params* upper, const float* x,
+                         const float* y_cov, const float* labels, const uint8_t* teacher_forcing, const float* d_output,
+                         const float* d_h_att, const float* d_query, const float* d_pos, const float* d_neg,
+                         const mcrn_params* grads, const mcrn_layer_params* upper_grads, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  Geo g;
+  MCRN_TRY(make_geo(dims, &g));
+  if (g.L == 1)
+    return mcrn_backward(dims, params, x, y_cov, labels, teacher_forcing, d_output, d_h_att, d_query, d_pos, d_neg, grads,
+                         workspace, workspace_bytes, stream);
+  MCRN_TRY(check_params(params, "params"));
+  MCRN_TRY(check_params(grads, "grads"));
+  MCRN_TRY(check_layer_params(upper, g.L, "upper"));
+  MCRN_TRY(check_layer_params(upper_grads, g.L, "upper_grads"));
+  if (!workspace) { set_error("workspace is null"); return MCRN_ERR_BAD_POINTER; }
+  MCRN_TRY(check_device());
+  Plan p;
+  make_plan(g, true, &p);
+  if (workspace_bytes < p.bytes) { set_error("workspace too small: %zu < %zu", workspace_bytes, p.bytes); return MCRN_ERR_WORKSPACE; }
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_saved.find(workspace);
+    if (it == g_saved.end() || it->second != dims_hash(dims)) {
+      set_error("mcrn_backward_layers: no matching mcrn_forward_layers(MCRN_FWD_SAVE_FOR_BACKWARD) on this workspace");
+      return MCRN_ERR_STATE;
+    }
+  }
+  const int s = backward_impl_layers(g, p, params, upper, teacher_forcing, d_output, d_h_att, d_query, d_pos, d_neg, grads,
+                                     upper_grads, static_cast<float*>(workspace), static_cast<cudaStream_t>(stream));
+  {
     std::lock_guard<std::mutex> lk(g_mu);
     g_saved.erase(workspace);
   }
@@ -347,6 +442,7 @@ int mcrn_forward_host(const mcrn_dims* dims, const mcrn_params* host_params, con
                       void* stream) {
   Geo g;
   MCRN_TRY(make_geo(dims, &g));
+  MCRN_TRY(single_layer_only(g, "mcrn_forward_host"));
   MCRN_TRY(check_params(host_params, "host_params"));
   if (!x || !y_cov || !output || !h_att || !query || !pos || !neg || !device_workspace) {
     set_error("mcrn_forward_host: null pointer");

@@ -84,6 +84,7 @@ struct Geo {
   int Cdec;     // decoder input channels: Cout + Ycov
   int ldS;      // leading dimension of a support matrix row (multiple of 4 floats)
   int64_t R;    // rows of the node-major state: N*B
+  int L;        // num_layers (stacked cells per encoder / decoder, model/MegaCRN.py:62-63)
 };
 
 static inline int support_ld(int n) { return (n + 3) / 4 * 4; }

@@ -43,8 +43,8 @@ int make_geo(const mcrn_dims* dm, Geo* g) {
               dm->mem_dim);
     return MCRN_ERR_BAD_DIMS;
   }
-  if (dm->num_layers != 1) {
-    set_error("num_layers=%d: only the reference default num_layers=1 is implemented", dm->num_layers);
+  if (dm->num_layers < 1 || dm->num_layers > MCRN_MAX_LAYERS) {
+    set_error("num_layers=%d: 1..%d are implemented", dm->num_layers, MCRN_MAX_LAYERS);
     return MCRN_ERR_BAD_DIMS;
   }
   if (dm->cheb_k < 2) { set_error("cheb_k=%d: need >= 2", dm->cheb_k); return MCRN_ERR_BAD_DIMS; }
@@ -55,6 +55,7 @@ int make_geo(const mcrn_dims* dm, Geo* g) {
   g->Cdec = g->Cout + g->Ycov;
   g->ldS = support_ld(g->N);
   g->R = (int64_t)g->N * g->B;
+  g->L = dm->num_layers;
   // the input channels and the bias ride in one extra K-block of width H (resp. D) of every AGCN contraction
   if (g->NB * g->Cin + 1 > g->H || g->NB * g->Cdec + 1 > g->D) {
     set_error("rnn_units=%d too small: need (1+2(cheb_k-1))*input_channels + 1 <= hidden width (enc %d<=%d, dec %d<=%d)",
@@ -1340,6 +1341,8 @@ int backward_impl(const Geo& g, const Plan& p, const mcrn_params* prm, const uin
   MCRN_LAUNCH(k_unfold_grads, 128, 256, 0, st, ws + p.a_d_wu, grads->dec_update_w, grads->dec_update_b, g.Cdec, g.D, g.D, g.cheb_k);
   return MCRN_OK;
 }
+
+#include "layers.cuh"      // num_layers > 1: forward_impl_layers / backward_impl_layers
 
 int supports_forward_entry(const Geo& g, const Plan& p, float* ws, const float* mem, const float* we1,
                            const float* we2, float* S, float* Sr, cudaStream_t st) {

@@ -7,6 +7,16 @@
 
 namespace mcrn {
 
+// Buffers of one stacked cell pair (encoder + decoder cell of layer l >= 1, model/MegaCRN.py:62-63, :100-101).  Their AGCN
+// operand is V = [x_in | h] of width 2*Hs (x_in = the state of the layer below), so every XP block is [R][2*Hs].
+struct UpperPlan {
+  size_t e_wg, e_wu, d_wg, d_wu;                 // folded weights [hi|lo][NB+1][2Hs][O] (cin = 0: block NB carries the bias row only)
+  size_t e_xpg, e_xpu, e_z, e_r, e_hc, e_hseq;   // per slot; e_hseq: the layer's output of EVERY step [T_in][R][H] (input of the layer above)
+  size_t d_xpg, d_xpu, d_z, d_r, d_hc, d_hseq;   // d_hseq [T_out][R][D]
+  size_t e_dU, e_dG, d_dU, d_dG, d_dH;           // backward: dU / dG of every step, the layer's recurrent decoder gradient [R][D]
+  size_t a_e_wg, a_e_wu, a_d_wg, a_d_wu;         // weight-gradient accumulators [NB+1][2Hs][O] (inside the zeroed region)
+};
+
 struct Plan {
   Geo g;
   bool save;
@@ -47,6 +57,13 @@ struct Plan {
   size_t dXPin_sz;
   // loss scratch
   size_t loss_scratch;                   // 8 floats
+  // ---- stacked layers (num_layers > 1): all zero-sized when num_layers == 1 ----
+  UpperPlan up[MCRN_MAX_LAYERS - 1];
+  int up_slots_e, up_slots_d;            // slots of the per-step buffers (all steps when saving, else 1)
+  size_t up_e_xp_sz, up_d_xp_sz;         // floats per XP slot: (NB+1)*R*2H / (NB+1)*R*2D
+  size_t up_zero, up_zh;                 // [R][D] zeros (initial encoder state of a stacked layer); z*h scratch [R][D]
+  size_t up_dXP, up_dXP2, up_dV0, up_dhp, up_dxa, up_dx;   // backward temporaries of a stacked cell
+  size_t up_dxseq, up_dHe2;              // [T_in][R][H] gradient w.r.t. the outputs of the layer below; [R][H] recurrent encoder gradient
 };
 
 static inline int make_plan(const Geo& g, bool save, Plan* p) {
@@ -70,7 +87,7 @@ static inline int make_plan(const Geo& g, bool save, Plan* p) {
   p->e_wu = take(2 * (NB + 1) * g.H * g.H);
   p->d_wg = take(2 * (NB + 1) * g.D * 2 * g.D);
   p->d_wu = take(2 * (NB + 1) * g.D * g.D);
-  p->enc_slots = save ? g.T_in : 2;
+  p->enc_slots = (save || g.L > 1) ? g.T_in : 2;      // a stacked layer reads the outputs of every step of the layer below
   p->dec_slots = save ? g.T_out : 2;
   p->enc_xpin = take(NB * N * g.T_in * g.B * g.Cin);
   p->enc_xp_sz = ((NB + 1) * R * g.H + 63) / 64 * 64;      // NB state blocks + the input block
@@ -118,6 +135,34 @@ static inline int make_plan(const Geo& g, bool save, Plan* p) {
     p->dec_ib32c = take(save ? (size_t)g.T_out * R * 16 : 0);
   }
   p->loss_scratch = take(64);
+  if (g.L > 1) {
+    const size_t kwe = 2 * (size_t)g.H, kwd = 2 * (size_t)g.D;
+    p->up_slots_e = save ? g.T_in : 1;
+    p->up_slots_d = save ? g.T_out : 1;
+    p->up_e_xp_sz = ((NB + 1) * R * kwe + 63) / 64 * 64;
+    p->up_d_xp_sz = ((NB + 1) * R * kwd + 63) / 64 * 64;
+    p->up_zero = take(R * g.D);
+    p->up_zh = take(R * g.D);
+    for (int l = 0; l + 1 < g.L; ++l) {
+      UpperPlan& u = p->up[l];
+      u.e_wg = take(2 * (NB + 1) * kwe * 2 * g.H);
+      u.e_wu = take(2 * (NB + 1) * kwe * g.H);
+      u.d_wg = take(2 * (NB + 1) * kwd * 2 * g.D);
+      u.d_wu = take(2 * (NB + 1) * kwd * g.D);
+      u.e_xpg = take(p->up_e_xp_sz * p->up_slots_e);
+      u.e_xpu = take(p->up_e_xp_sz * p->up_slots_e);
+      u.e_z = take(p->enc_v_sz * p->up_slots_e);
+      u.e_r = take(p->enc_v_sz * p->up_slots_e);
+      u.e_hc = take(p->enc_v_sz * p->up_slots_e);
+      u.e_hseq = take(p->enc_v_sz * (size_t)g.T_in);
+      u.d_xpg = take(p->up_d_xp_sz * p->up_slots_d);
+      u.d_xpu = take(p->up_d_xp_sz * p->up_slots_d);
+      u.d_z = take(p->dec_v_sz * p->up_slots_d);
+      u.d_r = take(p->dec_v_sz * p->up_slots_d);
+      u.d_hc = take(p->dec_v_sz * p->up_slots_d);
+      u.d_hseq = take(p->dec_v_sz * (size_t)g.T_out);
+    }
+  }
   if (save) {
     const size_t Cm = (size_t)(g.Cin > g.Cdec ? g.Cin : g.Cdec);
     p->dH = take(R * g.D);
@@ -168,7 +213,36 @@ static inline int make_plan(const Geo& g, bool save, Plan* p) {
     p->dIBg16 = take(R * 16);
     p->dXPin_sz = (NB * R * Cm + 63) / 64 * 64;
     p->dXPin_all = take(p->dXPin_sz * (size_t)(g.T_in > g.T_out ? g.T_in : g.T_out));
+    if (g.L > 1) {
+      const size_t kwd = 2 * (size_t)g.D;
+      p->up_dXP = take((NB + 1) * R * kwd);
+      p->up_dXP2 = take((NB + 1) * R * kwd);
+      p->up_dV0 = take(R * kwd);
+      p->up_dhp = take(R * g.D);
+      p->up_dxa = take(R * g.D);
+      p->up_dx = take(R * g.D);
+      p->up_dxseq = take(p->enc_v_sz * (size_t)g.T_in);
+      p->up_dHe2 = take(R * g.H);
+      for (int l = 0; l + 1 < g.L; ++l) {
+        UpperPlan& u = p->up[l];
+        u.e_dU = take((size_t)g.T_in * R * g.H);
+        u.e_dG = take((size_t)g.T_in * R * 2 * g.H);
+        u.d_dU = take((size_t)g.T_out * R * g.D);
+        u.d_dG = take((size_t)g.T_out * R * 2 * g.D);
+        u.d_dH = take(R * g.D);
+      }
+    }
     p->acc_begin = off;
+    if (g.L > 1) {
+      const size_t kwe = 2 * (size_t)g.H, kwd = 2 * (size_t)g.D;
+      for (int l = 0; l + 1 < g.L; ++l) {
+        UpperPlan& u = p->up[l];
+        u.a_e_wg = take((NB + 1) * kwe * 2 * g.H);
+        u.a_e_wu = take((NB + 1) * kwe * g.H);
+        u.a_d_wg = take((NB + 1) * kwd * 2 * g.D);
+        u.a_d_wu = take((NB + 1) * kwd * g.D);
+      }
+    }
     p->dS = take(KS * N * ldS);
     p->a_e_wg = take((NB + 1) * g.H * 2 * g.H);
     p->a_e_wu = take((NB + 1) * g.H * g.H);

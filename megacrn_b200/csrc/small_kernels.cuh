@@ -492,4 +492,53 @@ __global__ void k_slice_add(const float* __restrict__ a, int lda, const float* _
   }
 }
 
+// ---- stacked cells (num_layers > 1; tests/kernel_spec.py: cell_fwd_wide / cell_bwd_wide) ----------------------
+// AGCN operand of a stacked cell: out[row][0:hs] = a[row] (the state of the layer below), out[row][hs:2hs] = b[row]
+// (own state h, or z*h for the candidate: model/MegaCRN.py:42, :46); TF32-rounded when rnd (tensor-core operand).
+__global__ void k_concat2(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t R,
+                          int hs, int rnd) {
+  const int kw = 2 * hs;
+  const int64_t total = R * kw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / kw;
+    const int c = (int)(i - row * kw);
+    const float v = (c < hs) ? a[row * hs + c] : b[row * hs + (c - hs)];
+    out[i] = rnd ? tf32_rn(v) : v;
+  }
+}
+
+// Gate backward of a stacked cell.  dV0 [R][2hs] = gradient of the candidate operand [x_in | z*h]:
+//   dG[:, :hs] = dZH*h*z(1-z), dG[:, hs:] = dH*(h-hc)*r(1-r), dh_part = dH*r + dZH*z, dx_part = dV0[:, :hs].
+__global__ void k_wide_gate_bwd(const float* __restrict__ dV0, const float* __restrict__ dH, const float* __restrict__ h,
+                                const float* __restrict__ z, const float* __restrict__ r, const float* __restrict__ hc,
+                                float* __restrict__ dG, float* __restrict__ dh_part, float* __restrict__ dx_part, int64_t R,
+                                int hs, int rnd) {
+  const int64_t total = R * hs;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / hs;
+    const int c = (int)(i - row * hs);
+    const float dzh = dV0[row * 2 * hs + hs + c], hh = h[i], zz = z[i], rr = r[i], dh = dH[i];
+    float gz = dzh * hh * zz * (1.0f - zz);
+    float gr = dh * (hh - hc[i]) * rr * (1.0f - rr);
+    if (rnd) { gz = tf32_rn(gz); gr = tf32_rn(gr); }
+    dG[row * 2 * hs + c] = gz;
+    dG[row * 2 * hs + hs + c] = gr;
+    dh_part[i] = dh * rr + dzh * zz;
+    dx_part[i] = dV0[row * 2 * hs + c];
+  }
+}
+
+// dV0 [R][2hs] = gradient of the gate operand [x_in | h]:  dH = dh_part + dV0[:, hs:],  dx = dx_part + dV0[:, :hs].
+__global__ void k_wide_finish(const float* __restrict__ dV0, const float* __restrict__ dh_part,
+                              const float* __restrict__ dx_part, float* __restrict__ dH, float* __restrict__ dx, int64_t R,
+                              int hs) {
+  const int64_t total = R * hs;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / hs;
+    const int c = (int)(i - row * hs);
+    dH[i] = dh_part[i] + dV0[row * 2 * hs + hs + c];
+    dx[i] = dx_part[i] + dV0[row * 2 * hs + c];
+  }
+}
+
 }  // namespace mcrn

@@ -22,6 +22,9 @@ class FusedClipAdam:
 
     def __init__(self, model, lr=0.01, betas=(0.9, 0.999), eps=1e-3, max_grad_norm=5.0):
         self.model = model
+        if getattr(model, "num_layers", 1) != 1:
+            raise NotImplementedError("FusedClipAdam (mcrn_adam_step) covers the 14 tensors of num_layers=1; use "
+                                      "torch.nn.utils.clip_grad_norm_ + torch.optim.Adam, as the reference trainer does")
         sd = dict(model.named_parameters())
         self.params = [sd[k] for k in _abi.STATE_DICT_KEYS]
         dev = self.params[0].device

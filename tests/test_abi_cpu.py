@@ -42,7 +42,9 @@ def test_workspace_and_dim_validation():
     assert 0 < fwd < trn
     assert trn > 12 * 5 * 207 * 64 * (64 + 128) * 4          # per-step XP buffers are saved
     assert lib.mcrn_host_workspace_bytes(d, 0) > fwd
-    d.num_layers = 2
+    d.num_layers = 2                                         # stacked cells: more buffers, still valid
+    assert lib.mcrn_workspace_bytes(d, 1) > trn
+    d.num_layers = 5
     assert lib.mcrn_workspace_bytes(d, 0) == 0
     assert b"num_layers" in lib.mcrn_last_error()
     d.num_layers, d.cheb_k = 1, 1
@@ -84,7 +86,7 @@ def test_header_is_plain_c_and_links_against_the_library(tmp_path):
 int main(void) {
   mcrn_dims d = {64, 207, 12, 12, 1, 1, 1, 64, 1, 3, 20, 64};
   size_t fwd = mcrn_workspace_bytes(&d, 0), trn = mcrn_workspace_bytes(&d, MCRN_FWD_SAVE_FOR_BACKWARD);
-  d.num_layers = 2;
+  d.num_layers = 9;
   size_t bad = mcrn_workspace_bytes(&d, 0);
   printf("%d %zu %zu %zu %d\n", mcrn_abi_version(), fwd, trn, bad, mcrn_support_ld(207));
   return (mcrn_abi_version() == 1 && fwd > 0 && trn > fwd && bad == 0) ? 0 : 1;

@@ -143,7 +143,7 @@ def test_supports_stage_matches_spec():
         assert torch.allclose(got[0].sum(-1), torch.ones(d.num_nodes), atol=1e-5)      # softmax rows
 
 
-@pytest.mark.parametrize("name", [n for n in CASES if n != "layers2"])
+@pytest.mark.parametrize("name", list(CASES))
 def test_eval_forward_vs_reference_golden(name, engine):
     d, p, (x, y_cov, labels), gold, _ = load_case(name)
     m = _model(d, p).eval()
@@ -160,7 +160,7 @@ def test_eval_forward_vs_reference_golden(name, engine):
             assert close_mixed(o.cpu(), ref, 2 * FWD_TOL), k
 
 
-@pytest.mark.parametrize("name", [n for n in CASES if n != "layers2"])
+@pytest.mark.parametrize("name", list(CASES))
 def test_train_forward_and_grads_vs_reference_golden(name, engine):
     d, p, (x, y_cov, labels), gold, full = load_case(name)
     flags = [bool(f) for f in gold["train_flags"]]
@@ -288,6 +288,46 @@ def test_large_graph_full_sequence_vs_oracle(cfg, default_engine):
     print(cfg, "forward rel-L2", rel_l2(outs[0].detach().cpu(), ref_outs[0]), "grad rel-L2", {k: f"{v:.1e}" for k, v in errs.items()})
     for pname, e in errs.items():
         assert e < grad_tol("default", pname), (pname, e)
+
+
+@pytest.mark.parametrize("cfg", ["L2_small", "L3_small", "L2_metrla_width"])
+def test_stacked_layers_vs_oracle(cfg, engine):
+    """num_layers > 1 (model/MegaCRN.py:71-78, :109-112): forward (train and eval) and all 14 + 8(L-1) gradients against the
+    oracle, mixed teacher forcing.  L2_metrla_width: H = 64 / D = 128, the widths the fused single-layer kernels take --
+    with stacked cells every layer runs on the per-stage engine."""
+    if cfg == "L2_small":
+        d, B, t_in = O.Dims(num_nodes=37, horizon=4, rnn_units=16, mem_num=7, mem_dim=12, num_layers=2), 3, 5
+    elif cfg == "L3_small":
+        d, B, t_in = O.Dims(num_nodes=21, horizon=3, rnn_units=12, mem_num=5, mem_dim=8, num_layers=3, cheb_k=2), 2, 4
+    else:
+        d, B, t_in = O.Dims(num_nodes=207, horizon=3, rnn_units=64, num_layers=2), 2, 3
+    p = O.init_params(d, seed=4)
+    g = torch.Generator().manual_seed(5)
+    for k in p:                                   # non-zero AGCN biases: the bias column of the stacked cells' input block
+        if k.endswith("bias"):
+            p[k] = torch.randn(p[k].shape, generator=g) * 0.1
+    x, y_cov, labels = O.synthetic_batch(d, B, t_in, seed=31)
+    flags = [t % 2 == 0 for t in range(d.horizon)]
+    ref_loss, ref_outs, ref_grads = O.loss_and_grads(d, p, x, y_cov, labels, flags)
+    assert len(ref_grads) == 14 + 8 * (d.num_layers - 1)
+    m = _model(d, p).train()
+    dv = _dev()
+    outs = m(x.to(dv), y_cov.to(dv), labels.to(dv), teacher_forcing=flags)
+    d_out, d_q = reference_upstream(ref_outs[0], ref_outs[2], ref_outs[3], ref_outs[4], labels)
+    torch.autograd.backward([outs[0], outs[2]], [d_out.to(dv), d_q.to(dv)])
+    for k, a, b in zip(OUT_NAMES[:3], outs[:3], ref_outs[:3]):
+        assert rel_l2(a.detach().cpu(), b) < FWD_TOL, (k, rel_l2(a.detach().cpu(), b))
+    errs = {pname: rel_l2(prm.grad.cpu(), ref_grads[pname]) for pname, prm in m.named_parameters()}
+    print(cfg, engine, "forward rel-L2", rel_l2(outs[0].detach().cpu(), ref_outs[0]), "grad rel-L2", {k: f"{v:.1e}" for k, v in errs.items()})
+    for pname, e in errs.items():
+        assert e < grad_tol(engine, pname), (pname, e)
+    # eval: no saved activations (one slot per stacked cell), free-running decoder
+    m.eval()
+    with torch.no_grad():
+        ev = m(x.to(dv), y_cov.to(dv))
+        ref_ev = O.forward(d, p, x, y_cov)
+    for k, a, b in zip(OUT_NAMES[:3], ev[:3], ref_ev[:3]):
+        assert rel_l2(a.cpu(), b) < FWD_TOL, ("eval", k, rel_l2(a.cpu(), b))
 
 
 def test_all_output_gradients_including_pos_neg(engine):
@@ -551,7 +591,7 @@ def test_fused_trainer_loss_matches_torch():
 def test_unsupported_configs_fail_loudly():
     from megacrn_b200 import MegaCRN
     with pytest.raises(NotImplementedError):
-        MegaCRN(11, 1, 1, 3, 8, num_layers=2)
+        MegaCRN(11, 1, 1, 3, 8, num_layers=5)
     d, p, (x, y_cov, labels), gold, _ = load_case("tiny")
     m = _model(d, p)
     with pytest.raises(RuntimeError):
