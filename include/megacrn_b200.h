@@ -195,6 +195,15 @@ int mcrn_adam_step(const mcrn_dims* dims, const mcrn_params* params, const mcrn_
                    const mcrn_params* exp_avg, const mcrn_params* exp_avg_sq, float* dev_state,
                    float beta1, float beta2, float eps, float max_grad_norm, void* stream);
 
+/* Same over the 14 + 8*(num_layers-1) tensors of a model with stacked cells: ONE gradient norm over all of them (what
+ * clip_grad_norm_(model.parameters()) computes) and one update.  The upper_* arrays hold num_layers-1 structs (NULL when
+ * num_layers == 1, in which case this IS mcrn_adam_step). */
+int mcrn_adam_step_layers(const mcrn_dims* dims, const mcrn_params* params, const mcrn_layer_params* upper,
+                          const mcrn_params* grads, const mcrn_layer_params* upper_grads,
+                          const mcrn_params* exp_avg, const mcrn_layer_params* upper_exp_avg,
+                          const mcrn_params* exp_avg_sq, const mcrn_layer_params* upper_exp_avg_sq,
+                          float* dev_state, float beta1, float beta2, float eps, float max_grad_norm, void* stream);
+
 /* HOST-buffer convenience entries (what a non-PyTorch caller would bind): every
  * pointer in params/grads/x/... is a HOST pointer; the library stages through the
  * caller-provided DEVICE workspace, which must be at least

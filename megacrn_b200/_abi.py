@@ -105,6 +105,9 @@ def load() -> C.CDLL:
     lib.mcrn_adam_step.restype = C.c_int
     lib.mcrn_adam_step.argtypes = [C.POINTER(Dims), C.POINTER(Params), C.POINTER(Params), C.POINTER(Params), C.POINTER(Params),
                                    fp, C.c_float, C.c_float, C.c_float, C.c_float, vp]
+    lib.mcrn_adam_step_layers.restype = C.c_int
+    lib.mcrn_adam_step_layers.argtypes = [C.POINTER(Dims), C.POINTER(Params), vp, C.POINTER(Params), vp, C.POINTER(Params), vp,
+                                          C.POINTER(Params), vp, fp, C.c_float, C.c_float, C.c_float, C.c_float, vp]
     lib.mcrn_kernel_timing.restype = C.c_int
     lib.mcrn_kernel_timing.argtypes = [C.c_int]
     lib.mcrn_kernel_timing_read.restype = C.c_int

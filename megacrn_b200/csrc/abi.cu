@@ -34,6 +34,8 @@ int mask_count_impl(const float* labels, int64_t n, float mean, float std, float
 int adam_step_impl(const Geo& g, const mcrn_params* prm, const mcrn_params* grads, const mcrn_params* m, const mcrn_params* v,
                    float* state, float beta1, float beta2, float eps, float max_norm, cudaStream_t st);
 
+int adam_step_layers_impl(const Geo& g, const mcrn_params* const q[4], const mcrn_layer_params* const u[4], float* state,
+                          float beta1, float beta2, float eps, float max_norm, cudaStream_t st);
 bool set_option(const char* name, int value);
 int probe_mn16_entry(const void* A, const void* B, float* C, unsigned lbo, unsigned sbo, unsigned layout, unsigned kstep,
                      unsigned b_major, cudaStream_t st);
@@ -148,6 +150,25 @@ int mcrn_adam_step(const mcrn_dims* dims, const mcrn_params* params, const mcrn_
   MCRN_TRY(check_device());
   return adam_step_impl(g, params, grads, exp_avg, exp_avg_sq, dev_state, beta1, beta2, eps, max_grad_norm,
                         static_cast<cudaStream_t>(stream));
+}
+int mcrn_adam_step_layers(const mcrn_dims* dims, const mcrn_params* params, const mcrn_layer_params* upper,
+                          const mcrn_params* grads, const mcrn_layer_params* upper_grads, const mcrn_params* exp_avg,
+                          const mcrn_layer_params* upper_exp_avg, const mcrn_params* exp_avg_sq,
+                          const mcrn_layer_params* upper_exp_avg_sq, float* dev_state, float beta1, float beta2, float eps,
+                          float max_grad_norm, void* stream) {
+  Geo g;
+  MCRN_TRY(make_geo(dims, &g));
+  if (g.L == 1) return mcrn_adam_step(dims, params, grads, exp_avg, exp_avg_sq, dev_state, beta1, beta2, eps, max_grad_norm, stream);
+  const mcrn_params* const q[4] = {params, grads, exp_avg, exp_avg_sq};
+  const mcrn_layer_params* const u[4] = {upper, upper_grads, upper_exp_avg, upper_exp_avg_sq};
+  const char* names[4] = {"params", "grads", "exp_avg", "exp_avg_sq"};
+  for (int a = 0; a < 4; ++a) {
+    MCRN_TRY(check_params(q[a], names[a]));
+    MCRN_TRY(check_layer_params(u[a], g.L, names[a]));
+  }
+  if (!dev_state) { set_error("mcrn_adam_step_layers: dev_state is null"); return MCRN_ERR_BAD_POINTER; }
+  MCRN_TRY(check_device());
+  return adam_step_layers_impl(g, q, u, dev_state, beta1, beta2, eps, max_grad_norm, static_cast<cudaStream_t>(stream));
 }
 int mcrn_kernel_timing(int enable) {
   fused::g_prof.enabled = enable ? 1 : 0;

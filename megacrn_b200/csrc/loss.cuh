@@ -106,21 +106,27 @@ __global__ void __launch_bounds__(256) k_loss_grad_rows(const float* __restrict_
 
 // ---- fused gradient clipping + Adam over the 14 parameter tensors (model/traintest_MegaCRN.py:104, :129-130) ----
 namespace mcrn {
-struct ParamTable {
-  float* p[14]; const float* g[14]; float* m[14]; float* v[14];
-  int64_t off[15];                       // prefix sums of the element counts
+// NT = 14 (num_layers == 1) or 14 + 8*(MCRN_MAX_LAYERS-1) (stacked cells; unused trailing entries have zero elements)
+template <int NT>
+struct ParamTableT {
+  float* p[NT]; const float* g[NT]; float* m[NT]; float* v[NT];
+  int64_t off[NT + 1];                   // prefix sums of the element counts
 };
-__device__ __forceinline__ int table_find(const ParamTable& t, int64_t i) {
+using ParamTable = ParamTableT<14>;
+constexpr int PARAM_TABLE_MAX = 14 + 8 * (MCRN_MAX_LAYERS - 1);
+template <int NT>
+__device__ __forceinline__ int table_find(const ParamTableT<NT>& t, int64_t i) {
   int k = 0;
 #pragma unroll
-  for (int j = 1; j < 14; ++j) k += (i >= t.off[j]) ? 1 : 0;
+  for (int j = 1; j < NT; ++j) k += (i >= t.off[j]) ? 1 : 0;
   return k;
 }
 // state[0] = step count (incremented here), state[2] += sum of squared gradients (zeroed by the caller)
-__global__ void __launch_bounds__(256) k_grad_sqnorm(ParamTable t, float* __restrict__ state) {
+template <int NT>
+__global__ void __launch_bounds__(256) k_grad_sqnorm(ParamTableT<NT> t, float* __restrict__ state) {
   __shared__ float sh[8];
   float s = 0.f;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < t.off[14]; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < t.off[NT]; i += (int64_t)gridDim.x * blockDim.x) {
     const int k = table_find(t, i);
     const float g = t.g[k][i - t.off[k]];
     s = fmaf(g, g, s);
@@ -136,7 +142,8 @@ __global__ void __launch_bounds__(256) k_grad_sqnorm(ParamTable t, float* __rest
   if (blockIdx.x == 0 && threadIdx.x == 0) state[0] += 1.0f;
 }
 // torch.nn.utils.clip_grad_norm_ (coef = min(1, max_norm / (norm + 1e-6))) then torch.optim.Adam.step (no amsgrad, no decay)
-__global__ void __launch_bounds__(256) k_clip_adam(ParamTable t, float* __restrict__ state, float beta1, float beta2, float eps,
+template <int NT>
+__global__ void __launch_bounds__(256) k_clip_adam(ParamTableT<NT> t, float* __restrict__ state, float beta1, float beta2, float eps,
                                                    float max_norm) {
   const float step = state[0], lr = state[1];
   const float norm = sqrtf(state[2]);
@@ -149,7 +156,7 @@ __global__ void __launch_bounds__(256) k_clip_adam(ParamTable t, float* __restri
   const float coef = max_norm > 0.f ? fminf(1.0f, max_norm / (norm + 1e-6f)) : 1.0f;
   const float bc1 = 1.0f - powf(beta1, step), bc2 = 1.0f - powf(beta2, step);
   const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < t.off[14]; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < t.off[NT]; i += (int64_t)gridDim.x * blockDim.x) {
     const int k = table_find(t, i);
     const int64_t j = i - t.off[k];
     const float g = t.g[k][j] * coef;

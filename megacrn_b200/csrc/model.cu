@@ -1371,13 +1371,34 @@ int trainer_loss_impl(const Geo& g, const float* output, const float* labels, co
   return MCRN_OK;
 }
 
-int adam_step_impl(const Geo& g, const mcrn_params* prm, const mcrn_params* grads, const mcrn_params* m, const mcrn_params* v,
-                   float* state, float beta1, float beta2, float eps, float max_norm, cudaStream_t st) {
+// element counts of the 14 tensors of mcrn_params / the 8 of one mcrn_layer_params, field order
+static void param_counts(const Geo& g, int64_t (&n)[14]) {
   const int64_t ck2 = 2 * g.cheb_k;
-  const int64_t n[14] = {(int64_t)g.M * g.d, (int64_t)g.H * g.d, (int64_t)g.N * g.M, (int64_t)g.N * g.M,
+  const int64_t v[14] = {(int64_t)g.M * g.d, (int64_t)g.H * g.d, (int64_t)g.N * g.M, (int64_t)g.N * g.M,
                          ck2 * (g.Cin + g.H) * 2 * g.H, 2 * g.H, ck2 * (g.Cin + g.H) * g.H, g.H,
                          ck2 * (g.Cdec + g.D) * 2 * g.D, 2 * g.D, ck2 * (g.Cdec + g.D) * g.D, g.D,
                          (int64_t)g.Cout * g.D, g.Cout};
+  for (int i = 0; i < 14; ++i) n[i] = v[i];
+}
+static void layer_param_counts(const Geo& g, int64_t (&n)[8]) {
+  const int64_t ck2 = 2 * g.cheb_k, H = g.H, D = g.D;
+  const int64_t v[8] = {ck2 * 2 * H * 2 * H, 2 * H, ck2 * 2 * H * H, H, ck2 * 2 * D * 2 * D, 2 * D, ck2 * 2 * D * D, D};
+  for (int i = 0; i < 8; ++i) n[i] = v[i];
+}
+
+template <int NT>
+static int adam_launch(ParamTableT<NT>& t, float* state, float beta1, float beta2, float eps, float max_norm, cudaStream_t st) {
+  MCRN_CUDA_OK(cudaMemsetAsync(state + 2, 0, sizeof(float), st));
+  const int grid = ew_grid(t.off[NT]) > 592 ? 592 : ew_grid(t.off[NT]);
+  MCRN_LAUNCH(k_grad_sqnorm<NT>, grid, 256, 0, st, t, state);
+  MCRN_LAUNCH(k_clip_adam<NT>, grid, 256, 0, st, t, state, beta1, beta2, eps, max_norm);
+  return MCRN_OK;
+}
+
+int adam_step_impl(const Geo& g, const mcrn_params* prm, const mcrn_params* grads, const mcrn_params* m, const mcrn_params* v,
+                   float* state, float beta1, float beta2, float eps, float max_norm, cudaStream_t st) {
+  int64_t n[14];
+  param_counts(g, n);
   ParamTable t;
   float* const* pp = reinterpret_cast<float* const*>(prm);
   float* const* gg = reinterpret_cast<float* const*>(grads);
@@ -1388,11 +1409,37 @@ int adam_step_impl(const Geo& g, const mcrn_params* prm, const mcrn_params* grad
     t.p[i] = pp[i]; t.g[i] = gg[i]; t.m[i] = mm[i]; t.v[i] = vv[i];
     t.off[i + 1] = t.off[i] + n[i];
   }
-  MCRN_CUDA_OK(cudaMemsetAsync(state + 2, 0, sizeof(float), st));
-  const int grid = ew_grid(t.off[14]) > 592 ? 592 : ew_grid(t.off[14]);
-  MCRN_LAUNCH(k_grad_sqnorm, grid, 256, 0, st, t, state);
-  MCRN_LAUNCH(k_clip_adam, grid, 256, 0, st, t, state, beta1, beta2, eps, max_norm);
-  return MCRN_OK;
+  return adam_launch(t, state, beta1, beta2, eps, max_norm, st);
+}
+
+// stacked cells: the 14 tensors plus 8 per layer >= 1 in ONE norm / ONE update (clip_grad_norm_ is global over all parameters)
+int adam_step_layers_impl(const Geo& g, const mcrn_params* const q[4], const mcrn_layer_params* const u[4], float* state,
+                          float beta1, float beta2, float eps, float max_norm, cudaStream_t st) {
+  int64_t n[14], nl[8];
+  param_counts(g, n);
+  layer_param_counts(g, nl);
+  ParamTableT<PARAM_TABLE_MAX> t;
+  float* const* base[4];
+  for (int a = 0; a < 4; ++a) base[a] = reinterpret_cast<float* const*>(q[a]);
+  t.off[0] = 0;
+  int k = 0;
+  for (int i = 0; i < 14; ++i, ++k) {
+    t.p[k] = base[0][i]; t.g[k] = base[1][i]; t.m[k] = base[2][i]; t.v[k] = base[3][i];
+    t.off[k + 1] = t.off[k] + n[i];
+  }
+  for (int l = 1; l < g.L; ++l) {
+    float* const* lv[4];
+    for (int a = 0; a < 4; ++a) lv[a] = reinterpret_cast<float* const*>(u[a] + (l - 1));
+    for (int i = 0; i < 8; ++i, ++k) {
+      t.p[k] = lv[0][i]; t.g[k] = lv[1][i]; t.m[k] = lv[2][i]; t.v[k] = lv[3][i];
+      t.off[k + 1] = t.off[k] + nl[i];
+    }
+  }
+  for (; k < PARAM_TABLE_MAX; ++k) {           // unused entries: no elements
+    t.p[k] = nullptr; t.g[k] = nullptr; t.m[k] = nullptr; t.v[k] = nullptr;
+    t.off[k + 1] = t.off[k];
+  }
+  return adam_launch(t, state, beta1, beta2, eps, max_norm, st);
 }
 
 int probe_mn16_entry(const void* A, const void* B, float* C, unsigned lbo, unsigned sbo, unsigned layout, unsigned kstep,

@@ -3,7 +3,8 @@
     torch.nn.utils.clip_grad_norm_(model.parameters(), max_grad_norm)      model/traintest_MegaCRN.py:129
     torch.optim.Adam(model.parameters(), lr, eps=...).step()               :104, :130
 
-as two kernels over the 14 parameter tensors (``mcrn_adam_step``): a squared-norm reduction and the clipped Adam update.
+as two kernels over the 14 parameter tensors (``mcrn_adam_step``; 14 + 8 per stacked layer: ``mcrn_adam_step_layers``):
+a squared-norm reduction and the clipped Adam update.
 Step count, learning rate, gradient norm and clip coefficient live in a 4-float device tensor, so the call needs no
 host synchronisation and can be captured in the same CUDA graph as forward + loss + backward.
 """
@@ -22,11 +23,8 @@ class FusedClipAdam:
 
     def __init__(self, model, lr=0.01, betas=(0.9, 0.999), eps=1e-3, max_grad_norm=5.0):
         self.model = model
-        if getattr(model, "num_layers", 1) != 1:
-            raise NotImplementedError("FusedClipAdam (mcrn_adam_step) covers the 14 tensors of num_layers=1; use "
-                                      "torch.nn.utils.clip_grad_norm_ + torch.optim.Adam, as the reference trainer does")
         sd = dict(model.named_parameters())
-        self.params = [sd[k] for k in _abi.STATE_DICT_KEYS]
+        self.params = [sd[k] for k in _abi.param_keys(getattr(model, "num_layers", 1))]      # 14, + 8 per stacked layer
         dev = self.params[0].device
         if dev.type != "cuda":
             raise RuntimeError("FusedClipAdam needs the model on a CUDA device (megacrn_b200 has no CPU path)")
@@ -70,16 +68,26 @@ class FusedClipAdam:
                 raise RuntimeError("FusedClipAdam.step(): every parameter needs a gradient (run backward first)")
             grads.append(p.grad if p.grad.is_contiguous() else p.grad.contiguous())
         m = self.model
+        layers = getattr(m, "num_layers", 1)
         dims = _abi.Dims(batch=1, num_nodes=m.num_nodes, seq_len=1, horizon=m.horizon, input_dim=m.input_dim,
-                         output_dim=m.output_dim, ycov_dim=m.ycov_dim, rnn_units=m.rnn_units, num_layers=1,
+                         output_dim=m.output_dim, ycov_dim=m.ycov_dim, rnn_units=m.rnn_units, num_layers=layers,
                          cheb_k=m.cheb_k, mem_num=m.mem_num, mem_dim=m.mem_dim)
         dev = self.params[0].device
+        sets = (self.params, grads, self.exp_avg, self.exp_avg_sq)
+        base = [_abi.make_params(t[:14]) for t in sets]
         with torch.cuda.device(dev):
-            st = lib.mcrn_adam_step(dims, _abi.make_params(self.params), _abi.make_params(grads),
-                                    _abi.make_params(self.exp_avg), _abi.make_params(self.exp_avg_sq),
-                                    self.state.data_ptr(), self.betas[0], self.betas[1], self.eps,
-                                    self.max_grad_norm if self.max_grad_norm else 0.0,
-                                    torch.cuda.current_stream(dev).cuda_stream)
+            if layers == 1:
+                st = lib.mcrn_adam_step(dims, base[0], base[1], base[2], base[3],
+                                        self.state.data_ptr(), self.betas[0], self.betas[1], self.eps,
+                                        self.max_grad_norm if self.max_grad_norm else 0.0,
+                                        torch.cuda.current_stream(dev).cuda_stream)
+            else:
+                upper = [_abi.make_layer_params(t[14:]) for t in sets]
+                st = lib.mcrn_adam_step_layers(dims, base[0], _abi.layer_ptr(upper[0]), base[1], _abi.layer_ptr(upper[1]),
+                                               base[2], _abi.layer_ptr(upper[2]), base[3], _abi.layer_ptr(upper[3]),
+                                               self.state.data_ptr(), self.betas[0], self.betas[1], self.eps,
+                                               self.max_grad_norm if self.max_grad_norm else 0.0,
+                                               torch.cuda.current_stream(dev).cuda_stream)
         _abi.check(st, "mcrn_adam_step")
         self.note_update()
 

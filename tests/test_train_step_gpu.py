@@ -76,12 +76,14 @@ def test_graphed_step_equals_eager_step_and_oracle_c2(flags_kind):
         assert rel_l2(q.grad.cpu(), ref_grads[n]) < 3e-2, (n, rel_l2(q.grad.cpu(), ref_grads[n]))
 
 
-def test_adam_trajectory_graphed_vs_torch_adam_on_oracle():
+@pytest.mark.parametrize("layers", [1, 2])
+def test_adam_trajectory_graphed_vs_torch_adam_on_oracle(layers):
     """5 steps of GraphedTrainStep(optimizer=FusedClipAdam) against clip_grad_norm_(5) + torch.optim.Adam(lr .01, eps 1e-3)
-    driving the CPU oracle (model/traintest_MegaCRN.py:104, :128-130)."""
+    driving the CPU oracle (model/traintest_MegaCRN.py:104, :128-130).  layers = 2: stacked cells -- 22 tensors in one
+    gradient norm and one update (mcrn_adam_step_layers), the per-stage engine captured in the graph."""
     from megacrn_b200.optim import FusedClipAdam
     from megacrn_b200.train_step import GraphedTrainStep
-    d, B, T = O.Dims(num_nodes=60, horizon=4, rnn_units=64, mem_num=8, mem_dim=64), 8, 4
+    d, B, T = O.Dims(num_nodes=60, horizon=4, rnn_units=64, mem_num=8, mem_dim=64, num_layers=layers), 8, 4
     p = O.init_params(d, seed=4)
     flags = [True, False, True, True]
     batches = [O.synthetic_batch(d, B, T, seed=100 + i) for i in range(5)]
