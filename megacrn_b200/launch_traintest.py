@@ -14,6 +14,10 @@ The reference script (model/traintest_MegaCRN.py) imports ``MegaCRN`` and ``util
   * executes the reference file with ``runpy.run_path(..., run_name="__main__")`` with the shim directory first on
     ``sys.path``.  Nothing of the reference is modified or copied into this repository.
 
+``--stock-model`` swaps the shim for the reference's own ``MegaCRN.py`` (the unmodified reference end to end: the baseline
+arm of a side-by-side run) and ``--seed`` seeds torch / numpy / random first, so that both arms start from the same weights
+and draw the same batches and teacher-forcing coins.
+
 ``--harness model_EXPYTKY`` runs the EXPY-TKY harness (model_EXPYTKY/traintest_MegaCRN.py) the same way: it also reads
 ``params.txt`` from the CWD (:182) and copies ``metrics.py`` / ``params.txt`` next to the model (:205-206), its data directory
 is always ``../EXPYTKY`` (params.txt), it calls ``torchsummary.summary`` (:27, stubbed to a no-op when the package is absent)
@@ -37,11 +41,15 @@ SHIM = '"""Shim written by megacrn_b200.launch_traintest: the reference trainer 
 HARNESS_FILES = {"model": ("utils.py",), "model_EXPYTKY": ("utils.py", "metrics.py", "params.txt")}
 
 
-def prepare(reference: str, workdir: str, dataset: str, data: str | None, harness: str = "model") -> str:
+def prepare(reference: str, workdir: str, dataset: str, data: str | None, harness: str = "model",
+            stock_model: bool = False) -> str:
     model_dir = os.path.join(workdir, harness)
     os.makedirs(model_dir, exist_ok=True)
-    with open(os.path.join(model_dir, "MegaCRN.py"), "w") as f:
-        f.write(SHIM)
+    if stock_model:          # baseline arm: the reference's own model file, i.e. the unmodified reference end to end
+        shutil.copy2(os.path.join(reference, harness, "MegaCRN.py"), os.path.join(model_dir, "MegaCRN.py"))
+    else:
+        with open(os.path.join(model_dir, "MegaCRN.py"), "w") as f:
+            f.write(SHIM)
     for name in HARNESS_FILES[harness]:
         shutil.copy2(os.path.join(reference, harness, name), os.path.join(model_dir, name))
     src = os.path.abspath(data or os.path.join(reference, dataset))
@@ -75,6 +83,11 @@ def main(argv=None):
     ap.add_argument("--data", default=None, help="directory holding train/val/test.npz (default <reference>/<DATASET>)")
     ap.add_argument("--script", default="traintest_MegaCRN.py")
     ap.add_argument("--harness", default="model", choices=sorted(HARNESS_FILES), help="reference directory holding the trainer")
+    ap.add_argument("--stock-model", action="store_true",
+                    help="baseline arm: run the harness against the reference's OWN MegaCRN.py (nothing of this package on the path)")
+    ap.add_argument("--seed", type=int, default=None,
+                    help="seed torch / numpy / random before the script starts (the reference scripts leave seeding commented "
+                         "out): two arms with the same seed see the same initial weights, batches and teacher-forcing coins")
     ap.add_argument("rest", nargs=argparse.REMAINDER, help="arguments after -- go to the reference script")
     args = ap.parse_args(argv)
     rest = [a for a in args.rest if a != "--"]
@@ -84,7 +97,7 @@ def main(argv=None):
     if args.harness == "model_EXPYTKY":
         dataset = "EXPYTKY"                    # 'EXPYTKY' and 'EXPYTKY*' both live in ../EXPYTKY (params.txt)
     workdir = os.path.abspath(args.workdir)
-    model_dir = prepare(os.path.abspath(args.reference), workdir, dataset, args.data, args.harness)
+    model_dir = prepare(os.path.abspath(args.reference), workdir, dataset, args.data, args.harness, args.stock_model)
     script = os.path.join(os.path.abspath(args.reference), args.harness, args.script)
     try:
         import torchsummary  # noqa: F401
@@ -105,6 +118,14 @@ def main(argv=None):
             sys.path.remove(p)
         sys.path.insert(0, p)
     os.chdir(model_dir)
+    if args.seed is not None:
+        import random
+
+        import numpy as np
+        import torch
+        random.seed(args.seed)
+        np.random.seed(args.seed)
+        torch.manual_seed(args.seed)
     sys.argv = [script] + rest
     runpy.run_path(script, run_name="__main__")
 
