@@ -448,14 +448,17 @@ __global__ void __launch_bounds__(256) k_grad_amax(AmaxSrc a, unsigned* __restri
     if (threadIdx.x == 0 && m > 0.f && m < INFINITY) atomicMax(amax, __float_as_uint(m));
   }
 }
-// gs = {2^e, 2^-e} with amax * 2^e in [2^7, 2^8): x2600 of head-room below fp16's 65504, full fp16 precision down to 2^-22 amax
+// gs = {2^e, 2^-e} with amax * 2^e in [2^3, 2^4): x4096-8192 of head-room below fp16's 65504 for the gradients BPTT builds up
+// from the upstream ones (amax is taken over the UPSTREAM gradients only), full fp16 precision down to 2^-18 amax and
+// subnormals down to 2^-28 amax.  (Round 2 first used [2^7, 2^8): a real METR-LA run hit an fp16 overflow -> NaN after 21 k
+// steps, profiles/r2_metrla_real_run.txt.)  Beyond the head-room the operand conversions saturate (fusedh::pack_h2 / round_h).
 __global__ void k_grad_scale(const unsigned* __restrict__ amax, float* __restrict__ gs) {
   const float m = __uint_as_float(*amax);
   int e = 0;
   if (m > 0.f) {
     int ex;
     frexpf(m, &ex);                 // m = f * 2^ex, f in [0.5, 1)
-    e = 8 - ex;
+    e = 4 - ex;
     e = e > 60 ? 60 : (e < -60 ? -60 : e);
   }
   gs[0] = exp2f((float)e);

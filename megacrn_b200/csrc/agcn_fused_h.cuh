@@ -84,11 +84,19 @@ template <int N_>
 __device__ __forceinline__ constexpr uint32_t make_idesc_f16() {
   return (1u << 4) | ((uint32_t)(N_ >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
+// fp32 -> fp16, round to nearest, SATURATING to +-65504 (one F2FP.SATFINITE, same cost as the plain conversion): a scaled
+// gradient operand that outgrows fp16's range (BPTT can amplify the recurrent gradient far beyond the upstream maximum the
+// loss scale is chosen from) is clipped instead of becoming inf -- no inf, hence no inf - inf = NaN, can enter an MMA.
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
-  __half2 h = __floats2half2_rn(lo, hi);       // .x (low 16 bits) = lo
-  return *reinterpret_cast<uint32_t*>(&h);
+  uint32_t r;                                  // low 16 bits = lo
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
-__device__ __forceinline__ float round_h(float v) { return __half2float(__float2half_rn(v)); }
+__device__ __forceinline__ float round_h(float v) {
+  unsigned short h;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+  return __half2float(__ushort_as_half(h));
+}
 // Gate activations: one ex2 and one rcp (MUFU) each, flush-to-zero forms -- no range-check code around them (the epilogue
 // issues 2 x 32 K of these per tile).  ex2.approx: max rel. error 2^-22; |x| large: e -> 0 or +inf, rcp(inf) = 0: exact limits.
 __device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }

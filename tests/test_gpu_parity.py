@@ -487,6 +487,26 @@ def test_fp16_backward_loss_scale_is_magnitude_invariant(scale, default_engine):
         assert rel_l2(res[scale][k], res[1.0][k]) < 5e-5, (k, rel_l2(res[scale][k], res[1.0][k]))
 
 
+def test_fp16_backward_saturates_instead_of_overflowing(default_engine):
+    """BPTT can amplify the recurrent gradient far beyond max|upstream|, which is all the loss scale is chosen from (a real
+    METR-LA run went NaN this way after 21 k steps, profiles/r2_metrla_real_run.txt).  Here the projection weights are blown up
+    so that d(out) * Wp exceeds the x8192 head-room: the fp16 operand conversions must clip (finite gradients, the in-range
+    ones still right), never produce inf / NaN."""
+    d = O.Dims(num_nodes=150, horizon=3, rnn_units=64)
+    p = O.init_params(d, seed=2)
+    p["proj.0.weight"] = p["proj.0.weight"] * 3.0e5
+    x, y_cov, labels = O.synthetic_batch(d, 2, 3, seed=4)
+    dv = _dev()
+    m = _model(d, p).train()
+    outs = m(x.to(dv), y_cov.to(dv), labels.to(dv), teacher_forcing=[True] * 3)
+    gen = torch.Generator().manual_seed(9)
+    ups = [torch.randn(outs[0].shape, generator=gen).to(dv) * 1e-3, torch.zeros_like(outs[2])]
+    torch.autograd.backward([outs[0], outs[2]], ups)
+    for k, t in m.named_parameters():
+        assert torch.isfinite(t.grad).all(), k
+    assert float(m.proj[0].bias.grad.abs().sum()) > 0
+
+
 def test_kernel_timing_api_counts_fused_launches(default_engine):
     import ctypes
     from megacrn_b200 import _abi
