@@ -12,7 +12,8 @@ REF = os.environ.get("MEGACRN_REFERENCE", "/root/reference")
 REF_MODEL = os.path.join(REF, "model", "MegaCRN.py")
 
 CASES = [dict(num_nodes=207, input_dim=1, output_dim=1, horizon=12, rnn_units=64),
-         dict(num_nodes=33, input_dim=2, output_dim=1, horizon=4, rnn_units=16, mem_num=6, mem_dim=12, cheb_k=2)]
+         dict(num_nodes=33, input_dim=2, output_dim=1, horizon=4, rnn_units=16, mem_num=6, mem_dim=12, cheb_k=2),
+         dict(num_nodes=21, input_dim=1, output_dim=1, horizon=3, rnn_units=12, mem_num=5, mem_dim=8, num_layers=3)]
 
 
 def _reference_class():
@@ -30,7 +31,15 @@ def test_state_dict_keys_and_shapes_follow_the_oracle_table():
         d = O.Dims(**kw)
         shapes = O.param_shapes(d)
         sd = m.state_dict()
-        assert list(sd.keys()) == list(shapes.keys()) == list(_abi.STATE_DICT_KEYS)
+        layers = kw.get("num_layers", 1)
+        assert list(sd.keys()) == list(shapes.keys())
+        if layers == 1:
+            assert list(sd.keys()) == list(_abi.STATE_DICT_KEYS)
+        # C-ABI order: the 14 tensors of mcrn_params, then 8 per stacked layer (mcrn_layer_params)
+        abi_keys = _abi.param_keys(layers)
+        assert abi_keys[:14] == _abi.STATE_DICT_KEYS and sorted(abi_keys) == sorted(sd.keys())
+        named = dict(m.named_parameters())
+        assert [id(named[k]) for k in abi_keys] == [id(t) for t in m._ordered_params()]
         for k, v in sd.items():
             assert tuple(v.shape) == tuple(shapes[k]), k
 
